@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- EPC-Net clouds/sec (4096 points) on N B200s, batch-sharded (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the embedding hot path (kNN graph -> ProxyConv backbone -> conv5 -> G_VLAD -> 256-d
+descriptor) over one batch of `--clouds` synthetic 4096-point clouds per GPU (weak scaling, no collective on the
+data path).  Rank 0 prints ONE JSON line:
+  value            clouds/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e              the same metric through evaluate.get_latent_vectors with HOST buffers (pinned H2D + D2H timed)
+  roofline         the dominant kernel's algorithmic FLOP/s (or B/s) vs MEASURED_PEAKS.json, timed live with events
+  cpu_baseline     the oracle (dense-as-written numpy restatement of the TF graph) on the host cores, bounded sample
+`--impl reference` times that CPU restatement alone (TF 1.12 itself cannot run here).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import _data  # noqa: E402
+
+METRIC = "EPC-Net clouds/sec (4096 pts)"
+UNIT = "clouds/s"
+ARCH = "epc-net"
+N_POINTS = 4096
+# algorithmic work per cloud, SURVEY.md Appendix C (N=4096, k=20)
+FLOPS = {"conv5": 2.0 * N_POINTS * 256 * 1024, "knn": 8.0 * N_POINTS * N_POINTS,
+         "assign_gemm": 2.0 * N_POINTS * 1024 * 64, "vlad_gemm": 2.0 * 64 * N_POINTS * 1024,
+         "proxy_block": 3 * 2.0 * N_POINTS * 64 * 64 + N_POINTS * 20 * 64, "hidden_gemm": 2.0 * 4 * 16384 * 256}
+TENSOR_STAGES = ("conv5", "assign_gemm", "vlad_gemm", "hidden_gemm")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--clouds", type=int, default=128, help="clouds per GPU per step")
+    ap.add_argument("--chunk", type=int, default=32, help="clouds per library call")
+    ap.add_argument("--cpu-sample", type=int, default=24, help="clouds in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-retrieval", action="store_true")
+    return ap.parse_args()
+
+
+def make_clouds(n, seed):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(-1.0, 1.0, (n, N_POINTS, 3)).astype(np.float32)       # SURVEY.md 8d C1/C2 inputs
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "bf16_tflops": d.get("bf16_tflops", 1590.0),
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", 1400.0), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(n_sample, V, params):
+    """The reference's CPU path: dense-as-written restatement (oracle), ONE cloud per call like evaluate.py:355."""
+    from oracle import epc_oracle
+    clouds = make_clouds(n_sample, 4242)
+    epc_oracle.forward(ARCH, clouds[:1][None], V, params)          # warm-up (BLAS thread pools)
+    ts = []
+    for i in range(n_sample):
+        t0 = time.perf_counter()
+        epc_oracle.forward(ARCH, clouds[i:i + 1][None], V, params)
+        ts.append(time.perf_counter() - t0)
+    return n_sample / float(np.sum(ts)), float(np.median(ts))
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement, every host thread the BLAS takes, same metric/config keys."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    variables = importlib.import_module("epc-net_b200.variables")
+    from oracle import epc_oracle
+    V = variables.synthetic_variables(ARCH, 1)
+    params = _data.default_params(ARCH)
+    per_step = 2                                                    # bounded sample: 2 clouds per step
+    clouds = make_clouds(per_step * (args.steps + args.warmup), 4242)
+    k = 0
+    for _ in range(args.warmup):
+        for j in range(per_step):
+            epc_oracle.forward(ARCH, clouds[k:k + 1][None], V, params)
+            k += 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for j in range(per_step):
+            epc_oracle.forward(ARCH, clouds[k:k + 1][None], V, params)
+            k += 1
+    dt = time.perf_counter() - t0
+    val = per_step * args.steps / dt
+    cores = os.cpu_count()
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "EPC-Net (configs/epc-net.yaml) embedding of synthetic 4096-point clouds, 1 cloud per call "
+                               "(evaluate.py:355), seeded random-init weights", "clouds_per_step": per_step},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d clouds/step x %d steps, numpy/BLAS dense-as-written restatement of the TF-1.12 "
+                                   "graph (TensorFlow not runnable here)" % (per_step, args.steps)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    lib_mod = importlib.import_module("epc-net_b200._lib")
+    variables = importlib.import_module("epc-net_b200.variables")
+    engine_mod = importlib.import_module("epc-net_b200.engine")
+    evaluate = importlib.import_module("epc-net_b200.evaluate")
+    models = importlib.import_module("epc-net_b200.models")
+
+    V = variables.synthetic_variables(ARCH, 1)
+    store = variables.VariableStore(V)
+    params = dict(_data.default_params(ARCH), EMBED_CHUNK=args.chunk, VARIABLES=store)
+    eng = engine_mod.get_engine(ARCH, params, store=store)
+    B, K, W = args.clouds, args.steps, args.warmup
+    nbatch = min(K + W, 4)                                         # rotate distinct inputs; intermediates >> L2 anyway
+    host_batches = [make_clouds(B, 1000 + 97 * rank + i) for i in range(nbatch)]
+    dev_batches = [torch.from_numpy(b).cuda() for b in host_batches]
+    out = torch.empty((B, 256), dtype=torch.float32, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput -------------------------------------------------------------------
+    for i in range(W):
+        eng.embed(dev_batches[i % nbatch], out=out)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib_mod.launch_count_reset()
+    lib_mod.profile_reset()
+    lib_mod.profile_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(K):
+        eng.embed(dev_batches[(W + i) % nbatch], out=out)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib_mod.launch_count()
+    stages = lib_mod.profile_read()
+    lib_mod.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * K / (ms * 1e-3)
+
+    # ---- end to end: host arrays in, host arrays out, through the reference-facing call ---------------------
+    ops = {"MODEL": models.load(ARCH), "params": params}
+    names = {i: {} for i in range(B)}
+    for i in range(min(W, 2)):
+        evaluate.get_latent_vectors(None, ops, names, host_batches[i % nbatch])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        desc = evaluate.get_latent_vectors(None, ops, names, host_batches[(W + i) % nbatch])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = world * B * K / e2e_s
+    assert desc.shape == (B, 256) and np.isfinite(desc).all()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (stage with the largest share of device time) ----------------
+    peaks = measured_peaks()
+    total_stage_ms = sum(v[0] for v in stages.values()) or 1.0
+    top = max(stages.items(), key=lambda kv: kv[1][0])[0]
+    top_ms, top_n = stages[top]
+    clouds_per_launch = B * K / float(top_n)
+    roof = {"kernel": top, "share_of_step": top_ms / total_stage_ms, "launches": top_n,
+            "avg_launch_ms": top_ms / top_n, "peak_source": peaks["source"], "traffic": None}
+    if top in FLOPS:
+        ach = FLOPS[top] * clouds_per_launch / (top_ms / top_n * 1e-3) / 1e12
+        roof.update({"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": ach / peaks["bf16_tflops_sustained"],
+                     "note": "algorithmic FLOP of the stage / event-timed duration; peak = measured sustained bf16 cuBLAS"})
+    else:
+        byt = (48 * 1024 + 1024) * clouds_per_launch
+        ach = byt / (top_ms / top_n * 1e-3) / 1e9
+        roof.update({"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"]})
+    stage_table = {k: {"ms_per_cloud": v[0] / (B * K), "share": v[0] / total_stage_ms} for k, v in stages.items()}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "EPC-Net (configs/epc-net.yaml: 4 ProxyConv blocks + G_VLAD, 256-d) batch embedding of "
+                               "synthetic uniform(-1,1) 4096-point clouds, seeded random-init weights, batch-sharded",
+                   "clouds_per_gpu_per_step": B, "clouds_per_call": args.chunk, "knn_arith": "muladd",
+                   "l2": "inputs rotate over %d distinct batches; every call streams >0.5 GB of intermediates "
+                         "(>> 126 MB L2)" % nbatch},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * N_POINTS * 3 * 4, "d2h_bytes_per_step": B * 256 * 4,
+                "api": "evaluate.get_latent_vectors(host ndarray) -> host ndarray"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "stages": stage_table,
+    }
+    if not args.no_retrieval:
+        line["retrieval"] = bench_retrieval(evaluate, torch)
+    if not args.no_cpu_baseline:
+        cps, med = cpu_baseline(args.cpu_sample, V, _data.default_params(ARCH))
+        line["cpu_baseline"] = {"value": cps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                "sample": "%d clouds, 1 cloud per call (evaluate.py:355), median %.3f s/cloud; numpy/BLAS "
+                                          "dense-as-written restatement of the TF-1.12 graph" % (args.cpu_sample, med)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_retrieval(evaluate, torch):
+    """Secondary metrics of BASELINE.json: retrieval queries/s and recall@1 on SURVEY 8d C5 (D=20k, Q=3k, k=25)."""
+    from oracle import retrieval_oracle
+    db, q, src = _data.retrieval_problem(D=20000, Q=3000, seed=7)
+    dbt, qt = torch.from_numpy(db).cuda(), torch.from_numpy(q).cuda()
+    for _ in range(2):
+        d, i = evaluate.retrieve_topk(dbt, qt, 25)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 5
+    for _ in range(reps):
+        d, i = evaluate.retrieve_topk(dbt, qt, 25)
+    e1.record()
+    torch.cuda.synchronize()
+    qps = reps * len(q) / (e0.elapsed_time(e1) * 1e-3)
+    idx = i.cpu().numpy()
+    t0 = time.perf_counter()
+    n_cpu = 200
+    _, ref = retrieval_oracle.kdtree_knn(db, q[:1], 25)
+    from sklearn.neighbors import KDTree
+    tree = KDTree(db)
+    t0 = time.perf_counter()
+    ref = np.stack([tree.query(q[j:j + 1], k=25)[1][0] for j in range(n_cpu)], 0)     # evaluate.py:481, one query per call
+    cpu_qps = n_cpu / (time.perf_counter() - t0)
+    return {"queries_per_s": qps, "recall_at_1": float((idx[:, 0] == src).mean()), "D": 20000, "Q": 3000, "k": 25,
+            "top25_identical_to_kdtree": bool(np.array_equal(idx[:n_cpu], ref)),
+            "cpu_kdtree_queries_per_s": cpu_qps, "cpu_sample": "%d queries, sklearn KDTree, 1 query per call" % n_cpu}
+
+
+if __name__ == "__main__":
+    main()

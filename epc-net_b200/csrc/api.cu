@@ -1,0 +1,588 @@
+// C ABI of libepc_b200.so (include/epc_b200.h): argument checking, BN folding / weight upload,
+// workspace carving and the kernel sequence of one embedding call.
+#include <stdarg.h>
+#include <string.h>
+
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace epc {
+
+static thread_local char g_err[512] = "";
+static thread_local long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+
+// ---- per-stage timing -------------------------------------------------------------------------------
+struct StageRec {
+    int id;
+    cudaEvent_t a, b;
+};
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<StageRec>* g_prof = nullptr;
+static thread_local double g_stage_ms[EPC_STAGE_COUNT] = {};
+static thread_local long long g_stage_n[EPC_STAGE_COUNT] = {};
+
+ScopedStage::ScopedStage(int stage_id, cudaStream_t stream) : id(stage_id), st(stream), on(g_prof_on) {
+    if (!on) return;
+    if (!g_prof) g_prof = new std::vector<StageRec>();
+    StageRec r;
+    r.id = id;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) {
+        on = false;
+        return;
+    }
+    cudaEventRecord(r.a, st);
+    g_prof->push_back(r);
+}
+ScopedStage::~ScopedStage() {
+    if (!on) return;
+    cudaEventRecord(g_prof->back().b, st);
+}
+
+static void prof_collect() {
+    if (!g_prof) return;
+    for (StageRec& r : *g_prof) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            g_stage_ms[r.id] += ms;
+            g_stage_n[r.id] += 1;
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_prof->clear();
+}
+
+}  // namespace epc
+
+using namespace epc;
+
+struct EpcModel {
+    int arch = 0, n_blocks = 0, K = 64, D = 256, G = 4, pooling = 0, gating = 1;
+    float divisor = 20.f;
+    bool vlad_head = true;
+    float* blob = nullptr;            // one device allocation holding every folded parameter
+    DenseDev conv[12];
+    DenseDev conv5;
+    const float *Wc = nullptr, *cbn_scale = nullptr, *cbn_shift = nullptr, *Wc2 = nullptr, *Wh = nullptr,
+                *hbn_scale = nullptr, *hbn_shift = nullptr, *Wg = nullptr, *gbn_scale = nullptr, *gbn_shift = nullptr;
+    int hidden_in = 0;                // rows of hidden1_weights
+    DenseDev fc1;
+};
+
+namespace {
+
+// inference BN -> per-channel affine:  y = x*scale + shift  (utils/tf_util.py:490; FusedBatchNorm is the same map)
+void bn_affine(const EpcBN& bn, int C, std::vector<float>& scale, std::vector<float>& shift) {
+    scale.resize(C);
+    shift.resize(C);
+    for (int c = 0; c < C; ++c) {
+        const float inv = (1.0f / std::sqrt(bn.var_host[c] + BN_EPS)) * bn.gamma_host[c];
+        scale[c] = inv;
+        shift[c] = bn.beta_host[c] - bn.mean_host[c] * inv;
+    }
+}
+
+bool bn_ok(const EpcBN& bn) { return bn.beta_host && bn.gamma_host && bn.mean_host && bn.var_host; }
+
+// y = relu(BN(xW+b)) = relu(x (W*scale) + (b*scale + shift))
+void fold_dense(const EpcDense& L, std::vector<float>& W, std::vector<float>& b) {
+    std::vector<float> sc, sh;
+    bn_affine(L.bn, L.cout, sc, sh);
+    W.resize((size_t)L.cin * L.cout);
+    b.resize(L.cout);
+    for (int k = 0; k < L.cin; ++k)
+        for (int n = 0; n < L.cout; ++n) W[(size_t)k * L.cout + n] = L.weights_host[(size_t)k * L.cout + n] * sc[n];
+    for (int n = 0; n < L.cout; ++n) b[n] = L.biases_host[n] * sc[n] + sh[n];
+}
+
+struct Packer {
+    std::vector<float> host;
+    size_t add(const float* p, size_t n) {
+        size_t off = (host.size() + 63) / 64 * 64;   // 256-byte alignment
+        host.resize(off + n);
+        memcpy(host.data() + off, p, n * sizeof(float));
+        return off;
+    }
+    size_t add(const std::vector<float>& v) { return add(v.data(), v.size()); }
+};
+
+// libepc_b200 links cudart statically; make the device that owns `p` current for this thread so that
+// launches go to the same device as the caller's (e.g. torch's) allocations.
+int ensure_device(const void* p) {
+    if (!p) return EPC_OK;
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) {
+        set_error("cudaPointerGetAttributes: %s (is a CUDA device present?)", cudaGetErrorString(e));
+        return EPC_ECUDA;
+    }
+    if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) {
+        cudaGetLastError();
+        set_error("pointer %p is not device memory (libepc_b200 has no CPU path)", p);
+        return EPC_EINVAL;
+    }
+    e = cudaSetDevice(at.device);
+    if (e != cudaSuccess) {
+        set_error("cudaSetDevice(%d): %s", at.device, cudaGetErrorString(e));
+        return EPC_ECUDA;
+    }
+    return EPC_OK;
+}
+
+bool dense_ok(const EpcDense& L) { return L.weights_host && L.biases_host && bn_ok(L.bn) && L.cin > 0 && L.cout > 0; }
+
+}  // namespace
+
+extern "C" {
+
+const char* epc_last_error(void) { return g_err; }
+int epc_abi_version(void) { return EPC_ABI_VERSION; }
+long long epc_launch_count(void) { return g_launches; }
+void epc_launch_count_reset(void) { g_launches = 0; }
+
+void epc_profile_enable(int on) { g_prof_on = (on != 0); }
+void epc_profile_reset(void) {
+    prof_collect();
+    for (int i = 0; i < EPC_STAGE_COUNT; ++i) {
+        g_stage_ms[i] = 0.0;
+        g_stage_n[i] = 0;
+    }
+}
+int epc_profile_read(int stage, double* ms, long long* launches) {
+    EPC_CHECK_ARG(stage >= 0 && stage < EPC_STAGE_COUNT, "bad stage %d", stage);
+    prof_collect();
+    if (ms) *ms = g_stage_ms[stage];
+    if (launches) *launches = g_stage_n[stage];
+    return EPC_OK;
+}
+const char* epc_stage_name(int stage) {
+    static const char* names[EPC_STAGE_COUNT] = {"sort", "knn", "conv_in", "proxy_block", "conv5", "rownorm",
+                                                 "assign_gemm", "assign_softmax", "vlad_gemm", "vlad_finalize",
+                                                 "hidden_gemm", "tail", "colmax", "fc", "kd_feat", "retrieve_score",
+                                                 "retrieve_select", "retrieve_rerank"};
+    return (stage >= 0 && stage < EPC_STAGE_COUNT) ? names[stage] : "?";
+}
+
+int epc_set_device(int device) {
+    EPC_CUDA(cudaSetDevice(device));
+    return EPC_OK;
+}
+int epc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// -------------------------------------------------------------------------------------------------
+// kNN
+// -------------------------------------------------------------------------------------------------
+size_t epc_knn_workspace_bytes(int B, int N) {
+    if (B <= 0 || N <= 0) return 256;
+    return knn_state_bytes(B, N) + align_up((size_t)B * N * sizeof(float)) + 256;
+}
+
+int epc_knn(const float* xyz, int B, int N, int arith, int32_t* idx, float* kth, int32_t* count, void* workspace,
+            size_t workspace_bytes, void* stream) {
+    EPC_CHECK_ARG(B >= 0 && xyz != nullptr || B == 0, "epc_knn: xyz is NULL");
+    if (int rc = ensure_device(xyz)) return rc;
+    if (int rc = knn_check_n(N)) return rc;
+    if (workspace_bytes < epc_knn_workspace_bytes(B, N) || !workspace) {
+        set_error("epc_knn: workspace %zu < required %zu", workspace_bytes, epc_knn_workspace_bytes(B, N));
+        return EPC_EWORKSPACE;
+    }
+    Arena ar(workspace, workspace_bytes);
+    KnnState s = knn_state_carve(ar, B, N);
+    return knn_build(xyz, B, N, arith, true, s.sorted, s.perm, s.nbr, s.kthd, s.cnt, idx, kth, count,
+                     static_cast<cudaStream_t>(stream));
+}
+
+// test hook: same as epc_knn with the AABB pruning switched off (results must be bit-identical)
+int epc_knn_noprune(const float* xyz, int B, int N, int arith, int32_t* idx, float* kth, int32_t* count, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+    if (int rc = ensure_device(xyz)) return rc;
+    if (int rc = knn_check_n(N)) return rc;
+    if (workspace_bytes < epc_knn_workspace_bytes(B, N) || !workspace) {
+        set_error("epc_knn_noprune: workspace too small");
+        return EPC_EWORKSPACE;
+    }
+    Arena ar(workspace, workspace_bytes);
+    KnnState s = knn_state_carve(ar, B, N);
+    return knn_build(xyz, B, N, arith, false, s.sorted, s.perm, s.nbr, s.kthd, s.cnt, idx, kth, count,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int epc_knn_dense(const float* xyz, int B, int N, int arith, float* mask, float* dist, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+    if (int rc = ensure_device(xyz)) return rc;
+    if (int rc = knn_check_n(N)) return rc;
+    if (workspace_bytes < epc_knn_workspace_bytes(B, N) || !workspace) {
+        set_error("epc_knn_dense: workspace %zu < required %zu", workspace_bytes, epc_knn_workspace_bytes(B, N));
+        return EPC_EWORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Arena ar(workspace, workspace_bytes);
+    KnnState s = knn_state_carve(ar, B, N);
+    float* kth = ar.take<float>((size_t)B * N);
+    if (mask) {
+        if (int rc = knn_build(xyz, B, N, arith, true, s.sorted, s.perm, s.nbr, s.kthd, s.cnt, nullptr, kth, nullptr, st))
+            return rc;
+    }
+    return knn_dense(xyz, B, N, arith, kth, mask, dist, st);
+}
+
+int epc_rows_topk_smallest(const float* adj, long long R, int M, int k, int32_t* idx, void* stream) {
+    if (int rc = ensure_device(adj)) return rc;
+    return rows_topk_smallest(adj, R, M, k, idx, static_cast<cudaStream_t>(stream));
+}
+
+// -------------------------------------------------------------------------------------------------
+// stand-alone layers
+// -------------------------------------------------------------------------------------------------
+int epc_dense_forward(const EpcDense* layer, const float* x, long long R, float* y, int relu, void* stream) {
+    EPC_CHECK_ARG(layer && dense_ok(*layer), "epc_dense_forward: incomplete layer description");
+    EPC_CHECK_ARG(R >= 0 && R < (1ll << 31), "epc_dense_forward: bad row count");
+    if (int rc = ensure_device(x)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    std::vector<float> W, b;
+    fold_dense(*layer, W, b);
+    float* dW = nullptr;
+    EPC_CUDA(cudaMalloc(&dW, (W.size() + b.size()) * sizeof(float)));
+    float* db = dW + W.size();
+    cudaError_t e = cudaMemcpyAsync(dW, W.data(), W.size() * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(db, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice, st);
+    int rc = EPC_OK;
+    if (e != cudaSuccess) {
+        set_error("epc_dense_forward: upload failed: %s", cudaGetErrorString(e));
+        rc = EPC_ECUDA;
+    } else {
+        GemmArgs g = {};
+        g.A = x; g.sAm = layer->cin; g.sAk = 1;
+        g.B = dW; g.sBk = layer->cout; g.sBn = 1;
+        g.C = y; g.ldc = layer->cout; g.M = (int)R; g.N = layer->cout; g.K = layer->cin;
+        g.bias = db; g.relu = relu; g.batch = 1; g.splitk = 1;
+        rc = sgemm(g, st);
+    }
+    cudaStreamSynchronize(st);   // W/b are pageable host vectors that die with this frame
+    cudaFree(dW);
+    return rc;
+}
+
+int epc_max_pool_points(const float* x, int B, int N, int C, float* y, void* stream) {
+    EPC_CHECK_ARG(x && y && B >= 0 && N > 0 && C > 0, "epc_max_pool_points: bad arguments");
+    if (int rc = ensure_device(x)) return rc;
+    return col_max(x, B, N, C, y, static_cast<cudaStream_t>(stream));
+}
+
+// -------------------------------------------------------------------------------------------------
+// model
+// -------------------------------------------------------------------------------------------------
+int epc_model_create(const EpcWeights* w, EpcModel** out) {
+    EPC_CHECK_ARG(w && out, "epc_model_create: NULL argument");
+    EPC_CHECK_ARG(w->arch >= EPC_ARCH_EPC_NET && w->arch <= EPC_ARCH_KD_EPC_NET_L, "unknown arch %d", w->arch);
+    const bool vlad = (w->arch == EPC_ARCH_EPC_NET || w->arch == EPC_ARCH_KD_EPC_NET);
+    const int nb = w->n_blocks;
+    EPC_CHECK_ARG(nb >= 1 && nb <= 4, "n_blocks=%d unsupported (1..4)", nb);
+    EPC_CHECK_ARG(w->knn_k > 0, "knn_k (the divisor of the neighbour mean) must be positive");
+    EPC_CHECK_ARG(w->output_dim >= 1 && w->output_dim <= 1024, "output_dim=%d unsupported", w->output_dim);
+    for (int i = 0; i < 3 * nb; ++i) {
+        EPC_CHECK_ARG(dense_ok(w->conv[i]), "conv layer %d incomplete", i);
+        EPC_CHECK_ARG(w->conv[i].cout == 64 && w->conv[i].cin == (i == 0 ? 3 : 64), "conv layer %d: shape %d->%d", i,
+                      w->conv[i].cin, w->conv[i].cout);
+    }
+    EPC_CHECK_ARG(dense_ok(w->conv5) && w->conv5.cin == 64 * nb && w->conv5.cout == 1024, "conv5 must be %d->1024",
+                  64 * nb);
+
+    EpcModel* m = new EpcModel();
+    m->arch = w->arch; m->n_blocks = nb; m->K = w->cluster_size; m->D = w->output_dim; m->G = w->groups;
+    m->pooling = w->pooling; m->gating = w->gating; m->divisor = (float)w->knn_k; m->vlad_head = vlad;
+
+    Packer pk;
+    std::vector<float> W, b, sc, sh;
+    size_t offW[13], offb[13];
+    for (int i = 0; i < 3 * nb; ++i) {
+        fold_dense(w->conv[i], W, b);
+        offW[i] = pk.add(W); offb[i] = pk.add(b);
+    }
+    fold_dense(w->conv5, W, b);
+    offW[12] = pk.add(W); offb[12] = pk.add(b);
+    size_t oWc = 0, oCs = 0, oCh = 0, oWc2 = 0, oWh = 0, oHs = 0, oHh = 0, oWg = 0, oGs = 0, oGh = 0, oFW = 0, oFb = 0;
+    if (vlad) {
+        const int K = w->cluster_size, D = w->output_dim;
+        if (!(K >= 1 && K <= 64)) { delete m; set_error("cluster_size=%d unsupported (1..64)", K); return EPC_EINVAL; }
+        const bool gv = (w->pooling == EPC_POOL_G_VLAD);
+        if (gv && !(w->groups >= 1 && (1024 * K) % w->groups == 0)) { delete m; set_error("bad groups=%d", w->groups); return EPC_EINVAL; }
+        if (!gv) m->G = 1;
+        m->hidden_in = 1024 * K / m->G;
+        if (!(w->cluster_weights_host && bn_ok(w->cluster_bn) && w->cluster_weights2_host && w->hidden1_weights_host &&
+              bn_ok(w->hidden_bn) && (!w->gating || (w->gating_weights_host && bn_ok(w->gating_bn))))) {
+            delete m; set_error("VLAD head weights incomplete"); return EPC_EINVAL;
+        }
+        oWc = pk.add(w->cluster_weights_host, (size_t)1024 * K);
+        bn_affine(w->cluster_bn, K, sc, sh); oCs = pk.add(sc); oCh = pk.add(sh);
+        oWc2 = pk.add(w->cluster_weights2_host, (size_t)1024 * K);
+        oWh = pk.add(w->hidden1_weights_host, (size_t)m->hidden_in * D);
+        bn_affine(w->hidden_bn, D, sc, sh); oHs = pk.add(sc); oHh = pk.add(sh);
+        if (w->gating) {
+            oWg = pk.add(w->gating_weights_host, (size_t)D * D);
+            bn_affine(w->gating_bn, D, sc, sh); oGs = pk.add(sc); oGh = pk.add(sh);
+        }
+    } else {
+        if (!(dense_ok(w->fc1) && w->fc1.cin == 1024 && w->fc1.cout == w->output_dim)) {
+            delete m; set_error("fc1 must be 1024->%d", w->output_dim); return EPC_EINVAL;
+        }
+        fold_dense(w->fc1, W, b);
+        oFW = pk.add(W); oFb = pk.add(b);
+    }
+    cudaError_t e = cudaMalloc(&m->blob, pk.host.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(m->blob, pk.host.data(), pk.host.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        set_error("epc_model_create: %s", cudaGetErrorString(e));
+        if (m->blob) cudaFree(m->blob);
+        delete m;
+        return EPC_ECUDA;
+    }
+    for (int i = 0; i < 3 * nb; ++i) m->conv[i] = DenseDev{m->blob + offW[i], m->blob + offb[i], w->conv[i].cin, 64};
+    m->conv5 = DenseDev{m->blob + offW[12], m->blob + offb[12], 64 * nb, 1024};
+    if (vlad) {
+        m->Wc = m->blob + oWc; m->cbn_scale = m->blob + oCs; m->cbn_shift = m->blob + oCh; m->Wc2 = m->blob + oWc2;
+        m->Wh = m->blob + oWh; m->hbn_scale = m->blob + oHs; m->hbn_shift = m->blob + oHh;
+        if (w->gating) { m->Wg = m->blob + oWg; m->gbn_scale = m->blob + oGs; m->gbn_shift = m->blob + oGh; }
+    } else {
+        m->fc1 = DenseDev{m->blob + oFW, m->blob + oFb, 1024, w->output_dim};
+    }
+    *out = m;
+    return EPC_OK;
+}
+
+void epc_model_destroy(EpcModel* m) {
+    if (!m) return;
+    if (m->blob) cudaFree(m->blob);
+    delete m;
+}
+
+namespace {
+
+struct HeadWs {
+    float *inv, *S, *a_sum, *V, *v, *Y;
+};
+
+size_t head_bytes(const EpcModel* m, int B, int N) {
+    const size_t R = (size_t)B * N;
+    return align_up(R * 4) + align_up(R * m->K * 4) + align_up((size_t)B * m->K * 4) +
+           2 * align_up((size_t)B * 1024 * m->K * 4) + align_up((size_t)B * m->G * m->D * 4);
+}
+
+HeadWs head_carve(Arena& ar, const EpcModel* m, int B, int N) {
+    const size_t R = (size_t)B * N;
+    HeadWs h;
+    h.inv = ar.take<float>(R);
+    h.S = ar.take<float>(R * m->K);
+    h.a_sum = ar.take<float>((size_t)B * m->K);
+    h.V = ar.take<float>((size_t)B * 1024 * m->K);
+    h.v = ar.take<float>((size_t)B * 1024 * m->K);
+    h.Y = ar.take<float>((size_t)B * m->G * m->D);
+    return h;
+}
+
+// G_VLAD / NetVLAD on per-point features H [B*N,1024]; inv = per-row scale (nullptr: rows used as given)
+int vlad_head(const EpcModel* m, const float* H, const float* inv, int B, int N, const HeadWs& h, int l2, float* out,
+              cudaStream_t st) {
+    const int K = m->K, D = m->D, F = 1024;
+    const size_t R = (size_t)B * N;
+    EPC_CHECK_ARG(R < (1ull << 31), "too many points in one call (B*N = %zu)", R);
+    {   // cluster assignment logits = H Wc   (loupe.py:255)
+        GemmArgs g = {};
+        g.A = H; g.sAm = F; g.sAk = 1;
+        g.B = m->Wc; g.sBk = K; g.sBn = 1;
+        g.C = h.S; g.ldc = K; g.M = (int)R; g.N = K; g.K = F; g.batch = 1; g.splitk = 1;
+        ScopedStage ss(EPC_STAGE_ASSIGN_GEMM, st);
+        if (int rc = sgemm(g, st)) return rc;
+    }
+    {
+        ScopedStage ss(EPC_STAGE_ASSIGN_SOFTMAX, st);
+        if (int rc = assign_softmax(h.S, inv, m->cbn_scale, m->cbn_shift, B, N, K, h.S, h.a_sum, st)) return rc;
+    }
+    {   // V[b] = H[b]^T S'[b]   (loupe.py:286-291)
+        GemmArgs g = {};
+        g.A = H; g.sAm = 1; g.sAk = F; g.bA = (long long)N * F;
+        g.B = h.S; g.sBk = K; g.sBn = 1; g.bB = (long long)N * K;
+        g.C = h.V; g.ldc = K; g.bC = (long long)F * K;
+        g.M = F; g.N = K; g.K = N; g.batch = B; g.splitk = 1;
+        ScopedStage ss(EPC_STAGE_VLAD_GEMM, st);
+        if (int rc = sgemm(g, st)) return rc;
+    }
+    {
+        ScopedStage ss(EPC_STAGE_VLAD_FINALIZE, st);
+        if (int rc = vlad_finalize(h.V, h.a_sum, m->Wc2, B, F, K, h.v, st)) return rc;
+    }
+    {   // hidden FC (loupe.py:302-320): rows of length hidden_in, G per cloud
+        EPC_CUDA(cudaMemsetAsync(h.Y, 0, sizeof(float) * (size_t)B * m->G * D, st));
+        GemmArgs g = {};
+        g.A = h.v; g.sAm = m->hidden_in; g.sAk = 1;
+        g.B = m->Wh; g.sBk = D; g.sBn = 1;
+        g.C = h.Y; g.ldc = D; g.M = B * m->G; g.N = D; g.K = m->hidden_in; g.batch = 1;
+        g.splitk = 32;
+        ScopedStage ss(EPC_STAGE_HIDDEN_GEMM, st);
+        if (int rc = sgemm(g, st)) return rc;
+    }
+    ScopedStage ss(EPC_STAGE_TAIL, st);
+    return vlad_tail(h.Y, B, m->G, D, m->hbn_scale, m->hbn_shift, m->Wg, m->gbn_scale, m->gbn_shift, m->gating, l2, out, st);
+}
+
+}  // namespace
+
+size_t epc_embed_workspace_bytes(const EpcModel* m, int B, int N) {
+    if (!m || B <= 0 || N <= 0) return 256;
+    const size_t R = (size_t)B * N;
+    const int ctot = 64 * m->n_blocks;
+    size_t s = knn_state_bytes(B, N) + 2 * align_up(R * 64 * 4) + align_up(R * ctot * 4) + align_up(R * 1024 * 4);
+    if (m->vlad_head)
+        s += head_bytes(m, B, N);
+    else
+        s += align_up(R * 4) + align_up((size_t)B * 1024 * 4) + align_up((size_t)B * m->D * 4);
+    return s + 256;
+}
+
+int epc_embed(const EpcModel* m, const float* xyz, int B, int N, int knn_arith, float* out, float* feat, void* workspace,
+              size_t workspace_bytes, void* stream) {
+    EPC_CHECK_ARG(m && out && (xyz || B == 0), "epc_embed: NULL argument");
+    EPC_CHECK_ARG(B >= 0, "epc_embed: B=%d", B);
+    if (int rc = ensure_device(xyz)) return rc;
+    if (int rc = knn_check_n(N)) return rc;
+    if (B == 0) return EPC_OK;
+    if (!workspace || workspace_bytes < epc_embed_workspace_bytes(m, B, N)) {
+        set_error("epc_embed: workspace %zu < required %zu", workspace_bytes, epc_embed_workspace_bytes(m, B, N));
+        return EPC_EWORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t R = (size_t)B * N;
+    EPC_CHECK_ARG(R < (1ull << 31), "too many points in one call (B*N = %zu)", R);
+    const int nb = m->n_blocks, ctot = 64 * nb;
+    Arena ar(workspace, workspace_bytes);
+    KnnState ks = knn_state_carve(ar, B, N);
+    float* xa = ar.take<float>(R * 64);
+    float* xb = ar.take<float>(R * 64);
+    float* concat = ar.take<float>(R * ctot);
+    float* H = ar.take<float>(R * 1024);
+
+    if (int rc = knn_build(xyz, B, N, knn_arith, true, ks.sorted, ks.perm, ks.nbr, ks.kthd, ks.cnt, nullptr, nullptr,
+                           nullptr, st))
+        return rc;
+    {
+        ScopedStage ss(EPC_STAGE_CONV_IN, st);
+        if (int rc = conv_in(ks.sorted, (long long)R, m->conv[0], xa, st)) return rc;
+    }
+    float *cur = xa, *nxt = xb;
+    for (int blk = 0; blk < nb; ++blk) {
+        const DenseDev* next = (blk + 1 < nb) ? &m->conv[3 * (blk + 1)] : nullptr;
+        {
+            ScopedStage ss(EPC_STAGE_BLOCK, st);
+            if (int rc = proxy_block(cur, ks, B, N, knn_arith, m->divisor, m->conv[3 * blk + 1], m->conv[3 * blk + 2],
+                                     next, concat, ctot, 64 * blk, nxt, st))
+                return rc;
+        }
+        float* t = cur; cur = nxt; nxt = t;
+    }
+    {   // conv5 (models/epc-net.py:136-139)
+        GemmArgs g = {};
+        g.A = concat; g.sAm = ctot; g.sAk = 1;
+        g.B = m->conv5.W; g.sBk = 1024; g.sBn = 1;
+        g.C = H; g.ldc = 1024; g.M = (int)R; g.N = 1024; g.K = ctot; g.bias = m->conv5.b; g.relu = 1;
+        g.batch = 1; g.splitk = 1;
+        ScopedStage ss(EPC_STAGE_CONV5, st);
+        if (int rc = sgemm(g, st)) return rc;
+    }
+    if (m->vlad_head) {
+        HeadWs h = head_carve(ar, m, B, N);
+        {
+            ScopedStage ss(EPC_STAGE_ROWNORM, st);
+            if (int rc = row_inv_norm(H, (long long)R, 1024, h.inv, st)) return rc;
+        }
+        if (int rc = vlad_head(m, H, h.inv, B, N, h, /*l2=*/1, out, st)) return rc;
+        if (feat) {
+            ScopedStage ss(EPC_STAGE_KD_FEAT, st);
+            if (int rc = kd_feat(H, h.inv, ks.perm, B, N, 1024, feat, st)) return rc;
+        }
+    } else {
+        float* inv = ar.take<float>(R);
+        float* gmax = ar.take<float>((size_t)B * 1024);
+        float* o = ar.take<float>((size_t)B * m->D);
+        {
+            ScopedStage ss(EPC_STAGE_COLMAX, st);
+            if (int rc = col_max(H, B, N, 1024, gmax, st)) return rc;
+        }
+        ScopedStage ss(EPC_STAGE_FC, st);
+        GemmArgs g = {};
+        g.A = gmax; g.sAm = 1024; g.sAk = 1;
+        g.B = m->fc1.W; g.sBk = m->D; g.sBn = 1;
+        g.C = o; g.ldc = m->D; g.M = B; g.N = m->D; g.K = 1024; g.bias = m->fc1.b; g.relu = 1; g.batch = 1; g.splitk = 1;
+        if (int rc = sgemm(g, st)) return rc;
+        if (int rc = row_l2_normalize(o, B, m->D, out, st)) return rc;
+        if (feat) {
+            if (int rc = row_inv_norm(H, (long long)R, 1024, inv, st)) return rc;
+            if (int rc = kd_feat(H, inv, ks.perm, B, N, 1024, feat, st)) return rc;
+        }
+    }
+    if (!ar.ok()) {
+        set_error("epc_embed: internal workspace accounting error");
+        return EPC_EWORKSPACE;
+    }
+    return EPC_OK;
+}
+
+size_t epc_vlad_workspace_bytes(const EpcModel* m, int B, int N) {
+    if (!m || !m->vlad_head || B <= 0 || N <= 0) return 256;
+    return head_bytes(m, B, N) + 256;
+}
+
+int epc_vlad_forward(const EpcModel* m, const float* X, int B, int N, float* out, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+    EPC_CHECK_ARG(m && X && out, "epc_vlad_forward: NULL argument");
+    EPC_CHECK_ARG(m->vlad_head, "epc_vlad_forward: this model (EPC-Net-L) has no VLAD head");
+    EPC_CHECK_ARG(B >= 0 && N > 0, "epc_vlad_forward: bad sizes");
+    if (int rc = ensure_device(X)) return rc;
+    if (B == 0) return EPC_OK;
+    if (!workspace || workspace_bytes < epc_vlad_workspace_bytes(m, B, N)) {
+        set_error("epc_vlad_forward: workspace %zu < required %zu", workspace_bytes, epc_vlad_workspace_bytes(m, B, N));
+        return EPC_EWORKSPACE;
+    }
+    Arena ar(workspace, workspace_bytes);
+    HeadWs h = head_carve(ar, m, B, N);
+    return vlad_head(m, X, nullptr, B, N, h, /*l2=*/0, out, static_cast<cudaStream_t>(stream));
+}
+
+// -------------------------------------------------------------------------------------------------
+// retrieval
+// -------------------------------------------------------------------------------------------------
+size_t epc_retrieve_workspace_bytes(int D, int Q, int dim, int k) { return retrieve_workspace_bytes(D, Q, dim, k); }
+
+int epc_retrieve_topk(const float* db, int D, const float* q, int Q, int dim, int k, long long id_offset, int64_t* idx,
+                      double* dist, void* workspace, size_t workspace_bytes, void* stream) {
+    EPC_CHECK_ARG(db && (q || Q == 0) && idx && dist && workspace, "epc_retrieve_topk: NULL argument");
+    if (int rc = ensure_device(db)) return rc;
+    return retrieve_topk(db, D, q, Q, dim, k, id_offset, idx, dist, workspace, workspace_bytes,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int epc_merge_topk(const double* dist, const int64_t* idx, int R, int Q, int k, double* out_dist, int64_t* out_idx,
+                   void* stream) {
+    EPC_CHECK_ARG(dist && idx && out_dist && out_idx, "epc_merge_topk: NULL argument");
+    if (int rc = ensure_device(dist)) return rc;
+    return merge_topk(dist, idx, R, Q, k, out_dist, out_idx, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+// Internal (C++) interface between the translation units of libepc_b200.so.
+#pragma once
+#include "common.cuh"
+
+namespace epc {
+
+// ---- knn.cu ------------------------------------------------------------------------------------
+struct KnnState {          // per-cloud kNN graph in *sorted* (Morton) point order
+    float4* sorted;        // [B,N]   (x,y,z,|p|^2)
+    int* perm;             // [B,N]   sorted position -> original index
+    uint16_t* nbr;         // [B,N,20] neighbour positions (sorted space), ascending (d, original index)
+    float* kthd;           // [B,N]   20th smallest d
+    int* cnt;              // [B,N]   |{j : d_ij <= kthd_i}| (>= 20)
+};
+int knn_check_n(int N);
+size_t knn_state_bytes(int B, int N);
+KnnState knn_state_carve(Arena& ar, int B, int N);
+int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sorted, int* perm, uint16_t* nbr,
+              float* kthd, int* cnt, int32_t* idx_out, float* kth_out, int32_t* count_out, cudaStream_t st);
+int knn_dense(const float* xyz, int B, int N, int arith, const float* kth, float* mask, float* dist, cudaStream_t st);
+int rows_topk_smallest(const float* adj, long long R, int M, int k, int32_t* idx, cudaStream_t st);
+
+// ---- backbone.cu -------------------------------------------------------------------------------
+struct DenseDev {          // BN-folded pointwise layer on the device: y = act(x W + b)
+    const float* W;        // [cin, cout]
+    const float* b;        // [cout]
+    int cin, cout;
+};
+struct BlockDev {          // one ProxyConv block (models/epc-net.py:66-81)
+    DenseDev conv, conv_a, conv_b;
+};
+int conv_in(const float4* sorted, long long R, const DenseDev& L, float* x, cudaStream_t st);
+int proxy_block(const float* x, const KnnState& g, int B, int N, int arith, float divisor, const DenseDev& conv_a,
+                const DenseDev& conv_b, const DenseDev* conv_next, float* concat, int ctot, int coff, float* xnext,
+                cudaStream_t st);
+
+// ---- gemm.cu -----------------------------------------------------------------------------------
+struct GemmArgs {
+    const float* A;        // element (m,k) at A[m*sAm + k*sAk]
+    const float* B;        // element (k,n) at B[k*sBk + n*sBn]
+    float* C;              // row-major [M, ldc]
+    int M, N, K;
+    long long sAm, sAk, sBk, sBn;
+    int ldc;
+    int batch;             // grid.z batches with the strides below
+    long long bA, bB, bC;
+    const float* bias;     // [N] or nullptr
+    int relu;
+    int splitk;            // >1: partial sums are atomically added into C (C must be zeroed; no bias/relu)
+};
+int sgemm(const GemmArgs& g, cudaStream_t st);
+
+// ---- vlad.cu -----------------------------------------------------------------------------------
+int row_inv_norm(const float* X, long long R, int F, float* inv, cudaStream_t st);
+int assign_softmax(const float* logits, const float* inv, const float* bn_scale, const float* bn_shift, int B, int N,
+                   int K, float* S, float* a_sum, cudaStream_t st);
+int vlad_finalize(const float* V, const float* a_sum, const float* Wc2, int B, int F, int K, float* v, cudaStream_t st);
+int vlad_tail(const float* Y, int B, int G, int D, const float* bn_scale, const float* bn_shift, const float* Wg,
+              const float* g_scale, const float* g_shift, int gating, int l2, float* out, cudaStream_t st);
+int col_max(const float* H, int B, int N, int F, float* g, cudaStream_t st);
+int row_l2_normalize(const float* X, int R, int D, float* out, cudaStream_t st);
+int kd_feat(const float* H, const float* inv, const int* perm, int B, int N, int F, float* feat, cudaStream_t st);
+
+// ---- retrieval.cu ------------------------------------------------------------------------------
+size_t retrieve_workspace_bytes(int D, int Q, int dim, int k);
+int retrieve_topk(const float* db, int D, const float* q, int Q, int dim, int k, long long id_offset, int64_t* idx,
+                  double* dist, void* ws, size_t ws_bytes, cudaStream_t st);
+int merge_topk(const double* dist, const int64_t* idx, int R, int Q, int k, double* out_dist, int64_t* out_idx,
+               cudaStream_t st);
+
+}  // namespace epc

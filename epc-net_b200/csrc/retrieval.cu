@@ -1,0 +1,318 @@
+// K6 -- retrieval: exact Euclidean top-k of queries against a descriptor database.
+// Replaces `KDTree(database_output).query(q, k=25)` of evaluate.get_recall (evaluate.py:463,481), which
+// evaluates float64 Euclidean distances on the fp32 descriptors one query at a time on the CPU.
+//
+//   1. fp32 scoring  s_ij = (|q_i|^2 + |d_j|^2) - 2 q_i.d_j     (GEMM + norms)
+//   2. per query: the 32 smallest scores (warp-distributed list)            -> candidates
+//   3. float64 re-rank of the candidates, sequential sum_k (q_k - d_k)^2    -> top-k, ascending (dist, index)
+//   4. proof of exactness per query: every non-candidate has score >= a32 (the 32nd candidate's score),
+//      hence exact d^2 >= a32 - err;  if the exact k-th distance^2 is < a32 - err the answer equals a
+//      float64 brute force.  Otherwise (rare: near-ties within fp32 resolution) the query is redone by an
+//      exact float64 scan of the whole database.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace epc {
+
+constexpr int RC = 32;   // candidates per query
+
+__global__ void sq_norm_kernel(const float* __restrict__ X, int R, int dim, float* __restrict__ out) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= R) return;
+    float ss = 0.f;
+    for (int i = lane; i < dim; i += 32) {
+        const float v = X[(size_t)r * dim + i];
+        ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) out[r] = ss;
+}
+
+// lexicographic (value, index) "a before b"
+__device__ __forceinline__ bool key_less(double av, long long ai, double bv, long long bi) {
+    return (av < bv) || (av == bv && ai < bi);
+}
+
+// One warp per query: 32 smallest of score_j = (qn + dn[j]) - 2 dot[j], ascending; columns ascend so ties keep
+// the lower index.
+__global__ void candidates_kernel(const float* __restrict__ dots, const float* __restrict__ qn,
+                                  const float* __restrict__ dn, int Qt, int D, int* __restrict__ cand,
+                                  float* __restrict__ a32) {
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (qi >= Qt) return;
+    const float* row = dots + (size_t)qi * D;
+    const float qq = qn[qi];
+    float val = INFINITY;
+    int vi = -1;
+    int filled = 0;
+    float thr = INFINITY;
+    for (int j0 = 0; j0 < D; j0 += 32) {
+        const int j = j0 + lane;
+        const float s = (j < D) ? fmaf(-2.0f, __ldg(row + j), qq + __ldg(dn + j)) : INFINITY;
+        unsigned m = __ballot_sync(FULL, (j < D) && (filled < RC || s < thr));
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const float c = __shfl_sync(FULL, s, src);
+            const bool before = (lane < filled) && (val <= c);
+            const int pos = __popc(__ballot_sync(FULL, before));
+            if (pos < RC) {
+                const float upv = __shfl_up_sync(FULL, val, 1);
+                const int upi = __shfl_up_sync(FULL, vi, 1);
+                if (lane == pos) {
+                    val = c;
+                    vi = j0 + src;
+                } else if (lane > pos) {
+                    val = upv;
+                    vi = upi;
+                }
+                filled = min(filled + 1, RC);
+                thr = (filled == RC) ? __shfl_sync(FULL, val, RC - 1) : INFINITY;
+            }
+        }
+    }
+    cand[(size_t)qi * RC + lane] = (lane < filled) ? vi : -1;
+    if (lane == 0) a32[qi] = thr;      // +inf when D < 32: every row is a candidate
+}
+
+__device__ __forceinline__ double exact_d2(const float* __restrict__ q, const float* __restrict__ d, int dim) {
+    double acc = 0.0;
+    for (int k = 0; k < dim; ++k) {
+        const double t = (double)q[k] - (double)d[k];
+        acc = __dadd_rn(acc, __dmul_rn(t, t));   // no FMA contraction: sklearn's rdist loop is mul then add
+    }
+    return acc;
+}
+
+// bitonic sort of one (value,index) pair per lane, ascending
+__device__ __forceinline__ void warp_sort_pairs(double& v, long long& i, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const double ov = __shfl_xor_sync(FULL, v, j);
+            const long long oi = __shfl_xor_sync(FULL, i, j);
+            const bool up = ((lane & k) == 0), lower = ((lane & j) == 0);
+            const bool other_less = key_less(ov, oi, v, i);
+            const bool take = (lower == up) ? other_less : (!other_less && !(ov == v && oi == i));
+            if (take) {
+                v = ov;
+                i = oi;
+            }
+        }
+    }
+}
+
+__global__ void rerank_kernel(const float* __restrict__ db, const float* __restrict__ q, const int* __restrict__ cand,
+                              const float* __restrict__ a32, const float* __restrict__ qn, const float* __restrict__ dn_max_p, int Qt, int dim,
+                              int k, long long id_offset, int64_t* __restrict__ idx, double* __restrict__ dist,
+                              int* __restrict__ flags) {
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (qi >= Qt) return;
+    const int c = cand[(size_t)qi * RC + lane];
+    double v = INFINITY;
+    long long gi = 0x7fffffffffffffffLL;
+    if (c >= 0) {
+        v = exact_d2(q + (size_t)qi * dim, db + (size_t)c * dim, dim);
+        gi = (long long)c + id_offset;
+    }
+    warp_sort_pairs(v, gi, lane);
+    if (lane < k) {
+        idx[(size_t)qi * k + lane] = (v == INFINITY && gi == 0x7fffffffffffffffLL) ? -1 : gi;
+        dist[(size_t)qi * k + lane] = sqrt(v);
+    }
+    const double kth = __shfl_sync(FULL, v, k - 1);
+    if (lane == 0) {
+        // fp32 scoring error bound: |score - exact d^2| <= err  (dim-term FMA chain + norm sums), generous
+        const float err = 6e-8f * (float)(dim + 8) * (qn[qi] + *dn_max_p) * 2.0f;
+        const float a = a32[qi];
+        flags[qi] = (a == INFINITY) ? 0 : !((float)kth * (1.0f + 2e-7f) < a - err);
+    }
+}
+
+// Exact float64 scan for flagged queries (one warp per query).
+__global__ void exact_fallback_kernel(const float* __restrict__ db, const float* __restrict__ q,
+                                      const int* __restrict__ flags, int Qt, int D, int dim, int k, long long id_offset,
+                                      int64_t* __restrict__ idx, double* __restrict__ dist) {
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (qi >= Qt || !flags[qi]) return;
+    double val = INFINITY;
+    long long vi = 0x7fffffffffffffffLL;
+    int filled = 0;
+    double thr = INFINITY;
+    for (int j0 = 0; j0 < D; j0 += 32) {
+        const int j = j0 + lane;
+        const double s = (j < D) ? exact_d2(q + (size_t)qi * dim, db + (size_t)j * dim, dim) : (double)INFINITY;
+        unsigned m = __ballot_sync(FULL, (j < D) && (filled < k || s < thr));
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const double c = __shfl_sync(FULL, s, src);
+            const bool before = (lane < filled) && (val <= c);
+            const int pos = __popc(__ballot_sync(FULL, before));
+            if (pos < k) {
+                const double upv = __shfl_up_sync(FULL, val, 1);
+                const long long upi = __shfl_up_sync(FULL, vi, 1);
+                if (lane == pos) {
+                    val = c;
+                    vi = (long long)(j0 + src) + id_offset;
+                } else if (lane > pos && lane < k) {
+                    val = upv;
+                    vi = upi;
+                }
+                filled = min(filled + 1, k);
+                thr = (filled == k) ? __shfl_sync(FULL, val, k - 1) : (double)INFINITY;
+            }
+        }
+    }
+    if (lane < k) {
+        idx[(size_t)qi * k + lane] = (lane < filled) ? vi : -1;
+        dist[(size_t)qi * k + lane] = sqrt(val);
+    }
+}
+
+__global__ void max_reduce_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
+    __shared__ float s[32];
+    float m = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, x[i]);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, s[w]);
+        *out = m;
+    }
+}
+
+static int query_tile(int D, int Q) {
+    const long long budget = 256ll << 20;   // bytes of fp32 scores per tile
+    long long qt = budget / ((long long)(D > 0 ? D : 1) * 4);
+    if (qt < 32) qt = 32;
+    if (qt > Q) qt = Q;
+    return (int)(qt > 0 ? qt : 1);
+}
+
+size_t retrieve_workspace_bytes(int D, int Q, int dim, int k) {
+    (void)dim;
+    (void)k;
+    const int qt = query_tile(D, Q);
+    return align_up((size_t)D * 4) + align_up((size_t)Q * 4) + align_up((size_t)qt * D * 4) +
+           align_up((size_t)qt * RC * 4) + align_up((size_t)qt * 4) + align_up((size_t)qt * 4) + 256;
+}
+
+int retrieve_topk(const float* db, int D, const float* q, int Q, int dim, int k, long long id_offset, int64_t* idx,
+                  double* dist, void* ws, size_t ws_bytes, cudaStream_t st) {
+    EPC_CHECK_ARG(k >= 1 && k <= 32, "retrieve_topk: k=%d unsupported (1..32)", k);
+    EPC_CHECK_ARG(D >= 1 && dim >= 1 && Q >= 0, "retrieve_topk: bad sizes D=%d Q=%d dim=%d", D, Q, dim);
+    if (Q == 0) return EPC_OK;
+    if (ws_bytes < retrieve_workspace_bytes(D, Q, dim, k)) {
+        set_error("retrieve_topk: workspace %zu < required %zu", ws_bytes, retrieve_workspace_bytes(D, Q, dim, k));
+        return EPC_EWORKSPACE;
+    }
+    const int qt = query_tile(D, Q);
+    Arena ar(ws, ws_bytes);
+    float* dn = ar.take<float>(D);
+    float* qn = ar.take<float>(Q);
+    float* dots = ar.take<float>((size_t)qt * D);
+    int* cand = ar.take<int>((size_t)qt * RC);
+    float* a32 = ar.take<float>(qt);
+    int* flags = ar.take<int>(qt);
+    float* dn_max_dev = ar.take<float>(1);
+
+    sq_norm_kernel<<<(D + 7) / 8, 256, 0, st>>>(db, D, dim, dn);
+    EPC_LAUNCH_CHECK();
+    sq_norm_kernel<<<(Q + 7) / 8, 256, 0, st>>>(q, Q, dim, qn);
+    EPC_LAUNCH_CHECK();
+    max_reduce_kernel<<<1, 1024, 0, st>>>(dn, D, dn_max_dev);
+    EPC_LAUNCH_CHECK();
+
+    for (int q0 = 0; q0 < Q; q0 += qt) {
+        const int nq = (Q - q0 < qt) ? (Q - q0) : qt;
+        GemmArgs g = {};
+        g.A = q + (size_t)q0 * dim;  g.sAm = dim; g.sAk = 1;
+        g.B = db;                    g.sBk = 1;   g.sBn = dim;
+        g.C = dots; g.ldc = D; g.M = nq; g.N = D; g.K = dim; g.batch = 1; g.splitk = 1;
+        {
+            ScopedStage ss(EPC_STAGE_RETRIEVE_SCORE, st);
+            if (int rc = sgemm(g, st)) return rc;
+        }
+        {
+            ScopedStage ss(EPC_STAGE_RETRIEVE_SELECT, st);
+            candidates_kernel<<<(nq + 7) / 8, 256, 0, st>>>(dots, qn + q0, dn, nq, D, cand, a32);
+            EPC_LAUNCH_CHECK();
+        }
+        ScopedStage ss(EPC_STAGE_RETRIEVE_RERANK, st);
+        rerank_kernel<<<(nq + 7) / 8, 256, 0, st>>>(db, q + (size_t)q0 * dim, cand, a32, qn + q0, dn_max_dev, nq, dim, k,
+                                                    id_offset, idx + (size_t)q0 * k, dist + (size_t)q0 * k, flags);
+        EPC_LAUNCH_CHECK();
+        exact_fallback_kernel<<<(nq + 7) / 8, 256, 0, st>>>(db, q + (size_t)q0 * dim, flags, nq, D, dim, k, id_offset,
+                                                            idx + (size_t)q0 * k, dist + (size_t)q0 * k);
+        EPC_LAUNCH_CHECK();
+    }
+    return EPC_OK;
+}
+
+// Merge R shard lists per query by (distance, index): one warp per query, lists staged in shared memory.
+__global__ void merge_topk_kernel(const double* __restrict__ dist, const int64_t* __restrict__ idx, int R, int Q, int k,
+                                  double* __restrict__ out_dist, int64_t* __restrict__ out_idx) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int qi = blockIdx.x, lane = threadIdx.x;
+    const int n = R * k;
+    double* sd = reinterpret_cast<double*>(sm);
+    long long* si = reinterpret_cast<long long*>(sd + n);
+    for (int t = lane; t < n; t += 32) {
+        const int r = t / k, j = t % k;
+        const size_t src = ((size_t)r * Q + qi) * k + j;
+        long long id = idx[src];
+        sd[t] = (id < 0) ? (double)INFINITY : dist[src];
+        si[t] = (id < 0) ? 0x7fffffffffffffffLL : id;
+    }
+    __syncwarp();
+    for (int o = 0; o < k; ++o) {
+        double bv = INFINITY;
+        long long bi = 0x7fffffffffffffffLL;
+        int bt = -1;
+        for (int t = lane; t < n; t += 32) {
+            if (key_less(sd[t], si[t], bv, bi)) {
+                bv = sd[t];
+                bi = si[t];
+                bt = t;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ov = __shfl_xor_sync(FULL, bv, off);
+            const long long oi = __shfl_xor_sync(FULL, bi, off);
+            const int ot = __shfl_xor_sync(FULL, bt, off);
+            if (key_less(ov, oi, bv, bi)) {
+                bv = ov;
+                bi = oi;
+                bt = ot;
+            }
+        }
+        if (lane == 0) {
+            out_dist[(size_t)qi * k + o] = bv;
+            out_idx[(size_t)qi * k + o] = (bt < 0) ? -1 : bi;
+            if (bt >= 0) {
+                sd[bt] = INFINITY;
+                si[bt] = 0x7fffffffffffffffLL;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+int merge_topk(const double* dist, const int64_t* idx, int R, int Q, int k, double* out_dist, int64_t* out_idx,
+               cudaStream_t st) {
+    EPC_CHECK_ARG(R >= 1 && k >= 1 && (size_t)R * k * 16 <= 48 * 1024, "merge_topk: R=%d k=%d unsupported", R, k);
+    if (Q == 0) return EPC_OK;
+    merge_topk_kernel<<<Q, 32, (size_t)R * k * 16, st>>>(dist, idx, R, Q, k, out_dist, out_idx);
+    EPC_LAUNCH_CHECK();
+    return EPC_OK;
+}
+
+}  // namespace epc

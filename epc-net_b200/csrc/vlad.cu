@@ -1,0 +1,263 @@
+// K4 -- G_VLAD / NetVLAD aggregation tail and the EPC-Net-L head (loupe.py:233-333, 61-101;
+// models/epc-net.py:147-155; models/epc-net-l.py:88-100).  Small, bandwidth-bound pieces that sit
+// around the three dense contractions (cluster assignment, VLAD accumulate, hidden FC).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace epc {
+
+// inv[r] = 1 / sqrt(max(sum_f X[r,f]^2, 1e-12))     (tf.nn.l2_normalize, models/epc-net.py:147)
+__global__ void row_inv_norm_kernel(const float* __restrict__ X, long long R, int F, float* __restrict__ inv) {
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= R) return;
+    const float4* x4 = reinterpret_cast<const float4*>(X + r * F);
+    float ss = 0.f;
+    for (int i = lane; i < F / 4; i += 32) {
+        const float4 v = __ldg(x4 + i);
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) inv[r] = 1.0f / sqrtf(fmaxf(ss, L2_EPS));
+}
+
+int row_inv_norm(const float* X, long long R, int F, float* inv, cudaStream_t st) {
+    EPC_CHECK_ARG(F % 4 == 0, "row_inv_norm: F=%d must be a multiple of 4", F);
+    if (R == 0) return EPC_OK;
+    row_inv_norm_kernel<<<(unsigned)((R + 7) / 8), 256, 0, st>>>(X, R, F, inv);
+    EPC_LAUNCH_CHECK();
+    return EPC_OK;
+}
+
+// Soft assignment (loupe.py:255-276): logits are the RAW products H.Wc of un-normalised rows; the row
+// scale inv[n] = 1/|H_n| is applied here (exact: the product is linear in the row).
+//   act = softmax_c( BN(logit * inv) );  S'[n,c] = act * inv  (so that sum_n S'[n,c] H[n,f] = sum_n act X[n,f]);
+//   a_sum[b,c] += act.
+// One warp per point; K <= 64 (lane handles c = lane and lane + 32).
+__global__ void assign_softmax_kernel(const float* __restrict__ logits, const float* __restrict__ inv,
+                                      const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, int N,
+                                      int K, float* __restrict__ S, float* __restrict__ a_sum) {
+    __shared__ float s_sum[64];
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    if (threadIdx.x < 64) s_sum[threadIdx.x] = 0.f;
+    __syncthreads();
+    const int c0 = lane, c1 = lane + 32;
+    const float sc0 = (c0 < K) ? bn_scale[c0] : 0.f, sh0 = (c0 < K) ? bn_shift[c0] : 0.f;
+    const float sc1 = (c1 < K) ? bn_scale[c1] : 0.f, sh1 = (c1 < K) ? bn_shift[c1] : 0.f;
+    float acc0 = 0.f, acc1 = 0.f;
+    const int per = (N + gridDim.x - 1) / gridDim.x;
+    const int n_begin = blockIdx.x * per, n_end = min(N, n_begin + per);
+    for (int n = n_begin + warp; n < n_end; n += nwarp) {
+        const size_t row = (size_t)b * N + n;
+        const float iv = inv ? inv[row] : 1.0f;      // inv == nullptr: rows are used as given (loupe API)
+        const float l0 = (c0 < K) ? (logits[row * K + c0] * iv) * sc0 + sh0 : -INFINITY;
+        const float l1 = (c1 < K) ? (logits[row * K + c1] * iv) * sc1 + sh1 : -INFINITY;
+        const float mx = warp_max(fmaxf(l0, l1));
+        const float e0 = (c0 < K) ? expf(l0 - mx) : 0.f;
+        const float e1 = (c1 < K) ? expf(l1 - mx) : 0.f;
+        const float den = warp_sum(e0 + e1);
+        const float a0 = e0 / den, a1 = e1 / den;
+        if (c0 < K) S[row * K + c0] = a0 * iv;
+        if (c1 < K) S[row * K + c1] = a1 * iv;
+        acc0 += a0;
+        acc1 += a1;
+    }
+    if (c0 < K) atomicAdd(&s_sum[c0], acc0);
+    if (c1 < K) atomicAdd(&s_sum[c1], acc1);
+    __syncthreads();
+    if (threadIdx.x < K) atomicAdd(&a_sum[(size_t)b * K + threadIdx.x], s_sum[threadIdx.x]);
+}
+
+int assign_softmax(const float* logits, const float* inv, const float* bn_scale, const float* bn_shift, int B, int N,
+                   int K, float* S, float* a_sum, cudaStream_t st) {
+    EPC_CHECK_ARG(K >= 1 && K <= 64, "assign_softmax: cluster_size=%d unsupported (1..64)", K);
+    if (B == 0) return EPC_OK;
+    EPC_CUDA(cudaMemsetAsync(a_sum, 0, sizeof(float) * (size_t)B * K, st));
+    dim3 grid(16, B);
+    assign_softmax_kernel<<<grid, 256, 0, st>>>(logits, inv, bn_scale, bn_shift, N, K, S, a_sum);
+    EPC_LAUNCH_CHECK();
+    return EPC_OK;
+}
+
+// VLAD finalise (loupe.py:284-298): V[f,c] -= a_sum[c] * Wc2[f,c]; L2 over f per (b,c); flatten
+// f-major (index f*K + c); global L2.  One CTA per cloud.
+__global__ void __launch_bounds__(256)
+vlad_finalize_kernel(const float* __restrict__ V, const float* __restrict__ a_sum, const float* __restrict__ Wc2, int F,
+                     int K, float* __restrict__ v) {
+    __shared__ float s_part[4][64];
+    __shared__ float s_inv[64];
+    __shared__ float s_ginv;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int c = tid & 63, grp = tid >> 6;           // 4 row groups x 64 columns
+    const float* Vb = V + (size_t)b * F * K;
+    float ss = 0.f;
+    if (c < K) {
+        const float as = a_sum[(size_t)b * K + c];
+        for (int f = grp; f < F; f += 4) {
+            const float r = Vb[(size_t)f * K + c] - as * Wc2[(size_t)f * K + c];
+            ss += r * r;
+        }
+    }
+    s_part[grp][c] = ss;
+    __syncthreads();
+    if (tid < 64) {
+        const float tot = (s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid]);
+        const float iv = 1.0f / sqrtf(fmaxf(tot, L2_EPS));
+        s_inv[tid] = iv;
+        s_part[0][tid] = (tid < K) ? tot * iv * iv : 0.f;     // squared norm of the normalised column
+    }
+    __syncthreads();
+    if (tid < 32) {
+        float g = s_part[0][tid] + s_part[0][tid + 32];
+        g = warp_sum(g);
+        if (tid == 0) s_ginv = 1.0f / sqrtf(fmaxf(g, L2_EPS));
+    }
+    __syncthreads();
+    if (c < K) {
+        const float as = a_sum[(size_t)b * K + c];
+        const float sc = s_inv[c] * s_ginv;
+        float* vb = v + (size_t)b * F * K;
+        for (int f = grp; f < F; f += 4) {
+            const float r = Vb[(size_t)f * K + c] - as * Wc2[(size_t)f * K + c];
+            vb[(size_t)f * K + c] = r * sc;
+        }
+    }
+}
+
+int vlad_finalize(const float* V, const float* a_sum, const float* Wc2, int B, int F, int K, float* v, cudaStream_t st) {
+    EPC_CHECK_ARG(K >= 1 && K <= 64, "vlad_finalize: cluster_size=%d unsupported (1..64)", K);
+    if (B == 0) return EPC_OK;
+    vlad_finalize_kernel<<<B, 256, 0, st>>>(V, a_sum, Wc2, F, K, v);
+    EPC_LAUNCH_CHECK();
+    return EPC_OK;
+}
+
+// Tail (loupe.py:320-331, 61-101; models/epc-net.py:153): Y [B*G, D] raw hidden products ->
+//   y = sum_g BN_bn(Y[b,g,:]);  z = y * sigmoid(BN_gating(y Wg));  out = l2 ? z/|z| : z.   One CTA per cloud, D threads.
+__global__ void vlad_tail_kernel(const float* __restrict__ Y, int G, int D, const float* __restrict__ bn_scale,
+                                 const float* __restrict__ bn_shift, const float* __restrict__ Wg,
+                                 const float* __restrict__ g_scale, const float* __restrict__ g_shift, int gating,
+                                 int l2, float* __restrict__ out) {
+    extern __shared__ float sy[];          // [D] + [32]
+    float* sred = sy + D;
+    const int b = blockIdx.x, d = threadIdx.x;
+    float y = 0.f;
+    if (d < D) {
+        for (int g = 0; g < G; ++g) y += Y[((size_t)b * G + g) * D + d] * bn_scale[d] + bn_shift[d];
+        sy[d] = y;
+    }
+    __syncthreads();
+    float z = y;
+    if (gating && d < D) {
+        float acc = 0.f;
+        for (int k = 0; k < D; ++k) acc = fmaf(sy[k], Wg[(size_t)k * D + d], acc);
+        const float gt = acc * g_scale[d] + g_shift[d];
+        z = y * (1.0f / (1.0f + expf(-gt)));
+    }
+    if (l2) {
+        float ss = (d < D) ? z * z : 0.f;
+        ss = warp_sum(ss);
+        if ((d & 31) == 0) sred[d >> 5] = ss;
+        __syncthreads();
+        float tot = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += sred[w];
+        z *= 1.0f / sqrtf(fmaxf(tot, L2_EPS));
+    }
+    if (d < D) out[(size_t)b * D + d] = z;
+}
+
+int vlad_tail(const float* Y, int B, int G, int D, const float* bn_scale, const float* bn_shift, const float* Wg,
+              const float* g_scale, const float* g_shift, int gating, int l2, float* out, cudaStream_t st) {
+    EPC_CHECK_ARG(D >= 1 && D <= 1024, "vlad_tail: output_dim=%d unsupported (1..1024)", D);
+    if (B == 0) return EPC_OK;
+    const int threads = (D + 31) / 32 * 32;
+    vlad_tail_kernel<<<B, threads, (D + 32) * sizeof(float), st>>>(Y, G, D, bn_scale, bn_shift, Wg, g_scale, g_shift,
+                                                                   gating, l2, out);
+    EPC_LAUNCH_CHECK();
+    return EPC_OK;
+}
+
+// g[b,f] = max_n H[b,n,f]   (tf_util.max_pool2d over [N,1], models/epc-net-l.py:91).  H >= 0 is NOT assumed:
+// a float atomic max via the ordered-int trick.
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    if (v >= 0.f)
+        atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else
+        atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__global__ void fill_kernel(float* p, long long n, float v) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void col_max_kernel(const float* __restrict__ H, int N, int F, int rows_per_cta, float* __restrict__ g) {
+    const int b = blockIdx.z;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const int n0 = blockIdx.y * rows_per_cta, n1 = min(N, n0 + rows_per_cta);
+    const float* h = H + ((size_t)b * N) * F + f;
+    float m = -INFINITY;
+    for (int n = n0; n < n1; ++n) m = fmaxf(m, __ldg(h + (size_t)n * F));
+    if (n1 > n0) atomic_max_float(&g[(size_t)b * F + f], m);
+}
+
+int col_max(const float* H, int B, int N, int F, float* g, cudaStream_t st) {
+    if (B == 0) return EPC_OK;
+    const long long tot = (long long)B * F;
+    fill_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(g, tot, -INFINITY);
+    EPC_LAUNCH_CHECK();
+    const int rows = 128;
+    dim3 grid((F + 127) / 128, (N + rows - 1) / rows, B);
+    col_max_kernel<<<grid, 128, 0, st>>>(H, N, F, rows, g);
+    EPC_LAUNCH_CHECK();
+    return EPC_OK;
+}
+
+// out[r,:] = X[r,:] / sqrt(max(|X[r,:]|^2, 1e-12)); one warp per row
+__global__ void row_l2_normalize_kernel(const float* __restrict__ X, int R, int D, float* __restrict__ out) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= R) return;
+    float ss = 0.f;
+    for (int i = lane; i < D; i += 32) {
+        const float v = X[(size_t)r * D + i];
+        ss += v * v;
+    }
+    ss = warp_sum(ss);
+    const float iv = 1.0f / sqrtf(fmaxf(ss, L2_EPS));
+    for (int i = lane; i < D; i += 32) out[(size_t)r * D + i] = X[(size_t)r * D + i] * iv;
+}
+
+int row_l2_normalize(const float* X, int R, int D, float* out, cudaStream_t st) {
+    if (R == 0) return EPC_OK;
+    row_l2_normalize_kernel<<<(R + 7) / 8, 256, 0, st>>>(X, R, D, out);
+    EPC_LAUNCH_CHECK();
+    return EPC_OK;
+}
+
+// KD feature (models/kd_epc-net.py:158): feat[b, perm[pos], :] = H[b,pos,:] * inv[b,pos]  (back to original order)
+__global__ void kd_feat_kernel(const float* __restrict__ H, const float* __restrict__ inv, const int* __restrict__ perm,
+                               int N, int F, float* __restrict__ feat) {
+    const size_t row = blockIdx.x;     // b*N + pos
+    const size_t b = row / N;
+    const size_t orow = b * N + perm[row];
+    const float iv = inv[row];
+    const float4* src = reinterpret_cast<const float4*>(H + row * F);
+    float4* dst = reinterpret_cast<float4*>(feat + orow * F);
+    for (int i = threadIdx.x; i < F / 4; i += blockDim.x) {
+        float4 v = __ldg(src + i);
+        v.x *= iv; v.y *= iv; v.z *= iv; v.w *= iv;
+        dst[i] = v;
+    }
+}
+
+int kd_feat(const float* H, const float* inv, const int* perm, int B, int N, int F, float* feat, cudaStream_t st) {
+    if (B == 0) return EPC_OK;
+    kd_feat_kernel<<<(unsigned)((size_t)B * N), 256, 0, st>>>(H, inv, perm, N, F, feat);
+    EPC_LAUNCH_CHECK();
+    return EPC_OK;
+}
+
+}  // namespace epc

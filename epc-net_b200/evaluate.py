@@ -1,0 +1,174 @@
+"""Database/query recall flow of the reference's evaluate.py on the B200 path.
+
+  get_latent_vectors  evaluate.py:351-452   clouds -> descriptors (here: batched, pipelined H2D)
+  get_recall          evaluate.py:455-537   KDTree 25-NN per query -> recall@N / top-1 similarity / top-1%
+  evaluate            evaluate.py:226-348   all database sets, all query sets, the m != n pair loop
+
+Differences from the reference, by construction:
+  * no ``sess``: the argument is kept (and ignored) so call sites read the same;
+  * ``ops`` is a plain dict: {"MODEL": plugin module, "params": yaml dict, optional "BATCH_NUM_QUERIES",
+    "POSITIVES_PER_QUERY", "NEGATIVES_PER_QUERY" (defaults 1, 0, 0 as at evaluate.py:86-90)};
+  * the reference runs ONE cloud per sess.run; inference-mode batch norm makes every descriptor independent
+    of its batch (utils/tf_util.py:486-489), so clouds are embedded in large chunks instead -- same values;
+  * retrieval is an exact GPU k-NN (epc_retrieve_topk) instead of a CPU KD-tree -- same indices.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import _lib, variables
+from . import engine as _engine
+from .engine import _ptr, _stream, workspaces
+
+# the reference keeps these as module globals (evaluate.py:130-134, 227-229)
+DATABASE_SETS = []
+QUERY_SETS = []
+DATABASE_VECTORS = []
+QUERY_VECTORS = []
+NUM_NEIGHBORS = 25      # evaluate.py:465
+
+
+def _arch_of(ops):
+    model = ops["MODEL"]
+    return getattr(model, "ARCH", None) or ops["params"]["ARCH"]
+
+
+def get_latent_vectors(sess, ops, dict_to_process, data):
+    """evaluate.py:351-452.  ``data``: (n, NUM_POINTS, INPUT_DIM) host array for the n entries of
+    ``dict_to_process``; returns the (n, FEATURE_OUTPUT_DIM) fp32 descriptors as a host array.
+
+    The reference's grouping into (BATCH_NUM_QUERIES x (1+P+N)) tuples and its zero "fake" clouds for the tail
+    (:415-446) only pad sess.run feeds; they do not change any returned row, so rows are embedded directly.
+    """
+    n = len(dict_to_process.keys()) if dict_to_process is not None else len(data)
+    data = np.asarray(data, dtype=np.float32)
+    if data.shape[0] != n:
+        raise ValueError("data has %d clouds but dict_to_process has %d entries" % (data.shape[0], n))
+    params = ops["params"]
+    eng = _engine.get_engine(_arch_of(ops), params, store=params.get("VARIABLES"))
+    return eng.embed_host(data)
+
+
+def retrieve_topk(database_output, queries_output, k, id_offset=0):
+    """Exact Euclidean k-NN on the GPU: -> (dist [Q,k] float64, idx [Q,k] int64), ascending, like
+    ``KDTree(database_output).query(queries_output, k)`` (evaluate.py:463,481)."""
+    _engine._require_cuda()
+    lib = _lib.load()
+    db = torch.as_tensor(np.ascontiguousarray(database_output, dtype=np.float32)).cuda() \
+        if not isinstance(database_output, torch.Tensor) else database_output.contiguous()
+    q = torch.as_tensor(np.ascontiguousarray(queries_output, dtype=np.float32)).cuda() \
+        if not isinstance(queries_output, torch.Tensor) else queries_output.contiguous()
+    D, dim = db.shape
+    Q = q.shape[0]
+    idx = torch.empty((Q, k), dtype=torch.int64, device=db.device)
+    dist = torch.empty((Q, k), dtype=torch.float64, device=db.device)
+    with torch.cuda.device(db.device):
+        ws = workspaces.get(lib.epc_retrieve_workspace_bytes(D, Q, dim, k))
+        _lib.check(lib.epc_retrieve_topk(_ptr(db), D, _ptr(q), Q, dim, k, int(id_offset), _ptr(idx), _ptr(dist), _ptr(ws),
+                                         ws.numel(), _stream()))
+    return dist, idx
+
+
+def recall_from_neighbors(indices, valid, true_neighbors_list, queries_output, database_output, num_db,
+                          num_neighbors=NUM_NEIGHBORS):
+    """The bookkeeping of evaluate.py:466-530 given the retrieved ``indices`` (one row per evaluated query)."""
+    recall = [0] * num_neighbors
+    top1_similarity_score = []
+    one_percent_retrieved = 0
+    threshold = max(int(round(num_db / 100.0)), 1)                              # :470
+    for row, i in enumerate(valid):
+        true_neighbors = true_neighbors_list[row]
+        ind = indices[row]
+        tset = set(int(t) for t in true_neighbors)
+        for j in range(len(ind)):                                               # :513
+            if int(ind[j]) in tset:
+                if j == 0:
+                    top1_similarity_score.append(np.dot(queries_output[i], database_output[ind[j]]))   # :516
+                recall[j] += 1
+                break
+        if len(set(int(v) for v in ind[0:threshold]).intersection(tset)) > 0:    # :526
+            one_percent_retrieved += 1
+    num_evaluated = len(valid)
+    one_percent_recall = (one_percent_retrieved / float(num_evaluated)) * 100   # :529
+    recall = (np.cumsum(recall) / float(num_evaluated)) * 100                   # :530
+    return recall, top1_similarity_score, one_percent_recall
+
+
+def get_recall(sess, ops, m, n, fout=None):
+    """evaluate.py:455-537 on the module globals DATABASE_VECTORS / QUERY_VECTORS / QUERY_SETS.
+    Returns (recall, top1_similarity_score, one_percent_recall, for_plot)."""
+    database_output = np.asarray(DATABASE_VECTORS[m])
+    queries_output = np.asarray(QUERY_VECTORS[n])
+    valid, truth = [], []
+    for i in range(len(queries_output)):
+        true_neighbors = QUERY_SETS[n][i][m]                                    # :477
+        if len(true_neighbors) == 0:                                            # :478
+            continue
+        valid.append(i)
+        truth.append(true_neighbors)
+    if not valid:
+        raise ZeroDivisionError("no query of set %d has a true neighbour in set %d" % (n, m))   # :529 divides by 0
+    k = min(NUM_NEIGHBORS, len(database_output))
+    _, idx = retrieve_topk(database_output, queries_output[valid], k)
+    idx = idx.cpu().numpy()
+    recall, sim, opr = recall_from_neighbors(idx, valid, truth, queries_output, database_output, len(database_output))
+    for_plot = []
+    for row, i in enumerate(valid):                                             # :507-524
+        q = QUERY_SETS[n][i]
+        for_plot.append(q.get("easting"))
+        for_plot.append(q.get("northing"))
+        tset = set(int(t) for t in truth[row])
+        hit = [j for j in range(idx.shape[1]) if int(idx[row, j]) in tset]
+        for_plot.append(hit[0] if hit else 25)
+        if fout is not None:
+            fout.write("%s|%s|%s\n" % (q.get("query", ""), " ".join(str(int(v)) for v in idx[row]),
+                                       " ".join(str(int(t)) for t in truth[row])))
+    return recall, sim, opr, for_plot
+
+
+def evaluate(ops, eval_database_set, eval_query_set, database_sets, query_sets, output_file=None):
+    """evaluate.py:226-348 without the TF graph/session plumbing.
+
+    eval_database_set[i] / eval_query_set[j]: (n, NUM_POINTS, 3) host arrays (what load_pc_data_set returns,
+    evaluate.py:177-195); database_sets / query_sets: the evaluation pickles' dict lists.
+    Returns (ave_recall[25], average_similarity, ave_one_percent_recall).
+    """
+    global DATABASE_SETS, QUERY_SETS, DATABASE_VECTORS, QUERY_VECTORS
+    DATABASE_SETS, QUERY_SETS = database_sets, query_sets
+    DATABASE_VECTORS, QUERY_VECTORS = [], []
+    recall = np.zeros(NUM_NEIGHBORS)
+    count = 0
+    similarity = []
+    one_percent_recall = []
+    for i in range(len(DATABASE_SETS)):                                         # :297-299
+        DATABASE_VECTORS.append(get_latent_vectors(None, ops, DATABASE_SETS[i], eval_database_set[i]))
+    for j in range(len(QUERY_SETS)):                                            # :301-303
+        QUERY_VECTORS.append(get_latent_vectors(None, ops, QUERY_SETS[j], eval_query_set[j]))
+    for m in range(len(QUERY_SETS)):                                            # :305-317
+        for n in range(len(QUERY_SETS)):
+            if m == n:
+                continue
+            pair_recall, pair_similarity, pair_opr, _ = get_recall(None, ops, m, n, fout=None)
+            recall += np.array(pair_recall)
+            count += 1
+            one_percent_recall.append(pair_opr)
+            similarity.extend(pair_similarity)
+    ave_recall = recall / count                                                 # :320
+    average_similarity = np.mean(similarity)                                    # :326
+    ave_one_percent_recall = np.mean(one_percent_recall)                        # :330
+    if output_file:
+        os.makedirs(os.path.dirname(os.path.abspath(output_file)), exist_ok=True)
+        with open(output_file, "a") as output:                                  # :336-348
+            output.write(str(ops["params"].get("ARCH", _arch_of(ops))))
+            output.write("\n\nAverage Recall @N:\n")
+            output.write(str(ave_recall))
+            output.write("\n\nAverage Similarity:\n")
+            output.write(str(average_similarity))
+            output.write("\n\nAverage Top 1% Recall:\n")
+            output.write(str(ave_one_percent_recall))
+            output.write("\n\n")
+    return ave_recall, average_similarity, ave_one_percent_recall

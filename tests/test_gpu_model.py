@@ -1,0 +1,195 @@
+"""-m gpu: descriptor parity of MODEL.forward through the plugin surface (-> epc_embed in libepc_b200).
+
+Tolerance (BASELINE.json north_star): max-abs <= 1e-3 after L2-normalisation and cosine >= 0.9999."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+import _data
+from oracle import epc_oracle, knn_c
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+TOL_ABS, TOL_COS = 1e-3, 0.9999
+ARCHS = ["epc-net", "epc-net-l", "kd_epc-net", "kd_epc-net-l"]
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def pkg(built_lib):
+    class P:
+        variables = importlib.import_module("epc-net_b200.variables")
+        models = importlib.import_module("epc-net_b200.models")
+        loupe = importlib.import_module("epc-net_b200.loupe")
+        tf_util = importlib.import_module("epc-net_b200.utils.tf_util")
+        evaluate = importlib.import_module("epc-net_b200.evaluate")
+        engine = importlib.import_module("epc-net_b200.engine")
+    return P
+
+
+def _check_desc(out, ref, what=""):
+    out = np.asarray(out, np.float32).reshape(-1, ref.shape[-1])
+    ref = np.asarray(ref, np.float32).reshape(-1, ref.shape[-1])
+    err = np.abs(out - ref).max()
+    cos = ((out * ref).sum(-1) / np.maximum(np.linalg.norm(out, axis=-1) * np.linalg.norm(ref, axis=-1), 1e-30))
+    # the all-zero fake cloud yields a legitimate all-zero EPC-Net-L descriptor only if every FC output is <= 0; skip cos there
+    nz = np.linalg.norm(ref, axis=-1) > 0
+    assert err <= TOL_ABS, "%s max-abs %.3e > %.0e" % (what, err, TOL_ABS)
+    assert cos[nz].min() >= TOL_COS, "%s min cosine %.6f" % (what, cos[nz].min())
+    return float(err), float(cos[nz].min())
+
+
+@pytest.mark.parametrize("arch", ARCHS)
+def test_forward_matches_graph_golden(pkg, arch):
+    """18 clouds x 4096 points (incl. tie-heavy, duplicated and all-zero clouds) against the descriptors obtained
+    by executing the reference's shipped GraphDef (tests/golden/make_golden.py)."""
+    g = np.load(os.path.join(GOLDEN, "graph_%s.npz" % arch))
+    scope = str(g["scope"])
+    V = pkg.variables.synthetic_variables(arch, int(g["weight_seed"]), scope)
+    clouds = _data.golden_batch(int(g["cloud_seed"]))
+    params = dict(_data.default_params(arch), VARIABLES=pkg.variables.VariableStore(V))
+    outer, inner = (scope.split("/", 1) + [None])[:2] if "/" in scope else (None, scope)
+    model = pkg.models.load(arch)
+    x = torch.from_numpy(clouds[None]).cuda()
+    if outer:
+        with pkg.variables.variable_scope(outer), pkg.variables.variable_scope(inner):
+            res = model.forward(x, False, params=params)
+    else:
+        with pkg.variables.variable_scope(scope):
+            res = model.forward(x, False, params=params)
+    if arch.startswith("kd_"):
+        feat, out = res
+        feat = feat.cpu().numpy().reshape(18, 4096, 1024)[:, g["sample_points"], :]
+        assert np.abs(feat - g["kd_feat_rows"]).max() <= 1e-4, "KD per-point features (models/kd_epc-net.py:158)"
+    else:
+        out = res
+    assert tuple(out.shape) == (1, 18, 256)
+    err, cos = _check_desc(out.cpu().numpy(), g["output"], arch)
+    print("%s vs graph golden: max|d|=%.2e min cos=%.7f" % (arch, err, cos))
+
+
+@pytest.mark.parametrize("arch", ["epc-net", "epc-net-l"])
+@pytest.mark.parametrize("arith", ["muladd", "fma"])
+def test_forward_matches_oracle_small(pkg, arch, arith):
+    N = 512
+    kinds = ["uniform", "clustered", "coarse", "duplicated", "zeros", "planar"]
+    clouds = np.stack([_data.cloud(k, 700 + i, N) for i, k in enumerate(kinds)], 0).reshape(2, 3, N, 3)
+    V = pkg.variables.synthetic_variables(arch, 21)
+    params = dict(_data.default_params(arch), NUM_POINTS=N, KNN_ARITH=arith, VARIABLES=pkg.variables.VariableStore(V))
+    out = pkg.models.load(arch).forward(torch.from_numpy(clouds).cuda(), False, params=params)
+    mask = knn_c.mask(clouds.reshape(6, N, 3), arith=arith)
+    ref = epc_oracle.forward(arch, clouds, V, params, mask=mask)
+    assert tuple(out.shape) == (2, 3, 256)
+    _check_desc(out.cpu().numpy(), ref, "%s/%s" % (arch, arith))
+
+
+def test_batch_independence_and_determinism(pkg):
+    """Inference BN has no cross-sample coupling: a cloud's descriptor is bit-identical alone, in a batch, at any
+    chunking, and run to run (this is what lets get_latent_vectors batch where the reference runs 1 cloud/sess.run)."""
+    arch = "epc-net"
+    V = pkg.variables.synthetic_variables(arch, 3)
+    clouds = np.stack([_data.cloud("uniform", 900 + i, 4096) for i in range(5)], 0)
+    x = torch.from_numpy(clouds).cuda()
+    store = pkg.variables.VariableStore(V)
+    e_big = pkg.engine.Engine(arch, store, "query_triplets", dict(_data.default_params(arch), EMBED_CHUNK=8))
+    e_one = pkg.engine.Engine(arch, store, "query_triplets", dict(_data.default_params(arch), EMBED_CHUNK=1))
+    a = e_big.embed(x)
+    b = e_one.embed(x)
+    c = e_big.embed(x[2:3])
+    assert torch.equal(a, b) and torch.equal(a[2:3], c) and torch.equal(a, e_big.embed(x))
+
+
+def test_point_permutation_invariance(pkg):
+    """Full-size property: descriptors do not depend on the order of the points of a cloud (kNN sets, max-pool and
+    VLAD sums are permutation invariant; only fp32 summation order moves)."""
+    rng = np.random.default_rng(5)
+    for arch in ("epc-net", "epc-net-l"):
+        V = pkg.variables.synthetic_variables(arch, 4)
+        params = dict(_data.default_params(arch), VARIABLES=pkg.variables.VariableStore(V))
+        c = np.stack([_data.cloud("uniform", 40, 4096), _data.cloud("clustered", 41, 4096)], 0)
+        p = np.stack([c[0][rng.permutation(4096)], c[1][rng.permutation(4096)]], 0)
+        f = pkg.models.load(arch).forward
+        a = f(torch.from_numpy(c[None]).cuda(), False, params=params).cpu().numpy()
+        b = f(torch.from_numpy(p[None]).cuda(), False, params=params).cpu().numpy()
+        assert np.abs(a - b).max() <= 2e-5, arch
+
+
+def test_loupe_interface(pkg):
+    """loupe.G_VLAD / NetVLAD forward on caller-provided features (loupe.py:233-333, 119-214)."""
+    rng = np.random.default_rng(1)
+    B, N = 3, 256
+    X = rng.standard_normal((B * N, 1024)).astype(np.float32)
+    X = np.maximum(X, 0)
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    for pooling, groups in (("G_VLAD", 4), ("NetVLAD", 1)):
+        V = pkg.variables.synthetic_variables("epc-net", 8, "query_triplets", pooling=pooling)
+        store = pkg.variables.VariableStore(V)
+        with pkg.variables.variable_scope("query_triplets"), pkg.variables.variable_scope("VLAD"):
+            if pooling == "G_VLAD":
+                layer = pkg.loupe.G_VLAD(feature_size=1024, max_samples=N, cluster_size=64, output_dim=256, groups=4,
+                                         gating=True, add_batch_norm=True, is_training=False)
+            else:
+                layer = pkg.loupe.NetVLAD(feature_size=1024, max_samples=N, cluster_size=64, output_dim=256,
+                                          gating=True, add_batch_norm=True, is_training=False)
+            layer.variables = store
+            out = layer.forward(torch.from_numpy(X).cuda()).cpu().numpy()
+        ref = epc_oracle.vlad_forward(X, V, "query_triplets/VLAD/", N, 64, 256, groups, True, pooling)
+        assert out.shape == (B, 256)
+        scale = np.abs(ref).max()
+        assert np.abs(out - ref).max() <= 1e-3 * scale, pooling
+    with pytest.raises(NotImplementedError):
+        pkg.loupe.G_VLAD(1024, N, 64, 256, is_training=True).forward(torch.from_numpy(X).cuda())
+
+
+def test_tf_util_layers(pkg):
+    """conv1d / fully_connected / max_pool2d wrappers (utils/tf_util.py:52-107, 310-346, 349-372)."""
+    rng = np.random.default_rng(2)
+    V = pkg.variables.synthetic_variables("epc-net-l", 9)
+    store = pkg.variables.VariableStore(V)
+    x = rng.standard_normal((2, 300, 64)).astype(np.float32)
+    with pkg.variables.variable_scope("query_triplets"), pkg.variables.variable_scope("fastdgcnn"):
+        y = pkg.tf_util.conv1d(torch.from_numpy(x).cuda(), 64, 1, padding="VALID", stride=1, bn=True, is_training=False,
+                               scope="conv1_a", variables_store=store).cpu().numpy()
+    ref = epc_oracle.conv1d(x, V, "query_triplets/fastdgcnn/conv1_a")
+    assert np.abs(y - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+    g = rng.standard_normal((5, 1024)).astype(np.float32)
+    with pkg.variables.variable_scope("query_triplets"), pkg.variables.variable_scope("VLAD"):
+        o = pkg.tf_util.fully_connected(torch.from_numpy(g).cuda(), 256, bn=True, is_training=False, scope="fc1",
+                                        variables_store=store).cpu().numpy()
+    ref = epc_oracle.fully_connected(g, V, "query_triplets/VLAD/fc1")
+    assert np.abs(o - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+    h = rng.standard_normal((3, 128, 1, 1024)).astype(np.float32)
+    mp = pkg.tf_util.max_pool2d(torch.from_numpy(h).cuda(), [128, 1], padding="VALID", scope="maxpool").cpu().numpy()
+    assert np.array_equal(mp, h.max(axis=1, keepdims=True))
+
+
+def test_plugin_surface_errors(pkg):
+    m = pkg.models.load("epc-net")
+    ph = m.placeholder_inputs(1, 1, 4096, 3)
+    assert tuple(ph.shape) == (1, 1, 4096, 3) and ph.is_cuda
+    V = pkg.variables.synthetic_variables("epc-net", 1)
+    params = dict(_data.default_params("epc-net"), VARIABLES=pkg.variables.VariableStore(V))
+    with pytest.raises(NotImplementedError):
+        m.forward(ph, True, params=params)
+    with pytest.raises(KeyError):
+        m.forward(ph, False, params={"KNN": 20})
+    empty = m.forward(torch.zeros((1, 0, 4096, 3), device="cuda"), False, params=params)   # evaluate.py feeds P=0 tensors
+    assert tuple(empty.shape) == (1, 0, 256)
+
+
+def test_get_latent_vectors_host_path(pkg):
+    """evaluate.get_latent_vectors on host arrays == oracle restatement of evaluate.py:351-452 (ragged tail included)."""
+    arch = "epc-net-l"
+    N = 256
+    V = pkg.variables.synthetic_variables(arch, 30)
+    params = dict(_data.default_params(arch), NUM_POINTS=N, EMBED_CHUNK=4, VARIABLES=pkg.variables.VariableStore(V))
+    data = np.stack([_data.cloud("uniform", 1200 + i, N) for i in range(11)], 0)
+    ops = {"MODEL": pkg.models.load(arch), "params": params}
+    got = pkg.evaluate.get_latent_vectors(None, ops, {i: {} for i in range(11)}, data)
+    ref = epc_oracle.get_latent_vectors(arch, V, params, data, batch_num_queries=3, positives=0, negatives=0)
+    assert got.shape == (11, 256)
+    _check_desc(got, ref, "get_latent_vectors")
+    assert pkg.evaluate.get_latent_vectors(None, ops, {}, np.zeros((0, N, 3), np.float32)).shape == (0, 256)

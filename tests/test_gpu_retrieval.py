@@ -1,0 +1,89 @@
+"""-m gpu: K6 retrieval parity -- indices identical to sklearn's KDTree (golden) and to the float64 oracle."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+import _data
+from oracle import retrieval_oracle as R
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def ev(built_lib):
+    return importlib.import_module("epc-net_b200.evaluate")
+
+
+def test_matches_kdtree_golden(ev):
+    g = np.load(os.path.join(GOLDEN, "retrieval_kdtree.npz"))
+    db, q, _ = _data.retrieval_problem(D=int(g["D"]), Q=int(g["Q"]), seed=int(g["seed"]))
+    d, i = ev.retrieve_topk(db, q, 25)
+    assert np.array_equal(i.cpu().numpy(), g["idx"]), "top-25 indices must equal KDTree(db).query(q, 25)"
+    assert np.abs(d.cpu().numpy() - g["dist"]).max() <= 1e-12
+
+
+@pytest.mark.parametrize("D,Q,k", [(20000, 512, 25), (1000, 33, 10), (40, 7, 25), (20, 3, 25), (5000, 100, 1)])
+def test_matches_float64_oracle(ev, D, Q, k):
+    db, q, _ = _data.retrieval_problem(D=D, Q=Q, seed=11)
+    d, i = ev.retrieve_topk(db, q, k)
+    rd, ri = R.knn_f64(db, q, k)
+    kk = min(k, D)
+    assert np.array_equal(i.cpu().numpy()[:, :kk], ri)
+    assert np.abs(d.cpu().numpy()[:, :kk] - rd).max() <= 1e-12
+    if k > D:
+        assert (i.cpu().numpy()[:, D:] == -1).all()
+
+
+def test_near_ties_take_the_exact_fallback(ev):
+    """Database rows that differ below fp32 scoring resolution: the float64 re-rank / exact fallback must still
+    return the float64 order, ties -> lower index."""
+    rng = np.random.default_rng(0)
+    base = rng.standard_normal((1, 256)).astype(np.float32)
+    base /= np.linalg.norm(base)
+    db = np.repeat(base, 300, 0)
+    db[:, 0] += (np.arange(300, dtype=np.float32) % 7) * 1e-7       # many near-identical rows, some exactly equal
+    db = np.concatenate([db, rng.standard_normal((500, 256)).astype(np.float32) / 16], 0)
+    q = base + 1e-3 * rng.standard_normal((9, 256)).astype(np.float32)
+    d, i = ev.retrieve_topk(db, q, 25)
+    rd, ri = R.knn_f64(db, q, 25)
+    assert np.array_equal(i.cpu().numpy(), ri)
+
+
+def test_sharded_merge_is_shard_count_invariant(ev):
+    dist_mod = importlib.import_module("epc-net_b200.dist")
+    db, q, _ = _data.retrieval_problem(D=3001, Q=64, seed=5)
+    d0, i0 = ev.retrieve_topk(db, q, 25)
+    for world in (2, 3, 8):
+        ds, is_ = [], []
+        for r in range(world):
+            s, e = dist_mod.shard_range(len(db), r, world)
+            d, i = ev.retrieve_topk(db[s:e], q, 25, id_offset=s)
+            ds.append(d)
+            is_.append(i)
+        md, mi = dist_mod.cuda_merge(torch.stack(ds), torch.stack(is_))
+        assert torch.equal(mi, i0) and torch.equal(md, d0), world
+
+
+def test_get_recall_flow(ev):
+    """evaluate.get_recall / evaluate()'s pair loop against the oracle restatement of evaluate.py:305-334, 455-537."""
+    dbv, qv, qsets = _data.retrieval_sets()
+    ev.DATABASE_VECTORS, ev.QUERY_VECTORS, ev.QUERY_SETS = dbv, qv, qsets
+    tot = np.zeros(25)
+    sims, oprs, cnt = [], [], 0
+    for m in range(len(qsets)):
+        for n in range(len(qsets)):
+            if m == n:
+                continue
+            rec, sim, opr, for_plot = ev.get_recall(None, None, m, n)
+            orec, osim, oopr = R.get_recall(dbv[m], qv[n], qsets[n], m)
+            assert np.allclose(rec, orec) and opr == oopr and np.allclose(sim, osim)
+            tot += rec
+            cnt += 1
+            sims += list(sim)
+            oprs.append(opr)
+    ave, avs, avo = R.evaluate_pairs(dbv, qv, qsets)
+    assert np.allclose(tot / cnt, ave) and np.isclose(np.mean(sims), avs) and np.isclose(np.mean(oprs), avo)

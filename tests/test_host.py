@@ -1,0 +1,165 @@
+"""CPU suite: host logic -- variable store / checkpoint names, TF bundle reader, plugin surface, sharding (gloo x2)."""
+import importlib
+import os
+import socket
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+import _data
+
+variables = importlib.import_module("epc-net_b200.variables")
+tf_bundle = importlib.import_module("epc-net_b200.tf_bundle")
+dist_mod = importlib.import_module("epc-net_b200.dist")
+REF = "/root/reference"
+
+
+def test_variable_specs_sizes():
+    # parameter counts of SURVEY.md section 6 (trainable = weights, biases, beta, gamma, VLAD matrices)
+    def trainable(arch):
+        n = 0
+        for k, s in variables.variable_specs(arch).items():
+            if "ExponentialMovingAverage" in k or "moving_" in k:
+                continue
+            n += int(np.prod(s))
+        return n
+    assert trainable("epc-net") == 4704832
+    assert trainable("epc-net-l") == 418880
+    assert trainable("kd_epc-net-l") == 418880
+    s = variables.variable_specs("kd_epc-net-l", "student/query_triplets")
+    assert "student/query_triplets/BACKBONE/conv5/weights" in s and s["student/query_triplets/BACKBONE/conv5/weights"] == (1, 128, 1024)
+    assert variables.variable_specs("epc-net", pooling="NetVLAD")["query_triplets/VLAD/hidden1_weights"] == (65536, 256)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted (GPU box)")
+@pytest.mark.parametrize("arch,index,scope", [
+    ("epc-net", "exp/epc-net/saved_model/model_epoch22_iter18101.ckpt.index", "query_triplets"),
+    ("epc-net-l", "exp/epc-net-l/saved_model/model_epoch13_iter18101.ckpt.index", "query_triplets"),
+    ("kd_epc-net-l", "exp/epc-net-l-d/saved_model/student_model_epoch20_iter18101.ckpt.index", "student/query_triplets"),
+    ("kd_epc-net", "exp/epc-net-l-d/transfer_teacher/teacher_model_epoch22_iter18101.ckpt.index", "teacher/query_triplets"),
+])
+def test_names_and_shapes_match_shipped_checkpoints(arch, index, scope):
+    entries = tf_bundle.read_index(os.path.join(REF, index))
+    have = {k: tuple(e["shape"]) for k, e in entries.items()
+            if "Adam" not in k and not k.endswith("Variable") and "beta1_power" not in k and "beta2_power" not in k}
+    spec = variables.variable_specs(arch, scope)
+    assert set(have) == set(spec)
+    assert all(tuple(spec[k]) == have[k] for k in spec)
+
+
+def test_tf_bundle_round_trip_and_restore():
+    V = variables.synthetic_variables("epc-net-l", 3)
+    with tempfile.TemporaryDirectory() as d:
+        prefix = os.path.join(d, "model_epoch1_iter1.ckpt")
+        extra = dict(V)
+        extra["Variable"] = np.array(7, np.int32)
+        extra["query_triplets/fastdgcnn/conv1/weights/Adam"] = np.zeros((1, 3, 64), np.float32)
+        tf_bundle.write_checkpoint(prefix, extra)
+        got = tf_bundle.read_checkpoint(prefix)
+        assert "query_triplets/fastdgcnn/conv1/weights/Adam" not in got and int(got["Variable"]) == 7
+        store = variables.VariableStore()
+        store.restore(prefix)
+        assert set(store.keys()) == set(V.keys())
+        assert all(np.array_equal(store[k], V[k]) for k in V)
+        with pytest.raises(ValueError):
+            tf_bundle.read_index(prefix + ".data-00000-of-00001")
+    with pytest.raises(KeyError):
+        variables.VariableStore()["query_triplets/nope"]
+
+
+def test_variable_scope_nesting():
+    assert variables.current_scope("dflt") == "dflt"
+    with variables.variable_scope("student"), variables.variable_scope("query_triplets") as s:
+        assert s == "student/query_triplets" == variables.current_scope()
+    assert variables.current_scope() == ""
+
+
+def test_plugin_modules_expose_reference_surface():
+    models = importlib.import_module("epc-net_b200.models")
+    import inspect
+    for arch in models.ARCHS:
+        m = models.load(arch)
+        assert list(inspect.signature(m.forward).parameters) == ["point_cloud", "is_training", "bn_decay", "params"]
+        assert list(inspect.signature(m.placeholder_inputs).parameters) == ["batch_num_queries", "num_pointclouds_per_query",
+                                                                             "num_point", "input_dim"]
+    with pytest.raises(ImportError):
+        models.load("pointnetvlad")
+    loupe = importlib.import_module("epc-net_b200.loupe")
+    g = loupe.G_VLAD(feature_size=1024, max_samples=4096, cluster_size=64, output_dim=256, groups=4, gating=True,
+                     add_batch_norm=True, is_training=False)
+    assert (g.groups, g.cluster_size, g.max_samples) == (4, 64, 4096)
+    with pytest.raises(NotImplementedError):
+        loupe.PoolingBaseModel(1024, 4096, 64, 256).forward(None)
+    # the alias module gives the very same objects
+    import epc_net_b200
+    from epc_net_b200 import variables as v2
+    assert v2 is variables and epc_net_b200.__version__
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 8, 20000, 3001):
+        for w in (1, 2, 3, 8):
+            cuts = [dist_mod.shard_range(n, r, w) for r in range(w)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in cuts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import retrieval_oracle as R
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        db, qs, _ = _data.retrieval_problem(D=1001, Q=40, seed=9)
+        s, e = dist_mod.shard_range(len(db), rank, world)
+
+        def local_topk(dbl, queries, k, off):          # injected checker implementation (CPU): host logic under test
+            d, i = R.knn_f64(dbl, queries, k)
+            return torch.from_numpy(d), torch.from_numpy(i + off)
+
+        def merge(gd, gi):
+            Rr, Q, k = gd.shape
+            d = gd.permute(1, 0, 2).reshape(Q, Rr * k).numpy()
+            i = gi.permute(1, 0, 2).reshape(Q, Rr * k).numpy()
+            order = np.lexsort((i, d), axis=1)[:, :k]
+            return torch.from_numpy(np.take_along_axis(d, order, 1)), torch.from_numpy(np.take_along_axis(i, order, 1))
+
+        md, mi = dist_mod.retrieve_sharded(local_topk, merge, db[s:e], s, qs, 25)
+        rd, ri = R.knn_f64(db, qs, 25)
+        ok_r = bool(np.array_equal(mi.numpy(), ri))
+        clouds = np.arange(7 * 4 * 3, dtype=np.float32).reshape(7, 4, 3)
+        full, (a, b) = dist_mod.embed_sharded(lambda c: c.reshape(len(c), -1)[:, :5] * 2.0, clouds, gather=True)
+        ok_e = bool(np.array_equal(full, clouds.reshape(7, -1)[:, :5] * 2.0)) and (b - a) in (3, 4)
+        q.put((rank, ok_r, ok_e))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_retrieval_and_embedding_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(2)]
+    for p in procs:
+        p.join(60)
+    assert sorted(r[0] for r in res) == [0, 1]
+    assert all(r[1] and r[2] for r in res), res
