@@ -382,8 +382,8 @@ struct HeadWs {
 
 size_t head_bytes(const EpcModel* m, int B, int N) {
     const size_t R = (size_t)B * N;
-    return align_up(R * 4) + align_up(R * m->K * 4) + align_up((size_t)B * m->K * 4) +
-           2 * align_up((size_t)B * 1024 * m->K * 4) + align_up((size_t)B * m->G * m->D * 4);
+    return align_up(R * 4) + align_up(R * m->K * 4) + align_up((size_t)B * ASSIGN_PARTS * m->K * 4) +
+           2 * align_up((size_t)B * 1024 * m->K * 4) + align_up((size_t)HIDDEN_SPLITK * B * m->G * m->D * 4);
 }
 
 HeadWs head_carve(Arena& ar, const EpcModel* m, int B, int N) {
@@ -391,10 +391,10 @@ HeadWs head_carve(Arena& ar, const EpcModel* m, int B, int N) {
     HeadWs h;
     h.inv = ar.take<float>(R);
     h.S = ar.take<float>(R * m->K);
-    h.a_sum = ar.take<float>((size_t)B * m->K);
+    h.a_sum = ar.take<float>((size_t)B * ASSIGN_PARTS * m->K);
     h.V = ar.take<float>((size_t)B * 1024 * m->K);
     h.v = ar.take<float>((size_t)B * 1024 * m->K);
-    h.Y = ar.take<float>((size_t)B * m->G * m->D);
+    h.Y = ar.take<float>((size_t)HIDDEN_SPLITK * B * m->G * m->D);
     return h;
 }
 
@@ -430,17 +430,16 @@ int vlad_head(const EpcModel* m, const float* H, const float* inv, int B, int N,
         if (int rc = vlad_finalize(h.V, h.a_sum, m->Wc2, B, F, K, h.v, st)) return rc;
     }
     {   // hidden FC (loupe.py:302-320): rows of length hidden_in, G per cloud
-        EPC_CUDA(cudaMemsetAsync(h.Y, 0, sizeof(float) * (size_t)B * m->G * D, st));
         GemmArgs g = {};
         g.A = h.v; g.sAm = m->hidden_in; g.sAk = 1;
         g.B = m->Wh; g.sBk = D; g.sBn = 1;
         g.C = h.Y; g.ldc = D; g.M = B * m->G; g.N = D; g.K = m->hidden_in; g.batch = 1;
-        g.splitk = 32;
+        g.splitk = HIDDEN_SPLITK; g.slab = (long long)B * m->G * D;
         ScopedStage ss(EPC_STAGE_HIDDEN_GEMM, st);
         if (int rc = sgemm(g, st)) return rc;
     }
     ScopedStage ss(EPC_STAGE_TAIL, st);
-    return vlad_tail(h.Y, B, m->G, D, m->hbn_scale, m->hbn_shift, m->Wg, m->gbn_scale, m->gbn_shift, m->gating, l2, out, st);
+    return vlad_tail(h.Y, HIDDEN_SPLITK, B, m->G, D, m->hbn_scale, m->hbn_shift, m->Wg, m->gbn_scale, m->gbn_shift, m->gating, l2, out, st);
 }
 
 }  // namespace

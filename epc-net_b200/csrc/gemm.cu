@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
     const int batch = z / g.splitk, split = z % g.splitk;
     const float* A = g.A + (long long)batch * g.bA;
     const float* B = g.B + (long long)batch * g.bB;
-    float* C = g.C + (long long)batch * g.bC;
+    float* C = g.C + (long long)batch * g.bC + (long long)split * g.slab;
     const int m0 = blockIdx.x * GT, n0 = blockIdx.y * GT;
     const int ksteps = (g.K + GK - 1) / GK;
     const int per = (ksteps + g.splitk - 1) / g.splitk;
@@ -103,13 +103,11 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
             if (n >= g.N) continue;
             float v = acc[i][j];
             float* dst = C + (long long)m * g.ldc + n;
-            if (g.splitk > 1) {
-                atomicAdd(dst, v);
-            } else {
+            if (g.splitk == 1) {
                 if (g.bias) v += g.bias[n];
                 if (g.relu) v = fmaxf(v, 0.f);
-                *dst = v;
             }
+            *dst = v;
         }
     }
 }

@@ -46,7 +46,8 @@ struct GemmArgs {
     long long bA, bB, bC;
     const float* bias;     // [N] or nullptr
     int relu;
-    int splitk;            // >1: partial sums are atomically added into C (C must be zeroed; no bias/relu)
+    int splitk;            // >1: split s writes its partial sums to the slab C + s*slab (no bias/relu; no atomics)
+    long long slab;        // elements between split-K slabs
 };
 int sgemm(const GemmArgs& g, cudaStream_t st);
 
@@ -55,7 +56,9 @@ int row_inv_norm(const float* X, long long R, int F, float* inv, cudaStream_t st
 int assign_softmax(const float* logits, const float* inv, const float* bn_scale, const float* bn_shift, int B, int N,
                    int K, float* S, float* a_sum, cudaStream_t st);
 int vlad_finalize(const float* V, const float* a_sum, const float* Wc2, int B, int F, int K, float* v, cudaStream_t st);
-int vlad_tail(const float* Y, int B, int G, int D, const float* bn_scale, const float* bn_shift, const float* Wg,
+constexpr int ASSIGN_PARTS = 16;   // a_sum is produced as [B, ASSIGN_PARTS, K] partials (deterministic reduction)
+constexpr int HIDDEN_SPLITK = 32;  // hidden FC split-K slabs [HIDDEN_SPLITK, B*G, D]
+int vlad_tail(const float* Y, int nslab, int B, int G, int D, const float* bn_scale, const float* bn_shift, const float* Wg,
               const float* g_scale, const float* g_shift, int gating, int l2, float* out, cudaStream_t st);
 int col_max(const float* H, int B, int N, int F, float* g, cudaStream_t st);
 int row_l2_normalize(const float* X, int R, int D, float* out, cudaStream_t st);

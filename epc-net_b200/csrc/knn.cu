@@ -122,6 +122,7 @@ __device__ __forceinline__ void insert_hits(RowList& L, unsigned m, float d, int
         const int src = __ffs(m) - 1;
         m &= m - 1;
         const float c = __shfl_sync(FULL, d, src);
+        if (c > L.thr) continue;   // the mask was taken against an older (larger) threshold: no longer a member
         const int cj = jbase + src;
         const int co = __ldg(gperm + cj);
         const int vo = __ldg(gperm + L.vi);

@@ -37,11 +37,9 @@ int row_inv_norm(const float* X, long long R, int F, float* inv, cudaStream_t st
 __global__ void assign_softmax_kernel(const float* __restrict__ logits, const float* __restrict__ inv,
                                       const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, int N,
                                       int K, float* __restrict__ S, float* __restrict__ a_sum) {
-    __shared__ float s_sum[64];
+    __shared__ float s_part[8][64];
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    if (threadIdx.x < 64) s_sum[threadIdx.x] = 0.f;
-    __syncthreads();
     const int c0 = lane, c1 = lane + 32;
     const float sc0 = (c0 < K) ? bn_scale[c0] : 0.f, sh0 = (c0 < K) ? bn_shift[c0] : 0.f;
     const float sc1 = (c1 < K) ? bn_scale[c1] : 0.f, sh1 = (c1 < K) ? bn_shift[c1] : 0.f;
@@ -63,18 +61,21 @@ __global__ void assign_softmax_kernel(const float* __restrict__ logits, const fl
         acc0 += a0;
         acc1 += a1;
     }
-    if (c0 < K) atomicAdd(&s_sum[c0], acc0);
-    if (c1 < K) atomicAdd(&s_sum[c1], acc1);
+    s_part[warp][c0] = acc0;
+    s_part[warp][c1] = acc1;
     __syncthreads();
-    if (threadIdx.x < K) atomicAdd(&a_sum[(size_t)b * K + threadIdx.x], s_sum[threadIdx.x]);
+    if (threadIdx.x < K) {     // fixed summation order => bit-reproducible; a_sum is [B, ASSIGN_PARTS, K] partials
+        float t = 0.f;
+        for (int w = 0; w < nwarp; ++w) t += s_part[w][threadIdx.x];
+        a_sum[((size_t)b * gridDim.x + blockIdx.x) * K + threadIdx.x] = t;
+    }
 }
 
 int assign_softmax(const float* logits, const float* inv, const float* bn_scale, const float* bn_shift, int B, int N,
                    int K, float* S, float* a_sum, cudaStream_t st) {
     EPC_CHECK_ARG(K >= 1 && K <= 64, "assign_softmax: cluster_size=%d unsupported (1..64)", K);
     if (B == 0) return EPC_OK;
-    EPC_CUDA(cudaMemsetAsync(a_sum, 0, sizeof(float) * (size_t)B * K, st));
-    dim3 grid(16, B);
+    dim3 grid(ASSIGN_PARTS, B);
     assign_softmax_kernel<<<grid, 256, 0, st>>>(logits, inv, bn_scale, bn_shift, N, K, S, a_sum);
     EPC_LAUNCH_CHECK();
     return EPC_OK;
@@ -92,8 +93,10 @@ vlad_finalize_kernel(const float* __restrict__ V, const float* __restrict__ a_su
     const int c = tid & 63, grp = tid >> 6;           // 4 row groups x 64 columns
     const float* Vb = V + (size_t)b * F * K;
     float ss = 0.f;
+    float as = 0.f;
+    if (c < K)
+        for (int p = 0; p < ASSIGN_PARTS; ++p) as += a_sum[((size_t)b * ASSIGN_PARTS + p) * K + c];
     if (c < K) {
-        const float as = a_sum[(size_t)b * K + c];
         for (int f = grp; f < F; f += 4) {
             const float r = Vb[(size_t)f * K + c] - as * Wc2[(size_t)f * K + c];
             ss += r * r;
@@ -115,7 +118,6 @@ vlad_finalize_kernel(const float* __restrict__ V, const float* __restrict__ a_su
     }
     __syncthreads();
     if (c < K) {
-        const float as = a_sum[(size_t)b * K + c];
         const float sc = s_inv[c] * s_ginv;
         float* vb = v + (size_t)b * F * K;
         for (int f = grp; f < F; f += 4) {
@@ -135,7 +137,7 @@ int vlad_finalize(const float* V, const float* a_sum, const float* Wc2, int B, i
 
 // Tail (loupe.py:320-331, 61-101; models/epc-net.py:153): Y [B*G, D] raw hidden products ->
 //   y = sum_g BN_bn(Y[b,g,:]);  z = y * sigmoid(BN_gating(y Wg));  out = l2 ? z/|z| : z.   One CTA per cloud, D threads.
-__global__ void vlad_tail_kernel(const float* __restrict__ Y, int G, int D, const float* __restrict__ bn_scale,
+__global__ void vlad_tail_kernel(const float* __restrict__ Y, int nslab, size_t slab, int G, int D, const float* __restrict__ bn_scale,
                                  const float* __restrict__ bn_shift, const float* __restrict__ Wg,
                                  const float* __restrict__ g_scale, const float* __restrict__ g_shift, int gating,
                                  int l2, float* __restrict__ out) {
@@ -144,7 +146,11 @@ __global__ void vlad_tail_kernel(const float* __restrict__ Y, int G, int D, cons
     const int b = blockIdx.x, d = threadIdx.x;
     float y = 0.f;
     if (d < D) {
-        for (int g = 0; g < G; ++g) y += Y[((size_t)b * G + g) * D + d] * bn_scale[d] + bn_shift[d];
+        for (int g = 0; g < G; ++g) {
+            float h = 0.f;                    // split-K partial slabs, summed in a fixed order
+            for (int s = 0; s < nslab; ++s) h += Y[s * slab + ((size_t)b * G + g) * D + d];
+            y += h * bn_scale[d] + bn_shift[d];
+        }
         sy[d] = y;
     }
     __syncthreads();
@@ -167,12 +173,12 @@ __global__ void vlad_tail_kernel(const float* __restrict__ Y, int G, int D, cons
     if (d < D) out[(size_t)b * D + d] = z;
 }
 
-int vlad_tail(const float* Y, int B, int G, int D, const float* bn_scale, const float* bn_shift, const float* Wg,
+int vlad_tail(const float* Y, int nslab, int B, int G, int D, const float* bn_scale, const float* bn_shift, const float* Wg,
               const float* g_scale, const float* g_shift, int gating, int l2, float* out, cudaStream_t st) {
     EPC_CHECK_ARG(D >= 1 && D <= 1024, "vlad_tail: output_dim=%d unsupported (1..1024)", D);
     if (B == 0) return EPC_OK;
     const int threads = (D + 31) / 32 * 32;
-    vlad_tail_kernel<<<B, threads, (D + 32) * sizeof(float), st>>>(Y, G, D, bn_scale, bn_shift, Wg, g_scale, g_shift,
+    vlad_tail_kernel<<<B, threads, (D + 32) * sizeof(float), st>>>(Y, nslab, (size_t)B * G * D, G, D, bn_scale, bn_shift, Wg, g_scale, g_shift,
                                                                    gating, l2, out);
     EPC_LAUNCH_CHECK();
     return EPC_OK;

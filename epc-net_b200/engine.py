@@ -210,12 +210,20 @@ class Engine(object):
         if n == 0:
             return out
         with torch.cuda.device(self.device):
-            pin_in = [torch.empty((chunk, N, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
-            pin_out = torch.empty((n, D), dtype=torch.float32).pin_memory()
-            dev_in = [torch.empty((chunk, N, 3), dtype=torch.float32, device=self.device) for _ in range(2)]
-            dev_out = torch.empty((n, D), dtype=torch.float32, device=self.device)
-            copy_stream = torch.cuda.Stream()
+            # staging buffers are cached: pinning host memory costs far more than the copy itself
+            st = getattr(self, "_staging", None)
+            if st is None or st["chunk"] != chunk or st["N"] != N or st["n"] < n:
+                st = {"chunk": chunk, "N": N, "n": n,
+                      "pin_in": [torch.empty((chunk, N, 3), dtype=torch.float32).pin_memory() for _ in range(2)],
+                      "pin_out": torch.empty((n, D), dtype=torch.float32).pin_memory(),
+                      "dev_in": [torch.empty((chunk, N, 3), dtype=torch.float32, device=self.device) for _ in range(2)],
+                      "dev_out": torch.empty((n, D), dtype=torch.float32, device=self.device),
+                      "copy_stream": torch.cuda.Stream()}
+                self._staging = st
+            pin_in, dev_in, copy_stream = st["pin_in"], st["dev_in"], st["copy_stream"]
+            pin_out, dev_out = st["pin_out"][:n], st["dev_out"][:n]
             main = torch.cuda.current_stream()
+            copy_stream.wait_stream(main)
             in_ready = [torch.cuda.Event() for _ in range(2)]
             in_free = [torch.cuda.Event() for _ in range(2)]
             starts = list(range(0, n, chunk))

@@ -72,7 +72,7 @@ __global__ void gather_kernel(const float2* __restrict__ tab, int rows, int row_
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             h = h * 1664525u + 1013904223u;
-            int r = window ? (base + (int)((h >> 8) % (unsigned)window)) % rows : (int)((h >> 8) % (unsigned)rows);
+            int r = window ? ((base + (int)((h >> 8) & (unsigned)(window - 1))) & (rows - 1)) : (int)((h >> 8) & (unsigned)(rows - 1));   // rows, window: powers of two
             v[u] = (lane < row_f2) ? __ldg(tab + (size_t)r * row_f2 + lane) : make_float2(0.f, 0.f);
         }
 #pragma unroll
