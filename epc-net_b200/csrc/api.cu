@@ -6,6 +6,8 @@
 #include <cmath>
 #include <vector>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -73,8 +75,10 @@ struct EpcModel {
     bool vlad_head = true;
     float* blob = nullptr;            // one device allocation holding every folded parameter
     DenseDev conv[12];
-    DenseDev conv5;
-    const float *Wc = nullptr, *cbn_scale = nullptr, *cbn_shift = nullptr, *Wc2 = nullptr, *Wh = nullptr,
+    const float *W5t = nullptr, *b5 = nullptr;         // BN-folded conv5, transposed [1024, cin] (fp32: TF32 operand)
+    __nv_bfloat16* blob16 = nullptr;                    // bf16 operands of the EPC-Net head
+    const __nv_bfloat16 *W5t16 = nullptr, *Wct16 = nullptr;   // [1024, cin], [64, 1024]
+    const float *cbn_scale = nullptr, *cbn_shift = nullptr, *Wc2 = nullptr, *Wh = nullptr,
                 *hbn_scale = nullptr, *hbn_shift = nullptr, *Wg = nullptr, *gbn_scale = nullptr, *gbn_shift = nullptr;
     int hidden_in = 0;                // rows of hidden1_weights
     DenseDev fc1;
@@ -318,11 +322,17 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
         offW[i] = pk.add(W); offb[i] = pk.add(b);
     }
     fold_dense(w->conv5, W, b);
-    offW[12] = pk.add(W); offb[12] = pk.add(b);
-    size_t oWc = 0, oCs = 0, oCh = 0, oWc2 = 0, oWh = 0, oHs = 0, oHh = 0, oWg = 0, oGs = 0, oGh = 0, oFW = 0, oFb = 0;
+    const int c5 = 64 * nb;
+    std::vector<float> W5t((size_t)1024 * c5);                 // [cout, cin]: the K-major B operand of the tensor-core conv5
+    for (int k = 0; k < c5; ++k)
+        for (int n = 0; n < 1024; ++n) W5t[(size_t)n * c5 + k] = W[(size_t)k * 1024 + n];
+    offW[12] = pk.add(W5t); offb[12] = pk.add(b);
+    std::vector<__nv_bfloat16> h16;                              // bf16 operands (EPC-Net head)
+    size_t o16_W5 = 0, o16_Wc = 0;
+    size_t oCs = 0, oCh = 0, oWc2 = 0, oWh = 0, oHs = 0, oHh = 0, oWg = 0, oGs = 0, oGh = 0, oFW = 0, oFb = 0;
     if (vlad) {
         const int K = w->cluster_size, D = w->output_dim;
-        if (!(K >= 1 && K <= 64)) { delete m; set_error("cluster_size=%d unsupported (1..64)", K); return EPC_EINVAL; }
+        if (K != 64) { delete m; set_error("cluster_size=%d unsupported: the tensor-core assignment kernel is built for 64", K); return EPC_EUNSUPPORTED; }
         const bool gv = (w->pooling == EPC_POOL_G_VLAD);
         if (gv && !(w->groups >= 1 && (1024 * K) % w->groups == 0)) { delete m; set_error("bad groups=%d", w->groups); return EPC_EINVAL; }
         if (!gv) m->G = 1;
@@ -331,7 +341,12 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
               bn_ok(w->hidden_bn) && (!w->gating || (w->gating_weights_host && bn_ok(w->gating_bn))))) {
             delete m; set_error("VLAD head weights incomplete"); return EPC_EINVAL;
         }
-        oWc = pk.add(w->cluster_weights_host, (size_t)1024 * K);
+        o16_W5 = 0;
+        h16.resize((size_t)1024 * c5 + (size_t)64 * 1024);
+        for (size_t i = 0; i < W5t.size(); ++i) h16[i] = __float2bfloat16(W5t[i]);
+        o16_Wc = W5t.size();
+        for (int f = 0; f < 1024; ++f)                          // Wc^T [K, 1024]: K-major B operand of the assignment GEMM
+            for (int c = 0; c < K; ++c) h16[o16_Wc + (size_t)c * 1024 + f] = __float2bfloat16(w->cluster_weights_host[(size_t)f * K + c]);
         bn_affine(w->cluster_bn, K, sc, sh); oCs = pk.add(sc); oCh = pk.add(sh);
         oWc2 = pk.add(w->cluster_weights2_host, (size_t)1024 * K);
         oWh = pk.add(w->hidden1_weights_host, (size_t)m->hidden_in * D);
@@ -349,16 +364,23 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
     }
     cudaError_t e = cudaMalloc(&m->blob, pk.host.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(m->blob, pk.host.data(), pk.host.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !h16.empty()) {
+        e = cudaMalloc(&m->blob16, h16.size() * sizeof(__nv_bfloat16));
+        if (e == cudaSuccess) e = cudaMemcpy(m->blob16, h16.data(), h16.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) {
         set_error("epc_model_create: %s", cudaGetErrorString(e));
         if (m->blob) cudaFree(m->blob);
+        if (m->blob16) cudaFree(m->blob16);
         delete m;
         return EPC_ECUDA;
     }
     for (int i = 0; i < 3 * nb; ++i) m->conv[i] = DenseDev{m->blob + offW[i], m->blob + offb[i], w->conv[i].cin, 64};
-    m->conv5 = DenseDev{m->blob + offW[12], m->blob + offb[12], 64 * nb, 1024};
+    m->W5t = m->blob + offW[12];
+    m->b5 = m->blob + offb[12];
     if (vlad) {
-        m->Wc = m->blob + oWc; m->cbn_scale = m->blob + oCs; m->cbn_shift = m->blob + oCh; m->Wc2 = m->blob + oWc2;
+        m->W5t16 = m->blob16 + o16_W5; m->Wct16 = m->blob16 + o16_Wc;
+        m->cbn_scale = m->blob + oCs; m->cbn_shift = m->blob + oCh; m->Wc2 = m->blob + oWc2;
         m->Wh = m->blob + oWh; m->hbn_scale = m->blob + oHs; m->hbn_shift = m->blob + oHh;
         if (w->gating) { m->Wg = m->blob + oWg; m->gbn_scale = m->blob + oGs; m->gbn_shift = m->blob + oGh; }
     } else {
@@ -371,65 +393,66 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
 void epc_model_destroy(EpcModel* m) {
     if (!m) return;
     if (m->blob) cudaFree(m->blob);
+    if (m->blob16) cudaFree(m->blob16);
     delete m;
 }
 
 namespace {
 
-struct HeadWs {
-    float *inv, *S, *a_sum, *V, *v, *Y;
+constexpr int HEAD_SUB = 8;     // clouds per head sub-batch: 8 x 8 MiB of bf16 H stays L2-resident between its 3 GEMMs
+
+struct HeadWs {                 // buffers of the G_VLAD / NetVLAD head
+    __nv_bfloat16* H16;         // [sub*N, 1024]   conv5 output (operand of the assignment and VLAD GEMMs)
+    float* rowss;               // [sub*N, 4]      partial |H_n|^2
+    __nv_bfloat16* S16;         // [sub*N, 64]     S' = softmax/|H|
+    float* a_part;              // [B*N/128, 64]   partial column sums of the soft assignment
+    float* V;                   // [VLAD_SPLITK][B,1024,64]
+    float* v;                   // [B, 65536]
+    float* Y;                   // [HIDDEN_SPLITK][B*G, D]
 };
 
 size_t head_bytes(const EpcModel* m, int B, int N) {
-    const size_t R = (size_t)B * N;
-    return align_up(R * 4) + align_up(R * m->K * 4) + align_up((size_t)B * ASSIGN_PARTS * m->K * 4) +
-           2 * align_up((size_t)B * 1024 * m->K * 4) + align_up((size_t)HIDDEN_SPLITK * B * m->G * m->D * 4);
+    const size_t sub = (size_t)(B < HEAD_SUB ? B : HEAD_SUB) * N;
+    return align_up(sub * 1024 * 2) + align_up(sub * CONV5_ROWSS_PARTS * 4) + align_up(sub * 64 * 2) +
+           align_up((size_t)B * (N / 128) * 64 * 4) + align_up((size_t)VLAD_SPLITK * B * 1024 * 64 * 4) +
+           align_up((size_t)B * 1024 * 64 * 4) + align_up((size_t)HIDDEN_SPLITK * B * m->G * m->D * 4);
 }
 
 HeadWs head_carve(Arena& ar, const EpcModel* m, int B, int N) {
-    const size_t R = (size_t)B * N;
+    const size_t sub = (size_t)(B < HEAD_SUB ? B : HEAD_SUB) * N;
     HeadWs h;
-    h.inv = ar.take<float>(R);
-    h.S = ar.take<float>(R * m->K);
-    h.a_sum = ar.take<float>((size_t)B * ASSIGN_PARTS * m->K);
-    h.V = ar.take<float>((size_t)B * 1024 * m->K);
-    h.v = ar.take<float>((size_t)B * 1024 * m->K);
+    h.H16 = ar.take<__nv_bfloat16>(sub * 1024);
+    h.rowss = ar.take<float>(sub * CONV5_ROWSS_PARTS);
+    h.S16 = ar.take<__nv_bfloat16>(sub * 64);
+    h.a_part = ar.take<float>((size_t)B * (N / 128) * 64);
+    h.V = ar.take<float>((size_t)VLAD_SPLITK * B * 1024 * 64);
+    h.v = ar.take<float>((size_t)B * 1024 * 64);
     h.Y = ar.take<float>((size_t)HIDDEN_SPLITK * B * m->G * m->D);
     return h;
 }
 
-// G_VLAD / NetVLAD on per-point features H [B*N,1024]; inv = per-row scale (nullptr: rows used as given)
-int vlad_head(const EpcModel* m, const float* H, const float* inv, int B, int N, const HeadWs& h, int l2, float* out,
-              cudaStream_t st) {
-    const int K = m->K, D = m->D, F = 1024;
-    const size_t R = (size_t)B * N;
-    EPC_CHECK_ARG(R < (1ull << 31), "too many points in one call (B*N = %zu)", R);
-    {   // cluster assignment logits = H Wc   (loupe.py:255)
-        GemmArgs g = {};
-        g.A = H; g.sAm = F; g.sAk = 1;
-        g.B = m->Wc; g.sBk = K; g.sBn = 1;
-        g.C = h.S; g.ldc = K; g.M = (int)R; g.N = K; g.K = F; g.batch = 1; g.splitk = 1;
-        ScopedStage ss(EPC_STAGE_ASSIGN_GEMM, st);
-        if (int rc = sgemm(g, st)) return rc;
-    }
+// assignment + VLAD accumulate for clouds [b0, b0+nb) whose bf16 features and rowss are in h.H16 / h.rowss
+int head_assign_vlad(const EpcModel* m, int B, int N, int b0, int nb, const HeadWs& h, int rowss_parts, cudaStream_t st) {
+    const long long Rs = (long long)nb * N;
     {
-        ScopedStage ss(EPC_STAGE_ASSIGN_SOFTMAX, st);
-        if (int rc = assign_softmax(h.S, inv, m->cbn_scale, m->cbn_shift, B, N, K, h.S, h.a_sum, st)) return rc;
+        ScopedStage ss(EPC_STAGE_ASSIGN_GEMM, st);
+        if (int rc = tc_assign(h.H16, Rs, m->Wct16, h.rowss, rowss_parts, m->cbn_scale, m->cbn_shift, h.S16,
+                               h.a_part + (size_t)b0 * (N / 128) * 64, st))
+            return rc;
     }
-    {   // V[b] = H[b]^T S'[b]   (loupe.py:286-291)
-        GemmArgs g = {};
-        g.A = H; g.sAm = 1; g.sAk = F; g.bA = (long long)N * F;
-        g.B = h.S; g.sBk = K; g.sBn = 1; g.bB = (long long)N * K;
-        g.C = h.V; g.ldc = K; g.bC = (long long)F * K;
-        g.M = F; g.N = K; g.K = N; g.batch = B; g.splitk = 1;
-        ScopedStage ss(EPC_STAGE_VLAD_GEMM, st);
-        if (int rc = sgemm(g, st)) return rc;
-    }
+    ScopedStage ss(EPC_STAGE_VLAD_GEMM, st);
+    return tc_vlad(h.H16, h.S16, nb, N, h.V + (size_t)b0 * 1024 * 64, VLAD_SPLITK, (long long)B * 1024 * 64, st);
+}
+
+// finalise + hidden FC + gating (+ L2) for all B clouds
+int head_tail(const EpcModel* m, int B, int N, const HeadWs& h, int l2, float* out, cudaStream_t st) {
+    const int D = m->D;
     {
         ScopedStage ss(EPC_STAGE_VLAD_FINALIZE, st);
-        if (int rc = vlad_finalize(h.V, h.a_sum, m->Wc2, B, F, K, h.v, st)) return rc;
+        if (int rc = vlad_finalize(h.V, VLAD_SPLITK, (long long)B * 1024 * 64, h.a_part, N / 128, m->Wc2, B, 1024, 64, h.v, st))
+            return rc;
     }
-    {   // hidden FC (loupe.py:302-320): rows of length hidden_in, G per cloud
+    {   // hidden FC (loupe.py:302-320): rows of length hidden_in, G per cloud; 16 MiB of weights => bandwidth bound
         GemmArgs g = {};
         g.A = h.v; g.sAm = m->hidden_in; g.sAk = 1;
         g.B = m->Wh; g.sBk = D; g.sBn = 1;
@@ -439,7 +462,17 @@ int vlad_head(const EpcModel* m, const float* H, const float* inv, int B, int N,
         if (int rc = sgemm(g, st)) return rc;
     }
     ScopedStage ss(EPC_STAGE_TAIL, st);
-    return vlad_tail(h.Y, HIDDEN_SPLITK, B, m->G, D, m->hbn_scale, m->hbn_shift, m->Wg, m->gbn_scale, m->gbn_shift, m->gating, l2, out, st);
+    return vlad_tail(h.Y, HIDDEN_SPLITK, B, m->G, D, m->hbn_scale, m->hbn_shift, m->Wg, m->gbn_scale, m->gbn_shift,
+                     m->gating, l2, out, st);
+}
+
+int check_embed_n(int N) {
+    if (int rc = knn_check_n(N)) return rc;
+    if (N % 128 != 0) {
+        set_error("N=%d unsupported by the embedding path: the tensor-core tiles need a multiple of 128 points", N);
+        return EPC_EINVAL;
+    }
+    return EPC_OK;
 }
 
 }  // namespace
@@ -447,12 +480,14 @@ int vlad_head(const EpcModel* m, const float* H, const float* inv, int B, int N,
 size_t epc_embed_workspace_bytes(const EpcModel* m, int B, int N) {
     if (!m || B <= 0 || N <= 0) return 256;
     const size_t R = (size_t)B * N;
+    const size_t sub = (size_t)(B < HEAD_SUB ? B : HEAD_SUB) * N;
     const int ctot = 64 * m->n_blocks;
-    size_t s = knn_state_bytes(B, N) + 2 * align_up(R * 64 * 4) + align_up(R * ctot * 4) + align_up(R * 1024 * 4);
+    size_t s = knn_state_bytes(B, N) + 2 * align_up(R * 64 * 4) + align_up(R * ctot * 4) /*concat32 (L, or KD export)*/ +
+               align_up(R * ctot * 2) /*concat16*/ + align_up(sub * 1024 * 4) /*H32 (KD export)*/ + align_up(sub * 4);
     if (m->vlad_head)
         s += head_bytes(m, B, N);
     else
-        s += align_up(R * 4) + align_up((size_t)B * 1024 * 4) + align_up((size_t)B * m->D * 4);
+        s += align_up((size_t)B * 1024 * 4) + align_up((size_t)B * m->D * 4);
     return s + 256;
 }
 
@@ -461,7 +496,7 @@ int epc_embed(const EpcModel* m, const float* xyz, int B, int N, int knn_arith, 
     EPC_CHECK_ARG(m && out && (xyz || B == 0), "epc_embed: NULL argument");
     EPC_CHECK_ARG(B >= 0, "epc_embed: B=%d", B);
     if (int rc = ensure_device(xyz)) return rc;
-    if (int rc = knn_check_n(N)) return rc;
+    if (int rc = check_embed_n(N)) return rc;
     if (B == 0) return EPC_OK;
     if (!workspace || workspace_bytes < epc_embed_workspace_bytes(m, B, N)) {
         set_error("epc_embed: workspace %zu < required %zu", workspace_bytes, epc_embed_workspace_bytes(m, B, N));
@@ -471,12 +506,16 @@ int epc_embed(const EpcModel* m, const float* xyz, int B, int N, int knn_arith, 
     const size_t R = (size_t)B * N;
     EPC_CHECK_ARG(R < (1ull << 31), "too many points in one call (B*N = %zu)", R);
     const int nb = m->n_blocks, ctot = 64 * nb;
+    const int subB = B < HEAD_SUB ? B : HEAD_SUB;
+    const bool want32 = !m->vlad_head || feat != nullptr;     // fp32 concat: TF32 conv5 of EPC-Net-L and the KD feature export
     Arena ar(workspace, workspace_bytes);
     KnnState ks = knn_state_carve(ar, B, N);
     float* xa = ar.take<float>(R * 64);
     float* xb = ar.take<float>(R * 64);
-    float* concat = ar.take<float>(R * ctot);
-    float* H = ar.take<float>(R * 1024);
+    float* concat32 = ar.take<float>(R * ctot);
+    __nv_bfloat16* concat16 = ar.take<__nv_bfloat16>(R * ctot);
+    float* H32 = ar.take<float>((size_t)subB * N * 1024);
+    float* inv = ar.take<float>((size_t)subB * N);
 
     if (int rc = knn_build(xyz, B, N, knn_arith, true, ks.sorted, ks.perm, ks.nbr, ks.kthd, ks.cnt, nullptr, nullptr,
                            nullptr, st))
@@ -491,50 +530,61 @@ int epc_embed(const EpcModel* m, const float* xyz, int B, int N, int knn_arith, 
         {
             ScopedStage ss(EPC_STAGE_BLOCK, st);
             if (int rc = proxy_block(cur, ks, B, N, knn_arith, m->divisor, m->conv[3 * blk + 1], m->conv[3 * blk + 2],
-                                     next, concat, ctot, 64 * blk, nxt, st))
+                                     next, want32 ? concat32 : nullptr, m->vlad_head ? concat16 : nullptr, ctot,
+                                     64 * blk, nxt, st))
                 return rc;
         }
         float* t = cur; cur = nxt; nxt = t;
     }
-    {   // conv5 (models/epc-net.py:136-139)
-        GemmArgs g = {};
-        g.A = concat; g.sAm = ctot; g.sAk = 1;
-        g.B = m->conv5.W; g.sBk = 1024; g.sBn = 1;
-        g.C = H; g.ldc = 1024; g.M = (int)R; g.N = 1024; g.K = ctot; g.bias = m->conv5.b; g.relu = 1;
-        g.batch = 1; g.splitk = 1;
-        ScopedStage ss(EPC_STAGE_CONV5, st);
-        if (int rc = sgemm(g, st)) return rc;
-    }
-    if (m->vlad_head) {
-        HeadWs h = head_carve(ar, m, B, N);
+    // KD feature export (models/kd_epc-net.py:158): l2norm(relu(BN(conv5))) per point, fp32 via TF32 tensor cores
+    auto export_feat = [&](int b0, int nbs) -> int {
+        const long long Rs = (long long)nbs * N;
+        const float* xc = concat32 + (size_t)b0 * N * ctot;
+        {
+            ScopedStage ss(EPC_STAGE_CONV5, st);
+            if (int rc = tc_conv5_f32(xc, Rs, ctot, m->W5t, m->b5, H32, st)) return rc;
+        }
         {
             ScopedStage ss(EPC_STAGE_ROWNORM, st);
-            if (int rc = row_inv_norm(H, (long long)R, 1024, h.inv, st)) return rc;
+            if (int rc = row_inv_norm(H32, Rs, 1024, inv, st)) return rc;
         }
-        if (int rc = vlad_head(m, H, h.inv, B, N, h, /*l2=*/1, out, st)) return rc;
-        if (feat) {
-            ScopedStage ss(EPC_STAGE_KD_FEAT, st);
-            if (int rc = kd_feat(H, h.inv, ks.perm, B, N, 1024, feat, st)) return rc;
+        ScopedStage ss(EPC_STAGE_KD_FEAT, st);
+        return kd_feat(H32, inv, ks.perm + (size_t)b0 * N, nbs, N, 1024, feat + (size_t)b0 * N * 1024, st);
+    };
+    if (m->vlad_head) {
+        HeadWs h = head_carve(ar, m, B, N);
+        for (int b0 = 0; b0 < B; b0 += HEAD_SUB) {
+            const int nbs = (B - b0 < HEAD_SUB) ? (B - b0) : HEAD_SUB;
+            {   // conv5 (models/epc-net.py:136-139) on bf16 tensor cores; H stays in L2 for the next two GEMMs
+                ScopedStage ss(EPC_STAGE_CONV5, st);
+                if (int rc = tc_conv5_bf16(concat16 + (size_t)b0 * N * ctot, (long long)nbs * N, ctot, m->W5t16, m->b5, h.H16,
+                                           h.rowss, st))
+                    return rc;
+            }
+            if (int rc = head_assign_vlad(m, B, N, b0, nbs, h, CONV5_ROWSS_PARTS, st)) return rc;
+            if (feat)
+                if (int rc = export_feat(b0, nbs)) return rc;
         }
+        if (int rc = head_tail(m, B, N, h, /*l2=*/1, out, st)) return rc;
     } else {
-        float* inv = ar.take<float>(R);
         float* gmax = ar.take<float>((size_t)B * 1024);
         float* o = ar.take<float>((size_t)B * m->D);
+        {   // conv5 + global max-pool fused (models/epc-net-l.py:84-91): the 16 MiB/cloud activation is never written
+            ScopedStage ss(EPC_STAGE_CONV5, st);
+            if (int rc = tc_conv5_colmax(concat32, (long long)R, ctot, N, m->W5t, m->b5, gmax, B, st)) return rc;
+        }
         {
-            ScopedStage ss(EPC_STAGE_COLMAX, st);
-            if (int rc = col_max(H, B, N, 1024, gmax, st)) return rc;
+            ScopedStage ss(EPC_STAGE_FC, st);
+            GemmArgs g = {};
+            g.A = gmax; g.sAm = 1024; g.sAk = 1;
+            g.B = m->fc1.W; g.sBk = m->D; g.sBn = 1;
+            g.C = o; g.ldc = m->D; g.M = B; g.N = m->D; g.K = 1024; g.bias = m->fc1.b; g.relu = 1; g.batch = 1; g.splitk = 1;
+            if (int rc = sgemm(g, st)) return rc;
+            if (int rc = row_l2_normalize(o, B, m->D, out, st)) return rc;
         }
-        ScopedStage ss(EPC_STAGE_FC, st);
-        GemmArgs g = {};
-        g.A = gmax; g.sAm = 1024; g.sAk = 1;
-        g.B = m->fc1.W; g.sBk = m->D; g.sBn = 1;
-        g.C = o; g.ldc = m->D; g.M = B; g.N = m->D; g.K = 1024; g.bias = m->fc1.b; g.relu = 1; g.batch = 1; g.splitk = 1;
-        if (int rc = sgemm(g, st)) return rc;
-        if (int rc = row_l2_normalize(o, B, m->D, out, st)) return rc;
-        if (feat) {
-            if (int rc = row_inv_norm(H, (long long)R, 1024, inv, st)) return rc;
-            if (int rc = kd_feat(H, inv, ks.perm, B, N, 1024, feat, st)) return rc;
-        }
+        if (feat)
+            for (int b0 = 0; b0 < B; b0 += HEAD_SUB)
+                if (int rc = export_feat(b0, (B - b0 < HEAD_SUB) ? (B - b0) : HEAD_SUB)) return rc;
     }
     if (!ar.ok()) {
         set_error("epc_embed: internal workspace accounting error");
@@ -552,16 +602,23 @@ int epc_vlad_forward(const EpcModel* m, const float* X, int B, int N, float* out
                      void* stream) {
     EPC_CHECK_ARG(m && X && out, "epc_vlad_forward: NULL argument");
     EPC_CHECK_ARG(m->vlad_head, "epc_vlad_forward: this model (EPC-Net-L) has no VLAD head");
-    EPC_CHECK_ARG(B >= 0 && N > 0, "epc_vlad_forward: bad sizes");
+    EPC_CHECK_ARG(B >= 0 && N > 0 && N % 128 == 0, "epc_vlad_forward: max_samples=%d must be a positive multiple of 128", N);
     if (int rc = ensure_device(X)) return rc;
     if (B == 0) return EPC_OK;
     if (!workspace || workspace_bytes < epc_vlad_workspace_bytes(m, B, N)) {
         set_error("epc_vlad_forward: workspace %zu < required %zu", workspace_bytes, epc_vlad_workspace_bytes(m, B, N));
         return EPC_EWORKSPACE;
     }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
     Arena ar(workspace, workspace_bytes);
     HeadWs h = head_carve(ar, m, B, N);
-    return vlad_head(m, X, nullptr, B, N, h, /*l2=*/0, out, static_cast<cudaStream_t>(stream));
+    for (int b0 = 0; b0 < B; b0 += HEAD_SUB) {
+        const int nbs = (B - b0 < HEAD_SUB) ? (B - b0) : HEAD_SUB;
+        // the caller's rows are used as given (loupe.py does not normalise): bf16 operands, |row| := 1
+        if (int rc = f32_to_bf16_rows(X + (size_t)b0 * N * 1024, (long long)nbs * N, 1024, h.H16, h.rowss, st)) return rc;
+        if (int rc = head_assign_vlad(m, B, N, b0, nbs, h, 1, st)) return rc;
+    }
+    return head_tail(m, B, N, h, /*l2=*/0, out, st);
 }
 
 // -------------------------------------------------------------------------------------------------

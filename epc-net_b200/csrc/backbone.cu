@@ -86,7 +86,8 @@ proxy_block_kernel(const float* __restrict__ x, const uint16_t* __restrict__ nbr
                    const int* __restrict__ cnt, const float4* __restrict__ sorted, int N, int arith, float divisor,
                    const float* __restrict__ Wa, const float* __restrict__ ba, const float* __restrict__ Wb,
                    const float* __restrict__ bb, const float* __restrict__ Wn, const float* __restrict__ bn,
-                   float* __restrict__ concat, int ctot, int coff, float* __restrict__ xnext) {
+                   float* __restrict__ concat, __nv_bfloat16* __restrict__ concat16, int ctot, int coff,
+                   float* __restrict__ xnext) {
     extern __shared__ __align__(16) float smem[];
     float* sWa = smem;                    // [64][64]
     float* sWb = sWa + 4096;
@@ -170,7 +171,12 @@ proxy_block_kernel(const float* __restrict__ x, const uint16_t* __restrict__ nbr
     __syncthreads();
     for (int i = tid; i < PB_TILE * 64; i += PB_THREADS) {
         const int pl = i >> 6, c = i & 63;
-        if (tile0 + pl < N) concat[((size_t)b * N + tile0 + pl) * ctot + coff + c] = sT[pl * PB_LD + c];
+        if (tile0 + pl < N) {
+            const size_t o = ((size_t)b * N + tile0 + pl) * ctot + coff + c;
+            const float val = sT[pl * PB_LD + c];
+            if (concat) concat[o] = val;
+            if (concat16) concat16[o] = __float2bfloat16(val);      // operand of the bf16 tensor-core conv5
+        }
     }
     if (HAS_NEXT) {
         tile_dense64(sT, sWn, sBias + 128, nullptr, sU, warp, lane);   // conv of the next block
@@ -183,8 +189,8 @@ proxy_block_kernel(const float* __restrict__ x, const uint16_t* __restrict__ nbr
 }
 
 int proxy_block(const float* x, const KnnState& g, int B, int N, int arith, float divisor, const DenseDev& conv_a,
-                const DenseDev& conv_b, const DenseDev* conv_next, float* concat, int ctot, int coff, float* xnext,
-                cudaStream_t st) {
+                const DenseDev& conv_b, const DenseDev* conv_next, float* concat, __nv_bfloat16* concat16, int ctot,
+                int coff, float* xnext, cudaStream_t st) {
     EPC_CHECK_ARG(conv_a.cin == 64 && conv_a.cout == 64 && conv_b.cin == 64 && conv_b.cout == 64,
                   "ProxyConv block layers must be 64->64");
     if (B == 0) return EPC_OK;
@@ -199,11 +205,11 @@ int proxy_block(const float* x, const KnnState& g, int B, int N, int arith, floa
     if (conv_next) {
         proxy_block_kernel<true><<<grid, PB_THREADS, smem, st>>>(x, g.nbr, g.kthd, g.cnt, g.sorted, N, arith, divisor,
                                                                  conv_a.W, conv_a.b, conv_b.W, conv_b.b, conv_next->W,
-                                                                 conv_next->b, concat, ctot, coff, xnext);
+                                                                 conv_next->b, concat, concat16, ctot, coff, xnext);
     } else {
         proxy_block_kernel<false><<<grid, PB_THREADS, smem, st>>>(x, g.nbr, g.kthd, g.cnt, g.sorted, N, arith, divisor,
                                                                   conv_a.W, conv_a.b, conv_b.W, conv_b.b, nullptr,
-                                                                  nullptr, concat, ctot, coff, nullptr);
+                                                                  nullptr, concat, concat16, ctot, coff, nullptr);
     }
     EPC_LAUNCH_CHECK();
     return EPC_OK;

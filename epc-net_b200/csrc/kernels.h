@@ -1,5 +1,6 @@
 // Internal (C++) interface between the translation units of libepc_b200.so.
 #pragma once
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace epc {
@@ -30,9 +31,11 @@ struct BlockDev {          // one ProxyConv block (models/epc-net.py:66-81)
     DenseDev conv, conv_a, conv_b;
 };
 int conv_in(const float4* sorted, long long R, const DenseDev& L, float* x, cudaStream_t st);
+// concat32 / concat16: the block's 64-channel output is written into column slice [coff, coff+64) of the fp32
+// and/or bf16 concat buffer (either may be nullptr)
 int proxy_block(const float* x, const KnnState& g, int B, int N, int arith, float divisor, const DenseDev& conv_a,
-                const DenseDev& conv_b, const DenseDev* conv_next, float* concat, int ctot, int coff, float* xnext,
-                cudaStream_t st);
+                const DenseDev& conv_b, const DenseDev* conv_next, float* concat32, __nv_bfloat16* concat16, int ctot,
+                int coff, float* xnext, cudaStream_t st);
 
 // ---- gemm.cu -----------------------------------------------------------------------------------
 struct GemmArgs {
@@ -55,13 +58,29 @@ int sgemm(const GemmArgs& g, cudaStream_t st);
 int row_inv_norm(const float* X, long long R, int F, float* inv, cudaStream_t st);
 int assign_softmax(const float* logits, const float* inv, const float* bn_scale, const float* bn_shift, int B, int N,
                    int K, float* S, float* a_sum, cudaStream_t st);
-int vlad_finalize(const float* V, const float* a_sum, const float* Wc2, int B, int F, int K, float* v, cudaStream_t st);
-constexpr int ASSIGN_PARTS = 16;   // a_sum is produced as [B, ASSIGN_PARTS, K] partials (deterministic reduction)
+// V: nslab split-K slabs of [B,F,K] (slab elements apart); a_sum: [B, a_parts, K] partial column sums
+int vlad_finalize(const float* V, int nslab, long long slab, const float* a_sum, int a_parts, const float* Wc2, int B,
+                  int F, int K, float* v, cudaStream_t st);
+constexpr int ASSIGN_PARTS = 16;   // FFMA assign path: a_sum is produced as [B, ASSIGN_PARTS, K] partials
 constexpr int HIDDEN_SPLITK = 32;  // hidden FC split-K slabs [HIDDEN_SPLITK, B*G, D]
+constexpr int VLAD_SPLITK = 2;     // VLAD accumulate split-K slabs
+
+// ---- tc_gemm.cu (tcgen05 tensor-core contractions) ---------------------------------------------------
+int tc_conv5_bf16(const __nv_bfloat16* Xc, long long R, int cin, const __nv_bfloat16* W5t, const float* b5,
+                  __nv_bfloat16* H, float* rowss, cudaStream_t st);
+constexpr int CONV5_ROWSS_PARTS = 4;   // 1024 / BN(256)
+int tc_assign(const __nv_bfloat16* H, long long R, const __nv_bfloat16* Wct, const float* rowss, int parts,
+              const float* bn_scale, const float* bn_shift, __nv_bfloat16* S, float* a_part, cudaStream_t st);
+int tc_vlad(const __nv_bfloat16* H, const __nv_bfloat16* S, int B, int N, float* V, int splitk, long long slab,
+            cudaStream_t st);
+int tc_conv5_colmax(const float* Xc, long long R, int cin, int rows_per_cloud, const float* W5t, const float* b5,
+                    float* g, int clouds, cudaStream_t st);
+int tc_conv5_f32(const float* Xc, long long R, int cin, const float* W5t, const float* b5, float* H, cudaStream_t st);
 int vlad_tail(const float* Y, int nslab, int B, int G, int D, const float* bn_scale, const float* bn_shift, const float* Wg,
               const float* g_scale, const float* g_shift, int gating, int l2, float* out, cudaStream_t st);
 int col_max(const float* H, int B, int N, int F, float* g, cudaStream_t st);
 int row_l2_normalize(const float* X, int R, int D, float* out, cudaStream_t st);
+int f32_to_bf16_rows(const float* X, long long R, int F, __nv_bfloat16* Y, float* rowss, cudaStream_t st);
 int kd_feat(const float* H, const float* inv, const int* perm, int B, int N, int F, float* feat, cudaStream_t st);
 
 // ---- retrieval.cu ------------------------------------------------------------------------------

@@ -1,0 +1,54 @@
+// Instantiations of the tcgen05 GEMM template (tc_gemm.cuh) for the dense contractions of the EPC-Net head.
+#include "tc_gemm.cuh"
+#include "kernels.h"
+
+namespace epc {
+
+// conv5 (models/epc-net.py:136-139): H = relu(Xc W5 + b5) as bf16 [R,1024] + rowss [R, 1024/256] partial |H_n|^2
+int tc_conv5_bf16(const __nv_bfloat16* Xc, long long R, int cin, const __nv_bfloat16* W5t, const float* b5,
+                  __nv_bfloat16* H, float* rowss, cudaStream_t st) {
+    tc::GemmParams p = {};
+    p.M = (int)R; p.N = 1024; p.K = cin; p.splitk = 1; p.C = H; p.ldc = 1024; p.bias = b5; p.relu = 1; p.aux = rowss;
+    Operand<__nv_bfloat16> a{Xc, R, cin, cin}, b{W5t, 1024, cin, cin};
+    return tc_gemm_launch<__nv_bfloat16, 256, false, false, tc::EPI_CONV5_BF16>(a, b, p, 1, st, 2);
+}
+
+// cluster assignment (loupe.py:255-276): S' = softmax(BN((H Wc)/|H|))/|H| as bf16 [R,64]; a_part [R/128, 64]
+int tc_assign(const __nv_bfloat16* H, long long R, const __nv_bfloat16* Wct, const float* rowss, int parts,
+              const float* bn_scale, const float* bn_shift, __nv_bfloat16* S, float* a_part, cudaStream_t st) {
+    tc::GemmParams p = {};
+    p.M = (int)R; p.N = 64; p.K = 1024; p.splitk = 1; p.C = S; p.ldc = 64; p.aux = a_part; p.rowss = rowss;
+    p.rowss_parts = parts; p.bn_scale = bn_scale; p.bn_shift = bn_shift;
+    Operand<__nv_bfloat16> a{H, R, 1024, 1024}, b{Wct, 64, 1024, 1024};
+    return tc_gemm_launch<__nv_bfloat16, 64, false, false, tc::EPI_ASSIGN>(a, b, p, 1, st, 1);
+}
+
+// VLAD accumulate (loupe.py:286-291): V[b] = H[b]^T S'[b]  -> fp32 slabs [splitk][B,1024,64]
+int tc_vlad(const __nv_bfloat16* H, const __nv_bfloat16* S, int B, int N, float* V, int splitk, long long slab,
+            cudaStream_t st) {
+    tc::GemmParams p = {};
+    p.M = 1024; p.N = 64; p.K = N / splitk; p.k_batch_rows = N; p.splitk = splitk; p.C = V; p.ldc = 64;
+    p.c_batch = 1024ll * 64; p.c_slab = slab;
+    Operand<__nv_bfloat16> a{H, (long long)B * N, 1024, 1024}, b{S, (long long)B * N, 64, 64};
+    return tc_gemm_launch<__nv_bfloat16, 64, true, true, tc::EPI_STORE_F32>(a, b, p, B, st, 1);
+}
+
+// EPC-Net-L (models/epc-net-l.py:84-91): g[b,:] = max_n relu(Xc W5 + b5) -- H is never written.  TF32.
+int tc_conv5_colmax(const float* Xc, long long R, int cin, int rows_per_cloud, const float* W5t, const float* b5,
+                    float* g, int clouds, cudaStream_t st) {
+    EPC_CUDA(cudaMemsetAsync(g, 0, sizeof(float) * (size_t)clouds * 1024, st));
+    tc::GemmParams p = {};
+    p.M = (int)R; p.N = 1024; p.K = cin; p.splitk = 1; p.bias = b5; p.aux = g; p.rows_per_cloud = rows_per_cloud;
+    Operand<float> a{Xc, R, cin, cin}, b{W5t, 1024, cin, cin};
+    return tc_gemm_launch<float, 256, false, false, tc::EPI_COLMAX>(a, b, p, 1, st, 2);
+}
+
+// fp32-output conv5 on TF32 tensor cores (KD feature export, models/kd_epc-net.py:158)
+int tc_conv5_f32(const float* Xc, long long R, int cin, const float* W5t, const float* b5, float* H, cudaStream_t st) {
+    tc::GemmParams p = {};
+    p.M = (int)R; p.N = 1024; p.K = cin; p.splitk = 1; p.C = H; p.ldc = 1024; p.bias = b5; p.relu = 1;
+    Operand<float> a{Xc, R, cin, cin}, b{W5t, 1024, cin, cin};
+    return tc_gemm_launch<float, 256, false, false, tc::EPI_STORE_F32>(a, b, p, 1, st, 2);
+}
+
+}  // namespace epc

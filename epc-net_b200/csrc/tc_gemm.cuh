@@ -1,9 +1,16 @@
-// Tensor-core GEMMs for sm_100a: tcgen05.mma (kind::tf32) with TMEM accumulators, operands staged by TMA into
-// 128B-swizzled shared memory, mbarrier producer/consumer pipeline, one elected thread issuing the MMAs.
-// Hand-written PTX; descriptor bit layouts follow the PTX ISA "tcgen05 matrix/instruction descriptor" tables
-// (cross-checked against cute/arch/mma_sm100_desc.hpp).
+// Tensor-core GEMMs for sm_100a: tcgen05.mma (kind::tf32 / kind::f16-bf16) with TMEM accumulators, operands
+// staged by TMA into 128B-swizzled shared memory, an mbarrier producer/consumer ring, one elected thread issuing
+// the MMAs, four epilogue warps draining TMEM with tcgen05.ld.  Hand-written PTX; descriptor bit layouts follow the
+// PTX ISA tcgen05 descriptor tables (cross-checked against cute/arch/mma_sm100_desc.hpp).
+//
+// One kernel template serves every dense contraction of the EPC-Net head:
+//   conv5            H  = relu(Xc W5 + b)        A K-major, B K-major   epilogue CONV5_BF16 (bf16 H + row sum-of-squares)
+//   conv5 (EPC-Net-L) max_n relu(Xc W5 + b)      A K-major, B K-major   epilogue COLMAX     (H never written)
+//   cluster assign   S' = softmax(BN(X Wc))/|H|  A K-major, B K-major   epilogue ASSIGN     (BN = 64)
+//   VLAD accumulate  V  = H^T S'                 A MN-major, B MN-major epilogue STORE_F32  (batched, split-K slabs)
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace epc {
@@ -13,18 +20,6 @@ namespace tc {
 // PTX wrappers
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred = 0;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "elect.sync _|p, 0xffffffff;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(pred));
-    return pred != 0;
-}
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -77,27 +72,28 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc]; issued by ONE thread
-__device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n"
-        "}\n"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
-        : "memory");
-}
-// A operand from TMEM (M lanes x K columns of 32-bit), B from shared memory
-__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n"
-        "}\n"
-        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
-        : "memory");
+// D[tmem] (+)= A[smem desc] * B[smem desc]; issued by ONE thread.  KIND_F16: bf16/fp16 operands; else tf32.
+template <bool KIND_F16>
+__device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if (KIND_F16) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n"
+            "}\n"
+            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n"
+            "}\n"
+            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+            : "memory");
+    }
 }
 // arrive on an mbarrier when every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
@@ -125,65 +121,103 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 // ---------------------------------------------------------------------------------------------------------
 // Descriptors
 // ---------------------------------------------------------------------------------------------------------
-// Shared-memory matrix descriptor, K-major operand tile in the 128B-swizzle layout TMA writes for a
-// {32 x fp32 = 128 B, rows} box: row r at r*128 B, 16-byte chunks XOR-ed with (r & 7); 8-row groups 1024 B apart.
-//   bits [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major) |
-//   [32,46) stride byte offset >> 4 (= 1024 B between 8-row groups) | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t smem_addr) {
+// Shared-memory matrix descriptor for the 128B-swizzle layouts TMA writes ({128 B, rows} boxes: row r at r*128 B,
+// 16-byte chunks XOR-ed with (r & 7), 8-row groups 1024 B apart):
+//   bits [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4 |
+//   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+//  K-major operand : rows = M/N index, the 128 B = one K slab.  SBO = 1024 (next 8 rows); LBO unused.
+//  MN-major operand: rows = K index, the 128 B = one chunk of 32 (tf32) / 64 (bf16) M/N elements.
+//                    SBO = 1024 (next 8 K rows); LBO = bytes between consecutive M/N chunks (separate TMA boxes).
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
     return d;
 }
-// Instruction descriptor for kind::tf32, fp32 accumulate, both operands K-major:
-//   [4,6) D format = 1 (F32) | [7,10) A format = 2 (TF32) | [10,13) B format = 2 | [15] A major = 0 (K) | [16] B major = 0 (K)
-//   [17,23) N >> 3 | [24,29) M >> 4
-__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn_major = 0, int b_mn_major = 0) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+// Instruction descriptor: [4,6) D format = 1 (F32) | [7,10) A format | [10,13) B format (kind::f16: 0 = F16, 1 = BF16;
+// kind::tf32: 2 = TF32) | [15] A major (0 = K, 1 = MN) | [16] B major | [17,23) N >> 3 | [24,29) M >> 4
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// C[M,N] = act(A[M,K] . B[N,K]^T + bias)     A, B fp32 K-major (row-major), TF32 tensor cores, fp32 out
-// grid (ceil(M/128), N/BN); 192 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2-5 epilogue
+// kernel
 // ---------------------------------------------------------------------------------------------------------
-constexpr int TC_BM = 128;
-constexpr int TC_BK = 32;   // 32 fp32 = 128 B = one swizzle row
+enum { EPI_STORE_F32 = 0, EPI_CONV5_BF16 = 1, EPI_COLMAX = 2, EPI_ASSIGN = 3 };
 
-template <int BN>
-struct NtCfg {
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-    static constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4;
-    static constexpr uint32_t B_BYTES = BN * TC_BK * 4;
-    static constexpr size_t SMEM = (size_t)STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+struct GemmParams {
+    int M, N, K;              // per batch; K = contraction length handled by one split
+    int k_batch_rows;         // MN-major operands: K-row offset between batches in the 2-D tensor maps (0 if unbatched)
+    int splitk;               // grid.z = batch * splitk
+    // epilogue
+    void* C;                  // STORE_F32: float [M, ldc] (+ bias, relu); CONV5_BF16: bf16 [M, ldc]; ASSIGN: bf16 S' [M, 64]
+    long long c_batch, c_slab;  // element offsets per batch / per split-K slab
+    int ldc;
+    const float* bias;        // [N] or nullptr
+    int relu;
+    float* aux;               // CONV5_BF16: rowss [M, gridDim.y]; COLMAX: g [clouds, N] (zero-initialised);
+                              // ASSIGN: a_part [M/128, 64]
+    const float* rowss;       // ASSIGN: [M, rowss_parts] partial sums of squares of the rows of H
+    int rowss_parts;
+    const float* bn_scale;    // ASSIGN: cluster_bn affine [64]
+    const float* bn_shift;
+    int rows_per_cloud;       // COLMAX: N points per cloud
 };
 
-template <int BN>
-__global__ void __launch_bounds__(192, 1)
-tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
-                  const float* __restrict__ bias, int M, int N, int K, int ldc, int relu) {
-    using Cfg = NtCfg<BN>;
-    constexpr int STAGES = Cfg::STAGES;
+template <typename T> struct ElemTraits;
+template <> struct ElemTraits<float> {
+    static constexpr int PER128 = 32, UMMA_K = 8, FMT = 2;
+    static constexpr bool F16 = false;
+};
+template <> struct ElemTraits<__nv_bfloat16> {
+    static constexpr int PER128 = 64, UMMA_K = 16, FMT = 1;
+    static constexpr bool F16 = true;
+};
+
+constexpr int TC_BM = 128;
+
+template <typename T, int BN>
+struct TileCfg {
+    static constexpr int BK = ElemTraits<T>::PER128;                      // k elements (or k rows) per pipeline stage
+    static constexpr uint32_t A_BYTES = TC_BM * 128;                      // 16 KB
+    static constexpr uint32_t B_BYTES = BN * 128;
+    static constexpr int STAGES_MAX = (int)((200 * 1024) / (A_BYTES + B_BYTES));
+    static constexpr int STAGES = STAGES_MAX > 8 ? 8 : STAGES_MAX;
+    static constexpr size_t smem(int stages) { return (size_t)stages * (A_BYTES + B_BYTES) + 1024 + 256; }
+};
+
+template <typename T, int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(192)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p,
+               const int stages) {
+    using Tr = ElemTraits<T>;
+    using Cfg = TileCfg<T, BN>;
+    constexpr int BK = Cfg::BK;
+    constexpr int CH = Tr::PER128;                 // M/N elements per 128-byte chunk of an MN-major operand
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = base;
-    uint8_t* sB = base + (size_t)STAGES * Cfg::A_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
-    uint64_t* empty = full + STAGES;
-    uint64_t* acc_full = empty + STAGES;
+    uint8_t* sB = base + (size_t)stages * Cfg::A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)stages * (Cfg::A_BYTES + Cfg::B_BYTES));
+    uint64_t* empty = full + stages;
+    uint64_t* acc_full = empty + stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
-    const int nkb = K / TC_BK;
+    const int batch = blockIdx.z / p.splitk, split = blockIdx.z % p.splitk;
+    const int nkb = p.K / BK;                       // k-blocks handled by this CTA
+    const int krow0 = batch * p.k_batch_rows + split * p.K;   // first K coordinate (MN-major operands / split-K)
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < stages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
@@ -191,7 +225,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+        tmem_alloc(tmem_slot, TMEM_COLS);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -202,64 +236,187 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 0) {
         if (lane == 0) {
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
+                const int s = kb % stages;
+                const uint32_t ph = (kb / stages) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
                 mbar_expect_tx(&full[s], Cfg::A_BYTES + Cfg::B_BYTES);
-                tma_load_2d(sA + (size_t)s * Cfg::A_BYTES, &tmA, &full[s], kb * TC_BK, m0);
-                tma_load_2d(sB + (size_t)s * Cfg::B_BYTES, &tmB, &full[s], kb * TC_BK, n0);
+                uint8_t* a = sA + (size_t)s * Cfg::A_BYTES;
+                uint8_t* b = sB + (size_t)s * Cfg::B_BYTES;
+                const int k0 = krow0 + kb * BK;
+                if (!A_MN) {
+                    tma_load_2d(a, &tmA, &full[s], k0, m0);                    // box {BK, 128}
+                } else {
+#pragma unroll
+                    for (int c = 0; c < TC_BM / CH; ++c)                        // boxes {CH, BK}: one 128 B chunk of M each
+                        tma_load_2d(a + (size_t)c * BK * 128, &tmA, &full[s], m0 + c * CH, k0);
+                }
+                if (!B_MN) {
+                    tma_load_2d(b, &tmB, &full[s], k0, n0);                    // box {BK, BN}
+                } else {
+#pragma unroll
+                    for (int c = 0; c < BN / CH; ++c)
+                        tma_load_2d(b + (size_t)c * BK * 128, &tmB, &full[s], n0 + c * CH, k0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = idesc_tf32(TC_BM, BN);
+            constexpr uint32_t idesc = make_idesc(Tr::FMT, TC_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            // per-MMA K advance inside a stage: K-major: UMMA_K elements = 32 B along the swizzled row;
+            //                                   MN-major: UMMA_K rows of 128 B
+            constexpr uint32_t a_step = A_MN ? Tr::UMMA_K * 128 : 32;
+            constexpr uint32_t b_step = B_MN ? Tr::UMMA_K * 128 : 32;
+            constexpr uint32_t a_lbo = A_MN ? BK * 128 : 16, b_lbo = B_MN ? BK * 128 : 16;
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
+                const int s = kb % stages;
+                const uint32_t ph = (kb / stages) & 1;
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                const uint64_t da = smem_desc_k_sw128(smem_u32(sA + (size_t)s * Cfg::A_BYTES));
-                const uint64_t db = smem_desc_k_sw128(smem_u32(sB + (size_t)s * Cfg::B_BYTES));
+                const uint32_t a_addr = smem_u32(sA + (size_t)s * Cfg::A_BYTES);
+                const uint32_t b_addr = smem_u32(sB + (size_t)s * Cfg::B_BYTES);
 #pragma unroll
-                for (int kk = 0; kk < TC_BK / 8; ++kk) {
-                    // advance 8 tf32 = 32 bytes along K inside the 128B swizzle row: +2 in the (addr >> 4) field
-                    mma_tf32_ss(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb | kk) != 0);
+                for (int kk = 0; kk < BK / Tr::UMMA_K; ++kk) {
+                    const uint64_t da = smem_desc_sw128(a_addr + kk * a_step, a_lbo, 1024);
+                    const uint64_t db = smem_desc_sw128(b_addr + kk * b_step, b_lbo, 1024);
+                    mma_ss<Tr::F16>(tmem_d, da, db, idesc, (kb | kk) != 0);
                 }
                 mma_commit(&empty[s]);          // frees the smem stage when these MMAs have read it
             }
             mma_commit(acc_full);               // accumulator complete
         }
     } else {
-        // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
+        // ---- epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31 ------------------------------------------------
         const int q = warp & 3;
         const int row = q * 32 + lane;
+        const int m = m0 + row;
+        const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16);
         mbar_wait(acc_full, 0);
         tc_fence_after();
-        const int m = m0 + row;
+        if (EPI == EPI_STORE_F32) {
+            float* C = reinterpret_cast<float*>(p.C) + (long long)batch * p.c_batch + (long long)split * p.c_slab;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            float v[32];
-            tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            if (m < M) {
-                float* dst = C + (size_t)m * ldc + n0 + c0;
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                float v[32];
+                tmem_ld32(trow + (uint32_t)c0, v);
+                if (m < p.M) {
+                    float* dst = C + (size_t)m * p.ldc + n0 + c0;
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    float4 o;
-                    o.x = v[i] + (bias ? __ldg(bias + n0 + c0 + i) : 0.f);
-                    o.y = v[i + 1] + (bias ? __ldg(bias + n0 + c0 + i + 1) : 0.f);
-                    o.z = v[i + 2] + (bias ? __ldg(bias + n0 + c0 + i + 2) : 0.f);
-                    o.w = v[i + 3] + (bias ? __ldg(bias + n0 + c0 + i + 3) : 0.f);
-                    if (relu) {
-                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                    for (int i = 0; i < 32; i += 4) {
+                        float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        if (p.bias) {
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + i));
+                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                        }
+                        if (p.relu) {
+                            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                        }
+                        *reinterpret_cast<float4*>(dst + i) = o;
                     }
-                    *reinterpret_cast<float4*>(dst + i) = o;
                 }
+            }
+        } else if (EPI == EPI_CONV5_BF16) {
+            // H = relu(acc + b) stored as bf16; per-row sum of squares of the fp32 values for the later L2 norm
+            __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(p.C);
+            float ss = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                float v[32];
+                tmem_ld32(trow + (uint32_t)c0, v);
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float2 bb = __ldg(reinterpret_cast<const float2*>(p.bias + n0 + c0 + i));
+                    const float x = fmaxf(v[i] + bb.x, 0.f), y = fmaxf(v[i + 1] + bb.y, 0.f);
+                    ss = fmaf(x, x, ss);
+                    ss = fmaf(y, y, ss);
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+                    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                if (m < p.M) {
+                    uint4* dst = reinterpret_cast<uint4*>(H + (size_t)m * p.ldc + n0 + c0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                }
+            }
+            if (m < p.M) p.aux[(size_t)m * gridDim.y + blockIdx.y] = ss;
+        } else if (EPI == EPI_COLMAX) {
+            // max over the tile's rows of relu(acc + b): values >= 0, so unsigned-int order == float order
+            const int cloud = m0 / p.rows_per_cloud;
+            int* g = reinterpret_cast<int*>(p.aux) + (size_t)cloud * p.N;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                float v[32];
+                tmem_ld32(trow + (uint32_t)c0, v);
+                unsigned mine = 0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float x = (m < p.M) ? fmaxf(v[i] + __ldg(p.bias + n0 + c0 + i), 0.f) : 0.f;
+                    const unsigned r = __reduce_max_sync(FULL, __float_as_uint(x));
+                    if (lane == i) mine = r;
+                }
+                atomicMax(g + n0 + c0 + lane, (int)mine);
+            }
+        } else if (EPI == EPI_ASSIGN) {
+            // BN == 64: this thread owns all 64 cluster logits of its point (loupe.py:255-276)
+            float v[64];
+            {
+                float t[32];
+                tmem_ld32(trow, t);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = t[i];
+                tmem_ld32(trow + 32u, t);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[32 + i] = t[i];
+            }
+            float ssq = 0.f;
+            if (m < p.M)
+                for (int i = 0; i < p.rowss_parts; ++i) ssq += p.rowss[(size_t)m * p.rowss_parts + i];
+            const float inv = 1.0f / sqrtf(fmaxf(ssq, L2_EPS));
+            float mx = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+                v[i] = (v[i] * inv) * __ldg(p.bn_scale + i) + __ldg(p.bn_shift + i);
+                mx = fmaxf(mx, v[i]);
+            }
+            float den = 0.f;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+                v[i] = expf(v[i] - mx);
+                den += v[i];
+            }
+            const float rden = 1.0f / den;
+            // column sums of the soft assignment over this tile: stage through (now idle) pipeline smem
+            float* sS = reinterpret_cast<float*>(sA);        // [128][65]
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+                v[i] *= rden;
+                sS[row * 65 + i] = (m < p.M) ? v[i] : 0.f;
+            }
+            if (m < p.M) {
+                uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)m * 64);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * i + 2 * j] * inv, v[8 * i + 2 * j + 1] * inv);
+                        pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    dst[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");     // the four epilogue warps only
+            const int t = threadIdx.x - 64;
+            if (t < 64) {
+                float a = 0.f;
+                for (int r = 0; r < TC_BM; ++r) a += sS[r * 65 + t];
+                p.aux[(size_t)blockIdx.x * 64 + t] = a;
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_d, BN < 32 ? 32 : BN);
+    if (warp == 1) tmem_dealloc(tmem_d, TMEM_COLS);
 }
 
 }  // namespace tc
@@ -283,8 +440,9 @@ inline PFN_encodeTiled get_encode_tiled() {
     return fn;
 }
 
-// 2-D fp32 tensor [rows, cols] (cols contiguous, row pitch `ld` elements); box = {box_cols, box_rows}, 128B swizzle
-inline int make_tmap_2d(CUtensorMap* tm, const float* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+// 2-D tensor [rows, cols] (cols contiguous, row pitch `ld` elements); box = {box_cols, box_rows}, 128B swizzle
+template <typename T>
+inline int make_tmap_2d(CUtensorMap* tm, const T* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
                         uint32_t box_rows) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) {
@@ -292,12 +450,12 @@ inline int make_tmap_2d(CUtensorMap* tm, const float* ptr, uint64_t rows, uint64
         return EPC_ECUDA;
     }
     cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {ld * sizeof(float)};
+    cuuint64_t strides[1] = {ld * sizeof(T)};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    CUresult r = enc(tm, dt, 2, const_cast<T*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u ptr=%p", (int)r,
                   (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_cols, box_rows, ptr);
@@ -306,46 +464,50 @@ inline int make_tmap_2d(CUtensorMap* tm, const float* ptr, uint64_t rows, uint64
     return EPC_OK;
 }
 
-struct TcGemmNT {
-    const float* A;      // [M, K] row-major (lda = K)
-    const float* B;      // [N, K] row-major
-    float* C;            // [M, ldc]
-    const float* bias;   // [N] or nullptr
-    int M, N, K, ldc, relu;
-    int BN;              // 64 | 128 | 256
+// Operand description: a 2-D row-major array [rows, cols] with pitch ld.
+//   K-major operand  : rows = M (or N), cols = K.      MN-major operand: rows = K (all batches stacked), cols = M (or N).
+template <typename T>
+struct Operand {
+    const T* ptr;
+    long long rows, cols, ld;
 };
 
-template <int BN>
-inline int tc_gemm_nt_launch(const TcGemmNT& g, cudaStream_t st) {
+template <typename T, int BN, bool A_MN, bool B_MN, int EPI>
+inline int tc_gemm_launch(const Operand<T>& A, const Operand<T>& B, const tc::GemmParams& p, int batch, cudaStream_t st,
+                          int ctas_per_sm = 1) {
+    using Cfg = tc::TileCfg<T, BN>;
+    constexpr int PER128 = tc::ElemTraits<T>::PER128;
+    EPC_CHECK_ARG(p.K % Cfg::BK == 0 && p.K >= Cfg::BK, "tc_gemm: K=%d must be a multiple of %d", p.K, Cfg::BK);
+    EPC_CHECK_ARG(p.N % BN == 0, "tc_gemm: N=%d must be a multiple of %d", p.N, BN);
+    EPC_CHECK_ARG((reinterpret_cast<uintptr_t>(A.ptr) & 15) == 0 && (reinterpret_cast<uintptr_t>(B.ptr) & 15) == 0 &&
+                      (A.ld * sizeof(T)) % 16 == 0 && (B.ld * sizeof(T)) % 16 == 0,
+                  "tc_gemm: operands must be 16-byte aligned with 16-byte pitches");
+    if (p.M == 0 || batch == 0) return EPC_OK;
     CUtensorMap tmA, tmB;
-    if (int rc = make_tmap_2d(&tmA, g.A, g.M, g.K, g.K, tc::TC_BK, tc::TC_BM)) return rc;
-    if (int rc = make_tmap_2d(&tmB, g.B, g.N, g.K, g.K, tc::TC_BK, BN)) return rc;
-    static bool attr = false;
-    if (!attr) {
-        EPC_CUDA(cudaFuncSetAttribute(tc::tc_gemm_nt_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)tc::NtCfg<BN>::SMEM));
-        attr = true;
+    if (int rc = A_MN ? make_tmap_2d(&tmA, A.ptr, A.rows, A.cols, A.ld, PER128, Cfg::BK)
+                      : make_tmap_2d(&tmA, A.ptr, A.rows, A.cols, A.ld, Cfg::BK, tc::TC_BM))
+        return rc;
+    if (int rc = B_MN ? make_tmap_2d(&tmB, B.ptr, B.rows, B.cols, B.ld, PER128, Cfg::BK)
+                      : make_tmap_2d(&tmB, B.ptr, B.rows, B.cols, B.ld, Cfg::BK, BN))
+        return rc;
+    int stages = Cfg::STAGES;
+    if (ctas_per_sm > 1) {           // leave room for a second resident CTA (its epilogue overlaps our main loop)
+        const int fit = (int)((110 * 1024 - 1280) / (Cfg::A_BYTES + Cfg::B_BYTES));
+        stages = fit < 2 ? 2 : (fit < stages ? fit : stages);
     }
-    dim3 grid((g.M + tc::TC_BM - 1) / tc::TC_BM, g.N / BN);
-    tc::tc_gemm_nt_kernel<BN><<<grid, 192, tc::NtCfg<BN>::SMEM, st>>>(tmA, tmB, g.C, g.bias, g.M, g.N, g.K, g.ldc, g.relu);
+    const int nkb = p.K / Cfg::BK;
+    if (stages > nkb) stages = nkb < 2 ? 2 : nkb;
+    const size_t smem = Cfg::smem(stages);
+    auto kern = tc::tc_gemm_kernel<T, BN, A_MN, B_MN, EPI>;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        EPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem(Cfg::STAGES)));
+        attr_smem = Cfg::smem(Cfg::STAGES);
+    }
+    dim3 grid((p.M + tc::TC_BM - 1) / tc::TC_BM, p.N / BN, batch * p.splitk);
+    kern<<<grid, 192, smem, st>>>(tmA, tmB, p, stages);
     EPC_LAUNCH_CHECK();
     return EPC_OK;
-}
-
-inline int tc_gemm_nt(const TcGemmNT& g, cudaStream_t st) {
-    EPC_CHECK_ARG(g.K % tc::TC_BK == 0 && g.K >= tc::TC_BK, "tc_gemm_nt: K=%d must be a multiple of %d", g.K, tc::TC_BK);
-    EPC_CHECK_ARG(g.N % g.BN == 0, "tc_gemm_nt: N=%d must be a multiple of BN=%d", g.N, g.BN);
-    EPC_CHECK_ARG((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0 &&
-                      (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && g.ldc % 4 == 0,
-                  "tc_gemm_nt: operands must be 16-byte aligned");
-    if (g.M == 0) return EPC_OK;
-    switch (g.BN) {
-        case 64: return tc_gemm_nt_launch<64>(g, st);
-        case 128: return tc_gemm_nt_launch<128>(g, st);
-        case 256: return tc_gemm_nt_launch<256>(g, st);
-    }
-    set_error("tc_gemm_nt: BN=%d unsupported", g.BN);
-    return EPC_EINVAL;
 }
 
 }  // namespace epc

@@ -84,8 +84,8 @@ int assign_softmax(const float* logits, const float* inv, const float* bn_scale,
 // VLAD finalise (loupe.py:284-298): V[f,c] -= a_sum[c] * Wc2[f,c]; L2 over f per (b,c); flatten
 // f-major (index f*K + c); global L2.  One CTA per cloud.
 __global__ void __launch_bounds__(256)
-vlad_finalize_kernel(const float* __restrict__ V, const float* __restrict__ a_sum, const float* __restrict__ Wc2, int F,
-                     int K, float* __restrict__ v) {
+vlad_finalize_kernel(const float* __restrict__ V, int nslab, long long slab, const float* __restrict__ a_sum, int a_parts,
+                     const float* __restrict__ Wc2, int F, int K, float* __restrict__ v) {
     __shared__ float s_part[4][64];
     __shared__ float s_inv[64];
     __shared__ float s_ginv;
@@ -95,10 +95,12 @@ vlad_finalize_kernel(const float* __restrict__ V, const float* __restrict__ a_su
     float ss = 0.f;
     float as = 0.f;
     if (c < K)
-        for (int p = 0; p < ASSIGN_PARTS; ++p) as += a_sum[((size_t)b * ASSIGN_PARTS + p) * K + c];
+        for (int p = 0; p < a_parts; ++p) as += a_sum[((size_t)b * a_parts + p) * K + c];
     if (c < K) {
         for (int f = grp; f < F; f += 4) {
-            const float r = Vb[(size_t)f * K + c] - as * Wc2[(size_t)f * K + c];
+            float acc = 0.f;
+            for (int s = 0; s < nslab; ++s) acc += Vb[s * slab + (size_t)f * K + c];
+            const float r = acc - as * Wc2[(size_t)f * K + c];
             ss += r * r;
         }
     }
@@ -121,16 +123,19 @@ vlad_finalize_kernel(const float* __restrict__ V, const float* __restrict__ a_su
         const float sc = s_inv[c] * s_ginv;
         float* vb = v + (size_t)b * F * K;
         for (int f = grp; f < F; f += 4) {
-            const float r = Vb[(size_t)f * K + c] - as * Wc2[(size_t)f * K + c];
+            float acc = 0.f;
+            for (int s = 0; s < nslab; ++s) acc += Vb[s * slab + (size_t)f * K + c];
+            const float r = acc - as * Wc2[(size_t)f * K + c];
             vb[(size_t)f * K + c] = r * sc;
         }
     }
 }
 
-int vlad_finalize(const float* V, const float* a_sum, const float* Wc2, int B, int F, int K, float* v, cudaStream_t st) {
+int vlad_finalize(const float* V, int nslab, long long slab, const float* a_sum, int a_parts, const float* Wc2, int B,
+                  int F, int K, float* v, cudaStream_t st) {
     EPC_CHECK_ARG(K >= 1 && K <= 64, "vlad_finalize: cluster_size=%d unsupported (1..64)", K);
     if (B == 0) return EPC_OK;
-    vlad_finalize_kernel<<<B, 256, 0, st>>>(V, a_sum, Wc2, F, K, v);
+    vlad_finalize_kernel<<<B, 256, 0, st>>>(V, nslab, slab, a_sum, a_parts, Wc2, F, K, v);
     EPC_LAUNCH_CHECK();
     return EPC_OK;
 }
@@ -262,6 +267,27 @@ __global__ void kd_feat_kernel(const float* __restrict__ H, const float* __restr
 int kd_feat(const float* H, const float* inv, const int* perm, int B, int N, int F, float* feat, cudaStream_t st) {
     if (B == 0) return EPC_OK;
     kd_feat_kernel<<<(unsigned)((size_t)B * N), 256, 0, st>>>(H, inv, perm, N, F, feat);
+    EPC_LAUNCH_CHECK();
+    return EPC_OK;
+}
+
+// X fp32 [R,F] -> bf16, and rowss[r] := 1 (the stand-alone loupe API uses the caller's rows as given)
+__global__ void f32_to_bf16_rows_kernel(const float* __restrict__ X, long long n4, __nv_bfloat16* __restrict__ Y,
+                                        float* __restrict__ rowss, long long R) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(X) + i);
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        reinterpret_cast<uint2*>(Y)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    }
+    if (i < R) rowss[i] = 1.0f;
+}
+
+int f32_to_bf16_rows(const float* X, long long R, int F, __nv_bfloat16* Y, float* rowss, cudaStream_t st) {
+    EPC_CHECK_ARG(F % 4 == 0, "f32_to_bf16_rows: F=%d must be a multiple of 4", F);
+    if (R == 0) return EPC_OK;
+    const long long n4 = R * F / 4;
+    f32_to_bf16_rows_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(X, n4, Y, rowss, R);
     EPC_LAUNCH_CHECK();
     return EPC_OK;
 }
