@@ -110,6 +110,17 @@ void fold_dense(const EpcDense& L, std::vector<float>& W, std::vector<float>& b)
     for (int n = 0; n < L.cout; ++n) b[n] = L.biases_host[n] * sc[n] + sh[n];
 }
 
+// round-to-nearest-even to TF32 precision (the tensor core would otherwise truncate)
+float host_round_tf32(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return x;
+    u += 0x0fffu + ((u >> 13) & 1u);
+    u &= 0xffffe000u;
+    memcpy(&x, &u, 4);
+    return x;
+}
+
 struct Packer {
     std::vector<float> host;
     size_t add(const float* p, size_t n) {
@@ -316,16 +327,23 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
 
     Packer pk;
     std::vector<float> W, b, sc, sh;
-    size_t offW[13], offb[13];
+    size_t offW[13], offb[13], offI[13];
+    std::vector<float> img(4096);
     for (int i = 0; i < 3 * nb; ++i) {
         fold_dense(w->conv[i], W, b);
         offW[i] = pk.add(W); offb[i] = pk.add(b);
+        offI[i] = 0;
+        if (i > 0) {
+            for (auto& x : W) x = host_round_tf32(x);
+            make_w64_image(W.data(), img.data());
+            offI[i] = pk.add(img);
+        }
     }
     fold_dense(w->conv5, W, b);
     const int c5 = 64 * nb;
     std::vector<float> W5t((size_t)1024 * c5);                 // [cout, cin]: the K-major B operand of the tensor-core conv5
     for (int k = 0; k < c5; ++k)
-        for (int n = 0; n < 1024; ++n) W5t[(size_t)n * c5 + k] = W[(size_t)k * 1024 + n];
+        for (int n = 0; n < 1024; ++n) W5t[(size_t)n * c5 + k] = host_round_tf32(W[(size_t)k * 1024 + n]);
     offW[12] = pk.add(W5t); offb[12] = pk.add(b);
     std::vector<__nv_bfloat16> h16;                              // bf16 operands (EPC-Net head)
     size_t o16_W5 = 0, o16_Wc = 0;
@@ -375,7 +393,8 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
         delete m;
         return EPC_ECUDA;
     }
-    for (int i = 0; i < 3 * nb; ++i) m->conv[i] = DenseDev{m->blob + offW[i], m->blob + offb[i], w->conv[i].cin, 64};
+    for (int i = 0; i < 3 * nb; ++i)
+        m->conv[i] = DenseDev{m->blob + offW[i], m->blob + offb[i], w->conv[i].cin, 64, i > 0 ? m->blob + offI[i] : nullptr};
     m->W5t = m->blob + offW[12];
     m->b5 = m->blob + offb[12];
     if (vlad) {
@@ -384,7 +403,7 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
         m->Wh = m->blob + oWh; m->hbn_scale = m->blob + oHs; m->hbn_shift = m->blob + oHh;
         if (w->gating) { m->Wg = m->blob + oWg; m->gbn_scale = m->blob + oGs; m->gbn_shift = m->blob + oGh; }
     } else {
-        m->fc1 = DenseDev{m->blob + oFW, m->blob + oFb, 1024, w->output_dim};
+        m->fc1 = DenseDev{m->blob + oFW, m->blob + oFb, 1024, w->output_dim, nullptr};
     }
     *out = m;
     return EPC_OK;
@@ -409,13 +428,15 @@ struct HeadWs {                 // buffers of the G_VLAD / NetVLAD head
     float* V;                   // [VLAD_SPLITK][B,1024,64]
     float* v;                   // [B, 65536]
     float* Y;                   // [HIDDEN_SPLITK][B*G, D]
+    float* colss;               // [B, 8, 64] partial column sums of squares of the VLAD residuals
 };
 
 size_t head_bytes(const EpcModel* m, int B, int N) {
     const size_t sub = (size_t)(B < HEAD_SUB ? B : HEAD_SUB) * N;
     return align_up(sub * 1024 * 2) + align_up(sub * CONV5_ROWSS_PARTS * 4) + align_up(sub * 64 * 2) +
            align_up((size_t)B * (N / 128) * 64 * 4) + align_up((size_t)VLAD_SPLITK * B * 1024 * 64 * 4) +
-           align_up((size_t)B * 1024 * 64 * 4) + align_up((size_t)HIDDEN_SPLITK * B * m->G * m->D * 4);
+           align_up((size_t)B * 1024 * 64 * 4) + align_up((size_t)HIDDEN_SPLITK * B * m->G * m->D * 4) +
+           align_up((size_t)B * 8 * 64 * 4);
 }
 
 HeadWs head_carve(Arena& ar, const EpcModel* m, int B, int N) {
@@ -428,6 +449,7 @@ HeadWs head_carve(Arena& ar, const EpcModel* m, int B, int N) {
     h.V = ar.take<float>((size_t)VLAD_SPLITK * B * 1024 * 64);
     h.v = ar.take<float>((size_t)B * 1024 * 64);
     h.Y = ar.take<float>((size_t)HIDDEN_SPLITK * B * m->G * m->D);
+    h.colss = ar.take<float>((size_t)B * 8 * 64);
     return h;
 }
 
@@ -449,7 +471,7 @@ int head_tail(const EpcModel* m, int B, int N, const HeadWs& h, int l2, float* o
     const int D = m->D;
     {
         ScopedStage ss(EPC_STAGE_VLAD_FINALIZE, st);
-        if (int rc = vlad_finalize(h.V, VLAD_SPLITK, (long long)B * 1024 * 64, h.a_part, N / 128, m->Wc2, B, 1024, 64, h.v, st))
+        if (int rc = vlad_finalize(h.V, VLAD_SPLITK, (long long)B * 1024 * 64, h.a_part, N / 128, m->Wc2, B, 1024, 64, h.v, h.colss, st))
             return rc;
     }
     {   // hidden FC (loupe.py:302-320): rows of length hidden_in, G per cloud; 16 MiB of weights => bandwidth bound

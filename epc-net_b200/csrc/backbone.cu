@@ -6,7 +6,7 @@
 //     t = m - x ; t = conv_a(t) ; t = conv_b(t) ; out = t + m ; x' = conv_{b+1}(out)
 // runs on the tile while it is in shared memory.  Rows whose thresholded set has > 20 members (ties at
 // the 20th distance, utils/tf_util.py:663-665) take an exact dense re-scan of the cloud.
-#include "common.cuh"
+#include "tc_gemm.cuh"
 #include "kernels.h"
 
 namespace epc {
@@ -45,147 +45,245 @@ int conv_in(const float4* sorted, long long R, const DenseDev& L, float* x, cuda
     return EPC_OK;
 }
 
-constexpr int PB_TILE = 64;       // points per CTA
-constexpr int PB_LD = 65;         // smem row stride (floats): conflict-free column walks
+// ------------------------------------------------------------------------------------------------
+// ProxyConv block on tcgen05 tensor cores (TF32).  One CTA = 128 consecutive (Morton-ordered) points:
+//   gather  : all 8 warps; warp per point, lane = channel pair; 20 x 256 B row loads in flight per warp
+//   GEMM a/b/n : [128 x 64] . [64 x 64] on the tensor cores, accumulator in TMEM; the A operand tile lives in
+//               shared memory in the UMMA K-major 128B-swizzle layout and is rewritten in place by the epilogue
+//               warps (t -> relu(conv_a) -> x_b), so activations never leave the SM between the three layers.
+// Weights arrive as pre-swizzled 16 KB shared-memory images (prepared once at model creation).
+// ------------------------------------------------------------------------------------------------
+constexpr int PB_TILE = 128;
 constexpr int PB_THREADS = 256;
+constexpr int PB_MLD = 66;                       // row stride (floats) of the fp32 neighbour-mean tile
+constexpr uint32_t PB_A_BYTES = 2 * 128 * 128;   // A tile: 2 k-blocks x 128 rows x 128 B
+constexpr uint32_t PB_W_BYTES = 2 * 64 * 128;    // weight image: 2 k-blocks x 64 rows x 128 B
+constexpr size_t PB_SMEM = 1024 + PB_A_BYTES + 2 * PB_W_BYTES + PB_TILE * PB_MLD * 4 + 3 * 64 * 4 + 64;
 
-// One 64->64 pointwise layer on the smem tile: out[p][c] = relu(b[c] + sum_k in[p][k] W[k][c]) (+ res[p][c]).
-// Warp w: points (w&1)*32 + lane, output chunk (w>>1)*16 .. +16  => weight reads are warp broadcasts.
-__device__ __forceinline__ void tile_dense64(const float* __restrict__ sIn, const float* __restrict__ sW,
-                                             const float* __restrict__ sB, const float* __restrict__ sRes,
-                                             float* __restrict__ sOut, int warp, int lane) {
-    const int p = (warp & 1) * 32 + lane;
-    const int c0 = (warp >> 1) * 16;
-    float acc[16];
+// byte offset of the 16-byte chunk holding channels [4*k4, 4*k4+4) of row r in a [rows x 64] fp32 K-major SW128 tile
+__device__ __forceinline__ uint32_t sw128_chunk(int r, int k4, uint32_t kblock_bytes) {
+    return (uint32_t)(k4 >> 3) * kblock_bytes + (uint32_t)r * 128u + (uint32_t)(((k4 & 7) ^ (r & 7)) << 4);
+}
+
+__device__ __forceinline__ void pb_issue_gemm(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, uint64_t* bar) {
+    constexpr uint32_t idesc = tc::make_idesc(2 /*TF32*/, 128, 64, 0, 0);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = sB[c0 + i];
-#pragma unroll 8
-    for (int k = 0; k < 64; ++k) {
-        const float a = sIn[p * PB_LD + k];
-        const float4* w4 = reinterpret_cast<const float4*>(sW + k * 64 + c0);
+    for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 w = w4[q];
-            acc[4 * q + 0] = fmaf(a, w.x, acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(a, w.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(a, w.z, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(a, w.w, acc[4 * q + 3]);
+        for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t da = tc::smem_desc_sw128(a_addr + kb * (PB_A_BYTES / 2) + kk * 32, 16, 1024);
+            const uint64_t db = tc::smem_desc_sw128(w_addr + kb * (PB_W_BYTES / 2) + kk * 32, 16, 1024);
+            tc::mma_ss<false>(tmem_d, da, db, idesc, (kb | kk) != 0);
         }
-    }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        float v = fmaxf(acc[i], 0.f);
-        if (sRes) v += sRes[p * PB_LD + c0 + i];
-        sOut[p * PB_LD + c0 + i] = v;
-    }
+    tc::mma_commit(bar);
 }
 
 template <bool HAS_NEXT>
-__global__ void __launch_bounds__(PB_THREADS)
+__global__ void __launch_bounds__(PB_THREADS, 2)
 proxy_block_kernel(const float* __restrict__ x, const uint16_t* __restrict__ nbr, const float* __restrict__ kthd,
                    const int* __restrict__ cnt, const float4* __restrict__ sorted, int N, int arith, float divisor,
-                   const float* __restrict__ Wa, const float* __restrict__ ba, const float* __restrict__ Wb,
-                   const float* __restrict__ bb, const float* __restrict__ Wn, const float* __restrict__ bn,
+                   const float* __restrict__ Wa_img, const float* __restrict__ ba, const float* __restrict__ Wb_img,
+                   const float* __restrict__ bb, const float* __restrict__ Wn_img, const float* __restrict__ bn,
                    float* __restrict__ concat, __nv_bfloat16* __restrict__ concat16, int ctot, int coff,
                    float* __restrict__ xnext) {
-    extern __shared__ __align__(16) float smem[];
-    float* sWa = smem;                    // [64][64]
-    float* sWb = sWa + 4096;
-    float* sWn = sWb + 4096;
-    float* sBias = sWn + 4096;            // [3][64]
-    float* sT = sBias + 192;              // [64][65]
-    float* sU = sT + PB_TILE * PB_LD;
-    float* sM = sU + PB_TILE * PB_LD;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = base;                                  // A operand tile (t, then relu(conv_a), then x_b)
+    uint8_t* sW0 = sA + PB_A_BYTES;                      // conv_a weights, later conv_next
+    uint8_t* sW1 = sW0 + PB_W_BYTES;                     // conv_b weights
+    float* sM = reinterpret_cast<float*>(sW1 + PB_W_BYTES);   // neighbour mean m, [128][66] fp32
+    float* sBias = sM + PB_TILE * PB_MLD;                // [3][64]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sBias + 192);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
     const int tile0 = blockIdx.x * PB_TILE;
 
-    for (int i = tid; i < 4096; i += PB_THREADS) {
-        sWa[i] = Wa[i];
-        sWb[i] = Wb[i];
-        if (HAS_NEXT) sWn[i] = Wn[i];
-    }
-    if (tid < 64) {
-        sBias[tid] = ba[tid];
-        sBias[64 + tid] = bb[tid];
-        if (HAS_NEXT) sBias[128 + tid] = bn[tid];
+    // ---- prologue: weights, barrier, TMEM ------------------------------------------------------------------
+    {
+        const uint4* ga = reinterpret_cast<const uint4*>(Wa_img);
+        const uint4* gb = reinterpret_cast<const uint4*>(Wb_img);
+        uint4* s0 = reinterpret_cast<uint4*>(sW0);
+        uint4* s1 = reinterpret_cast<uint4*>(sW1);
+        for (int i = tid; i < (int)(PB_W_BYTES / 16); i += PB_THREADS) {
+            s0[i] = __ldg(ga + i);
+            s1[i] = __ldg(gb + i);
+        }
+        if (tid < 64) {
+            sBias[tid] = ba[tid];
+            sBias[64 + tid] = bb[tid];
+            sBias[128 + tid] = HAS_NEXT ? bn[tid] : 0.f;
+        }
+        if (tid == 0) {
+            tc::mbar_init(bar, 1);
+            tc::fence_barrier_init();
+        }
+        if (warp == 1) {
+            tc::tmem_alloc(tmem_slot, 64);
+            tc::tmem_relinquish();
+        }
     }
 
-    // ---- gather-mean: warp per point, lane = channel pair ------------------------------------------
+    // ---- gather-mean: warp per point, lane = channel pair (2*lane, 2*lane+1) ------------------------------------
     const float* xb = x + (size_t)b * N * 64;
     for (int pl = warp; pl < PB_TILE; pl += PB_THREADS / 32) {
         const int pos = tile0 + pl;
-        float2 m = make_float2(0.f, 0.f), t = make_float2(0.f, 0.f);
-        if (pos < N) {
-            const size_t row = (size_t)b * N + pos;
-            const int c = cnt[row];
-            float2 acc = make_float2(0.f, 0.f);
-            if (c == KNN_K) {
-                const int mine = (lane < KNN_K) ? (int)nbr[row * KNN_K + lane] : 0;
-                float2 v[KNN_K];
+        const size_t row = (size_t)b * N + pos;
+        const int c = cnt[row];
+        float2 acc = make_float2(0.f, 0.f);
+        if (c == KNN_K) {
+            const int mine = (lane < KNN_K) ? (int)nbr[row * KNN_K + lane] : 0;
+            float2 v[KNN_K];
 #pragma unroll
-                for (int q = 0; q < KNN_K; ++q) {
-                    const int j = __shfl_sync(FULL, mine, q);
-                    v[q] = __ldg(reinterpret_cast<const float2*>(xb + (size_t)j * 64) + lane);
-                }
+            for (int q = 0; q < KNN_K; ++q) {
+                const int j = __shfl_sync(FULL, mine, q);
+                v[q] = __ldg(reinterpret_cast<const float2*>(xb + (size_t)j * 64) + lane);
+            }
 #pragma unroll
-                for (int q = 0; q < KNN_K; ++q) {
-                    acc.x += v[q].x;
-                    acc.y += v[q].y;
-                }
-            } else {
-                // ties at the 20th distance: the set is {j : d_ij <= kthd_i}; re-scan the cloud exactly
-                const float thr = kthd[row];
-                const float4 qp = sorted[row];
-                const float4* sp = sorted + (size_t)b * N;
-                for (int j0 = 0; j0 < N; j0 += 32) {
-                    const float4 pj = sp[j0 + lane];
-                    const float d = (arith == EPC_KNN_ARITH_MULADD)
-                                        ? canon_dist<0>(qp.x, qp.y, qp.z, qp.w, pj.x, pj.y, pj.z, pj.w)
-                                        : canon_dist<1>(qp.x, qp.y, qp.z, qp.w, pj.x, pj.y, pj.z, pj.w);
-                    unsigned mk = __ballot_sync(FULL, d <= thr);
-                    while (mk) {
-                        const int j = j0 + __ffs(mk) - 1;
-                        mk &= mk - 1;
-                        const float2 v = __ldg(reinterpret_cast<const float2*>(xb + (size_t)j * 64) + lane);
-                        acc.x += v.x;
-                        acc.y += v.y;
-                    }
+            for (int q = 0; q < KNN_K; ++q) {
+                acc.x += v[q].x;
+                acc.y += v[q].y;
+            }
+        } else {
+            // ties at the 20th distance: the set is {j : d_ij <= kthd_i}; re-scan the cloud exactly
+            const float thr = kthd[row];
+            const float4 qp = sorted[row];
+            const float4* sp = sorted + (size_t)b * N;
+            for (int j0 = 0; j0 < N; j0 += 32) {
+                const float4 pj = sp[j0 + lane];
+                const float d = (arith == EPC_KNN_ARITH_MULADD)
+                                    ? canon_dist<0>(qp.x, qp.y, qp.z, qp.w, pj.x, pj.y, pj.z, pj.w)
+                                    : canon_dist<1>(qp.x, qp.y, qp.z, qp.w, pj.x, pj.y, pj.z, pj.w);
+                unsigned mk = __ballot_sync(FULL, d <= thr);
+                while (mk) {
+                    const int j = j0 + __ffs(mk) - 1;
+                    mk &= mk - 1;
+                    const float2 v = __ldg(reinterpret_cast<const float2*>(xb + (size_t)j * 64) + lane);
+                    acc.x += v.x;
+                    acc.y += v.y;
                 }
             }
-            m.x = __fdiv_rn(acc.x, divisor);                      // x1 = matmul(dpist, x) / float(k)
-            m.y = __fdiv_rn(acc.y, divisor);
-            const float2 xi = __ldg(reinterpret_cast<const float2*>(xb + (size_t)pos * 64) + lane);
-            t.x = m.x - xi.x;                                     // t1 = x1 - x
-            t.y = m.y - xi.y;
         }
-        sM[pl * PB_LD + 2 * lane] = m.x;
-        sM[pl * PB_LD + 2 * lane + 1] = m.y;
-        sT[pl * PB_LD + 2 * lane] = t.x;
-        sT[pl * PB_LD + 2 * lane + 1] = t.y;
+        float2 m;
+        m.x = __fdiv_rn(acc.x, divisor);                      // x1 = matmul(dpist, x) / float(k)
+        m.y = __fdiv_rn(acc.y, divisor);
+        const float2 xi = __ldg(reinterpret_cast<const float2*>(xb + (size_t)pos * 64) + lane);
+        const float2 t = make_float2(round_tf32(m.x - xi.x), round_tf32(m.y - xi.y));   // t1 = x1 - x (TF32 MMA operand)
+        *reinterpret_cast<float2*>(sM + pl * PB_MLD + 2 * lane) = m;
+        *reinterpret_cast<float2*>(sA + sw128_chunk(pl, lane >> 1, PB_A_BYTES / 2) + (lane & 1) * 8) = t;
     }
+    tc::fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+    tc::tc_fence_before();
     __syncthreads();
-    tile_dense64(sT, sWa, sBias, nullptr, sU, warp, lane);        // conv_a
+    tc::tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+    const uint32_t a_addr = tc::smem_u32(sA), w0_addr = tc::smem_u32(sW0), w1_addr = tc::smem_u32(sW1);
+    const bool epi = warp >= 4;                         // warps 4..7 own TMEM lane quarters 0..3
+    const int erow = (warp & 3) * 32 + lane;            // this epilogue thread's point within the tile
+    const uint32_t trow = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+    const size_t grow = (size_t)b * N + tile0 + erow;
+
+    // ---- conv_a -----------------------------------------------------------------------------------------------
+    if (tid == 0) pb_issue_gemm(tmem_d, a_addr, w0_addr, bar);
+    tc::mbar_wait(bar, 0);
+    tc::tc_fence_after();
+    if (epi) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float v[32];
+            tc::tmem_ld32(trow + 32u * h, v);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const int k = 32 * h + i;
+                float4 o;
+                o.x = round_tf32(fmaxf(v[i] + sBias[k], 0.f));
+                o.y = round_tf32(fmaxf(v[i + 1] + sBias[k + 1], 0.f));
+                o.z = round_tf32(fmaxf(v[i + 2] + sBias[k + 2], 0.f));
+                o.w = round_tf32(fmaxf(v[i + 3] + sBias[k + 3], 0.f));
+                *reinterpret_cast<float4*>(sA + sw128_chunk(erow, k >> 2, PB_A_BYTES / 2)) = o;
+            }
+        }
+    } else if (HAS_NEXT) {
+        // conv_a's weights are dead now: bring in the next block's first conv while the epilogue runs
+        const uint4* gn = reinterpret_cast<const uint4*>(Wn_img);
+        uint4* s0 = reinterpret_cast<uint4*>(sW0);
+        for (int i = tid; i < (int)(PB_W_BYTES / 16); i += 128) s0[i] = __ldg(gn + i);
+    }
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
     __syncthreads();
-    tile_dense64(sU, sWb, sBias + 64, sM, sT, warp, lane);        // conv_b, then  + m
-    __syncthreads();
-    for (int i = tid; i < PB_TILE * 64; i += PB_THREADS) {
-        const int pl = i >> 6, c = i & 63;
-        if (tile0 + pl < N) {
-            const size_t o = ((size_t)b * N + tile0 + pl) * ctot + coff + c;
-            const float val = sT[pl * PB_LD + c];
-            if (concat) concat[o] = val;
-            if (concat16) concat16[o] = __float2bfloat16(val);      // operand of the bf16 tensor-core conv5
+    tc::tc_fence_after();
+
+    // ---- conv_b, residual, concat ---------------------------------------------------------------------------------
+    if (tid == 0) pb_issue_gemm(tmem_d, a_addr, w1_addr, bar);
+    tc::mbar_wait(bar, 1);
+    tc::tc_fence_after();
+    if (epi) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float v[32];
+            tc::tmem_ld32(trow + 32u * h, v);
+            float o[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int k = 32 * h + i;
+                o[i] = fmaxf(v[i] + sBias[64 + k], 0.f) + sM[erow * PB_MLD + k];      // x_b = relu(conv_b) + m
+            }
+            if (HAS_NEXT) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(sA + sw128_chunk(erow, (32 * h + i) >> 2, PB_A_BYTES / 2)) =
+                        make_float4(round_tf32(o[i]), round_tf32(o[i + 1]), round_tf32(o[i + 2]), round_tf32(o[i + 3]));
+            }
+            if (concat) {
+                float4* dst = reinterpret_cast<float4*>(concat + grow * ctot + coff + 32 * h);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)       // operand of the TF32 conv5 (EPC-Net-L, KD export): store it rounded
+                    dst[i] = make_float4(round_tf32(o[4 * i]), round_tf32(o[4 * i + 1]), round_tf32(o[4 * i + 2]), round_tf32(o[4 * i + 3]));
+            }
+            if (concat16) {
+                uint4* dst = reinterpret_cast<uint4*>(concat16 + grow * ctot + coff + 32 * h);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const __nv_bfloat162 hh = __floats2bfloat162_rn(o[8 * i + 2 * j], o[8 * i + 2 * j + 1]);
+                        pk[j] = *reinterpret_cast<const uint32_t*>(&hh);
+                    }
+                    dst[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            }
         }
     }
     if (HAS_NEXT) {
-        tile_dense64(sT, sWn, sBias + 128, nullptr, sU, warp, lane);   // conv of the next block
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
         __syncthreads();
-        for (int i = tid; i < PB_TILE * 64; i += PB_THREADS) {
-            const int pl = i >> 6, c = i & 63;
-            if (tile0 + pl < N) xnext[((size_t)b * N + tile0 + pl) * 64 + c] = sU[pl * PB_LD + c];
+        tc::tc_fence_after();
+        // ---- first conv of the next block ----------------------------------------------------------------------
+        if (tid == 0) pb_issue_gemm(tmem_d, a_addr, w0_addr, bar);
+        tc::mbar_wait(bar, 0);
+        tc::tc_fence_after();
+        if (epi) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float v[32];
+                tc::tmem_ld32(trow + 32u * h, v);
+                float4* dst = reinterpret_cast<float4*>(xnext + grow * 64 + 32 * h);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int k = 32 * h + 4 * i;
+                    dst[i] = make_float4(fmaxf(v[4 * i] + sBias[128 + k], 0.f), fmaxf(v[4 * i + 1] + sBias[129 + k], 0.f),
+                                         fmaxf(v[4 * i + 2] + sBias[130 + k], 0.f), fmaxf(v[4 * i + 3] + sBias[131 + k], 0.f));
+                }
+            }
         }
     }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_d, 64);
 }
 
 int proxy_block(const float* x, const KnnState& g, int B, int N, int arith, float divisor, const DenseDev& conv_a,
@@ -193,26 +291,39 @@ int proxy_block(const float* x, const KnnState& g, int B, int N, int arith, floa
                 int coff, float* xnext, cudaStream_t st) {
     EPC_CHECK_ARG(conv_a.cin == 64 && conv_a.cout == 64 && conv_b.cin == 64 && conv_b.cout == 64,
                   "ProxyConv block layers must be 64->64");
+    EPC_CHECK_ARG(N % PB_TILE == 0, "proxy_block: N=%d must be a multiple of %d", N, PB_TILE);
+    EPC_CHECK_ARG(conv_a.Wimg && conv_b.Wimg && (!conv_next || conv_next->Wimg), "proxy_block: missing swizzled weight images");
     if (B == 0) return EPC_OK;
-    const size_t smem = (size_t)(3 * 4096 + 192 + 3 * PB_TILE * PB_LD) * sizeof(float);
     static bool attr_done = false;
     if (!attr_done) {
-        EPC_CUDA(cudaFuncSetAttribute(proxy_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        EPC_CUDA(cudaFuncSetAttribute(proxy_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        EPC_CUDA(cudaFuncSetAttribute(proxy_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM));
+        EPC_CUDA(cudaFuncSetAttribute(proxy_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM));
         attr_done = true;
     }
-    dim3 grid((N + PB_TILE - 1) / PB_TILE, B);
+    dim3 grid(N / PB_TILE, B);
     if (conv_next) {
-        proxy_block_kernel<true><<<grid, PB_THREADS, smem, st>>>(x, g.nbr, g.kthd, g.cnt, g.sorted, N, arith, divisor,
-                                                                 conv_a.W, conv_a.b, conv_b.W, conv_b.b, conv_next->W,
-                                                                 conv_next->b, concat, concat16, ctot, coff, xnext);
+        proxy_block_kernel<true><<<grid, PB_THREADS, PB_SMEM, st>>>(x, g.nbr, g.kthd, g.cnt, g.sorted, N, arith, divisor,
+                                                                    conv_a.Wimg, conv_a.b, conv_b.Wimg, conv_b.b,
+                                                                    conv_next->Wimg, conv_next->b, concat, concat16, ctot,
+                                                                    coff, xnext);
     } else {
-        proxy_block_kernel<false><<<grid, PB_THREADS, smem, st>>>(x, g.nbr, g.kthd, g.cnt, g.sorted, N, arith, divisor,
-                                                                  conv_a.W, conv_a.b, conv_b.W, conv_b.b, nullptr,
-                                                                  nullptr, concat, concat16, ctot, coff, nullptr);
+        proxy_block_kernel<false><<<grid, PB_THREADS, PB_SMEM, st>>>(x, g.nbr, g.kthd, g.cnt, g.sorted, N, arith, divisor,
+                                                                     conv_a.Wimg, conv_a.b, conv_b.Wimg, conv_b.b, nullptr,
+                                                                     nullptr, concat, concat16, ctot, coff, nullptr);
     }
     EPC_LAUNCH_CHECK();
     return EPC_OK;
+}
+
+// Host: [cin=64][cout=64] folded weights -> the shared-memory image of the K-major, 128B-swizzled B operand
+// (element (n,k) = W[k][n]): 2 k-blocks x 64 rows x 128 B.
+void make_w64_image(const float* W, float* img) {
+    for (int k = 0; k < 64; ++k)
+        for (int n = 0; n < 64; ++n) {
+            const int kb = k >> 5, chunk = (k & 31) >> 2, within = k & 3;
+            const size_t off_bytes = (size_t)kb * 8192 + (size_t)n * 128 + (size_t)((chunk ^ (n & 7)) << 4) + within * 4;
+            img[off_bytes / 4] = W[k * 64 + n];
+        }
 }
 
 }  // namespace epc

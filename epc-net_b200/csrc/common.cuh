@@ -114,6 +114,14 @@ __device__ __forceinline__ float2 canon_dist2(float2 qx, float2 qy, float2 qz, f
     return __fadd2_rn(__ffma2_rn(make_float2(-2.0f, -2.0f), inner, qs), ps);
 }
 
+// round to the nearest TF32 (10-bit mantissa): kind::tf32 MMAs ignore the low 13 mantissa bits, i.e. truncate;
+// rounding the operand when it is produced removes that bias
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);

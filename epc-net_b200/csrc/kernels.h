@@ -26,7 +26,9 @@ struct DenseDev {          // BN-folded pointwise layer on the device: y = act(x
     const float* W;        // [cin, cout]
     const float* b;        // [cout]
     int cin, cout;
+    const float* Wimg;     // 64->64 layers: 16 KB shared-memory image of the swizzled tensor-core B operand
 };
+void make_w64_image(const float* W /*[64][64] folded*/, float* img /*[4096]*/);
 struct BlockDev {          // one ProxyConv block (models/epc-net.py:66-81)
     DenseDev conv, conv_a, conv_b;
 };
@@ -60,7 +62,7 @@ int assign_softmax(const float* logits, const float* inv, const float* bn_scale,
                    int K, float* S, float* a_sum, cudaStream_t st);
 // V: nslab split-K slabs of [B,F,K] (slab elements apart); a_sum: [B, a_parts, K] partial column sums
 int vlad_finalize(const float* V, int nslab, long long slab, const float* a_sum, int a_parts, const float* Wc2, int B,
-                  int F, int K, float* v, cudaStream_t st);
+                  int F, int K, float* v, float* colss /*[B, F/128, K] scratch*/, cudaStream_t st);
 constexpr int ASSIGN_PARTS = 16;   // FFMA assign path: a_sum is produced as [B, ASSIGN_PARTS, K] partials
 constexpr int HIDDEN_SPLITK = 32;  // hidden FC split-K slabs [HIDDEN_SPLITK, B*G, D]
 constexpr int VLAD_SPLITK = 2;     // VLAD accumulate split-K slabs

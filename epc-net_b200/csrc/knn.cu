@@ -124,9 +124,12 @@ __device__ __forceinline__ void insert_hits(RowList& L, unsigned m, float d, int
         const float c = __shfl_sync(FULL, d, src);
         if (c > L.thr) continue;   // the mask was taken against an older (larger) threshold: no longer a member
         const int cj = jbase + src;
-        const int co = __ldg(gperm + cj);
-        const int vo = __ldg(gperm + L.vi);
-        const bool before = (L.val < c) || (L.val == c && vo < co);
+        bool before = (L.val < c);
+        if (__any_sync(FULL, L.val == c)) {      // rare: equal distances are ordered by ORIGINAL index (tf.nn.top_k)
+            const int co = __ldg(gperm + cj);
+            const int vo = __ldg(gperm + L.vi);
+            before = before || (L.val == c && vo < co);
+        }
         const int pos = __popc(__ballot_sync(FULL, before) & 0xFFFFFu);
         if (pos < KNN_K) {
             const float ev = L.thr;

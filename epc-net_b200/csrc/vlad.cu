@@ -81,61 +81,74 @@ int assign_softmax(const float* logits, const float* inv, const float* bn_scale,
     return EPC_OK;
 }
 
-// VLAD finalise (loupe.py:284-298): V[f,c] -= a_sum[c] * Wc2[f,c]; L2 over f per (b,c); flatten
-// f-major (index f*K + c); global L2.  One CTA per cloud.
+// VLAD finalise (loupe.py:284-298): r[f,c] = V[f,c] - a_sum[c] * Wc2[f,c]; L2 over f per (b,c); flatten f-major
+// (index f*K + c); global L2.  Two passes over (cloud, 128-feature slice) CTAs:
+//   pass 1: r -> v (unnormalised), partial column sums of squares -> colss [B, F/128, K]
+//   pass 2: every CTA re-derives the 64 column scales and the global scale from colss (fixed order) and scales its slice.
+constexpr int VF_ROWS = 128;
+
 __global__ void __launch_bounds__(256)
-vlad_finalize_kernel(const float* __restrict__ V, int nslab, long long slab, const float* __restrict__ a_sum, int a_parts,
-                     const float* __restrict__ Wc2, int F, int K, float* __restrict__ v) {
+vlad_residual_kernel(const float* __restrict__ V, int nslab, long long slab, const float* __restrict__ a_sum, int a_parts,
+                     const float* __restrict__ Wc2, int F, int K, float* __restrict__ v, float* __restrict__ colss) {
     __shared__ float s_part[4][64];
-    __shared__ float s_inv[64];
-    __shared__ float s_ginv;
-    const int b = blockIdx.x, tid = threadIdx.x;
-    const int c = tid & 63, grp = tid >> 6;           // 4 row groups x 64 columns
-    const float* Vb = V + (size_t)b * F * K;
-    float ss = 0.f;
+    const int b = blockIdx.y, sl = blockIdx.x, tid = threadIdx.x;
+    const int c = tid & 63, grp = tid >> 6;
     float as = 0.f;
     if (c < K)
         for (int p = 0; p < a_parts; ++p) as += a_sum[((size_t)b * a_parts + p) * K + c];
+    const float* Vb = V + (size_t)b * F * K;
+    float* vb = v + (size_t)b * F * K;
+    float ss = 0.f;
     if (c < K) {
-        for (int f = grp; f < F; f += 4) {
+        for (int f = sl * VF_ROWS + grp; f < (sl + 1) * VF_ROWS && f < F; f += 4) {
             float acc = 0.f;
             for (int s = 0; s < nslab; ++s) acc += Vb[s * slab + (size_t)f * K + c];
             const float r = acc - as * Wc2[(size_t)f * K + c];
+            vb[(size_t)f * K + c] = r;
             ss += r * r;
         }
     }
     s_part[grp][c] = ss;
     __syncthreads();
+    if (tid < K) colss[((size_t)b * gridDim.x + sl) * K + tid] = (s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid]);
+}
+
+__global__ void __launch_bounds__(256)
+vlad_scale_kernel(float* __restrict__ v, const float* __restrict__ colss, int F, int K) {
+    __shared__ float s_inv[64];
+    __shared__ float s_g[64];
+    __shared__ float s_ginv;
+    const int b = blockIdx.y, sl = blockIdx.x, tid = threadIdx.x;
     if (tid < 64) {
-        const float tot = (s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid]);
+        float tot = 0.f;
+        if (tid < K)
+            for (int p = 0; p < (int)gridDim.x; ++p) tot += colss[((size_t)b * gridDim.x + p) * K + tid];
         const float iv = 1.0f / sqrtf(fmaxf(tot, L2_EPS));
         s_inv[tid] = iv;
-        s_part[0][tid] = (tid < K) ? tot * iv * iv : 0.f;     // squared norm of the normalised column
+        s_g[tid] = (tid < K) ? tot * iv * iv : 0.f;          // squared norm of the normalised column
     }
     __syncthreads();
     if (tid < 32) {
-        float g = s_part[0][tid] + s_part[0][tid + 32];
-        g = warp_sum(g);
+        float g = warp_sum(s_g[tid] + s_g[tid + 32]);
         if (tid == 0) s_ginv = 1.0f / sqrtf(fmaxf(g, L2_EPS));
     }
     __syncthreads();
+    const int c = tid & 63, grp = tid >> 6;
     if (c < K) {
         const float sc = s_inv[c] * s_ginv;
         float* vb = v + (size_t)b * F * K;
-        for (int f = grp; f < F; f += 4) {
-            float acc = 0.f;
-            for (int s = 0; s < nslab; ++s) acc += Vb[s * slab + (size_t)f * K + c];
-            const float r = acc - as * Wc2[(size_t)f * K + c];
-            vb[(size_t)f * K + c] = r * sc;
-        }
+        for (int f = sl * VF_ROWS + grp; f < (sl + 1) * VF_ROWS && f < F; f += 4) vb[(size_t)f * K + c] *= sc;
     }
 }
 
 int vlad_finalize(const float* V, int nslab, long long slab, const float* a_sum, int a_parts, const float* Wc2, int B,
-                  int F, int K, float* v, cudaStream_t st) {
+                  int F, int K, float* v, float* colss, cudaStream_t st) {
     EPC_CHECK_ARG(K >= 1 && K <= 64, "vlad_finalize: cluster_size=%d unsupported (1..64)", K);
     if (B == 0) return EPC_OK;
-    vlad_finalize_kernel<<<B, 256, 0, st>>>(V, nslab, slab, a_sum, a_parts, Wc2, F, K, v);
+    dim3 grid((F + VF_ROWS - 1) / VF_ROWS, B);
+    vlad_residual_kernel<<<grid, 256, 0, st>>>(V, nslab, slab, a_sum, a_parts, Wc2, F, K, v, colss);
+    EPC_LAUNCH_CHECK();
+    vlad_scale_kernel<<<grid, 256, 0, st>>>(v, colss, F, K);
     EPC_LAUNCH_CHECK();
     return EPC_OK;
 }
