@@ -127,13 +127,26 @@ proxy_block_kernel(const float* __restrict__ x, const uint16_t* __restrict__ nbr
 
     // ---- gather-mean: warp per point, lane = channel pair (2*lane, 2*lane+1) ------------------------------------
     const float* xb = x + (size_t)b * N * 64;
-    for (int pl = warp; pl < PB_TILE; pl += PB_THREADS / 32) {
+    // this warp's 16 points are consecutive; their counts and neighbour lists are fetched up front so that the
+    // only dependent global latency inside the loop is the feature-row gather itself
+    constexpr int PPW = PB_TILE / (PB_THREADS / 32);        // points per warp (16)
+    const int p_first = warp * PPW;
+    const size_t row_first = (size_t)b * N + tile0 + p_first;
+    const int my_cnt = (lane < PPW) ? cnt[row_first + lane] : KNN_K;
+    int my_nbr[PPW];
+#pragma unroll
+    for (int i = 0; i < PPW; ++i) my_nbr[i] = (lane < KNN_K) ? (int)nbr[(row_first + i) * KNN_K + lane] : 0;
+#pragma unroll 1
+    for (int i = 0; i < PPW; ++i) {
+        const int pl = p_first + i;
         const int pos = tile0 + pl;
         const size_t row = (size_t)b * N + pos;
-        const int c = cnt[row];
+        const int c = __shfl_sync(FULL, my_cnt, i);
         float2 acc = make_float2(0.f, 0.f);
         if (c == KNN_K) {
-            const int mine = (lane < KNN_K) ? (int)nbr[row * KNN_K + lane] : 0;
+            int mine = my_nbr[0];
+#pragma unroll
+            for (int u = 1; u < PPW; ++u) mine = (i == u) ? my_nbr[u] : mine;
             float2 v[KNN_K];
 #pragma unroll
             for (int q = 0; q < KNN_K; ++q) {

@@ -12,11 +12,12 @@ struct KnnState {          // per-cloud kNN graph in *sorted* (Morton) point ord
     uint16_t* nbr;         // [B,N,20] neighbour positions (sorted space), ascending (d, original index)
     float* kthd;           // [B,N]   20th smallest d
     int* cnt;              // [B,N]   |{j : d_ij <= kthd_i}| (>= 20)
+    float4* aabb;          // [B][2][N/32] per 32-point block: (lo.xyz, max |p|^2), then (hi.xyz, -)
 };
 int knn_check_n(int N);
 size_t knn_state_bytes(int B, int N);
 KnnState knn_state_carve(Arena& ar, int B, int N);
-int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sorted, int* perm, uint16_t* nbr,
+int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sorted, int* perm, float4* aabb, uint16_t* nbr,
               float* kthd, int* cnt, int32_t* idx_out, float* kth_out, int32_t* count_out, cudaStream_t st);
 int knn_dense(const float* xyz, int B, int N, int arith, const float* kth, float* mask, float* dist, cudaStream_t st);
 int rows_topk_smallest(const float* adj, long long R, int M, int k, int32_t* idx, cudaStream_t st);

@@ -25,7 +25,8 @@ __device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 10 bits -> every t
 }
 
 __global__ void __launch_bounds__(1024) sort_kernel(const float* __restrict__ xyz, int N, int NP,
-                                                     float4* __restrict__ sorted, int* __restrict__ perm) {
+                                                     float4* __restrict__ sorted, int* __restrict__ perm,
+                                                     float4* __restrict__ aabb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
     __shared__ float red[6][32];
@@ -100,84 +101,163 @@ __global__ void __launch_bounds__(1024) sort_kernel(const float* __restrict__ xy
     for (int i = tid; i < N; i += blockDim.x) {
         int src = (int)(keys[i] & 0xffffffffu);
         float x = p[3 * src], y = p[3 * src + 1], z = p[3 * src + 2];
-        sorted[(size_t)b * N + i] = make_float4(x, y, z, canon_sq(x, y, z));
+        const float sq = canon_sq(x, y, z);
+        sorted[(size_t)b * N + i] = make_float4(x, y, z, sq);
         perm[(size_t)b * N + i] = src;
+        // axis-aligned box (and max |p|^2) of every 32-point block of the sorted order: the kNN kernel's pruning test
+        const int nblk = N >> 5;                   // N % 32 == 0 and i ascends by blockDim (a multiple of 32):
+        const float lx = warp_min(x), ly = warp_min(y), lz = warp_min(z);      // each warp holds exactly one block
+        const float hx = warp_max(x), hy = warp_max(y), hz = warp_max(z);
+        const float sm = warp_max(sq);
+        if (lane == 0) {
+            aabb[(size_t)b * nblk * 2 + (i >> 5)] = make_float4(lx, ly, lz, sm);
+            aabb[(size_t)b * nblk * 2 + nblk + (i >> 5)] = make_float4(hx, hy, hz, 0.f);
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Warp-distributed sorted list: lane l (< 20) holds the l-th smallest (d, original index) seen so far.
+// Per-row candidate buffer in shared memory: up to 64 (value, key) pairs; after a compaction the first 20 are the
+// current best set (unsorted) and `thr` is the 20th smallest value.  A block's hits are *appended* with one ballot,
+// one popc and a predicated store, however many there are.  A *compaction* selects the 20th smallest VALUE with a
+// value-only bitonic network (one shuffle + one min/max per step), then keeps the entries below it (plus the ties
+// needed, by lowest original index) with a ballot-rank scatter.  Only the final 20 are sorted by the full key
+// (d, original index) = tf.nn.top_k order.  `extra` counts dropped candidates equal to the 20th value (the size of
+// the thresholded set minus 20).
 // ------------------------------------------------------------------------------------------------
-struct RowList {
-    float val;    // this lane's entry value (+inf on lanes >= 20)
-    int vi;       // sorted-space position of the entry
-    float thr;    // value of entry 19 (warp-uniform)
-    int extra;    // # seen candidates with d == thr that are not in the list (warp-uniform)
+struct RowState {
+    float thr;           // 20th smallest value at the last compaction (warp-uniform)
+    int n;               // entries in the buffer (warp-uniform)
+    int extra;           // # dropped candidates with value == thr (warp-uniform)
 };
+constexpr uint32_t KEY_EMPTY = 0xffffffffu;
+constexpr int KNN_CAP = 64;      // buffer entries per row = two per lane during a compaction
 
-// Insert every candidate flagged in `m` (lane s holds candidate value d at sorted position jbase+s).
-__device__ __forceinline__ void insert_hits(RowList& L, unsigned m, float d, int jbase, const int* __restrict__ gperm,
-                                            int lane) {
-    while (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        const float c = __shfl_sync(FULL, d, src);
-        if (c > L.thr) continue;   // the mask was taken against an older (larger) threshold: no longer a member
-        const int cj = jbase + src;
-        bool before = (L.val < c);
-        if (__any_sync(FULL, L.val == c)) {      // rare: equal distances are ordered by ORIGINAL index (tf.nn.top_k)
-            const int co = __ldg(gperm + cj);
-            const int vo = __ldg(gperm + L.vi);
-            before = before || (L.val == c && vo < co);
-        }
-        const int pos = __popc(__ballot_sync(FULL, before) & 0xFFFFFu);
-        if (pos < KNN_K) {
-            const float ev = L.thr;
-            const float upv = __shfl_up_sync(FULL, L.val, 1);
-            const int upi = __shfl_up_sync(FULL, L.vi, 1);
-            if (lane == pos) {
-                L.val = c;
-                L.vi = cj;
-            } else if (lane > pos && lane < KNN_K) {
-                L.val = upv;
-                L.vi = upi;
+__device__ __forceinline__ bool key_lt(float av, uint32_t ak, float bv, uint32_t bk) {
+    return (av < bv) || (av == bv && ak < bk);
+}
+
+// full-key ascending bitonic sort, one (v,k) per lane
+__device__ __forceinline__ void warp_sort32_keys(float& v, uint32_t& k, int lane) {
+#pragma unroll
+    for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            const float ov = __shfl_xor_sync(FULL, v, j);
+            const uint32_t ok = __shfl_xor_sync(FULL, k, j);
+            const bool up = ((lane & kk) == 0);
+            const bool lower = ((lane & j) == 0);
+            const bool other_less = key_lt(ov, ok, v, k);
+            const bool take = (lower == up) ? other_less : (!other_less && !(ov == v && ok == k));
+            if (take) {
+                v = ov;
+                k = ok;
             }
-            const float nthr = __shfl_sync(FULL, L.val, KNN_K - 1);
-            L.extra = (nthr == ev) ? L.extra + 1 : 0;
-            L.thr = nthr;
-        } else {
-            L.extra += 1;   // c == thr and it loses the index tie-break: member of the thresholded set only
         }
     }
 }
 
-// Build the list from one full block of 32 candidates (bitonic sort across lanes on (d, original idx)).
-__device__ __forceinline__ void init_list(RowList& L, float d, int jbase, const int* __restrict__ gperm, int lane) {
-    float val = d;
-    int vi = jbase + lane;
-    int vo = __ldg(gperm + vi);
+// value-only bitonic sort of one float per lane (ASC or descending)
+template <bool ASC>
+__device__ __forceinline__ float warp_sort32_vals(float v, int lane) {
 #pragma unroll
-    for (int k = 2; k <= 32; k <<= 1) {
+    for (int kk = 2; kk <= 32; kk <<= 1) {
 #pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            const float ov = __shfl_xor_sync(FULL, val, j);
-            const int oi = __shfl_xor_sync(FULL, vi, j);
-            const int oo = __shfl_xor_sync(FULL, vo, j);
-            const bool up = ((lane & k) == 0);
-            const bool lower = ((lane & j) == 0);
-            const bool other_less = (ov < val) || (ov == val && oo < vo);
-            const bool take = (lower == up) ? other_less : !other_less;
-            if (take) {
-                val = ov;
-                vi = oi;
-                vo = oo;
-            }
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            const float o = __shfl_xor_sync(FULL, v, j);
+            const bool keep_min = (((lane & j) == 0) == ((((lane & kk) == 0)) == ASC));
+            v = keep_min ? fminf(v, o) : fmaxf(v, o);
         }
     }
-    L.thr = __shfl_sync(FULL, val, KNN_K - 1);
-    L.extra = __popc(__ballot_sync(FULL, lane >= KNN_K && val == L.thr));
-    L.val = (lane < KNN_K) ? val : INFINITY;
-    L.vi = (lane < KNN_K) ? vi : jbase;
+    return v;
+}
+
+// buffer [0,n) -> its 20 smallest keys in [0,20) (unsorted), thr, extra.   NOT inlined, state by value: one copy of
+// the networks (inlining them per row and call site blew the instruction cache: 40 no-instruction stalls per issue).
+__device__ __noinline__ RowState compact(RowState R, float* __restrict__ bv, uint32_t* __restrict__ bk) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    const float o0 = (lane < R.n) ? bv[lane] : INFINITY;
+    const float o1 = (lane + 32 < R.n) ? bv[lane + 32] : INFINITY;
+    const uint32_t k0 = (lane < R.n) ? bk[lane] : KEY_EMPTY;
+    const uint32_t k1 = (lane + 32 < R.n) ? bk[lane + 32] : KEY_EMPTY;
+    float s = warp_sort32_vals<true>(o0, lane);
+    if (R.n > 32) {
+        const float s1 = warp_sort32_vals<false>(o1, lane);
+        s = fminf(s, s1);                           // bitonic sequence holding the 32 smallest values
+#pragma unroll
+        for (int j = 16; j > 0; j >>= 1) {
+            const float o = __shfl_xor_sync(FULL, s, j);
+            s = ((lane & j) == 0) ? fminf(s, o) : fmaxf(s, o);
+        }
+    }
+    const float thr_new = __shfl_sync(FULL, s, KNN_K - 1);
+    bool keep0 = o0 < thr_new, keep1 = o1 < thr_new;
+    const bool eq0 = (o0 == thr_new), eq1 = (o1 == thr_new);
+    const int c_less = __popc(__ballot_sync(FULL, keep0)) + __popc(__ballot_sync(FULL, keep1));
+    const unsigned me0 = __ballot_sync(FULL, eq0), me1 = __ballot_sync(FULL, eq1);
+    const int c_eq = __popc(me0) + __popc(me1);
+    const int need_eq = KNN_K - c_less;            // >= 1
+    if (c_eq == need_eq) {
+        keep0 |= eq0;
+        keep1 |= eq1;
+    } else {
+        // ties straddle the 20th place: keep the need_eq tied entries with the lowest original index (rare)
+        bool t0 = eq0, t1 = eq1;
+        for (int i = 0; i < need_eq; ++i) {
+            uint32_t best = min(t0 ? k0 : KEY_EMPTY, t1 ? k1 : KEY_EMPTY);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(FULL, best, o));
+            if (t0 && k0 == best) { t0 = false; keep0 = true; }
+            if (t1 && k1 == best) { t1 = false; keep1 = true; }
+        }
+    }
+    R.extra = ((thr_new == R.thr) ? R.extra : 0) + (c_eq - need_eq);
+    R.thr = thr_new;
+    R.n = KNN_K;
+    const unsigned mk0 = __ballot_sync(FULL, keep0), mk1 = __ballot_sync(FULL, keep1);
+    const unsigned lt = (1u << lane) - 1u;
+    __syncwarp();                                   // every lane has read its entries: safe to overwrite [0,20)
+    if (keep0) {
+        const int e = __popc(mk0 & lt);
+        bv[e] = o0;
+        bk[e] = k0;
+    }
+    if (keep1) {
+        const int e = __popc(mk0) + __popc(mk1 & lt);
+        bv[e] = o1;
+        bk[e] = k1;
+    }
+    __syncwarp();
+    return R;
+}
+
+// the row's 20 survivors -> lane l gets the key of the l-th smallest (d, original index).  Not inlined (code size).
+__device__ __noinline__ uint32_t sorted_key(const float* __restrict__ rv, const uint32_t* __restrict__ rk) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    float v = (lane < KNN_K) ? rv[lane] : INFINITY;
+    uint32_t k = (lane < KNN_K) ? rk[lane] : KEY_EMPTY;
+    warp_sort32_keys(v, k, lane);
+    return k;
+}
+
+// queue the candidates flagged in m (lane s holds value d for sorted position jbase + s)
+__device__ __forceinline__ void append_hits(RowState& R, unsigned m, float d, int jbase, const unsigned short* __restrict__ sperm,
+                                            float* __restrict__ bv, uint32_t* __restrict__ bk, int lane) {
+    int h = __popc(m);
+    if (R.n + h > KNN_CAP) {
+        R = compact(R, bv, bk);
+        m &= __ballot_sync(FULL, d <= R.thr);      // the bound just tightened
+        h = __popc(m);
+        if (h == 0) return;
+    }
+    if ((m >> lane) & 1u) {
+        const int e = R.n + __popc(m & ((1u << lane) - 1u));
+        bv[e] = d;
+        bk[e] = ((uint32_t)sperm[jbase + lane] << 16) | (uint32_t)(jbase + lane);
+    }
+    R.n += h;
 }
 
 constexpr int KNN_ROWS_PER_WARP = 8;
@@ -186,30 +266,27 @@ constexpr int KNN_ROWS_PER_CTA = KNN_ROWS_PER_WARP * KNN_WARPS;
 
 template <int ARITH, bool PRUNE>
 __global__ void __launch_bounds__(KNN_WARPS * 32)
-knn_kernel(const float4* __restrict__ sorted, const int* __restrict__ perm, int N, uint16_t* __restrict__ nbr,
-           float* __restrict__ kthd, int* __restrict__ cnt, int32_t* __restrict__ idx_out,
+knn_kernel(const float4* __restrict__ sorted, const int* __restrict__ perm, const float4* __restrict__ aabb, int N,
+           uint16_t* __restrict__ nbr, float* __restrict__ kthd, int* __restrict__ cnt, int32_t* __restrict__ idx_out,
            float* __restrict__ kth_out, int32_t* __restrict__ count_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nblk = N >> 5;
     float4* spts = reinterpret_cast<float4*>(smem_raw);   // [N]   (x,y,z,s)
     float4* sblo = spts + N;                              // [nblk] (lo.xyz, max s)
     float4* sbhi = sblo + nblk;                           // [nblk] (hi.xyz, -)
+    unsigned short* sperm = reinterpret_cast<unsigned short*>(sbhi + nblk);   // [N] sorted position -> original index
+    float* sbv = reinterpret_cast<float*>(sperm + N);                         // [warps][rows][CAP] candidate values
+    uint32_t* sbk = reinterpret_cast<uint32_t*>(sbv + KNN_WARPS * KNN_ROWS_PER_WARP * KNN_CAP);   // ... and keys
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const float4* gp = sorted + (size_t)b * N;
     const int* gperm = perm + (size_t)b * N;
+    const float4* gbox = aabb + (size_t)b * nblk * 2;
 
-    for (int i = tid; i < N; i += blockDim.x) spts[i] = gp[i];
-    __syncthreads();
-    for (int blk = wid; blk < nblk; blk += KNN_WARPS) {
-        const float4 p = spts[blk * 32 + lane];
-        const float lx = warp_min(p.x), ly = warp_min(p.y), lz = warp_min(p.z);
-        const float hx = warp_max(p.x), hy = warp_max(p.y), hz = warp_max(p.z);
-        const float sm = warp_max(p.w);
-        if (lane == 0) {
-            sblo[blk] = make_float4(lx, ly, lz, sm);
-            sbhi[blk] = make_float4(hx, hy, hz, 0.f);
-        }
+    for (int i = tid; i < N; i += blockDim.x) {
+        spts[i] = gp[i];
+        sperm[i] = (unsigned short)gperm[i];
     }
+    for (int i = tid; i < 2 * nblk; i += blockDim.x) sblo[i] = gbox[i];      // [lo x nblk][hi x nblk]
     __syncthreads();
 
     const int r0 = blockIdx.x * KNN_ROWS_PER_CTA + wid * KNN_ROWS_PER_WARP;
@@ -225,7 +302,9 @@ knn_kernel(const float4* __restrict__ sorted, const int* __restrict__ perm, int 
         qz[rr] = make_float2(a.z, c.z);
         qs[rr] = make_float2(a.w, c.w);
     }
-    RowList L[KNN_ROWS_PER_WARP];
+    RowState L[KNN_ROWS_PER_WARP];
+    float* bv = sbv + (size_t)wid * KNN_ROWS_PER_WARP * KNN_CAP;
+    uint32_t* bk = sbk + (size_t)wid * KNN_ROWS_PER_WARP * KNN_CAP;
 
     auto distances = [&](int blk, float (&d)[KNN_ROWS_PER_WARP]) {
         const float4 p = spts[blk * 32 + lane];
@@ -248,12 +327,12 @@ knn_kernel(const float4* __restrict__ sorted, const int* __restrict__ perm, int 
 #pragma unroll
             for (int r = 0; r < KNN_ROWS_PER_WARP; ++r) {
                 const unsigned m = __ballot_sync(FULL, d[r] <= L[r].thr);
-                if (m) insert_hits(L[r], m, d[r], blk * 32, gperm, lane);
+                if (m) append_hits(L[r], m, d[r], blk * 32, sperm, bv + r * KNN_CAP, bk + r * KNN_CAP, lane);
             }
         }
     };
 
-    // ---- phase 1: the query rows' own block builds the lists; its index-neighbours tighten them ----
+    // ---- phase 1: the rows' own block and its index-neighbours (thr = +inf until the first compaction) --------
     int init_blk[5];
     int n_init = 0;
     {
@@ -266,13 +345,20 @@ knn_kernel(const float4* __restrict__ sorted, const int* __restrict__ perm, int 
             if (!dup) init_blk[n_init++] = blk;
         }
     }
-    {
-        float d[KNN_ROWS_PER_WARP];
-        distances(b0, d);
 #pragma unroll
-        for (int r = 0; r < KNN_ROWS_PER_WARP; ++r) init_list(L[r], d[r], b0 * 32, gperm, lane);
+    for (int r = 0; r < KNN_ROWS_PER_WARP; ++r) {
+        L[r].thr = INFINITY;
+        L[r].n = 0;
+        L[r].extra = 0;
     }
-    for (int t = 1; t < n_init; ++t) scan_block(init_blk[t]);
+    for (int t = 0; t < n_init; ++t) {
+        scan_block(init_blk[t]);
+        if (t == 1 || t == n_init - 1) {           // 64 candidates -> first bound; then a tight one before pruning
+#pragma unroll
+            for (int r = 0; r < KNN_ROWS_PER_WARP; ++r)
+                if (L[r].n > KNN_K) L[r] = compact(L[r], bv + r * KNN_CAP, bk + r * KNN_CAP);
+        }
+    }
 
     // ---- phase 2: every remaining block whose AABB can still hold a candidate <= thr --------------
     const int nw = (nblk + 31) >> 5;
@@ -313,18 +399,22 @@ knn_kernel(const float4* __restrict__ sorted, const int* __restrict__ perm, int 
         }
     }
 
-    // ---- outputs ------------------------------------------------------------------------------
+    // ---- outputs: final compaction, then one full-key sort of the 20 survivors ----------------------------------
 #pragma unroll
     for (int r = 0; r < KNN_ROWS_PER_WARP; ++r) {
+        float* rv = bv + r * KNN_CAP;
+        uint32_t* rk = bk + r * KNN_CAP;
+        if (L[r].n > KNN_K) L[r] = compact(L[r], rv, rk);
+        const uint32_t k = sorted_key(rv, rk);
         const size_t row = (size_t)b * N + r0 + r;
-        if (lane < KNN_K) nbr[row * KNN_K + lane] = (uint16_t)L[r].vi;
+        if (lane < KNN_K) nbr[row * KNN_K + lane] = (uint16_t)(k & 0xffffu);
         if (lane == 0) {
             kthd[row] = L[r].thr;
             cnt[row] = KNN_K + L[r].extra;
         }
         if (idx_out || kth_out || count_out) {
-            const size_t orow = (size_t)b * N + __ldg(gperm + r0 + r);
-            if (idx_out && lane < KNN_K) idx_out[orow * KNN_K + lane] = __ldg(gperm + L[r].vi);
+            const size_t orow = (size_t)b * N + sperm[r0 + r];
+            if (idx_out && lane < KNN_K) idx_out[orow * KNN_K + lane] = (int32_t)(k >> 16);
             if (kth_out && lane == 0) kth_out[orow] = -L[r].thr;
             if (count_out && lane == 0) count_out[orow] = KNN_K + L[r].extra;
         }
@@ -404,7 +494,7 @@ int knn_check_n(int N) {
     return EPC_OK;
 }
 
-int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sorted, int* perm, uint16_t* nbr,
+int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sorted, int* perm, float4* aabb, uint16_t* nbr,
               float* kthd, int* cnt, int32_t* idx_out, float* kth_out, int32_t* count_out, cudaStream_t st) {
     if (int rc = knn_check_n(N)) return rc;
     EPC_CHECK_ARG(arith == EPC_KNN_ARITH_MULADD || arith == EPC_KNN_ARITH_FMA, "bad knn arith %d", arith);
@@ -412,18 +502,18 @@ int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sor
     const int NP = next_pow2(N);
     const size_t sort_smem = (size_t)NP * sizeof(unsigned long long);
     static bool attr_done = false;
-    const size_t knn_smem = (size_t)N * 16 + (size_t)(N / 32) * 32;
+    const size_t knn_smem = (size_t)N * 16 + (size_t)(N / 32) * 32 + (size_t)N * 2 + (size_t)KNN_WARPS * KNN_ROWS_PER_WARP * KNN_CAP * 8;
     if (!attr_done) {
         EPC_CUDA(cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        EPC_CUDA(cudaFuncSetAttribute(knn_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024));
-        EPC_CUDA(cudaFuncSetAttribute(knn_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024));
-        EPC_CUDA(cudaFuncSetAttribute(knn_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024));
-        EPC_CUDA(cudaFuncSetAttribute(knn_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024));
+        EPC_CUDA(cudaFuncSetAttribute(knn_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        EPC_CUDA(cudaFuncSetAttribute(knn_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        EPC_CUDA(cudaFuncSetAttribute(knn_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        EPC_CUDA(cudaFuncSetAttribute(knn_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_done = true;
     }
     {
         ScopedStage ss(EPC_STAGE_SORT, st);
-        sort_kernel<<<B, 1024, sort_smem, st>>>(xyz, N, NP, sorted, perm);
+        sort_kernel<<<B, 1024, sort_smem, st>>>(xyz, N, NP, sorted, perm, aabb);
         EPC_LAUNCH_CHECK();
     }
     ScopedStage ss(EPC_STAGE_KNN, st);
@@ -431,14 +521,14 @@ int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sor
     const int th = KNN_WARPS * 32;
     if (arith == EPC_KNN_ARITH_MULADD) {
         if (prune)
-            knn_kernel<0, true><<<grid, th, knn_smem, st>>>(sorted, perm, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
+            knn_kernel<0, true><<<grid, th, knn_smem, st>>>(sorted, perm, aabb, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
         else
-            knn_kernel<0, false><<<grid, th, knn_smem, st>>>(sorted, perm, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
+            knn_kernel<0, false><<<grid, th, knn_smem, st>>>(sorted, perm, aabb, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
     } else {
         if (prune)
-            knn_kernel<1, true><<<grid, th, knn_smem, st>>>(sorted, perm, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
+            knn_kernel<1, true><<<grid, th, knn_smem, st>>>(sorted, perm, aabb, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
         else
-            knn_kernel<1, false><<<grid, th, knn_smem, st>>>(sorted, perm, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
+            knn_kernel<1, false><<<grid, th, knn_smem, st>>>(sorted, perm, aabb, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
     }
     EPC_LAUNCH_CHECK();
     return EPC_OK;
@@ -447,7 +537,7 @@ int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sor
 size_t knn_state_bytes(int B, int N) {
     const size_t R = (size_t)B * N;
     return align_up(R * sizeof(float4)) + align_up(R * sizeof(int)) + align_up(R * KNN_K * sizeof(uint16_t)) +
-           align_up(R * sizeof(float)) + align_up(R * sizeof(int));
+           align_up(R * sizeof(float)) + align_up(R * sizeof(int)) + align_up(R / 16 * sizeof(float4));
 }
 
 KnnState knn_state_carve(Arena& ar, int B, int N) {
@@ -458,6 +548,7 @@ KnnState knn_state_carve(Arena& ar, int B, int N) {
     s.nbr = ar.take<uint16_t>(R * KNN_K);
     s.kthd = ar.take<float>(R);
     s.cnt = ar.take<int>(R);
+    s.aabb = ar.take<float4>(R / 16);      // [B][2][N/32]
     return s;
 }
 
