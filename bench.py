@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--clouds", type=int, default=128, help="clouds per GPU per step")
-    ap.add_argument("--chunk", type=int, default=32, help="clouds per library call")
+    ap.add_argument("--chunk", type=int, default=128, help="clouds per library call")
     ap.add_argument("--cpu-sample", type=int, default=24, help="clouds in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-retrieval", action="store_true")

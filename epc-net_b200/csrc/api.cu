@@ -367,7 +367,12 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
             for (int c = 0; c < K; ++c) h16[o16_Wc + (size_t)c * 1024 + f] = __float2bfloat16(w->cluster_weights_host[(size_t)f * K + c]);
         bn_affine(w->cluster_bn, K, sc, sh); oCs = pk.add(sc); oCh = pk.add(sh);
         oWc2 = pk.add(w->cluster_weights2_host, (size_t)1024 * K);
-        oWh = pk.add(w->hidden1_weights_host, (size_t)m->hidden_in * D);
+        {   // hidden1_weights [hidden_in, D] -> transposed [D, hidden_in], TF32-rounded: K-major B operand of the tensor-core FC
+            std::vector<float> Wht((size_t)D * m->hidden_in);
+            for (int k = 0; k < m->hidden_in; ++k)
+                for (int n = 0; n < D; ++n) Wht[(size_t)n * m->hidden_in + k] = host_round_tf32(w->hidden1_weights_host[(size_t)k * D + n]);
+            oWh = pk.add(Wht);
+        }
         bn_affine(w->hidden_bn, D, sc, sh); oHs = pk.add(sc); oHh = pk.add(sh);
         if (w->gating) {
             oWg = pk.add(w->gating_weights_host, (size_t)D * D);
@@ -474,14 +479,14 @@ int head_tail(const EpcModel* m, int B, int N, const HeadWs& h, int l2, float* o
         if (int rc = vlad_finalize(h.V, VLAD_SPLITK, (long long)B * 1024 * 64, h.a_part, N / 128, m->Wc2, B, 1024, 64, h.v, h.colss, st))
             return rc;
     }
-    {   // hidden FC (loupe.py:302-320): rows of length hidden_in, G per cloud; 16 MiB of weights => bandwidth bound
-        GemmArgs g = {};
-        g.A = h.v; g.sAm = m->hidden_in; g.sAk = 1;
-        g.B = m->Wh; g.sBk = D; g.sBn = 1;
-        g.C = h.Y; g.ldc = D; g.M = B * m->G; g.N = D; g.K = m->hidden_in; g.batch = 1;
-        g.splitk = HIDDEN_SPLITK; g.slab = (long long)B * m->G * D;
+    {   // hidden FC (loupe.py:302-320): rows of length hidden_in, G per cloud; TF32 tensor cores, split-K slabs
         ScopedStage ss(EPC_STAGE_HIDDEN_GEMM, st);
-        if (int rc = sgemm(g, st)) return rc;
+        if (D == 256 && m->hidden_in % (HIDDEN_SPLITK * 32) == 0) {
+            if (int rc = tc_hidden(h.v, B * m->G, m->hidden_in, m->Wh, D, h.Y, HIDDEN_SPLITK, st)) return rc;
+        } else {
+            set_error("hidden FC: output_dim=%d / hidden_in=%d unsupported by the tensor-core path", D, m->hidden_in);
+            return EPC_EUNSUPPORTED;
+        }
     }
     ScopedStage ss(EPC_STAGE_TAIL, st);
     return vlad_tail(h.Y, HIDDEN_SPLITK, B, m->G, D, m->hbn_scale, m->hbn_shift, m->Wg, m->gbn_scale, m->gbn_shift,

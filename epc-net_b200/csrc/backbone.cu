@@ -55,10 +55,11 @@ int conv_in(const float4* sorted, long long R, const DenseDev& L, float* x, cuda
 // ------------------------------------------------------------------------------------------------
 constexpr int PB_TILE = 128;
 constexpr int PB_THREADS = 256;
-constexpr int PB_MLD = 66;                       // row stride (floats) of the fp32 neighbour-mean tile
+constexpr int PB_MLD = 68;                       // row stride (floats) of the fp32 neighbour-mean tile (16 B aligned rows)
 constexpr uint32_t PB_A_BYTES = 2 * 128 * 128;   // A tile: 2 k-blocks x 128 rows x 128 B
 constexpr uint32_t PB_W_BYTES = 2 * 64 * 128;    // weight image: 2 k-blocks x 64 rows x 128 B
-constexpr size_t PB_SMEM = 1024 + PB_A_BYTES + 2 * PB_W_BYTES + PB_TILE * PB_MLD * 4 + 3 * 64 * 4 + 64;
+constexpr size_t PB_SMEM = 1024 + PB_A_BYTES + 2 * PB_W_BYTES + PB_TILE * PB_MLD * 4 + 3 * 64 * 4 + 64 +
+                           PB_TILE * KNN_K * 2 + PB_TILE * 4;
 
 // byte offset of the 16-byte chunk holding channels [4*k4, 4*k4+4) of row r in a [rows x 64] fp32 K-major SW128 tile
 __device__ __forceinline__ uint32_t sw128_chunk(int r, int k4, uint32_t kblock_bytes) {
@@ -95,6 +96,8 @@ proxy_block_kernel(const float* __restrict__ x, const uint16_t* __restrict__ nbr
     float* sBias = sM + PB_TILE * PB_MLD;                // [3][64]
     uint64_t* bar = reinterpret_cast<uint64_t*>(sBias + 192);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    int* sCnt = reinterpret_cast<int*>(bar + 8);                         // [128] size of each point's thresholded set
+    unsigned short* sNbr = reinterpret_cast<unsigned short*>(sCnt + PB_TILE);   // [128][20] neighbour positions
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
@@ -125,41 +128,34 @@ proxy_block_kernel(const float* __restrict__ x, const uint16_t* __restrict__ nbr
         }
     }
 
-    // ---- gather-mean: warp per point, lane = channel pair (2*lane, 2*lane+1) ------------------------------------
+    // ---- gather-mean ---------------------------------------------------------------------------------------
+    // warp per point; the two half-warps fetch two different neighbour rows per instruction (lane & 15 = which
+    // float4 of the 256-byte row), so a point costs 10 LDG.128 instead of 20 LDG.64.
     const float* xb = x + (size_t)b * N * 64;
-    // this warp's 16 points are consecutive; their counts and neighbour lists are fetched up front so that the
-    // only dependent global latency inside the loop is the feature-row gather itself
-    constexpr int PPW = PB_TILE / (PB_THREADS / 32);        // points per warp (16)
-    const int p_first = warp * PPW;
-    const size_t row_first = (size_t)b * N + tile0 + p_first;
-    const int my_cnt = (lane < PPW) ? cnt[row_first + lane] : KNN_K;
-    int my_nbr[PPW];
-#pragma unroll
-    for (int i = 0; i < PPW; ++i) my_nbr[i] = (lane < KNN_K) ? (int)nbr[(row_first + i) * KNN_K + lane] : 0;
+    const size_t row_tile = (size_t)b * N + tile0;
+    for (int i = tid; i < PB_TILE * KNN_K; i += PB_THREADS) sNbr[i] = nbr[row_tile * KNN_K + i];
+    if (tid < PB_TILE) sCnt[tid] = cnt[row_tile + tid];
+    __syncthreads();
+    const int half = lane >> 4, c4 = lane & 15;
+    const float inv_div = 1.0f / divisor;               // x1 = matmul(dpist, x) / float(k): one rounding differs from a true division
 #pragma unroll 1
-    for (int i = 0; i < PPW; ++i) {
-        const int pl = p_first + i;
+    for (int pl = warp; pl < PB_TILE; pl += PB_THREADS / 32) {
         const int pos = tile0 + pl;
-        const size_t row = (size_t)b * N + pos;
-        const int c = __shfl_sync(FULL, my_cnt, i);
-        float2 acc = make_float2(0.f, 0.f);
-        if (c == KNN_K) {
-            int mine = my_nbr[0];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sCnt[pl] == KNN_K) {
+            float4 v[KNN_K / 2];
 #pragma unroll
-            for (int u = 1; u < PPW; ++u) mine = (i == u) ? my_nbr[u] : mine;
-            float2 v[KNN_K];
-#pragma unroll
-            for (int q = 0; q < KNN_K; ++q) {
-                const int j = __shfl_sync(FULL, mine, q);
-                v[q] = __ldg(reinterpret_cast<const float2*>(xb + (size_t)j * 64) + lane);
+            for (int q = 0; q < KNN_K / 2; ++q) {
+                const int j = sNbr[pl * KNN_K + 2 * q + half];
+                v[q] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)j * 64) + c4);
             }
 #pragma unroll
-            for (int q = 0; q < KNN_K; ++q) {
-                acc.x += v[q].x;
-                acc.y += v[q].y;
+            for (int q = 0; q < KNN_K / 2; ++q) {
+                acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w;
             }
         } else {
-            // ties at the 20th distance: the set is {j : d_ij <= kthd_i}; re-scan the cloud exactly
+            // ties at the 20th distance: the set is {j : d_ij <= kthd_i}; re-scan the cloud exactly (rare)
+            const size_t row = row_tile + pl;
             const float thr = kthd[row];
             const float4 qp = sorted[row];
             const float4* sp = sorted + (size_t)b * N;
@@ -172,19 +168,25 @@ proxy_block_kernel(const float* __restrict__ x, const uint16_t* __restrict__ nbr
                 while (mk) {
                     const int j = j0 + __ffs(mk) - 1;
                     mk &= mk - 1;
-                    const float2 v = __ldg(reinterpret_cast<const float2*>(xb + (size_t)j * 64) + lane);
-                    acc.x += v.x;
-                    acc.y += v.y;
+                    if (half == 0) {                     // one half-warp accumulates; the other contributes zeros
+                        const float4 vv = __ldg(reinterpret_cast<const float4*>(xb + (size_t)j * 64) + c4);
+                        acc.x += vv.x; acc.y += vv.y; acc.z += vv.z; acc.w += vv.w;
+                    }
                 }
             }
         }
-        float2 m;
-        m.x = __fdiv_rn(acc.x, divisor);                      // x1 = matmul(dpist, x) / float(k)
-        m.y = __fdiv_rn(acc.y, divisor);
-        const float2 xi = __ldg(reinterpret_cast<const float2*>(xb + (size_t)pos * 64) + lane);
-        const float2 t = make_float2(round_tf32(m.x - xi.x), round_tf32(m.y - xi.y));   // t1 = x1 - x (TF32 MMA operand)
-        *reinterpret_cast<float2*>(sM + pl * PB_MLD + 2 * lane) = m;
-        *reinterpret_cast<float2*>(sA + sw128_chunk(pl, lane >> 1, PB_A_BYTES / 2) + (lane & 1) * 8) = t;
+        acc.x += __shfl_xor_sync(FULL, acc.x, 16);
+        acc.y += __shfl_xor_sync(FULL, acc.y, 16);
+        acc.z += __shfl_xor_sync(FULL, acc.z, 16);
+        acc.w += __shfl_xor_sync(FULL, acc.w, 16);
+        const float4 m = make_float4(acc.x * inv_div, acc.y * inv_div, acc.z * inv_div, acc.w * inv_div);
+        if (half == 0) {
+            *reinterpret_cast<float4*>(sM + pl * PB_MLD + 4 * c4) = m;
+        } else {
+            const float4 xi = __ldg(reinterpret_cast<const float4*>(xb + (size_t)pos * 64) + c4);
+            *reinterpret_cast<float4*>(sA + sw128_chunk(pl, c4, PB_A_BYTES / 2)) =          // t1 = x1 - x (TF32 MMA operand)
+                make_float4(round_tf32(m.x - xi.x), round_tf32(m.y - xi.y), round_tf32(m.z - xi.z), round_tf32(m.w - xi.w));
+        }
     }
     tc::fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
     tc::tc_fence_before();
@@ -198,8 +200,11 @@ proxy_block_kernel(const float* __restrict__ x, const uint16_t* __restrict__ nbr
     const size_t grow = (size_t)b * N + tile0 + erow;
 
     // ---- conv_a -----------------------------------------------------------------------------------------------
-    if (tid == 0) pb_issue_gemm(tmem_d, a_addr, w0_addr, bar);
-    tc::mbar_wait(bar, 0);
+    if (tid == 0) {
+        pb_issue_gemm(tmem_d, a_addr, w0_addr, bar);
+        tc::mbar_wait(bar, 0);          // one thread polls; everybody else sleeps on the hardware barrier
+    }
+    __syncthreads();
     tc::tc_fence_after();
     if (epi) {
 #pragma unroll
@@ -229,8 +234,11 @@ proxy_block_kernel(const float* __restrict__ x, const uint16_t* __restrict__ nbr
     tc::tc_fence_after();
 
     // ---- conv_b, residual, concat ---------------------------------------------------------------------------------
-    if (tid == 0) pb_issue_gemm(tmem_d, a_addr, w1_addr, bar);
-    tc::mbar_wait(bar, 1);
+    if (tid == 0) {
+        pb_issue_gemm(tmem_d, a_addr, w1_addr, bar);
+        tc::mbar_wait(bar, 1);
+    }
+    __syncthreads();
     tc::tc_fence_after();
     if (epi) {
 #pragma unroll
@@ -239,9 +247,13 @@ proxy_block_kernel(const float* __restrict__ x, const uint16_t* __restrict__ nbr
             tc::tmem_ld32(trow + 32u * h, v);
             float o[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < 32; i += 4) {
                 const int k = 32 * h + i;
-                o[i] = fmaxf(v[i] + sBias[64 + k], 0.f) + sM[erow * PB_MLD + k];      // x_b = relu(conv_b) + m
+                const float4 mm = *reinterpret_cast<const float4*>(sM + erow * PB_MLD + k);
+                o[i] = fmaxf(v[i] + sBias[64 + k], 0.f) + mm.x;                        // x_b = relu(conv_b) + m
+                o[i + 1] = fmaxf(v[i + 1] + sBias[65 + k], 0.f) + mm.y;
+                o[i + 2] = fmaxf(v[i + 2] + sBias[66 + k], 0.f) + mm.z;
+                o[i + 3] = fmaxf(v[i + 3] + sBias[67 + k], 0.f) + mm.w;
             }
             if (HAS_NEXT) {
 #pragma unroll
@@ -276,8 +288,11 @@ proxy_block_kernel(const float* __restrict__ x, const uint16_t* __restrict__ nbr
         __syncthreads();
         tc::tc_fence_after();
         // ---- first conv of the next block ----------------------------------------------------------------------
-        if (tid == 0) pb_issue_gemm(tmem_d, a_addr, w0_addr, bar);
-        tc::mbar_wait(bar, 0);
+        if (tid == 0) {
+            pb_issue_gemm(tmem_d, a_addr, w0_addr, bar);
+            tc::mbar_wait(bar, 0);
+        }
+        __syncthreads();
         tc::tc_fence_after();
         if (epi) {
 #pragma unroll

@@ -20,7 +20,7 @@ int tc_assign(const __nv_bfloat16* H, long long R, const __nv_bfloat16* Wct, con
     p.M = (int)R; p.N = 64; p.K = 1024; p.splitk = 1; p.C = S; p.ldc = 64; p.aux = a_part; p.rowss = rowss;
     p.rowss_parts = parts; p.bn_scale = bn_scale; p.bn_shift = bn_shift;
     Operand<__nv_bfloat16> a{H, R, 1024, 1024}, b{Wct, 64, 1024, 1024};
-    return tc_gemm_launch<__nv_bfloat16, 64, false, false, tc::EPI_ASSIGN>(a, b, p, 1, st, 1);
+    return tc_gemm_launch<__nv_bfloat16, 64, false, false, tc::EPI_ASSIGN>(a, b, p, 1, st, 2);
 }
 
 // VLAD accumulate (loupe.py:286-291): V[b] = H[b]^T S'[b]  -> fp32 slabs [splitk][B,1024,64]
@@ -49,6 +49,15 @@ int tc_conv5_f32(const float* Xc, long long R, int cin, const float* W5t, const 
     p.M = (int)R; p.N = 1024; p.K = cin; p.splitk = 1; p.C = H; p.ldc = 1024; p.bias = b5; p.relu = 1;
     Operand<float> a{Xc, R, cin, cin}, b{W5t, 1024, cin, cin};
     return tc_gemm_launch<float, 256, false, false, tc::EPI_STORE_F32>(a, b, p, 1, st, 2);
+}
+
+// hidden FC of the VLAD head (loupe.py:302-320): Y[s] = v[:, ks] Wh[ks, :]   (rows = B*G, K = hidden_in), TF32, split-K slabs
+int tc_hidden(const float* v, int rows, int hidden_in, const float* Wht /*[D, hidden_in]*/, int D, float* Y, int splitk,
+              cudaStream_t st) {
+    tc::GemmParams p = {};
+    p.M = rows; p.N = D; p.K = hidden_in / splitk; p.splitk = splitk; p.C = Y; p.ldc = D; p.c_slab = (long long)rows * D;
+    Operand<float> a{v, rows, hidden_in, hidden_in}, b{Wht, D, hidden_in, hidden_in};
+    return tc_gemm_launch<float, 256, false, false, tc::EPI_STORE_F32>(a, b, p, 1, st, 1);
 }
 
 }  // namespace epc
