@@ -10,7 +10,7 @@ int tc_conv5_bf16(const __nv_bfloat16* Xc, long long R, int cin, const __nv_bflo
     tc::GemmParams p = {};
     p.M = (int)R; p.N = 1024; p.K = cin; p.splitk = 1; p.C = H; p.ldc = 1024; p.bias = b5; p.relu = 1; p.aux = rowss;
     Operand<__nv_bfloat16> a{Xc, R, cin, cin}, b{W5t, 1024, cin, cin};
-    return tc_gemm_launch<__nv_bfloat16, 256, false, false, tc::EPI_CONV5_BF16>(a, b, p, 1, st, 2);
+    return tc_gemm_bres_launch<__nv_bfloat16, 256, tc::EPI_CONV5_BF16, 8>(a, b, p, st);
 }
 
 // cluster assignment (loupe.py:255-276): S' = softmax(BN((H Wc)/|H|))/|H| as bf16 [R,64]; a_part [R/128, 64]
@@ -20,7 +20,7 @@ int tc_assign(const __nv_bfloat16* H, long long R, const __nv_bfloat16* Wct, con
     p.M = (int)R; p.N = 64; p.K = 1024; p.splitk = 1; p.C = S; p.ldc = 64; p.aux = a_part; p.rowss = rowss;
     p.rowss_parts = parts; p.bn_scale = bn_scale; p.bn_shift = bn_shift;
     Operand<__nv_bfloat16> a{H, R, 1024, 1024}, b{Wct, 64, 1024, 1024};
-    return tc_gemm_launch<__nv_bfloat16, 64, false, false, tc::EPI_ASSIGN>(a, b, p, 1, st, 2);
+    return tc_gemm_bres_launch<__nv_bfloat16, 64, tc::EPI_ASSIGN>(a, b, p, st);
 }
 
 // VLAD accumulate (loupe.py:286-291): V[b] = H[b]^T S'[b]  -> fp32 slabs [splitk][B,1024,64]
@@ -40,7 +40,7 @@ int tc_conv5_colmax(const float* Xc, long long R, int cin, int rows_per_cloud, c
     tc::GemmParams p = {};
     p.M = (int)R; p.N = 1024; p.K = cin; p.splitk = 1; p.bias = b5; p.aux = g; p.rows_per_cloud = rows_per_cloud;
     Operand<float> a{Xc, R, cin, cin}, b{W5t, 1024, cin, cin};
-    return tc_gemm_launch<float, 256, false, false, tc::EPI_COLMAX>(a, b, p, 1, st, 2);
+    return tc_gemm_bres_launch<float, 256, tc::EPI_COLMAX, 8>(a, b, p, st);
 }
 
 // fp32-output conv5 on TF32 tensor cores (KD feature export, models/kd_epc-net.py:158)
@@ -48,7 +48,9 @@ int tc_conv5_f32(const float* Xc, long long R, int cin, const float* W5t, const 
     tc::GemmParams p = {};
     p.M = (int)R; p.N = 1024; p.K = cin; p.splitk = 1; p.C = H; p.ldc = 1024; p.bias = b5; p.relu = 1;
     Operand<float> a{Xc, R, cin, cin}, b{W5t, 1024, cin, cin};
-    return tc_gemm_launch<float, 256, false, false, tc::EPI_STORE_F32>(a, b, p, 1, st, 2);
+    if (cin > 128)      // fp32 operands: a 256-column slice of W5 (256 KB at K = 256) would not fit in shared memory
+        return tc_gemm_bres_launch<float, 128, tc::EPI_STORE_F32, 8>(a, b, p, st);
+    return tc_gemm_bres_launch<float, 256, tc::EPI_STORE_F32, 8>(a, b, p, st);
 }
 
 // hidden FC of the VLAD head (loupe.py:302-320): Y[s] = v[:, ks] Wh[ks, :]   (rows = B*G, K = hidden_in), TF32, split-K slabs

@@ -190,6 +190,151 @@ struct TileCfg {
     static constexpr size_t smem(int stages) { return (size_t)stages * (A_BYTES + B_BYTES) + 1024 + 256; }
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// epilogues (shared by the one-tile-per-CTA kernel and the persistent B-resident kernel)
+// ---------------------------------------------------------------------------------------------------------
+struct EpiCtx {
+    uint32_t trow;      // TMEM address of this thread's accumulator row (lane quarter + column base)
+    int m, row, lane;   // global row, row within the tile, lane
+    int m0, n0;         // tile origin
+    int mtile;          // index of the 128-row tile (ASSIGN: a_part row)
+    int nparts, npart;  // CONV5: number / index of the N tile (rowss partials)
+    long long c_off;    // STORE_F32: element offset of this batch / split-K slab in C
+    float* scratch;     // ASSIGN: [128][65] fp32 shared-memory scratch
+    int epi_tid;        // 0..127 within the epilogue warps
+    const float* bias;  // bias of this N tile (global or shared), indexed by the column within the tile; may be nullptr
+    int col_begin, col_end;   // columns of the tile this warp drains (two warps per lane quarter split the tile)
+};
+
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, const EpiCtx& c) {
+    const uint32_t trow = c.trow;
+    const int m = c.m, row = c.row, lane = c.lane, n0 = c.n0;
+    (void)row; (void)lane; (void)n0;
+        if (EPI == EPI_STORE_F32) {
+            float* C = reinterpret_cast<float*>(p.C) + c.c_off;
+    #pragma unroll 1
+            for (int c0 = c.col_begin; c0 < c.col_end; c0 += 32) {
+                float v[32];
+                tmem_ld32(trow + (uint32_t)c0, v);
+                if (m < p.M) {
+                    float* dst = C + (size_t)m * p.ldc + n0 + c0;
+    #pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        if (p.bias) {
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + i));
+                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                        }
+                        if (p.relu) {
+                            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                        }
+                        *reinterpret_cast<float4*>(dst + i) = o;
+                    }
+                }
+            }
+        } else if (EPI == EPI_CONV5_BF16) {
+            // H = relu(acc + b) stored as bf16; per-row sum of squares of the fp32 values for the later L2 norm
+            __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(p.C);
+            float ss = 0.f;
+    #pragma unroll 1
+            for (int c0 = c.col_begin; c0 < c.col_end; c0 += 32) {
+                float v[32];
+                tmem_ld32(trow + (uint32_t)c0, v);
+                uint32_t pk[16];
+    #pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float2 bb = *reinterpret_cast<const float2*>(c.bias + c0 + i);
+                    const float x = fmaxf(v[i] + bb.x, 0.f), y = fmaxf(v[i + 1] + bb.y, 0.f);
+                    ss = fmaf(x, x, ss);
+                    ss = fmaf(y, y, ss);
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+                    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                if (m < p.M) {
+                    uint4* dst = reinterpret_cast<uint4*>(H + (size_t)m * p.ldc + n0 + c0);
+    #pragma unroll
+                    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                }
+            }
+            if (m < p.M) p.aux[(size_t)m * c.nparts + c.npart] = ss;
+        } else if (EPI == EPI_COLMAX) {
+            // max over the tile's rows of relu(acc + b): values >= 0, so unsigned-int order == float order
+            const int cloud = c.m0 / p.rows_per_cloud;
+            int* g = reinterpret_cast<int*>(p.aux) + (size_t)cloud * p.N;
+    #pragma unroll 1
+            for (int c0 = c.col_begin; c0 < c.col_end; c0 += 32) {
+                float v[32];
+                tmem_ld32(trow + (uint32_t)c0, v);
+                unsigned mine = 0;
+    #pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float x = (m < p.M) ? fmaxf(v[i] + c.bias[c0 + i], 0.f) : 0.f;
+                    const unsigned r = __reduce_max_sync(FULL, __float_as_uint(x));
+                    if (lane == i) mine = r;
+                }
+                atomicMax(g + n0 + c0 + lane, (int)mine);
+            }
+        } else if (EPI == EPI_ASSIGN) {
+            // BN == 64: this thread owns all 64 cluster logits of its point (loupe.py:255-276)
+            float v[64];
+            {
+                float t[32];
+                tmem_ld32(trow, t);
+    #pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = t[i];
+                tmem_ld32(trow + 32u, t);
+    #pragma unroll
+                for (int i = 0; i < 32; ++i) v[32 + i] = t[i];
+            }
+            float ssq = 0.f;
+            if (m < p.M)
+                for (int i = 0; i < p.rowss_parts; ++i) ssq += p.rowss[(size_t)m * p.rowss_parts + i];
+            const float inv = 1.0f / sqrtf(fmaxf(ssq, L2_EPS));
+            float mx = -INFINITY;
+    #pragma unroll
+            for (int i = 0; i < 64; ++i) {
+                v[i] = (v[i] * inv) * __ldg(p.bn_scale + i) + __ldg(p.bn_shift + i);
+                mx = fmaxf(mx, v[i]);
+            }
+            float den = 0.f;
+    #pragma unroll
+            for (int i = 0; i < 64; ++i) {
+                v[i] = expf(v[i] - mx);
+                den += v[i];
+            }
+            const float rden = 1.0f / den;
+            // column sums of the soft assignment over this tile: stage through (now idle) pipeline smem
+            float* sS = c.scratch;        // [128][65]
+    #pragma unroll
+            for (int i = 0; i < 64; ++i) {
+                v[i] *= rden;
+                sS[row * 65 + i] = (m < p.M) ? v[i] : 0.f;
+            }
+            if (m < p.M) {
+                uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)m * 64);
+    #pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    uint32_t pk[4];
+    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * i + 2 * j] * inv, v[8 * i + 2 * j + 1] * inv);
+                        pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    dst[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");     // the four epilogue warps only
+            const int t = c.epi_tid;
+            if (t < 64) {
+                float a = 0.f;
+                for (int r = 0; r < TC_BM; ++r) a += sS[r * 65 + t];
+                p.aux[(size_t)c.mtile * 64 + t] = a;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");     // scratch may be rewritten by the next tile (persistent kernel)
+        }
+}
+
 template <typename T, int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(192)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p,
@@ -292,131 +437,150 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16);
         mbar_wait(acc_full, 0);
         tc_fence_after();
-        if (EPI == EPI_STORE_F32) {
-            float* C = reinterpret_cast<float*>(p.C) + (long long)batch * p.c_batch + (long long)split * p.c_slab;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                float v[32];
-                tmem_ld32(trow + (uint32_t)c0, v);
-                if (m < p.M) {
-                    float* dst = C + (size_t)m * p.ldc + n0 + c0;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                        if (p.bias) {
-                            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + i));
-                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-                        }
-                        if (p.relu) {
-                            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                        }
-                        *reinterpret_cast<float4*>(dst + i) = o;
-                    }
-                }
-            }
-        } else if (EPI == EPI_CONV5_BF16) {
-            // H = relu(acc + b) stored as bf16; per-row sum of squares of the fp32 values for the later L2 norm
-            __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(p.C);
-            float ss = 0.f;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                float v[32];
-                tmem_ld32(trow + (uint32_t)c0, v);
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float2 bb = __ldg(reinterpret_cast<const float2*>(p.bias + n0 + c0 + i));
-                    const float x = fmaxf(v[i] + bb.x, 0.f), y = fmaxf(v[i + 1] + bb.y, 0.f);
-                    ss = fmaf(x, x, ss);
-                    ss = fmaf(y, y, ss);
-                    const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
-                    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-                }
-                if (m < p.M) {
-                    uint4* dst = reinterpret_cast<uint4*>(H + (size_t)m * p.ldc + n0 + c0);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-                }
-            }
-            if (m < p.M) p.aux[(size_t)m * gridDim.y + blockIdx.y] = ss;
-        } else if (EPI == EPI_COLMAX) {
-            // max over the tile's rows of relu(acc + b): values >= 0, so unsigned-int order == float order
-            const int cloud = m0 / p.rows_per_cloud;
-            int* g = reinterpret_cast<int*>(p.aux) + (size_t)cloud * p.N;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                float v[32];
-                tmem_ld32(trow + (uint32_t)c0, v);
-                unsigned mine = 0;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float x = (m < p.M) ? fmaxf(v[i] + __ldg(p.bias + n0 + c0 + i), 0.f) : 0.f;
-                    const unsigned r = __reduce_max_sync(FULL, __float_as_uint(x));
-                    if (lane == i) mine = r;
-                }
-                atomicMax(g + n0 + c0 + lane, (int)mine);
-            }
-        } else if (EPI == EPI_ASSIGN) {
-            // BN == 64: this thread owns all 64 cluster logits of its point (loupe.py:255-276)
-            float v[64];
-            {
-                float t[32];
-                tmem_ld32(trow, t);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = t[i];
-                tmem_ld32(trow + 32u, t);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[32 + i] = t[i];
-            }
-            float ssq = 0.f;
-            if (m < p.M)
-                for (int i = 0; i < p.rowss_parts; ++i) ssq += p.rowss[(size_t)m * p.rowss_parts + i];
-            const float inv = 1.0f / sqrtf(fmaxf(ssq, L2_EPS));
-            float mx = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < 64; ++i) {
-                v[i] = (v[i] * inv) * __ldg(p.bn_scale + i) + __ldg(p.bn_shift + i);
-                mx = fmaxf(mx, v[i]);
-            }
-            float den = 0.f;
-#pragma unroll
-            for (int i = 0; i < 64; ++i) {
-                v[i] = expf(v[i] - mx);
-                den += v[i];
-            }
-            const float rden = 1.0f / den;
-            // column sums of the soft assignment over this tile: stage through (now idle) pipeline smem
-            float* sS = reinterpret_cast<float*>(sA);        // [128][65]
-#pragma unroll
-            for (int i = 0; i < 64; ++i) {
-                v[i] *= rden;
-                sS[row * 65 + i] = (m < p.M) ? v[i] : 0.f;
-            }
-            if (m < p.M) {
-                uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)m * 64);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    uint32_t pk[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * i + 2 * j] * inv, v[8 * i + 2 * j + 1] * inv);
-                        pk[j] = *reinterpret_cast<const uint32_t*>(&h);
-                    }
-                    dst[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                }
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");     // the four epilogue warps only
-            const int t = threadIdx.x - 64;
-            if (t < 64) {
-                float a = 0.f;
-                for (int r = 0; r < TC_BM; ++r) a += sS[r * 65 + t];
-                p.aux[(size_t)blockIdx.x * 64 + t] = a;
-            }
-        }
+        EpiCtx c;
+        c.trow = trow; c.m = m; c.row = row; c.lane = lane; c.m0 = m0; c.n0 = n0; c.mtile = blockIdx.x;
+        c.nparts = gridDim.y; c.npart = blockIdx.y;
+        c.c_off = (long long)batch * p.c_batch + (long long)split * p.c_slab;
+        c.scratch = reinterpret_cast<float*>(sA); c.epi_tid = threadIdx.x - 64;
+        c.bias = p.bias ? p.bias + n0 : nullptr; c.col_begin = 0; c.col_end = BN;
+        epilogue_tile<BN, EPI>(p, c);
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Persistent, B-resident variant (both operands K-major).  The one-tile-per-CTA kernel re-fetches its B tile for
+// every 128-row tile, which makes conv5 (K = 256) and the assignment GEMM (N = 64) L2-bandwidth bound.  Here a CTA
+// owns one N tile, loads its whole [BN x K] slice of B once, and then streams 128-row A tiles through a ring:
+//   warp 0  TMA producer        warp 1  MMA issuer (accumulators double-buffered in TMEM: 2 x BN columns)
+//   warps 2-5  epilogue of tile i while the tensor core already works on tile i+1
+// grid.x = (#CTAs, a multiple of N/BN); CTA c: N tile c % (N/BN), row tiles c / (N/BN), + gridDim.x / (N/BN), ...
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, int BN, int EPI, int EW /*epilogue warps: 4, or 8 = two per TMEM lane quarter*/>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
+tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p,
+                    const int a_stages) {
+    using Tr = ElemTraits<T>;
+    constexpr int BK = Tr::PER128;
+    constexpr uint32_t A_BYTES = TC_BM * 128, B_BYTES = BN * 128;
+    constexpr size_t SCRATCH = (EPI == EPI_ASSIGN) ? (size_t)TC_BM * 65 * 4 : 0;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int nkb = p.K / BK;
+    uint8_t* sB = base;                                              // [nkb][BN x 128 B]   resident
+    uint8_t* sA = sB + (size_t)nkb * B_BYTES;                        // [a_stages][128 x 128 B] ring
+    float* scratch = reinterpret_cast<float*>(sA + (size_t)a_stages * A_BYTES);
+    float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + SCRATCH);     // [BN] bias of this N tile
+    uint64_t* full = reinterpret_cast<uint64_t*>(sBias + BN);
+    uint64_t* empty = full + a_stages;
+    uint64_t* b_full = empty + a_stages;
+    uint64_t* tfull = b_full + 1;          // [2] accumulator ready
+    uint64_t* tempty = tfull + 2;          // [2] accumulator drained (4 arrivals: one per epilogue warp)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NT = p.N / BN;
+    const int n_tile = blockIdx.x % NT, cta_m = blockIdx.x / NT, m_stride = gridDim.x / NT;
+    const int n0 = n_tile * BN;
+    const int num_m_tiles = (p.M + TC_BM - 1) / TC_BM;
+    constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < a_stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(b_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], EW);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    if (p.bias)
+        for (int i = threadIdx.x; i < BN; i += blockDim.x) sBias[i] = p.bias[n0 + i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(b_full, (uint32_t)nkb * B_BYTES);
+            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(sB + (size_t)kb * B_BYTES, &tmB, b_full, kb * BK, n0);
+            int it = 0;
+            for (int mt = cta_m; mt < num_m_tiles; mt += m_stride) {
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % a_stages;
+                    const uint32_t ph = (it / a_stages) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], A_BYTES);
+                    tma_load_2d(sA + (size_t)s * A_BYTES, &tmA, &full[s], kb * BK, mt * TC_BM);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(Tr::FMT, TC_BM, BN, 0, 0);
+            mbar_wait(b_full, 0);
+            int it = 0, tile = 0;
+            for (int mt = cta_m; mt < num_m_tiles; mt += m_stride, ++tile) {
+                const int buf = tile & 1;
+                mbar_wait(&tempty[buf], ((tile >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % a_stages;
+                    const uint32_t ph = (it / a_stages) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sA + (size_t)s * A_BYTES);
+                    const uint32_t b_addr = smem_u32(sB + (size_t)kb * B_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < BK / Tr::UMMA_K; ++kk) {
+                        const uint64_t da = smem_desc_sw128(a_addr + kk * 32, 16, 1024);
+                        const uint64_t db = smem_desc_sw128(b_addr + kk * 32, 16, 1024);
+                        mma_ss<Tr::F16>(tmem_d, da, db, idesc, (kb | kk) != 0);
+                    }
+                    mma_commit(&empty[s]);
+                }
+                mma_commit(&tfull[buf]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int tile = 0;
+        for (int mt = cta_m; mt < num_m_tiles; mt += m_stride, ++tile) {
+            const int buf = tile & 1;
+            mbar_wait(&tfull[buf], (tile >> 1) & 1);
+            tc_fence_after();
+            EpiCtx c;
+            c.trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+            c.m0 = mt * TC_BM; c.m = c.m0 + row; c.row = row; c.lane = lane; c.n0 = n0; c.mtile = mt;
+            c.c_off = 0; c.scratch = scratch; c.epi_tid = threadIdx.x - 64;
+            c.bias = p.bias ? sBias : nullptr;
+            constexpr int SPLIT = EW / 4;                       // warps per lane quarter
+            const int part = (warp - 2) >> 2;                   // which column share this warp drains
+            c.col_begin = part * (BN / SPLIT); c.col_end = c.col_begin + BN / SPLIT;
+            c.nparts = NT * SPLIT; c.npart = n_tile * SPLIT + part;
+            epilogue_tile<BN, EPI>(p, c);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 }  // namespace tc
@@ -506,6 +670,55 @@ inline int tc_gemm_launch(const Operand<T>& A, const Operand<T>& B, const tc::Ge
     }
     dim3 grid((p.M + tc::TC_BM - 1) / tc::TC_BM, p.N / BN, batch * p.splitk);
     kern<<<grid, 192, smem, st>>>(tmA, tmB, p, stages);
+    EPC_LAUNCH_CHECK();
+    return EPC_OK;
+}
+
+
+inline int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// Persistent B-resident launch: A [M,K], B [N,K] both K-major; one CTA per SM (rounded to a multiple of N/BN).
+template <typename T, int BN, int EPI, int EW = 4>
+inline int tc_gemm_bres_launch(const Operand<T>& A, const Operand<T>& B, const tc::GemmParams& p, cudaStream_t st) {
+    constexpr int BK = tc::ElemTraits<T>::PER128;
+    constexpr size_t A_BYTES = tc::TC_BM * 128, B_BYTES = BN * 128;
+    constexpr size_t SCRATCH = (EPI == tc::EPI_ASSIGN) ? (size_t)tc::TC_BM * 65 * 4 : 0;
+    EPC_CHECK_ARG(p.K % BK == 0 && p.K >= BK && p.N % BN == 0 && p.splitk == 1, "tc_gemm_bres: bad shape K=%d N=%d", p.K, p.N);
+    EPC_CHECK_ARG((reinterpret_cast<uintptr_t>(A.ptr) & 15) == 0 && (reinterpret_cast<uintptr_t>(B.ptr) & 15) == 0 &&
+                      (A.ld * sizeof(T)) % 16 == 0 && (B.ld * sizeof(T)) % 16 == 0,
+                  "tc_gemm_bres: operands must be 16-byte aligned with 16-byte pitches");
+    if (p.M == 0) return EPC_OK;
+    const int nkb = p.K / BK;
+    const size_t fixed = 1024 + (size_t)nkb * B_BYTES + SCRATCH + BN * 4 + 512;
+    int a_stages = (int)((227 * 1024 - fixed) / A_BYTES);
+    EPC_CHECK_ARG(a_stages >= 2, "tc_gemm_bres: B slice of %zu bytes leaves no room for the A ring", (size_t)nkb * B_BYTES);
+    if (a_stages > 8) a_stages = 8;
+    const size_t smem = fixed + (size_t)a_stages * A_BYTES;
+    CUtensorMap tmA, tmB;
+    if (int rc = make_tmap_2d(&tmA, A.ptr, A.rows, A.cols, A.ld, BK, tc::TC_BM)) return rc;
+    if (int rc = make_tmap_2d(&tmB, B.ptr, B.rows, B.cols, B.ld, BK, BN)) return rc;
+    static_assert(EW == 4 || (EW == 8 && EPI != tc::EPI_ASSIGN && BN >= 64), "8 epilogue warps split the tile's columns");
+    auto kern = tc::tc_gemm_bres_kernel<T, BN, EPI, EW>;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        EPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    const int NT = p.N / BN;
+    const int m_tiles = (p.M + tc::TC_BM - 1) / tc::TC_BM;
+    int per_nt = sm_count() / NT;
+    if (per_nt < 1) per_nt = 1;
+    if (per_nt > m_tiles) per_nt = m_tiles;
+    kern<<<per_nt * NT, 64 + 32 * EW, smem, st>>>(tmA, tmB, p, a_stages);
     EPC_LAUNCH_CHECK();
     return EPC_OK;
 }

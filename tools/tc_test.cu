@@ -72,17 +72,18 @@ template <int BN> int test_tf32_store(int M, int N, int K, bool timing) {
 }
 
 // ---- T2: bf16 conv5 epilogue: H = bf16(relu(A B^T + b)), rowss partials ---------------------------------------------
-template <int BN> int test_bf16_conv5(int M, int N, int K, bool timing) {
+template <int BN, bool PERSIST = false> int test_bf16_conv5(int M, int N, int K, bool timing) {
     std::vector<float> A((size_t)M * K), B((size_t)N * K), bias(N);
     for (auto& v : A) v = rnd_exact(8);
     for (auto& v : B) v = rnd_exact(8);
     for (auto& v : bias) v = rnd_exact(16);
     bf16 *dA = to_dev(to_bf16(A)), *dB = to_dev(to_bf16(B)), *dH; float* db = to_dev(bias); float* dss;
-    const int parts = N / BN;
+    const int parts = (N / BN) * (PERSIST ? 2 : 1);
     CK(cudaMalloc(&dH, (size_t)M * N * 2)); CK(cudaMalloc(&dss, (size_t)M * parts * 4));
     tc::GemmParams p = {}; p.M = M; p.N = N; p.K = K; p.splitk = 1; p.C = dH; p.ldc = N; p.bias = db; p.relu = 1; p.aux = dss;
     Operand<bf16> oa{dA, M, K, K}, ob{dB, N, K, K};
-    auto run = [&]() { return tc_gemm_launch<bf16, BN, false, false, tc::EPI_CONV5_BF16>(oa, ob, p, 1, 0, 2); };
+    auto run = [&]() { return PERSIST ? tc_gemm_bres_launch<bf16, BN, tc::EPI_CONV5_BF16, 8>(oa, ob, p, 0)
+                                      : tc_gemm_launch<bf16, BN, false, false, tc::EPI_CONV5_BF16>(oa, ob, p, 1, 0, 2); };
     if (run() || !sync_ok("bf16_conv5")) return 1;
     std::vector<bf16> H((size_t)M * N); std::vector<float> ss((size_t)M * parts);
     CK(cudaMemcpy(H.data(), dH, H.size() * 2, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(ss.data(), dss, ss.size() * 4, cudaMemcpyDeviceToHost));
@@ -92,19 +93,19 @@ template <int BN> int test_bf16_conv5(int M, int N, int K, bool timing) {
         for (int n = 0; n < N; ++n) {
             float acc = 0.f; for (int k = 0; k < K; ++k) acc += A[(size_t)m * K + k] * B[(size_t)n * K + k];
             acc = fmaxf(acc + bias[n], 0.f);
-            s2[n / BN] += (double)acc * acc;
+            s2[PERSIST ? n / (BN / 2) : n / BN] += (double)acc * acc;
             if (__bfloat162float(H[(size_t)m * N + n]) != bf16_round(acc)) { if (bad < 3) printf("  H(%d,%d) got %g want %g\n", m, n, __bfloat162float(H[(size_t)m * N + n]), bf16_round(acc)); ++bad; }
         }
         for (int q = 0; q < parts; ++q) if (fabs(ss[(size_t)m * parts + q] - s2[q]) > 1e-5 * (1 + s2[q])) { if (bad < 3) printf("  rowss(%d,%d) got %g want %g\n", m, q, ss[(size_t)m * parts + q], s2[q]); ++bad; }
     }
-    printf("T2 bf16 conv5   M=%d N=%d K=%d BN=%d : %s\n", M, N, K, BN, bad ? "FAIL" : "exact");
+    printf("T2 bf16 conv5%s M=%d N=%d K=%d BN=%d : %s\n", PERSIST ? "(P)" : "   ", M, N, K, BN, bad ? "FAIL" : "exact");
     if (timing && !bad) { float ms = time_ms(run); printf("    %.3f ms  %.1f TFLOP/s\n", ms, 2.0 * M * N * K / ms * 1e-9); }
     cudaFree(dA); cudaFree(dB); cudaFree(db); cudaFree(dH); cudaFree(dss);
     return bad != 0;
 }
 
 // ---- T3: bf16 assignment epilogue (N = 64) -----------------------------------------------------------------------
-int test_bf16_assign(int M, int K, bool timing) {
+int test_bf16_assign(int M, int K, bool timing, bool persist = false) {
     const int N = 64, parts = 4;
     std::vector<float> A((size_t)M * K), B((size_t)N * K), rowss((size_t)M * parts), sc(N), sh(N);
     for (auto& v : A) v = fabsf(rnd_exact(8));
@@ -118,7 +119,8 @@ int test_bf16_assign(int M, int K, bool timing) {
     tc::GemmParams p = {}; p.M = M; p.N = N; p.K = K; p.splitk = 1; p.C = dS; p.ldc = 64; p.aux = dap; p.rowss = dr; p.rowss_parts = parts;
     p.bn_scale = dsc; p.bn_shift = dsh;
     Operand<bf16> oa{dA, M, K, K}, ob{dB, N, K, K};
-    auto run = [&]() { return tc_gemm_launch<bf16, 64, false, false, tc::EPI_ASSIGN>(oa, ob, p, 1, 0, 1); };
+    auto run = [&]() { return persist ? tc_gemm_bres_launch<bf16, 64, tc::EPI_ASSIGN>(oa, ob, p, 0)
+                                      : tc_gemm_launch<bf16, 64, false, false, tc::EPI_ASSIGN>(oa, ob, p, 1, 0, 1); };
     if (run() || !sync_ok("bf16_assign")) return 1;
     std::vector<bf16> S((size_t)M * 64); std::vector<float> ap((size_t)tiles * 64);
     CK(cudaMemcpy(S.data(), dS, S.size() * 2, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(ap.data(), dap, ap.size() * 4, cudaMemcpyDeviceToHost));
@@ -143,7 +145,7 @@ int test_bf16_assign(int M, int K, bool timing) {
         }
         for (int n = 0; n < 64; ++n) if (fabs(ap[(size_t)t * 64 + n] - colsum[n]) > 1e-4 * (1 + colsum[n])) { if (bad < 3) printf("  a_part(%d,%d) got %g want %g\n", t, n, ap[(size_t)t * 64 + n], colsum[n]); ++bad; }
     }
-    printf("T3 bf16 assign  M=%d K=%d : %s\n", M, K, bad ? "FAIL" : "ok");
+    printf("T3 bf16 assign%s M=%d K=%d : %s\n", persist ? "(P)" : "   ", M, K, bad ? "FAIL" : "ok");
     if (timing && !bad) { float ms = time_ms(run); printf("    %.3f ms  %.1f TFLOP/s\n", ms, 2.0 * M * N * K / ms * 1e-9); }
     cudaFree(dA); cudaFree(dB); cudaFree(dS); cudaFree(dr); cudaFree(dsc); cudaFree(dsh); cudaFree(dap);
     return bad != 0;
@@ -178,7 +180,7 @@ int test_bf16_vlad(int batch, int Npts, int F, int splitk, bool timing) {
 }
 
 // ---- T5: tf32 column-max epilogue ---------------------------------------------------------------------------------
-template <int BN> int test_tf32_colmax(int clouds, int Npts, int N, int K, bool timing) {
+template <int BN> int test_tf32_colmax(int clouds, int Npts, int N, int K, bool timing, bool persist = false) {
     const int M = clouds * Npts;
     std::vector<float> A((size_t)M * K), B((size_t)N * K), bias(N), G((size_t)clouds * N);
     for (auto& v : A) v = rnd_exact(8);
@@ -187,7 +189,9 @@ template <int BN> int test_tf32_colmax(int clouds, int Npts, int N, int K, bool 
     float *dA = to_dev(A), *dB = to_dev(B), *db = to_dev(bias), *dG; CK(cudaMalloc(&dG, G.size() * 4));
     tc::GemmParams p = {}; p.M = M; p.N = N; p.K = K; p.splitk = 1; p.bias = db; p.aux = dG; p.rows_per_cloud = Npts;
     Operand<float> oa{dA, M, K, K}, ob{dB, N, K, K};
-    auto run = [&]() { cudaMemsetAsync(dG, 0, G.size() * 4, 0); return tc_gemm_launch<float, BN, false, false, tc::EPI_COLMAX>(oa, ob, p, 1, 0, 2); };
+    auto run = [&]() { cudaMemsetAsync(dG, 0, G.size() * 4, 0);
+                       return persist ? tc_gemm_bres_launch<float, BN, tc::EPI_COLMAX, 8>(oa, ob, p, 0)
+                                      : tc_gemm_launch<float, BN, false, false, tc::EPI_COLMAX>(oa, ob, p, 1, 0, 2); };
     if (run() || !sync_ok("tf32_colmax")) return 1;
     CK(cudaMemcpy(G.data(), dG, G.size() * 4, cudaMemcpyDeviceToHost));
     size_t bad = 0; const int nstep = M > 4096 ? 61 : 1;
@@ -196,7 +200,7 @@ template <int BN> int test_tf32_colmax(int clouds, int Npts, int N, int K, bool 
         for (int r = 0; r < Npts; ++r) { float acc = 0.f; const float* a = &A[((size_t)b * Npts + r) * K]; for (int k = 0; k < K; ++k) acc += a[k] * B[(size_t)n * K + k]; mx = fmaxf(mx, acc + bias[n]); }
         if (G[(size_t)b * N + n] != mx) { if (bad < 3) printf("  g(%d,%d) got %g want %g\n", b, n, G[(size_t)b * N + n], mx); ++bad; }
     }
-    printf("T5 tf32 colmax  clouds=%d N=%d K=%d BN=%d : %s\n", clouds, N, K, BN, bad ? "FAIL" : "exact");
+    printf("T5 tf32 colmax%s clouds=%d N=%d K=%d BN=%d : %s\n", persist ? "(P)" : "   ", clouds, N, K, BN, bad ? "FAIL" : "exact");
     if (timing && !bad) { float ms = time_ms(run); printf("    %.3f ms  %.1f TFLOP/s\n", ms, 2.0 * M * N * K / ms * 1e-9); }
     cudaFree(dA); cudaFree(dB); cudaFree(db); cudaFree(dG);
     return bad != 0;
@@ -212,6 +216,12 @@ int main() {
     fails += test_bf16_vlad(2, 256, 128, 1, false);
     fails += test_bf16_vlad(2, 512, 256, 2, false);
     fails += test_tf32_colmax<256>(2, 256, 256, 128, false);
+    fails += test_bf16_conv5<256, true>(256, 512, 256, false);
+    fails += test_bf16_conv5<256, true>(40000, 1024, 256, false);
+    fails += test_bf16_assign(300, 1024, false, true);
+    fails += test_bf16_assign(40000, 1024, false, true);
+    fails += test_tf32_colmax<256>(2, 256, 256, 128, false, true);
+    fails += test_tf32_colmax<256>(3, 4096, 1024, 128, false, true);
     printf(fails ? "SOME CORRECTNESS TESTS FAILED (%d)\n" : "ALL CORRECT\n", fails);
     // production shapes (32 clouds x 4096 points)
     test_tf32_store<256>(131072, 1024, 256, true);
@@ -221,5 +231,12 @@ int main() {
     test_bf16_vlad(32, 4096, 1024, 1, true);
     test_bf16_vlad(32, 4096, 1024, 2, true);
     test_tf32_colmax<256>(32, 4096, 1024, 128, true);
+    printf("-- persistent B-resident variants, 8 clouds (the head's L2-resident sub-batch) and 32 clouds\n");
+    test_bf16_conv5<256, false>(32768, 1024, 256, true);
+    test_bf16_conv5<256, true>(32768, 1024, 256, true);
+    test_bf16_conv5<256, true>(131072, 1024, 256, true);
+    test_bf16_assign(32768, 1024, true, false);
+    test_bf16_assign(32768, 1024, true, true);
+    test_tf32_colmax<256>(32, 4096, 1024, 128, true, true);
     return fails;
 }
