@@ -185,7 +185,7 @@ const char* epc_stage_name(int stage) {
     static const char* names[EPC_STAGE_COUNT] = {"sort", "knn", "conv_in", "proxy_block", "conv5", "rownorm",
                                                  "assign_gemm", "assign_softmax", "vlad_gemm", "vlad_finalize",
                                                  "hidden_gemm", "tail", "colmax", "fc", "kd_feat", "retrieve_score",
-                                                 "retrieve_select", "retrieve_rerank"};
+                                                 "retrieve_select", "retrieve_rerank", "proxy_block_safe"};
     return (stage >= 0 && stage < EPC_STAGE_COUNT) ? names[stage] : "?";
 }
 
@@ -328,15 +328,20 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
     Packer pk;
     std::vector<float> W, b, sc, sh;
     size_t offW[13], offb[13], offI[13];
-    std::vector<float> img(4096);
+    std::vector<uint16_t> img(4096);
+    std::vector<float> img32(4096);
+    size_t offI32[13];
     for (int i = 0; i < 3 * nb; ++i) {
         fold_dense(w->conv[i], W, b);
         offW[i] = pk.add(W); offb[i] = pk.add(b);
         offI[i] = 0;
+        offI32[i] = 0;
         if (i > 0) {
-            for (auto& x : W) x = host_round_tf32(x);
             make_w64_image(W.data(), img.data());
-            offI[i] = pk.add(img);
+            offI[i] = pk.add(reinterpret_cast<const float*>(img.data()), img.size() / 2);
+            for (auto& x : W) x = host_round_tf32(x);
+            make_w64_image_f32(W.data(), img32.data());
+            offI32[i] = pk.add(img32);
         }
     }
     fold_dense(w->conv5, W, b);
@@ -399,7 +404,8 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
         return EPC_ECUDA;
     }
     for (int i = 0; i < 3 * nb; ++i)
-        m->conv[i] = DenseDev{m->blob + offW[i], m->blob + offb[i], w->conv[i].cin, 64, i > 0 ? m->blob + offI[i] : nullptr};
+        m->conv[i] = DenseDev{m->blob + offW[i], m->blob + offb[i], w->conv[i].cin, 64, i > 0 ? m->blob + offI[i] : nullptr,
+                              i > 0 ? m->blob + offI32[i] : nullptr};
     m->W5t = m->blob + offW[12];
     m->b5 = m->blob + offb[12];
     if (vlad) {
@@ -408,7 +414,7 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
         m->Wh = m->blob + oWh; m->hbn_scale = m->blob + oHs; m->hbn_shift = m->blob + oHh;
         if (w->gating) { m->Wg = m->blob + oWg; m->gbn_scale = m->blob + oGs; m->gbn_shift = m->blob + oGh; }
     } else {
-        m->fc1 = DenseDev{m->blob + oFW, m->blob + oFb, 1024, w->output_dim, nullptr};
+        m->fc1 = DenseDev{m->blob + oFW, m->blob + oFb, 1024, w->output_dim, nullptr, nullptr};
     }
     *out = m;
     return EPC_OK;
@@ -509,7 +515,7 @@ size_t epc_embed_workspace_bytes(const EpcModel* m, int B, int N) {
     const size_t R = (size_t)B * N;
     const size_t sub = (size_t)(B < HEAD_SUB ? B : HEAD_SUB) * N;
     const int ctot = 64 * m->n_blocks;
-    size_t s = knn_state_bytes(B, N) + 2 * align_up(R * 64 * 4) + align_up(R * ctot * 4) /*concat32 (L, or KD export)*/ +
+    size_t s = knn_state_bytes(B, N) + 2 * align_up(R * 64 * 2) + 2 * align_up(R * 64 * 4) + align_up((size_t)B * 4) + align_up(R * ctot * 4) /*concat32 (L, or KD export)*/ +
                align_up(R * ctot * 2) /*concat16*/ + align_up(sub * 1024 * 4) /*H32 (KD export)*/ + align_up(sub * 4);
     if (m->vlad_head)
         s += head_bytes(m, B, N);
@@ -537,8 +543,11 @@ int epc_embed(const EpcModel* m, const float* xyz, int B, int N, int knn_arith, 
     const bool want32 = !m->vlad_head || feat != nullptr;     // fp32 concat: TF32 conv5 of EPC-Net-L and the KD feature export
     Arena ar(workspace, workspace_bytes);
     KnnState ks = knn_state_carve(ar, B, N);
-    float* xa = ar.take<float>(R * 64);
-    float* xb = ar.take<float>(R * 64);
+    uint16_t* xa = ar.take<uint16_t>(R * 64);
+    uint16_t* xb = ar.take<uint16_t>(R * 64);
+    float* xa32 = ar.take<float>(R * 64);                      // fp32 activations of the range-safe pass (flagged clouds only)
+    float* xb32 = ar.take<float>(R * 64);
+    int* flags = ar.take<int>(B);                              // clouds whose activations left the fp16 range
     float* concat32 = ar.take<float>(R * ctot);
     __nv_bfloat16* concat16 = ar.take<__nv_bfloat16>(R * ctot);
     float* H32 = ar.take<float>((size_t)subB * N * 1024);
@@ -547,21 +556,38 @@ int epc_embed(const EpcModel* m, const float* xyz, int B, int N, int knn_arith, 
     if (int rc = knn_build(xyz, B, N, knn_arith, true, ks.sorted, ks.perm, ks.aabb, ks.nbr, ks.kthd, ks.cnt, nullptr, nullptr,
                            nullptr, st))
         return rc;
+    // ProxyConv chain: fp16 fast pass over every cloud, then the range-safe fp32 pass over the clouds it flagged
+    EPC_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)B, st));
     {
-        ScopedStage ss(EPC_STAGE_CONV_IN, st);
-        if (int rc = conv_in(ks.sorted, (long long)R, m->conv[0], xa, st)) return rc;
-    }
-    float *cur = xa, *nxt = xb;
-    for (int blk = 0; blk < nb; ++blk) {
-        const DenseDev* next = (blk + 1 < nb) ? &m->conv[3 * (blk + 1)] : nullptr;
         {
-            ScopedStage ss(EPC_STAGE_BLOCK, st);
-            if (int rc = proxy_block(cur, ks, B, N, knn_arith, m->divisor, m->conv[3 * blk + 1], m->conv[3 * blk + 2],
-                                     next, want32 ? concat32 : nullptr, m->vlad_head ? concat16 : nullptr, ctot,
-                                     64 * blk, nxt, st))
-                return rc;
+            ScopedStage ss(EPC_STAGE_CONV_IN, st);
+            if (int rc = conv_in(ks.sorted, B, N, m->conv[0], xa, flags, st)) return rc;
         }
-        float* t = cur; cur = nxt; nxt = t;
+        uint16_t *cur = xa, *nxt = xb;
+        for (int blk = 0; blk < nb; ++blk) {
+            const DenseDev* next = (blk + 1 < nb) ? &m->conv[3 * (blk + 1)] : nullptr;
+            {
+                ScopedStage ss(EPC_STAGE_BLOCK, st);
+                if (int rc = proxy_block(cur, ks, B, N, knn_arith, m->divisor, m->conv[3 * blk + 1], m->conv[3 * blk + 2],
+                                         next, want32 ? concat32 : nullptr, m->vlad_head ? concat16 : nullptr, ctot,
+                                         64 * blk, nxt, flags, st))
+                    return rc;
+            }
+            uint16_t* t = cur; cur = nxt; nxt = t;
+        }
+    }
+    {
+        ScopedStage ss(EPC_STAGE_BLOCK_SAFE, st);
+        if (int rc = conv_in_f32(ks.sorted, B, N, m->conv[0], xa32, flags, st)) return rc;
+        float *cur = xa32, *nxt = xb32;
+        for (int blk = 0; blk < nb; ++blk) {
+            const DenseDev* next = (blk + 1 < nb) ? &m->conv[3 * (blk + 1)] : nullptr;
+            if (int rc = proxy_block_f32(flags, cur, ks, B, N, knn_arith, m->divisor, m->conv[3 * blk + 1], m->conv[3 * blk + 2],
+                                         next, want32 ? concat32 : nullptr, m->vlad_head ? concat16 : nullptr, ctot,
+                                         64 * blk, nxt, st))
+                return rc;
+            float* t = cur; cur = nxt; nxt = t;
+        }
     }
     // KD feature export (models/kd_epc-net.py:158): l2norm(relu(BN(conv5))) per point, fp32 via TF32 tensor cores
     auto export_feat = [&](int b0, int nbs) -> int {

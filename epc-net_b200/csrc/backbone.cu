@@ -2,355 +2,590 @@
 //
 // The reference realises  m_i = (1/20) sum_{j in N(i)} x_j  as a dense (N x N mask) x (N x 64) batch
 // matmul per block (2.15 GFLOP and a 64 MiB read each).  Here the neighbour lists of K1 are gathered
-// directly (20 x 256 B rows per point, L2/L1 resident thanks to the Morton order), and the block body
+// directly (20 x 128 B bf16 rows per point, L1/L2 resident thanks to the Morton order), and the block body
 //     t = m - x ; t = conv_a(t) ; t = conv_b(t) ; out = t + m ; x' = conv_{b+1}(out)
 // runs on the tile while it is in shared memory.  Rows whose thresholded set has > 20 members (ties at
 // the 20th distance, utils/tf_util.py:663-665) take an exact dense re-scan of the cloud.
+//
+// Activations between blocks travel in a 16-bit format (fp16, or bf16 for clouds that leave the fp16 range -- see
+// FMT_* below), fp32 accumulation everywhere; the three 64x64 layers run on tcgen05 (kind::f16) with TMEM accumulators.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "tc_gemm.cuh"
 #include "kernels.h"
 
 namespace epc {
 
-// x0 = relu(BN(p W1 + b1)), cin = 3  (models/epc-net.py:66-69)
-__global__ void conv_in_kernel(const float4* __restrict__ sorted, long long R, const float* __restrict__ W,
-                               const float* __restrict__ bias, float* __restrict__ x) {
+// ---- 16-bit storage formats of the inter-block activations ------------------------------------------------------
+//   FMT_F16  fast path: fp16 = the TF32 operand precision (10-bit mantissa); conversions saturate and every producer
+//            checks its fp32 values against the fp16 range -- a cloud whose activations leave it is flagged;
+//            and re-done afterwards by the fp32/TF32 pass of backbone_f32.cu (e.g. the all-zero "fake" clouds of
+//            evaluate.py:425-430, whose thresholded neighbour sets hold all N points so that activations grow by N/20
+//            per block);
+//   FMT_BF16 the bf16 slice of the concat buffer (operand of the bf16 conv5 GEMM).
+enum { FMT_F16 = 0, FMT_BF16 = 1 };
+constexpr float F16_MAX = 65504.f;
+
+template <int FMT>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {      // (a,b) -> 16-bit pair, a in the low half
+    uint32_t r;
+    if (FMT == FMT_F16)
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    else
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+template <int FMT>
+__device__ __forceinline__ float2 unpack2(uint32_t u) {
+    if (FMT == FMT_F16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+// lo += (float)u.lo ; hi += (float)u.hi   (one mixed-precision FHADD each on sm_100)
+template <int FMT>
+__device__ __forceinline__ void add2(float& lo, float& hi, uint32_t u) {
+    if (FMT == FMT_F16)
+        asm("{.reg .f16 l, h; mov.b32 {l, h}, %2; add.rn.f32.f16 %0, l, %0; add.rn.f32.f16 %1, h, %1;}" : "+f"(lo), "+f"(hi) : "r"(u));
+    else
+        asm("{.reg .b16 l, h; mov.b32 {l, h}, %2; add.rn.f32.bf16 %0, l, %0; add.rn.f32.bf16 %1, h, %1;}" : "+f"(lo), "+f"(hi) : "r"(u));
+}
+template <int FMT>
+__device__ __forceinline__ void add8(float (&acc)[8], const uint4& v) {
+    add2<FMT>(acc[0], acc[1], v.x);
+    add2<FMT>(acc[2], acc[3], v.y);
+    add2<FMT>(acc[4], acc[5], v.z);
+    add2<FMT>(acc[6], acc[7], v.w);
+}
+template <int FMT>
+__device__ __forceinline__ uint4 pack8(const float (&o)[8]) {
+    return make_uint4(pack2<FMT>(o[0], o[1]), pack2<FMT>(o[2], o[3]), pack2<FMT>(o[4], o[5]), pack2<FMT>(o[6], o[7]));
+}
+__device__ __forceinline__ float max8(const float (&o)[8]) {
+    return fmaxf(fmaxf(fmaxf(o[0], o[1]), fmaxf(o[2], o[3])), fmaxf(fmaxf(o[4], o[5]), fmaxf(o[6], o[7])));
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void load_bias8(uint32_t addr, float (&b)[8]) {
+    const uint4 lo = lds128(addr), hi = lds128(addr + 16);
+    b[0] = __uint_as_float(lo.x); b[1] = __uint_as_float(lo.y); b[2] = __uint_as_float(lo.z); b[3] = __uint_as_float(lo.w);
+    b[4] = __uint_as_float(hi.x); b[5] = __uint_as_float(hi.y); b[6] = __uint_as_float(hi.z); b[7] = __uint_as_float(hi.w);
+}
+// x0 = relu(BN(p W1 + b1)), cin = 3  (models/epc-net.py:66-69) -> 16-bit [B,N,64].  grid (N*8/256, B)
+template <int FMT>
+__global__ void conv_in_kernel(const float4* __restrict__ sorted, int N, const float* __restrict__ W,
+                               const float* __restrict__ bias, uint16_t* __restrict__ x, int* __restrict__ flags) {
+    const int b = blockIdx.y;
+    if (FMT == FMT_BF16 && flags[b] == 0) return;
     __shared__ float sW[3 * 64 + 64];
     for (int i = threadIdx.x; i < 3 * 64 + 64; i += blockDim.x) sW[i] = (i < 192) ? W[i] : bias[i - 192];
     __syncthreads();
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long r = t >> 4;
-    const int c4 = (int)(t & 15) * 4;
-    if (r >= R) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = t >> 3;
+    const int c8 = (t & 7) * 8;
+    if (n >= N) return;
+    const size_t r = (size_t)b * N + n;
     const float4 p = sorted[r];
-    float4 o;
-    float* op = reinterpret_cast<float*>(&o);
+    float o[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int c = c4 + i;
+    for (int i = 0; i < 8; ++i) {
+        const int c = c8 + i;
         float acc = sW[192 + c];
         acc = fmaf(p.x, sW[c], acc);
         acc = fmaf(p.y, sW[64 + c], acc);
         acc = fmaf(p.z, sW[128 + c], acc);
-        op[i] = fmaxf(acc, 0.f);
+        o[i] = fmaxf(acc, 0.f);
     }
-    *reinterpret_cast<float4*>(x + r * 64 + c4) = o;
+    if (FMT == FMT_F16 && max8(o) > F16_MAX) flags[b] = 1;
+    *reinterpret_cast<uint4*>(x + r * 64 + c8) = pack8<FMT>(o);
 }
 
-int conv_in(const float4* sorted, long long R, const DenseDev& L, float* x, cudaStream_t st) {
+int conv_in(const float4* sorted, int B, int N, const DenseDev& L, uint16_t* x, int* flags, cudaStream_t st) {
     EPC_CHECK_ARG(L.cin == 3 && L.cout == 64, "conv_in expects a 3->64 layer, got %d->%d", L.cin, L.cout);
-    if (R == 0) return EPC_OK;
-    const long long threads = R * 16;
-    conv_in_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(sorted, R, L.W, L.b, x);
+    if (B == 0) return EPC_OK;
+    dim3 grid((N * 8 + 255) / 256, B);
+    conv_in_kernel<FMT_F16><<<grid, 256, 0, st>>>(sorted, N, L.W, L.b, x, flags);
     EPC_LAUNCH_CHECK();
     return EPC_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
-// ProxyConv block on tcgen05 tensor cores (TF32).  One CTA = 128 consecutive (Morton-ordered) points:
-//   gather  : all 8 warps; warp per point, lane = channel pair; 20 x 256 B row loads in flight per warp
-//   GEMM a/b/n : [128 x 64] . [64 x 64] on the tensor cores, accumulator in TMEM; the A operand tile lives in
-//               shared memory in the UMMA K-major 128B-swizzle layout and is rewritten in place by the epilogue
-//               warps (t -> relu(conv_a) -> x_b), so activations never leave the SM between the three layers.
-// Weights arrive as pre-swizzled 16 KB shared-memory images (prepared once at model creation).
+// ProxyConv block: persistent, warp-specialised, one CTA per SM, tiles of 128 consecutive (Morton-ordered) points.
+//
+//   warps 8..23  GATHER   lane group (8 lanes) per point, 16 B of each 128 B neighbour row per lane.  The tile's own
+//                         128 rows (69 % of all neighbour links in Morton order) are brought into shared memory by one
+//                         TMA bulk copy, a tile ahead; K1 lists each point's out-of-tile neighbours first, so those go
+//                         out as LDG.128 (up to 10 in flight per lane) while the in-tile rows are summed from shared
+//                         memory.  fp32 accumulation (FHADD); writes m (16-bit) and t = m - x (the UMMA A tile, K-major
+//                         SW128) of ring stage s, then arrives on full[s]
+//   warps 0..3 / 4..7     two CONSUMER groups alternating tiles; thread = point (= TMEM lane).  Per tile
+//                         MMA conv_a -> relu -> A tile (in place) -> MMA conv_b -> relu + m -> A tile, block output
+//                         (bf16 concat slice via smem staging, coalesced) -> MMA conv_{b+1} -> relu -> 16-bit x' (staged,
+//                         coalesced); thread 0 of the group issues the tcgen05.mma's, accumulators live in TMEM.
+// Shared memory: 3 weight images (8 KB each, pre-swizzled at model creation) + 4 stages x (A 16 KB + m 16 KB + window 16 KB).
 // ------------------------------------------------------------------------------------------------
 constexpr int PB_TILE = 128;
-constexpr int PB_THREADS = 256;
-constexpr int PB_MLD = 68;                       // row stride (floats) of the fp32 neighbour-mean tile (16 B aligned rows)
-constexpr uint32_t PB_A_BYTES = 2 * 128 * 128;   // A tile: 2 k-blocks x 128 rows x 128 B
-constexpr uint32_t PB_W_BYTES = 2 * 64 * 128;    // weight image: 2 k-blocks x 64 rows x 128 B
-constexpr size_t PB_SMEM = 1024 + PB_A_BYTES + 2 * PB_W_BYTES + PB_TILE * PB_MLD * 4 + 3 * 64 * 4 + 64 +
-                           PB_TILE * KNN_K * 2 + PB_TILE * 4;
+constexpr int PB_CONS_WARPS = 8;                 // 2 groups x 4
+constexpr int PB_GATHER_WARPS = 16;
+constexpr int PB_THREADS = 32 * (PB_CONS_WARPS + PB_GATHER_WARPS);
+constexpr int PB_STAGES = 4;                     // A/M ring (gather -> consumers)
+constexpr int PB_WSTAGES = 3;                    // window ring (TMA -> gather), filled two tiles ahead
+constexpr uint32_t PB_A_BYTES = 128 * 128;       // 128 rows x 64 x 16 bit
+constexpr uint32_t PB_W_BYTES = 64 * 128;        // 64 rows (cout) x 64 (cin) x 16 bit
+constexpr uint32_t PB_NBR_BYTES = PB_TILE * KNN_K * 2;     // 5120
+constexpr uint32_t PB_CNT_BYTES = PB_TILE * 4;             // 512
+constexpr uint32_t PB_STAGE_BYTES = 2 * PB_A_BYTES;        // A | M            (SW128 tiles: 1024 B aligned)
+constexpr uint32_t PB_WSTAGE_BYTES = (PB_A_BYTES + PB_NBR_BYTES + PB_CNT_BYTES + 1023) / 1024 * 1024;     // window | nbr | cnt
+// offsets from the 1024-aligned base
+constexpr uint32_t PB_OFF_W = 0;
+constexpr uint32_t PB_OFF_STAGE = 3 * PB_W_BYTES;
+constexpr uint32_t PB_OFF_WSTAGE = PB_OFF_STAGE + PB_STAGES * PB_STAGE_BYTES;
+constexpr uint32_t PB_OFF_BIAS = PB_OFF_WSTAGE + PB_WSTAGES * PB_WSTAGE_BYTES;
+constexpr uint32_t PB_OFF_BAR = PB_OFF_BIAS + 3 * 64 * 4;          // full[S] empty[S] wfull[WS] wempty[WS] mma[2]
+constexpr uint32_t PB_OFF_TMEM = PB_OFF_BAR + (2 * PB_STAGES + 2 * PB_WSTAGES + 2) * 8;
+constexpr size_t PB_SMEM = 1024 + PB_OFF_TMEM + 16;
+static_assert(PB_SMEM <= 227 * 1024, "proxy_block shared memory");
+static_assert(PB_STAGE_BYTES % 1024 == 0 && PB_OFF_STAGE % 1024 == 0, "UMMA SW128 tiles must be 1024-byte aligned");
+// per stage
+constexpr uint32_t PB_ST_A = 0, PB_ST_M = PB_A_BYTES;
+constexpr uint32_t PB_WS_WIN = 0, PB_WS_NBR = PB_A_BYTES, PB_WS_CNT = PB_A_BYTES + PB_NBR_BYTES;
 
-// byte offset of the 16-byte chunk holding channels [4*k4, 4*k4+4) of row r in a [rows x 64] fp32 K-major SW128 tile
-__device__ __forceinline__ uint32_t sw128_chunk(int r, int k4, uint32_t kblock_bytes) {
-    return (uint32_t)(k4 >> 3) * kblock_bytes + (uint32_t)r * 128u + (uint32_t)(((k4 & 7) ^ (r & 7)) << 4);
+// byte offset of 16-byte chunk c (8 channels) of row r in a [rows x 64] 16-bit K-major SW128 tile
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4); }
+
+// mbarrier helpers on shared-space addresses (no generic->shared conversion per call)
+__device__ __forceinline__ void bar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool bar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {          // short waits (MMA completion)
+    while (!bar_try(bar, parity)) {}
+}
+template <int NS = 128>
+__device__ __forceinline__ void bar_wait_backoff(uint32_t bar, uint32_t parity) {  // long waits: leave the issue slots to the others
+    while (!bar_try(bar, parity)) __nanosleep(NS);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mma_commit_u32(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void pb_issue_gemm(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, uint64_t* bar) {
-    constexpr uint32_t idesc = tc::make_idesc(2 /*TF32*/, 128, 64, 0, 0);
+template <int FMT>
+__device__ __forceinline__ void pb_issue_gemm(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, uint32_t bar) {
+    constexpr uint32_t idesc = tc::make_idesc(FMT == FMT_F16 ? 0 : 1, 128, 64, 0, 0);
 #pragma unroll
-    for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t da = tc::smem_desc_sw128(a_addr + kb * (PB_A_BYTES / 2) + kk * 32, 16, 1024);
-            const uint64_t db = tc::smem_desc_sw128(w_addr + kb * (PB_W_BYTES / 2) + kk * 32, 16, 1024);
-            tc::mma_ss<false>(tmem_d, da, db, idesc, (kb | kk) != 0);
-        }
-    tc::mma_commit(bar);
+    for (int kk = 0; kk < 4; ++kk) {
+        const uint64_t da = tc::smem_desc_sw128(a_addr + kk * 32, 16, 1024);
+        const uint64_t db = tc::smem_desc_sw128(w_addr + kk * 32, 16, 1024);
+        tc::mma_ss<true>(tmem_d, da, db, idesc, kk != 0);
+    }
+    mma_commit_u32(bar);
 }
 
-template <bool HAS_NEXT>
-__global__ void __launch_bounds__(PB_THREADS, 2)
-proxy_block_kernel(const float* __restrict__ x, const uint16_t* __restrict__ nbr, const float* __restrict__ kthd,
-                   const int* __restrict__ cnt, const float4* __restrict__ sorted, int N, int arith, float divisor,
-                   const float* __restrict__ Wa_img, const float* __restrict__ ba, const float* __restrict__ Wb_img,
-                   const float* __restrict__ bb, const float* __restrict__ Wn_img, const float* __restrict__ bn,
-                   float* __restrict__ concat, __nv_bfloat16* __restrict__ concat16, int ctot, int coff,
-                   float* __restrict__ xnext) {
+__device__ __forceinline__ void group_sync(int group) { asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory"); }
+
+struct PbArgs {
+    const uint16_t* x;        // [B,N,64] 16-bit block input (output of the block's first conv)
+    const uint16_t* nbr;      // [B,N,20] neighbour positions, out-of-tile ones first
+    const float* kthd;        // [B,N]
+    const int* cnt;           // [B,N]  |thresholded set| | (#out-of-tile neighbours << 24)
+    const float4* sorted;     // [B,N]
+    int* flags;               // [B]  cloud left the fp16 range
+    int N, arith, tiles_per_cloud, num_tiles;
+    float inv_div;
+    const uint4 *Wa_img, *Wb_img, *Wn_img;     // swizzled weight images in the kernel's format
+    const float *ba, *bb, *bn;
+    float* concat32;          // [B,N,ctot] fp32 (TF32-rounded) or nullptr
+    __nv_bfloat16* concat16;  // [B,N,ctot] bf16 or nullptr
+    int ctot, coff;
+    uint16_t* xnext;          // [B,N,64] 16-bit (HAS_NEXT)
+};
+
+template <bool HAS_NEXT, int FMT>
+__global__ void __launch_bounds__(PB_THREADS, 1) proxy_block_kernel(const PbArgs p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = base;                                  // A operand tile (t, then relu(conv_a), then x_b)
-    uint8_t* sW0 = sA + PB_A_BYTES;                      // conv_a weights, later conv_next
-    uint8_t* sW1 = sW0 + PB_W_BYTES;                     // conv_b weights
-    float* sM = reinterpret_cast<float*>(sW1 + PB_W_BYTES);   // neighbour mean m, [128][66] fp32
-    float* sBias = sM + PB_TILE * PB_MLD;                // [3][64]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sBias + 192);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
-    int* sCnt = reinterpret_cast<int*>(bar + 8);                         // [128] size of each point's thresholded set
-    unsigned short* sNbr = reinterpret_cast<unsigned short*>(sCnt + PB_TILE);   // [128][20] neighbour positions
+    const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;      // shared-space address; every buffer is base + constant
+    uint8_t* gbase = smem_raw + (base - tc::smem_u32(smem_raw));          // same location as a generic pointer (prologue only)
+    const uint32_t bar_full = base + PB_OFF_BAR, bar_empty = bar_full + 8 * PB_STAGES, bar_wfull = bar_empty + 8 * PB_STAGES,
+                   bar_wempty = bar_wfull + 8 * PB_WSTAGES, bar_mma = bar_wempty + 8 * PB_WSTAGES;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.y;
-    const int tile0 = blockIdx.x * PB_TILE;
+    const int N = p.N;
 
-    // ---- prologue: weights, barrier, TMEM ------------------------------------------------------------------
+    // ---- prologue: weights, barriers, TMEM ------------------------------------------------------------------
     {
-        const uint4* ga = reinterpret_cast<const uint4*>(Wa_img);
-        const uint4* gb = reinterpret_cast<const uint4*>(Wb_img);
-        uint4* s0 = reinterpret_cast<uint4*>(sW0);
-        uint4* s1 = reinterpret_cast<uint4*>(sW1);
-        for (int i = tid; i < (int)(PB_W_BYTES / 16); i += PB_THREADS) {
-            s0[i] = __ldg(ga + i);
-            s1[i] = __ldg(gb + i);
+        uint4* s = reinterpret_cast<uint4*>(gbase + PB_OFF_W);
+        constexpr int per = PB_W_BYTES / 16;
+        for (int i = tid; i < 3 * per; i += PB_THREADS) {
+            const int w = i / per, o = i - w * per;
+            const uint4* src = (w == 0) ? p.Wa_img : (w == 1) ? p.Wb_img : p.Wn_img;
+            s[i] = (HAS_NEXT || w < 2) ? __ldg(src + o) : make_uint4(0, 0, 0, 0);
         }
+        float* sBias = reinterpret_cast<float*>(gbase + PB_OFF_BIAS);
         if (tid < 64) {
-            sBias[tid] = ba[tid];
-            sBias[64 + tid] = bb[tid];
-            sBias[128 + tid] = HAS_NEXT ? bn[tid] : 0.f;
+            sBias[tid] = p.ba[tid];
+            sBias[64 + tid] = p.bb[tid];
+            sBias[128 + tid] = HAS_NEXT ? p.bn[tid] : 0.f;
         }
         if (tid == 0) {
-            tc::mbar_init(bar, 1);
+            uint64_t* bars = reinterpret_cast<uint64_t*>(gbase + PB_OFF_BAR);
+            for (int s2 = 0; s2 < PB_STAGES; ++s2) {
+                tc::mbar_init(&bars[s2], PB_GATHER_WARPS);
+                tc::mbar_init(&bars[PB_STAGES + s2], 4);
+            }
+            for (int s2 = 0; s2 < PB_WSTAGES; ++s2) {
+                tc::mbar_init(&bars[2 * PB_STAGES + s2], 1);
+                tc::mbar_init(&bars[2 * PB_STAGES + PB_WSTAGES + s2], PB_GATHER_WARPS);
+            }
+            tc::mbar_init(&bars[2 * PB_STAGES + 2 * PB_WSTAGES], 1);
+            tc::mbar_init(&bars[2 * PB_STAGES + 2 * PB_WSTAGES + 1], 1);
             tc::fence_barrier_init();
         }
-        if (warp == 1) {
-            tc::tmem_alloc(tmem_slot, 64);
+        if (warp == 0) {
+            tc::tmem_alloc(reinterpret_cast<uint32_t*>(gbase + PB_OFF_TMEM), 128);
             tc::tmem_relinquish();
         }
-    }
-
-    // ---- gather-mean ---------------------------------------------------------------------------------------
-    // warp per point; the two half-warps fetch two different neighbour rows per instruction (lane & 15 = which
-    // float4 of the 256-byte row), so a point costs 10 LDG.128 instead of 20 LDG.64.
-    const float* xb = x + (size_t)b * N * 64;
-    const size_t row_tile = (size_t)b * N + tile0;
-    for (int i = tid; i < PB_TILE * KNN_K; i += PB_THREADS) sNbr[i] = nbr[row_tile * KNN_K + i];
-    if (tid < PB_TILE) sCnt[tid] = cnt[row_tile + tid];
-    __syncthreads();
-    const int half = lane >> 4, c4 = lane & 15;
-    const float inv_div = 1.0f / divisor;               // x1 = matmul(dpist, x) / float(k): one rounding differs from a true division
-#pragma unroll 1
-    for (int pl = warp; pl < PB_TILE; pl += PB_THREADS / 32) {
-        const int pos = tile0 + pl;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (sCnt[pl] == KNN_K) {
-            float4 v[KNN_K / 2];
-#pragma unroll
-            for (int q = 0; q < KNN_K / 2; ++q) {
-                const int j = sNbr[pl * KNN_K + 2 * q + half];
-                v[q] = __ldg(reinterpret_cast<const float4*>(xb + (size_t)j * 64) + c4);
-            }
-#pragma unroll
-            for (int q = 0; q < KNN_K / 2; ++q) {
-                acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w;
-            }
-        } else {
-            // ties at the 20th distance: the set is {j : d_ij <= kthd_i}; re-scan the cloud exactly (rare)
-            const size_t row = row_tile + pl;
-            const float thr = kthd[row];
-            const float4 qp = sorted[row];
-            const float4* sp = sorted + (size_t)b * N;
-            for (int j0 = 0; j0 < N; j0 += 32) {
-                const float4 pj = sp[j0 + lane];
-                const float d = (arith == EPC_KNN_ARITH_MULADD)
-                                    ? canon_dist<0>(qp.x, qp.y, qp.z, qp.w, pj.x, pj.y, pj.z, pj.w)
-                                    : canon_dist<1>(qp.x, qp.y, qp.z, qp.w, pj.x, pj.y, pj.z, pj.w);
-                unsigned mk = __ballot_sync(FULL, d <= thr);
-                while (mk) {
-                    const int j = j0 + __ffs(mk) - 1;
-                    mk &= mk - 1;
-                    if (half == 0) {                     // one half-warp accumulates; the other contributes zeros
-                        const float4 vv = __ldg(reinterpret_cast<const float4*>(xb + (size_t)j * 64) + c4);
-                        acc.x += vv.x; acc.y += vv.y; acc.z += vv.z; acc.w += vv.w;
-                    }
-                }
-            }
-        }
-        acc.x += __shfl_xor_sync(FULL, acc.x, 16);
-        acc.y += __shfl_xor_sync(FULL, acc.y, 16);
-        acc.z += __shfl_xor_sync(FULL, acc.z, 16);
-        acc.w += __shfl_xor_sync(FULL, acc.w, 16);
-        const float4 m = make_float4(acc.x * inv_div, acc.y * inv_div, acc.z * inv_div, acc.w * inv_div);
-        if (half == 0) {
-            *reinterpret_cast<float4*>(sM + pl * PB_MLD + 4 * c4) = m;
-        } else {
-            const float4 xi = __ldg(reinterpret_cast<const float4*>(xb + (size_t)pos * 64) + c4);
-            *reinterpret_cast<float4*>(sA + sw128_chunk(pl, c4, PB_A_BYTES / 2)) =          // t1 = x1 - x (TF32 MMA operand)
-                make_float4(round_tf32(m.x - xi.x), round_tf32(m.y - xi.y), round_tf32(m.z - xi.z), round_tf32(m.w - xi.w));
-        }
-    }
-    tc::fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    const uint32_t tmem_d = *tmem_slot;
-    const uint32_t a_addr = tc::smem_u32(sA), w0_addr = tc::smem_u32(sW0), w1_addr = tc::smem_u32(sW1);
-    const bool epi = warp >= 4;                         // warps 4..7 own TMEM lane quarters 0..3
-    const int erow = (warp & 3) * 32 + lane;            // this epilogue thread's point within the tile
-    const uint32_t trow = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
-    const size_t grow = (size_t)b * N + tile0 + erow;
-
-    // ---- conv_a -----------------------------------------------------------------------------------------------
-    if (tid == 0) {
-        pb_issue_gemm(tmem_d, a_addr, w0_addr, bar);
-        tc::mbar_wait(bar, 0);          // one thread polls; everybody else sleeps on the hardware barrier
-    }
-    __syncthreads();
-    tc::tc_fence_after();
-    if (epi) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            float v[32];
-            tc::tmem_ld32(trow + 32u * h, v);
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                const int k = 32 * h + i;
-                float4 o;
-                o.x = round_tf32(fmaxf(v[i] + sBias[k], 0.f));
-                o.y = round_tf32(fmaxf(v[i + 1] + sBias[k + 1], 0.f));
-                o.z = round_tf32(fmaxf(v[i + 2] + sBias[k + 2], 0.f));
-                o.w = round_tf32(fmaxf(v[i + 3] + sBias[k + 3], 0.f));
-                *reinterpret_cast<float4*>(sA + sw128_chunk(erow, k >> 2, PB_A_BYTES / 2)) = o;
-            }
-        }
-    } else if (HAS_NEXT) {
-        // conv_a's weights are dead now: bring in the next block's first conv while the epilogue runs
-        const uint4* gn = reinterpret_cast<const uint4*>(Wn_img);
-        uint4* s0 = reinterpret_cast<uint4*>(sW0);
-        for (int i = tid; i < (int)(PB_W_BYTES / 16); i += 128) s0[i] = __ldg(gn + i);
-    }
-    tc::fence_proxy_async();
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-
-    // ---- conv_b, residual, concat ---------------------------------------------------------------------------------
-    if (tid == 0) {
-        pb_issue_gemm(tmem_d, a_addr, w1_addr, bar);
-        tc::mbar_wait(bar, 1);
-    }
-    __syncthreads();
-    tc::tc_fence_after();
-    if (epi) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            float v[32];
-            tc::tmem_ld32(trow + 32u * h, v);
-            float o[32];
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                const int k = 32 * h + i;
-                const float4 mm = *reinterpret_cast<const float4*>(sM + erow * PB_MLD + k);
-                o[i] = fmaxf(v[i] + sBias[64 + k], 0.f) + mm.x;                        // x_b = relu(conv_b) + m
-                o[i + 1] = fmaxf(v[i + 1] + sBias[65 + k], 0.f) + mm.y;
-                o[i + 2] = fmaxf(v[i + 2] + sBias[66 + k], 0.f) + mm.z;
-                o[i + 3] = fmaxf(v[i + 3] + sBias[67 + k], 0.f) + mm.w;
-            }
-            if (HAS_NEXT) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<float4*>(sA + sw128_chunk(erow, (32 * h + i) >> 2, PB_A_BYTES / 2)) =
-                        make_float4(round_tf32(o[i]), round_tf32(o[i + 1]), round_tf32(o[i + 2]), round_tf32(o[i + 3]));
-            }
-            if (concat) {
-                float4* dst = reinterpret_cast<float4*>(concat + grow * ctot + coff + 32 * h);
-#pragma unroll
-                for (int i = 0; i < 8; ++i)       // operand of the TF32 conv5 (EPC-Net-L, KD export): store it rounded
-                    dst[i] = make_float4(round_tf32(o[4 * i]), round_tf32(o[4 * i + 1]), round_tf32(o[4 * i + 2]), round_tf32(o[4 * i + 3]));
-            }
-            if (concat16) {
-                uint4* dst = reinterpret_cast<uint4*>(concat16 + grow * ctot + coff + 32 * h);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    uint32_t pk[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const __nv_bfloat162 hh = __floats2bfloat162_rn(o[8 * i + 2 * j], o[8 * i + 2 * j + 1]);
-                        pk[j] = *reinterpret_cast<const uint32_t*>(&hh);
-                    }
-                    dst[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                }
-            }
-        }
-    }
-    if (HAS_NEXT) {
         tc::fence_proxy_async();
         tc::tc_fence_before();
         __syncthreads();
         tc::tc_fence_after();
-        // ---- first conv of the next block ----------------------------------------------------------------------
-        if (tid == 0) {
-            pb_issue_gemm(tmem_d, a_addr, w0_addr, bar);
-            tc::mbar_wait(bar, 0);
+    }
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + PB_OFF_TMEM);
+    const int n_local = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+    auto next_active = [&](int it) { return it + 1; };
+
+    if (warp >= PB_CONS_WARPS) {
+        // =========================================== GATHER ===========================================
+        const int gw = warp - PB_CONS_WARPS;
+        const int grp = lane >> 3, c = lane & 7;
+        auto issue_window = [&](int it, int u) {        // one thread: TMA the tile's own rows, neighbour lists and counts
+            const int ws = u % PB_WSTAGES;
+            const uint32_t use = (uint32_t)(u / PB_WSTAGES);
+            const size_t row0 = (size_t)(blockIdx.x + it * gridDim.x) * PB_TILE;
+            const uint32_t wst = base + PB_OFF_WSTAGE + (uint32_t)ws * PB_WSTAGE_BYTES;
+            bar_wait_backoff(bar_wempty + 8 * ws, (use & 1u) ^ 1u);      // every gather warp is done with this window
+            bar_expect_tx(bar_wfull + 8 * ws, PB_A_BYTES + PB_NBR_BYTES + PB_CNT_BYTES);
+            bulk_g2s(wst + PB_WS_WIN, p.x + row0 * 64, PB_A_BYTES, bar_wfull + 8 * ws);
+            bulk_g2s(wst + PB_WS_NBR, p.nbr + row0 * KNN_K, PB_NBR_BYTES, bar_wfull + 8 * ws);
+            bulk_g2s(wst + PB_WS_CNT, p.cnt + row0, PB_CNT_BYTES, bar_wfull + 8 * ws);
+        };
+        const bool elected = (gw == 0 && lane == 0);
+        int it = next_active(-1);
+        int it1 = (it < n_local) ? next_active(it) : n_local;       // the window ring runs two tiles ahead
+        int u = 0;
+        if (elected) {
+            if (it < n_local) issue_window(it, 0);
+            if (it1 < n_local) issue_window(it1, 1);
         }
-        __syncthreads();
-        tc::tc_fence_after();
-        if (epi) {
+        while (it < n_local) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int b = tile / p.tiles_per_cloud;
+            const int tile0 = (tile - b * p.tiles_per_cloud) * PB_TILE;
+            const int s = u % PB_STAGES, ws = u % PB_WSTAGES;
+            const uint32_t use = (uint32_t)(u / PB_STAGES), wuse = (uint32_t)(u / PB_WSTAGES);
+            const uint32_t st = base + PB_OFF_STAGE + (uint32_t)s * PB_STAGE_BYTES;
+            const uint32_t wst = base + PB_OFF_WSTAGE + (uint32_t)ws * PB_WSTAGE_BYTES;
+            uint32_t win = wst + PB_WS_WIN + (uint32_t)c * 16u - (uint32_t)tile0 * 128u;      // + j*128 = row j of the window
+            const uint8_t* xb = reinterpret_cast<const uint8_t*>(p.x + (size_t)b * N * 64) + c * 16;      // + j*128
+            asm volatile("" : "+l"(xb), "+r"(win));     // keep both bases in registers (ptxas otherwise re-derives them per row)
+            const int it2 = (it1 < n_local) ? next_active(it1) : n_local;
+            if (elected && it2 < n_local) issue_window(it2, u + 2);
+            __syncwarp();
+            bar_wait_backoff(bar_wfull + 8 * ws, wuse & 1u);
+#pragma unroll 1
+            for (int sub = 0; sub < 2; ++sub) {
+                const int pl = (gw + sub * PB_GATHER_WARPS) * 4 + grp;      // this lane group's point within the tile
+                uint32_t idx[10];
+                {
+                    const uint32_t ia = wst + PB_WS_NBR + (uint32_t)pl * (KNN_K * 2);
+#pragma unroll
+                    for (int q = 0; q < 5; ++q)
+                        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(idx[2 * q]), "=r"(idx[2 * q + 1]) : "r"(ia + 8 * q));
+                }
+                int cntw;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(cntw) : "r"(wst + PB_WS_CNT + (uint32_t)pl * 4u));
+                const int nout = (cntw >> 24) & 0xff;
+                const int count = cntw & 0xffffff;
+                auto jq = [&](int q) { return (idx[q >> 1] >> ((q & 1) * 16)) & 0xffffu; };
+                float acc[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+                // rows 0..9: the out-of-tile neighbours (listed first) go out as global loads, the rest come from the window
+                uint4 v[10];
+#pragma unroll
+                for (int q = 0; q < 10; ++q) {
+                    const uint32_t j = jq(q);
+                    if (q < nout)
+                        v[q] = __ldg(reinterpret_cast<const uint4*>(xb + j * 128u));
+                    else
+                        v[q] = lds128(win + j * 128u);
+                }
+                // rows 10..19 while those are in flight
+#pragma unroll
+                for (int q = 10; q < KNN_K; ++q) {
+                    const uint32_t j = jq(q);
+                    uint4 w;
+                    if (q < nout)
+                        w = __ldg(reinterpret_cast<const uint4*>(xb + j * 128u));
+                    else
+                        w = lds128(win + j * 128u);
+                    add8<FMT>(acc, w);
+                }
+                const uint4 xi = lds128(win + (uint32_t)(tile0 + pl) * 128u);
+#pragma unroll
+                for (int q = 0; q < 10; ++q) add8<FMT>(acc, v[q]);
+                // ties at the 20th distance: the set is {j : d_ij <= kthd_i}; re-scan the cloud exactly (rare)
+                const unsigned tie_mask = __ballot_sync(FULL, count != KNN_K);
+                if (tie_mask) {
+                    const size_t row_tile = (size_t)b * N + tile0;
+                    for (int g = 0; g < 4; ++g) {
+                        if (!((tie_mask >> (8 * g)) & 1u)) continue;                    // warp-uniform
+                        const size_t trow = row_tile + (pl - grp) + g;
+                        const float thr = __ldg(p.kthd + trow);
+                        const float4 qp = p.sorted[trow];
+                        const float4* sp = p.sorted + (size_t)b * N;
+                        float a2[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) a2[i] = 0.f;
+                        // N is a multiple of 128: four 32-point blocks per step, their loads in flight together (one warp
+                        // re-scans the cloud while its CTA waits: latency, not throughput, is what matters here)
+                        for (int j0 = 0; j0 < N; j0 += 128) {
+                            float4 pj[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) pj[k] = __ldg(sp + j0 + 32 * k + lane);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float d = (p.arith == EPC_KNN_ARITH_MULADD)
+                                                    ? canon_dist<0>(qp.x, qp.y, qp.z, qp.w, pj[k].x, pj[k].y, pj[k].z, pj[k].w)
+                                                    : canon_dist<1>(qp.x, qp.y, qp.z, qp.w, pj[k].x, pj[k].y, pj[k].z, pj[k].w);
+                                unsigned mk = __ballot_sync(FULL, d <= thr);
+                                while (mk) {
+                                    const int j = j0 + 32 * k + __ffs(mk) - 1;
+                                    mk &= mk - 1;
+                                    if (grp == g) add8<FMT>(a2, __ldg(reinterpret_cast<const uint4*>(xb + (size_t)j * 128)));
+                                }
+                            }
+                        }
+                        if (grp == g) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) acc[i] = a2[i];
+                        }
+                    }
+                }
+                float m[8], t[8];
+                const float2 x01 = unpack2<FMT>(xi.x), x23 = unpack2<FMT>(xi.y), x45 = unpack2<FMT>(xi.z), x67 = unpack2<FMT>(xi.w);
+                const float xs[8] = {x01.x, x01.y, x23.x, x23.y, x45.x, x45.y, x67.x, x67.y};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    m[i] = acc[i] * p.inv_div;           // x1 = matmul(mask, x) / float(k)   (models/epc-net.py:70-71)
+                    t[i] = m[i] - xs[i];                 // t1 = x1 - x                       (:72)
+                }
+                if (FMT == FMT_F16 && max8(m) > F16_MAX) p.flags[b] = 1;     // x >= 0, so |t| <= max(m, x)
+                if (sub == 0) bar_wait_backoff(bar_empty + 8 * s, (use & 1u) ^ 1u);      // the consumers have released this A/M stage
+                const uint32_t off = sw128_off(pl, c);
+                sts128(st + PB_ST_M + off, pack8<FMT>(m));
+                sts128(st + PB_ST_A + off, pack8<FMT>(t));
+            }
+            tc::fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+            __syncwarp();
+            if (lane == 0) {
+                bar_arrive(bar_full + 8 * s);
+                bar_arrive(bar_wempty + 8 * ws);
+            }
+            it = it1;
+            it1 = it2;
+            ++u;
+        }
+    } else {
+        // ========================================== CONSUMERS ==========================================
+        const int group = warp >> 2;                         // 0 / 1: alternate tiles
+        const int gtid = tid & 127;                          // thread within the group = point within the tile = TMEM lane
+        const bool leader = (gtid == 0);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(group * 64);
+        const uint32_t trow = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t w0 = base + PB_OFF_W, w1 = w0 + PB_W_BYTES, w2 = w1 + PB_W_BYTES;
+        const uint32_t bias_addr = base + PB_OFF_BIAS;
+        const uint32_t my_mma = bar_mma + 8 * group;
+        uint32_t mma_phase = 0;
+        int u = 0;
+        for (int it = next_active(-1); it < n_local; it = next_active(it), ++u) {
+            if ((u & 1) != group) continue;
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int b = tile / p.tiles_per_cloud;
+            const int s = u % PB_STAGES;
+            const uint32_t use = (uint32_t)(u / PB_STAGES);
+            const uint32_t a_st = base + PB_OFF_STAGE + (uint32_t)s * PB_STAGE_BYTES + PB_ST_A;
+            const uint32_t m_st = a_st + (PB_ST_M - PB_ST_A);
+            const size_t grow0 = (size_t)tile * PB_TILE;     // first global row of the tile
+            float vmax = 0.f;                                // largest value this thread converts to the 16-bit format
+
+            bar_wait_backoff<400>(bar_full + 8 * s, use & 1u);
+            tc::tc_fence_after();
+            // ---- conv_a --------------------------------------------------------------------------------------
+            if (leader) pb_issue_gemm<FMT>(tmem_d, a_st, w0, my_mma);
+            bar_wait(my_mma, mma_phase);
+            mma_phase ^= 1u;
+            tc::tc_fence_after();
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 float v[32];
                 tc::tmem_ld32(trow + 32u * h, v);
-                float4* dst = reinterpret_cast<float4*>(xnext + grow * 64 + 32 * h);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int k = 32 * h + 4 * i;
-                    dst[i] = make_float4(fmaxf(v[4 * i] + sBias[128 + k], 0.f), fmaxf(v[4 * i + 1] + sBias[129 + k], 0.f),
-                                         fmaxf(v[4 * i + 2] + sBias[130 + k], 0.f), fmaxf(v[4 * i + 3] + sBias[131 + k], 0.f));
+                for (int q = 0; q < 4; ++q) {
+                    float bs[8], o[8];
+                    load_bias8(bias_addr + (32 * h + 8 * q) * 4, bs);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = fmaxf(v[8 * q + e] + bs[e], 0.f);
+                    if (FMT == FMT_F16) vmax = fmaxf(vmax, max8(o));
+                    sts128(a_st + sw128_off(gtid, 4 * h + q), pack8<FMT>(o));
                 }
             }
+            tc::fence_proxy_async();
+            tc::tc_fence_before();
+            group_sync(group);
+            // ---- conv_b, residual, block output --------------------------------------------------------------
+            if (leader) {
+                tc::tc_fence_after();
+                pb_issue_gemm<FMT>(tmem_d, a_st, w1, my_mma);
+            }
+            bar_wait(my_mma, mma_phase);
+            mma_phase ^= 1u;
+            tc::tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float v[32];
+                tc::tmem_ld32(trow + 32u * h, v);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t off = sw128_off(gtid, 4 * h + q);
+                    const uint4 mm = lds128(m_st + off);
+                    const float2 m01 = unpack2<FMT>(mm.x), m23 = unpack2<FMT>(mm.y), m45 = unpack2<FMT>(mm.z), m67 = unpack2<FMT>(mm.w);
+                    const float ms[8] = {m01.x, m01.y, m23.x, m23.y, m45.x, m45.y, m67.x, m67.y};
+                    float bs[8], o[8];
+                    load_bias8(bias_addr + (64 + 32 * h + 8 * q) * 4, bs);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = fmaxf(v[8 * q + e] + bs[e], 0.f) + ms[e];        // x_b = relu(conv_b) + m  (:81)
+                    if (HAS_NEXT) {
+                        if (FMT == FMT_F16) vmax = fmaxf(vmax, max8(o));
+                        sts128(a_st + off, pack8<FMT>(o));
+                    }
+                    if (p.concat16) sts128(m_st + off, pack8<FMT_BF16>(o));   // bf16 concat slice, staged over the consumed m chunk
+                    if (p.concat32) {                      // operand of the TF32 conv5 (EPC-Net-L, KD export): store it rounded
+                        float4* dst = reinterpret_cast<float4*>(p.concat32 + (grow0 + gtid) * p.ctot + p.coff + 32 * h + 8 * q);
+                        dst[0] = make_float4(round_tf32(o[0]), round_tf32(o[1]), round_tf32(o[2]), round_tf32(o[3]));
+                        dst[1] = make_float4(round_tf32(o[4]), round_tf32(o[5]), round_tf32(o[6]), round_tf32(o[7]));
+                    }
+                }
+            }
+            tc::fence_proxy_async();
+            tc::tc_fence_before();
+            group_sync(group);
+            if (HAS_NEXT && leader) {
+                tc::tc_fence_after();
+                pb_issue_gemm<FMT>(tmem_d, a_st, w2, my_mma);     // first conv of the next block
+            }
+            if (p.concat16) {                              // coalesced copy-out: 8 lanes write one 128 B row slice
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int q = gtid + 128 * i, r = q >> 3, ch = q & 7;
+                    const uint4 val = lds128(m_st + sw128_off(r, ch));
+                    *reinterpret_cast<uint4*>(p.concat16 + (grow0 + r) * p.ctot + p.coff + 8 * ch) = val;
+                }
+            }
+            if (HAS_NEXT) {
+                bar_wait(my_mma, mma_phase);
+                mma_phase ^= 1u;
+                tc::tc_fence_after();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float v[32];
+                    tc::tmem_ld32(trow + 32u * h, v);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float bs[8], o[8];
+                        load_bias8(bias_addr + (128 + 32 * h + 8 * q) * 4, bs);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = fmaxf(v[8 * q + e] + bs[e], 0.f);
+                        if (FMT == FMT_F16) vmax = fmaxf(vmax, max8(o));
+                        sts128(a_st + sw128_off(gtid, 4 * h + q), pack8<FMT>(o));   // staging
+                    }
+                }
+                tc::tc_fence_before();
+                group_sync(group);
+                uint4* dst = reinterpret_cast<uint4*>(p.xnext + grow0 * 64);        // the tile is one contiguous 16 KB block
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int q = gtid + 128 * i;
+                    dst[q] = lds128(a_st + sw128_off(q >> 3, q & 7));
+                }
+            }
+            if (FMT == FMT_F16 && vmax > F16_MAX) p.flags[b] = 1;
+            __syncwarp();
+            if (lane == 0) bar_arrive(bar_empty + 8 * s);
         }
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tmem_d, 64);
+    if (warp == 0) tc::tmem_dealloc(tmem_base, 128);
 }
 
-int proxy_block(const float* x, const KnnState& g, int B, int N, int arith, float divisor, const DenseDev& conv_a,
+int proxy_block(const uint16_t* x, const KnnState& g, int B, int N, int arith, float divisor, const DenseDev& conv_a,
                 const DenseDev& conv_b, const DenseDev* conv_next, float* concat, __nv_bfloat16* concat16, int ctot,
-                int coff, float* xnext, cudaStream_t st) {
+                int coff, uint16_t* xnext, int* flags, cudaStream_t st) {
     EPC_CHECK_ARG(conv_a.cin == 64 && conv_a.cout == 64 && conv_b.cin == 64 && conv_b.cout == 64,
                   "ProxyConv block layers must be 64->64");
     EPC_CHECK_ARG(N % PB_TILE == 0, "proxy_block: N=%d must be a multiple of %d", N, PB_TILE);
     EPC_CHECK_ARG(conv_a.Wimg && conv_b.Wimg && (!conv_next || conv_next->Wimg), "proxy_block: missing swizzled weight images");
+    EPC_CHECK_ARG(ctot % 8 == 0 && coff % 8 == 0, "proxy_block: concat slice must be 16-byte aligned");
     if (B == 0) return EPC_OK;
     static bool attr_done = false;
     if (!attr_done) {
-        EPC_CUDA(cudaFuncSetAttribute(proxy_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM));
-        EPC_CUDA(cudaFuncSetAttribute(proxy_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM));
+        EPC_CUDA(cudaFuncSetAttribute(proxy_block_kernel<true, FMT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM));
+        EPC_CUDA(cudaFuncSetAttribute(proxy_block_kernel<false, FMT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM));
         attr_done = true;
     }
-    dim3 grid(N / PB_TILE, B);
-    if (conv_next) {
-        proxy_block_kernel<true><<<grid, PB_THREADS, PB_SMEM, st>>>(x, g.nbr, g.kthd, g.cnt, g.sorted, N, arith, divisor,
-                                                                    conv_a.Wimg, conv_a.b, conv_b.Wimg, conv_b.b,
-                                                                    conv_next->Wimg, conv_next->b, concat, concat16, ctot,
-                                                                    coff, xnext);
-    } else {
-        proxy_block_kernel<false><<<grid, PB_THREADS, PB_SMEM, st>>>(x, g.nbr, g.kthd, g.cnt, g.sorted, N, arith, divisor,
-                                                                     conv_a.Wimg, conv_a.b, conv_b.Wimg, conv_b.b, nullptr,
-                                                                     nullptr, concat, concat16, ctot, coff, nullptr);
-    }
+    auto img = [&](const DenseDev& L) { return reinterpret_cast<const uint4*>(L.Wimg); };
+    PbArgs a = {};
+    a.x = x; a.nbr = g.nbr; a.kthd = g.kthd; a.cnt = g.cnt; a.sorted = g.sorted; a.flags = flags;
+    a.N = N; a.arith = arith; a.tiles_per_cloud = N / PB_TILE; a.num_tiles = B * (N / PB_TILE);
+    a.inv_div = 1.0f / divisor;                           // one rounding away from a true division by float(k)
+    a.Wa_img = img(conv_a); a.ba = conv_a.b;
+    a.Wb_img = img(conv_b); a.bb = conv_b.b;
+    a.Wn_img = conv_next ? img(*conv_next) : nullptr;
+    a.bn = conv_next ? conv_next->b : nullptr;
+    a.concat32 = concat; a.concat16 = concat16; a.ctot = ctot; a.coff = coff; a.xnext = xnext;
+    const int grid = a.num_tiles < sm_count() ? a.num_tiles : sm_count();
+    if (conv_next)
+        proxy_block_kernel<true, FMT_F16><<<grid, PB_THREADS, PB_SMEM, st>>>(a);
+    else
+        proxy_block_kernel<false, FMT_F16><<<grid, PB_THREADS, PB_SMEM, st>>>(a);
     EPC_LAUNCH_CHECK();
     return EPC_OK;
 }
 
-// Host: [cin=64][cout=64] folded weights -> the shared-memory image of the K-major, 128B-swizzled B operand
-// (element (n,k) = W[k][n]): 2 k-blocks x 64 rows x 128 B.
-void make_w64_image(const float* W, float* img) {
+// Host: [cin=64][cout=64] folded weights -> shared-memory images of the K-major, 128B-swizzled 16-bit B operand
+// (element (n,k) = W[k][n]): 64 rows (n) x 128 B; 16-byte chunk (k>>3) XOR-ed with (n & 7).
+// img: 4096 fp16 = 8 KB.
+void make_w64_image(const float* W, uint16_t* img) {
     for (int k = 0; k < 64; ++k)
         for (int n = 0; n < 64; ++n) {
-            const int kb = k >> 5, chunk = (k & 31) >> 2, within = k & 3;
-            const size_t off_bytes = (size_t)kb * 8192 + (size_t)n * 128 + (size_t)((chunk ^ (n & 7)) << 4) + within * 4;
-            img[off_bytes / 4] = W[k * 64 + n];
+            const size_t off = ((size_t)n * 128 + (size_t)(((k >> 3) ^ (n & 7)) << 4) + (size_t)(k & 7) * 2) / 2;
+            const __half h = __float2half_rn(W[k * 64 + n]);
+            img[off] = *reinterpret_cast<const uint16_t*>(&h);
         }
 }
 

@@ -9,9 +9,9 @@ namespace epc {
 struct KnnState {          // per-cloud kNN graph in *sorted* (Morton) point order
     float4* sorted;        // [B,N]   (x,y,z,|p|^2)
     int* perm;             // [B,N]   sorted position -> original index
-    uint16_t* nbr;         // [B,N,20] neighbour positions (sorted space), ascending (d, original index)
+    uint16_t* nbr;         // [B,N,20] neighbour positions (sorted space); those outside the row's 128-point tile come first
     float* kthd;           // [B,N]   20th smallest d
-    int* cnt;              // [B,N]   |{j : d_ij <= kthd_i}| (>= 20)
+    int* cnt;              // [B,N]   |{j : d_ij <= kthd_i}| (>= 20) in the low 24 bits | (# neighbours outside the row's 128-point tile) << 24
     float4* aabb;          // [B][2][N/32] per 32-point block: (lo.xyz, max |p|^2), then (hi.xyz, -)
 };
 int knn_check_n(int N);
@@ -27,18 +27,26 @@ struct DenseDev {          // BN-folded pointwise layer on the device: y = act(x
     const float* W;        // [cin, cout]
     const float* b;        // [cout]
     int cin, cout;
-    const float* Wimg;     // 64->64 layers: 16 KB shared-memory image of the swizzled tensor-core B operand
+    const void* Wimg;      // 64->64 layers: 8 KB shared-memory image (fp16, swizzled) of the tensor-core B operand
+    const float* Wimg32;   // ... and the 16 KB TF32 image used by the range-safe fp32 pass (backbone_f32.cu)
 };
-void make_w64_image(const float* W /*[64][64] folded*/, float* img /*[4096]*/);
+void make_w64_image(const float* W /*[64][64] folded*/, uint16_t* img /*[4096] fp16 bits*/);
+void make_w64_image_f32(const float* W /*[64][64] folded, TF32-rounded*/, float* img /*[4096]*/);
 struct BlockDev {          // one ProxyConv block (models/epc-net.py:66-81)
     DenseDev conv, conv_a, conv_b;
 };
-int conv_in(const float4* sorted, long long R, const DenseDev& L, float* x, cudaStream_t st);
+// fp16 fast pass (backbone.cu): flags[b] is set when an activation of cloud b left the fp16 range
+int conv_in(const float4* sorted, int B, int N, const DenseDev& L, uint16_t* x, int* flags, cudaStream_t st);
 // concat32 / concat16: the block's 64-channel output is written into column slice [coff, coff+64) of the fp32
 // and/or bf16 concat buffer (either may be nullptr)
-int proxy_block(const float* x, const KnnState& g, int B, int N, int arith, float divisor, const DenseDev& conv_a,
+int proxy_block(const uint16_t* x, const KnnState& g, int B, int N, int arith, float divisor, const DenseDev& conv_a,
                 const DenseDev& conv_b, const DenseDev* conv_next, float* concat32, __nv_bfloat16* concat16, int ctot,
-                int coff, float* xnext, cudaStream_t st);
+                int coff, uint16_t* xnext, int* flags, cudaStream_t st);
+// range-safe fp32/TF32 pass over the flagged clouds only (backbone_f32.cu)
+int conv_in_f32(const float4* sorted, int B, int N, const DenseDev& L, float* x, const int* flags, cudaStream_t st);
+int proxy_block_f32(const int* flags, const float* x, const KnnState& g, int B, int N, int arith, float divisor, const DenseDev& conv_a,
+                    const DenseDev& conv_b, const DenseDev* conv_next, float* concat32, __nv_bfloat16* concat16, int ctot,
+                    int coff, float* xnext, cudaStream_t st);
 
 // ---- gemm.cu -----------------------------------------------------------------------------------
 struct GemmArgs {

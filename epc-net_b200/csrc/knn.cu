@@ -399,20 +399,38 @@ knn_kernel(const float4* __restrict__ sorted, const int* __restrict__ perm, cons
         }
     }
 
-    // ---- outputs: final compaction, then one full-key sort of the 20 survivors ----------------------------------
+    // ---- outputs: final compaction; the public idx output is sorted by the full key (tf.nn.top_k order), the internal
+    // list is partitioned instead: neighbours outside the row's 128-point tile first (the ProxyConv gather, backbone.cu,
+    // fetches those from global memory and the rest from its shared-memory window), their number in cnt's top byte.
 #pragma unroll
     for (int r = 0; r < KNN_ROWS_PER_WARP; ++r) {
         float* rv = bv + r * KNN_CAP;
         uint32_t* rk = bk + r * KNN_CAP;
         if (L[r].n > KNN_K) L[r] = compact(L[r], rv, rk);
-        const uint32_t k = sorted_key(rv, rk);
         const size_t row = (size_t)b * N + r0 + r;
-        if (lane < KNN_K) nbr[row * KNN_K + lane] = (uint16_t)(k & 0xffffu);
-        if (lane == 0) {
-            kthd[row] = L[r].thr;
-            cnt[row] = KNN_K + L[r].extra;
+        const bool want_pub = (idx_out || kth_out || count_out);
+        uint32_t k;
+        if (idx_out) {
+            k = sorted_key(rv, rk);
+        } else {
+            __syncwarp();
+            k = (lane < KNN_K) ? rk[lane] : KEY_EMPTY;
         }
-        if (idx_out || kth_out || count_out) {
+        {
+            const int j = (int)(k & 0xffffu);
+            const bool valid = lane < KNN_K;
+            const bool outside = valid && ((j >> 7) != ((r0 + r) >> 7));
+            const unsigned mo = __ballot_sync(FULL, outside), mi = __ballot_sync(FULL, valid && !outside);
+            const unsigned lt = (1u << lane) - 1u;
+            const int n_out = __popc(mo);
+            const int pos = outside ? __popc(mo & lt) : n_out + __popc(mi & lt);
+            if (valid) nbr[row * KNN_K + pos] = (uint16_t)j;
+            if (lane == 0) {
+                kthd[row] = L[r].thr;
+                cnt[row] = (KNN_K + L[r].extra) | (n_out << 24);
+            }
+        }
+        if (want_pub) {
             const size_t orow = (size_t)b * N + sperm[r0 + r];
             if (idx_out && lane < KNN_K) idx_out[orow * KNN_K + lane] = (int32_t)(k >> 16);
             if (kth_out && lane == 0) kth_out[orow] = -L[r].thr;
