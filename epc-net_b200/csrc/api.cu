@@ -1,6 +1,7 @@
 // C ABI of libepc_b200.so (include/epc_b200.h): argument checking, BN folding / weight upload,
 // workspace carving and the kernel sequence of one embedding call.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <cmath>
@@ -429,7 +430,15 @@ void epc_model_destroy(EpcModel* m) {
 
 namespace {
 
-constexpr int HEAD_SUB = 8;     // clouds per head sub-batch: 8 x 8 MiB of bf16 H stays L2-resident between its 3 GEMMs
+// clouds per head sub-batch: the bf16 conv5 output H (8 MiB per cloud) of one sub-batch is produced and consumed by
+// three GEMM launches back to back.  Measured on B200 (us/cloud for conv5+assign+VLAD): 8 -> 10.2, 32 -> 8.2, 64 -> 7.5,
+// 128 -> 7.1: launch/prologue/wave-quantisation costs outweigh keeping H inside the L2.  EPC_HEAD_SUB overrides (tuning aid).
+static int head_sub_init() {
+    const char* e = getenv("EPC_HEAD_SUB");
+    int v = e ? atoi(e) : 0;
+    return (v >= 1 && v <= 256) ? v : 64;
+}
+static const int HEAD_SUB = head_sub_init();
 
 struct HeadWs {                 // buffers of the G_VLAD / NetVLAD head
     __nv_bfloat16* H16;         // [sub*N, 1024]   conv5 output (operand of the assignment and VLAD GEMMs)

@@ -181,15 +181,23 @@ __device__ __noinline__ RowState compact(RowState R, float* __restrict__ bv, uin
     const float o1 = (lane + 32 < R.n) ? bv[lane + 32] : INFINITY;
     const uint32_t k0 = (lane < R.n) ? bk[lane] : KEY_EMPTY;
     const uint32_t k1 = (lane + 32 < R.n) ? bk[lane + 32] : KEY_EMPTY;
-    float s = warp_sort32_vals<true>(o0, lane);
-    if (R.n > 32) {
-        const float s1 = warp_sort32_vals<false>(o1, lane);
-        s = fminf(s, s1);                           // bitonic sequence holding the 32 smallest values
+    // two bitonic networks in lock step (o0 ascending, o1 descending): two independent shuffle chains in flight
+    float s = o0, s1 = o1;
 #pragma unroll
-        for (int j = 16; j > 0; j >>= 1) {
-            const float o = __shfl_xor_sync(FULL, s, j);
-            s = ((lane & j) == 0) ? fminf(s, o) : fmaxf(s, o);
+    for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            const bool keep_min = (((lane & j) == 0) == ((lane & kk) == 0));
+            const float oa = __shfl_xor_sync(FULL, s, j), od = __shfl_xor_sync(FULL, s1, j);
+            s = keep_min ? fminf(s, oa) : fmaxf(s, oa);
+            s1 = keep_min ? fmaxf(s1, od) : fminf(s1, od);
         }
+    }
+    s = fminf(s, s1);                               // bitonic sequence holding the 32 smallest values
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const float o = __shfl_xor_sync(FULL, s, j);
+        s = ((lane & j) == 0) ? fminf(s, o) : fmaxf(s, o);
     }
     const float thr_new = __shfl_sync(FULL, s, KNN_K - 1);
     bool keep0 = o0 < thr_new, keep1 = o1 < thr_new;
@@ -351,52 +359,57 @@ knn_kernel(const float4* __restrict__ sorted, const int* __restrict__ perm, cons
         L[r].n = 0;
         L[r].extra = 0;
     }
-    for (int t = 0; t < n_init; ++t) {
-        scan_block(init_blk[t]);
-        if (t == 1 || t == n_init - 1) {           // 64 candidates -> first bound; then a tight one before pruning
-#pragma unroll
-            for (int r = 0; r < KNN_ROWS_PER_WARP; ++r)
-                if (L[r].n > KNN_K) L[r] = compact(L[r], bv + r * KNN_CAP, bk + r * KNN_CAP);
-        }
-    }
-
-    // ---- phase 2: every remaining block whose AABB can still hold a candidate <= thr --------------
+    // Three stages, each closed by a compaction of all eight rows (a single call site):
+    //   0: the rows' own block and the next one (64 candidates, thr = +inf) -> first bound
+    //   1: the other index-neighbours                                       -> a tight bound before pruning
+    //   2: every remaining block whose AABB can still hold a candidate <= thr -> the final 20
     const int nw = (nblk + 31) >> 5;
-    for (int w = 0; w < nw; ++w) {
-        const int blk = w * 32 + lane;
-        bool need = false;
-        if (blk < nblk) {
-            bool done = false;
-            for (int u = 0; u < n_init; ++u) done |= (init_blk[u] == blk);
-            if (!done) {
-                if (!PRUNE) {
-                    need = true;
-                } else {
-                    const float4 lo = sblo[blk], hi = sbhi[blk];
+#pragma unroll 1
+    for (int stage = 0; stage < 3; ++stage) {
+        if (stage < 2) {
+            const int t0 = stage == 0 ? 0 : 2, t1 = stage == 0 ? (n_init < 2 ? n_init : 2) : n_init;
+            for (int t = t0; t < t1; ++t) scan_block(init_blk[t]);
+        } else {
+            for (int w = 0; w < nw; ++w) {
+                const int blk = w * 32 + lane;
+                bool need = false;
+                if (blk < nblk) {
+                    bool done = false;
+                    for (int u = 0; u < n_init; ++u) done |= (init_blk[u] == blk);
+                    if (!done) {
+                        if (!PRUNE) {
+                            need = true;
+                        } else {
+                            const float4 lo = sblo[blk], hi = sbhi[blk];
 #pragma unroll
-                    for (int r = 0; r < KNN_ROWS_PER_WARP; ++r) {
-                        const float x = (r & 1) ? qx[r >> 1].y : qx[r >> 1].x;
-                        const float y = (r & 1) ? qy[r >> 1].y : qy[r >> 1].x;
-                        const float z = (r & 1) ? qz[r >> 1].y : qz[r >> 1].x;
-                        const float s = (r & 1) ? qs[r >> 1].y : qs[r >> 1].x;
-                        const float dx = fmaxf(fmaxf(lo.x - x, x - hi.x), 0.f);
-                        const float dy = fmaxf(fmaxf(lo.y - y, y - hi.y), 0.f);
-                        const float dz = fmaxf(fmaxf(lo.z - z, z - hi.z), 0.f);
-                        const float lb = dx * dx + dy * dy + dz * dz;
-                        // rigorous lower bound of the *computed* d over the block (DESIGN.md "pruning"):
-                        // true |p-q|^2 >= lb_true >= lb(1-8u); computed d >= true - 16u (s_i + s_j)
-                        const float bound = lb * (1.0f - 1e-6f) - 1e-6f * (s + lo.w);
-                        need |= !(bound > L[r].thr);
+                            for (int r = 0; r < KNN_ROWS_PER_WARP; ++r) {
+                                const float x = (r & 1) ? qx[r >> 1].y : qx[r >> 1].x;
+                                const float y = (r & 1) ? qy[r >> 1].y : qy[r >> 1].x;
+                                const float z = (r & 1) ? qz[r >> 1].y : qz[r >> 1].x;
+                                const float s = (r & 1) ? qs[r >> 1].y : qs[r >> 1].x;
+                                const float dx = fmaxf(fmaxf(lo.x - x, x - hi.x), 0.f);
+                                const float dy = fmaxf(fmaxf(lo.y - y, y - hi.y), 0.f);
+                                const float dz = fmaxf(fmaxf(lo.z - z, z - hi.z), 0.f);
+                                const float lb = dx * dx + dy * dy + dz * dz;
+                                // rigorous lower bound of the *computed* d over the block (DESIGN.md "pruning"):
+                                // true |p-q|^2 >= lb_true >= lb(1-8u); computed d >= true - 16u (s_i + s_j)
+                                const float bound = lb * (1.0f - 1e-6f) - 1e-6f * (s + lo.w);
+                                need |= !(bound > L[r].thr);
+                            }
+                        }
                     }
+                }
+                unsigned mask = __ballot_sync(FULL, need);
+                while (mask) {
+                    const int bit = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    scan_block(w * 32 + bit);
                 }
             }
         }
-        unsigned mask = __ballot_sync(FULL, need);
-        while (mask) {
-            const int bit = __ffs(mask) - 1;
-            mask &= mask - 1;
-            scan_block(w * 32 + bit);
-        }
+#pragma unroll
+        for (int r = 0; r < KNN_ROWS_PER_WARP; ++r)
+            if (L[r].n > KNN_K) L[r] = compact(L[r], bv + r * KNN_CAP, bk + r * KNN_CAP);
     }
 
     // ---- outputs: final compaction; the public idx output is sorted by the full key (tf.nn.top_k order), the internal
@@ -406,7 +419,6 @@ knn_kernel(const float4* __restrict__ sorted, const int* __restrict__ perm, cons
     for (int r = 0; r < KNN_ROWS_PER_WARP; ++r) {
         float* rv = bv + r * KNN_CAP;
         uint32_t* rk = bk + r * KNN_CAP;
-        if (L[r].n > KNN_K) L[r] = compact(L[r], rv, rk);
         const size_t row = (size_t)b * N + r0 + r;
         const bool want_pub = (idx_out || kth_out || count_out);
         uint32_t k;

@@ -204,6 +204,7 @@ struct EpiCtx {
     int epi_tid;        // 0..127 within the epilogue warps
     const float* bias;  // bias of this N tile (global or shared), indexed by the column within the tile; may be nullptr
     int col_begin, col_end;   // columns of the tile this warp drains (two warps per lane quarter split the tile)
+    int warp_slot;            // CONV5: index of this epilogue warp (private 4 KB staging slot in scratch)
 };
 
 template <int BN, int EPI>
@@ -234,28 +235,49 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const EpiCtx&
                 }
             }
         } else if (EPI == EPI_CONV5_BF16) {
-            // H = relu(acc + b) stored as bf16; per-row sum of squares of the fp32 values for the later L2 norm
+            // H = relu(acc + b) stored as bf16; per-row sum of squares of the fp32 values for the later L2 norm.
+            // Thread = row, but a warp store of 32 x 16 B to 32 different rows only half-fills its 32 B sectors; so each warp
+            // stages its 32 rows x 64 columns in a private, swizzled 4 KB of shared memory and writes full 128 B rows
+            // (8 lanes x 16 B per row, 4 rows per instruction).
             __nv_bfloat16* H = reinterpret_cast<__nv_bfloat16*>(p.C);
+            const uint32_t stage = smem_u32(c.scratch) + (uint32_t)c.warp_slot * 4096u;
+            const int r_in = lane;                               // this thread's row within the warp's 32
+            const int m_warp = m - lane;                         // first row of the warp
             float ss = 0.f;
     #pragma unroll 1
-            for (int c0 = c.col_begin; c0 < c.col_end; c0 += 32) {
-                float v[32];
-                tmem_ld32(trow + (uint32_t)c0, v);
-                uint32_t pk[16];
+            for (int c0 = c.col_begin; c0 < c.col_end; c0 += 64) {
     #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float2 bb = *reinterpret_cast<const float2*>(c.bias + c0 + i);
-                    const float x = fmaxf(v[i] + bb.x, 0.f), y = fmaxf(v[i + 1] + bb.y, 0.f);
-                    ss = fmaf(x, x, ss);
-                    ss = fmaf(y, y, ss);
-                    const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
-                    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&h);
-                }
-                if (m < p.M) {
-                    uint4* dst = reinterpret_cast<uint4*>(H + (size_t)m * p.ldc + n0 + c0);
+                for (int h = 0; h < 2; ++h) {
+                    float v[32];
+                    tmem_ld32(trow + (uint32_t)(c0 + 32 * h), v);
     #pragma unroll
-                    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t pk[4];
+    #pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int i = 8 * q + 2 * e;
+                            const float2 bb = *reinterpret_cast<const float2*>(c.bias + c0 + 32 * h + i);
+                            const float x = fmaxf(v[i] + bb.x, 0.f), y = fmaxf(v[i + 1] + bb.y, 0.f);
+                            ss = fmaf(x, x, ss);
+                            ss = fmaf(y, y, ss);
+                            const __nv_bfloat162 hh = __floats2bfloat162_rn(x, y);
+                            pk[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                        }
+                        const int ch = 4 * h + q;                // 16-byte chunk of the 128-byte row segment
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (uint32_t)r_in * 128u + (uint32_t)((ch ^ (r_in & 7)) << 4)),
+                                     "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+                    }
                 }
+                __syncwarp();
+    #pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int idx = lane + 32 * i, r = idx >> 3, ch = idx & 7;
+                    uint4 val;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                                 : "r"(stage + (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4)) : "memory");
+                    if (m_warp + r < p.M) *reinterpret_cast<uint4*>(H + (size_t)(m_warp + r) * p.ldc + n0 + c0 + 8 * ch) = val;
+                }
+                __syncwarp();
             }
             if (m < p.M) p.aux[(size_t)m * c.nparts + c.npart] = ss;
         } else if (EPI == EPI_COLMAX) {
@@ -442,7 +464,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         c.nparts = gridDim.y; c.npart = blockIdx.y;
         c.c_off = (long long)batch * p.c_batch + (long long)split * p.c_slab;
         c.scratch = reinterpret_cast<float*>(sA); c.epi_tid = threadIdx.x - 64;
-        c.bias = p.bias ? p.bias + n0 : nullptr; c.col_begin = 0; c.col_end = BN;
+        c.bias = p.bias ? p.bias + n0 : nullptr; c.col_begin = 0; c.col_end = BN; c.warp_slot = warp - 2;
         epilogue_tile<BN, EPI>(p, c);
     }
     tc_fence_before();
@@ -465,7 +487,7 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     using Tr = ElemTraits<T>;
     constexpr int BK = Tr::PER128;
     constexpr uint32_t A_BYTES = TC_BM * 128, B_BYTES = BN * 128;
-    constexpr size_t SCRATCH = (EPI == EPI_ASSIGN) ? (size_t)TC_BM * 65 * 4 : 0;
+    constexpr size_t SCRATCH = (EPI == EPI_ASSIGN) ? (size_t)TC_BM * 65 * 4 : (EPI == EPI_CONV5_BF16) ? (size_t)EW * 4096 : 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int nkb = p.K / BK;
@@ -571,7 +593,7 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             constexpr int SPLIT = EW / 4;                       // warps per lane quarter
             const int part = (warp - 2) >> 2;                   // which column share this warp drains
             c.col_begin = part * (BN / SPLIT); c.col_end = c.col_begin + BN / SPLIT;
-            c.nparts = NT * SPLIT; c.npart = n_tile * SPLIT + part;
+            c.nparts = NT * SPLIT; c.npart = n_tile * SPLIT + part; c.warp_slot = warp - 2;
             epilogue_tile<BN, EPI>(p, c);
             tc_fence_before();
             __syncwarp();
@@ -691,7 +713,7 @@ template <typename T, int BN, int EPI, int EW = 4>
 inline int tc_gemm_bres_launch(const Operand<T>& A, const Operand<T>& B, const tc::GemmParams& p, cudaStream_t st) {
     constexpr int BK = tc::ElemTraits<T>::PER128;
     constexpr size_t A_BYTES = tc::TC_BM * 128, B_BYTES = BN * 128;
-    constexpr size_t SCRATCH = (EPI == tc::EPI_ASSIGN) ? (size_t)tc::TC_BM * 65 * 4 : 0;
+    constexpr size_t SCRATCH = (EPI == tc::EPI_ASSIGN) ? (size_t)tc::TC_BM * 65 * 4 : (EPI == tc::EPI_CONV5_BF16) ? (size_t)EW * 4096 : 0;
     EPC_CHECK_ARG(p.K % BK == 0 && p.K >= BK && p.N % BN == 0 && p.splitk == 1, "tc_gemm_bres: bad shape K=%d N=%d", p.K, p.N);
     EPC_CHECK_ARG((reinterpret_cast<uintptr_t>(A.ptr) & 15) == 0 && (reinterpret_cast<uintptr_t>(B.ptr) & 15) == 0 &&
                       (A.ld * sizeof(T)) % 16 == 0 && (B.ld * sizeof(T)) % 16 == 0,
