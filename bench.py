@@ -36,11 +36,36 @@ METRIC = "EPC-Net clouds/sec (4096 pts)"
 UNIT = "clouds/s"
 ARCH = "epc-net"
 N_POINTS = 4096
-# algorithmic work per cloud, SURVEY.md Appendix C (N=4096, k=20)
-FLOPS = {"conv5": 2.0 * N_POINTS * 256 * 1024, "knn": 8.0 * N_POINTS * N_POINTS,
-         "assign_gemm": 2.0 * N_POINTS * 1024 * 64, "vlad_gemm": 2.0 * 64 * N_POINTS * 1024,
-         "proxy_block": 3 * 2.0 * N_POINTS * 64 * 64 + N_POINTS * 20 * 64, "hidden_gemm": 2.0 * 4 * 16384 * 256}
-TENSOR_STAGES = ("conv5", "assign_gemm", "vlad_gemm", "hidden_gemm")
+# Algorithmic work per cloud (N=4096, k=20): FLOPs from SURVEY.md Appendix C; BYTES = compulsory HBM traffic of the stage as
+# the data is laid out here: inputs read once + outputs written once, weights amortised over the batch.
+MiB = 1024.0 * 1024.0
+STAGE_MODEL = {
+    # stage: (FLOP/cloud, HBM bytes/cloud, pipe that does the FLOPs)
+    "sort": (0.0, 48 * 1024 + 64 * 1024 + 16 * 1024 + 4 * 1024, "alu"),
+    "knn": (8.0 * N_POINTS * N_POINTS, 64 * 1024 + 16 * 1024 + 4 * 1024 + 160 * 1024 + 32 * 1024, "alu"),   # dense-equivalent pairs
+    "conv_in": (2.0 * N_POINTS * 3 * 64, 64 * 1024 + 0.5 * MiB, "alu"),
+    # 4 launches per cloud: x (fp16) in, neighbour lists + counts in, concat slice (bf16) out, next x (fp16) out
+    "proxy_block": (4 * (3 * 2.0 * N_POINTS * 64 * 64 + N_POINTS * 20 * 64), 4 * (0.5 * MiB + 176 * 1024 + 0.5 * MiB) + 3 * 0.5 * MiB, "tensor"),
+    "conv5": (2.0 * N_POINTS * 256 * 1024, 2 * MiB + 8 * MiB, "tensor"),           # concat16 in, H (bf16) out
+    "assign_gemm": (2.0 * N_POINTS * 1024 * 64, 8 * MiB + 0.5 * MiB, "tensor"),    # H in, S' out
+    "vlad_gemm": (2.0 * 64 * N_POINTS * 1024, 8 * MiB + 0.5 * MiB + 0.5 * MiB, "tensor"),
+    "vlad_finalize": (0.0, 3 * 0.25 * MiB + 2 * 0.25 * MiB, "alu"),
+    "hidden_gemm": (2.0 * 4 * 16384 * 256, 0.25 * MiB + 16.8e6 / 128.0, "tensor"),   # 16.8 MB of weights per 128-cloud call
+}
+FP32_ALU_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # non-tensor FFMA peak of a B200 at its 1965 MHz boost clock (74.4)
+
+
+def stage_roofline(stage, ms, clouds, peaks):
+    """Achieved algorithmic rate of one stage against the two rooflines that can bound it; `frac` is the larger."""
+    flop, byt, pipe = STAGE_MODEL[stage]
+    sec = ms * 1e-3
+    hbm = byt * clouds / sec / 1e9
+    out = {"hbm_gbs": hbm, "hbm_frac": hbm / peaks["hbm_gbs"]}
+    if flop:
+        tf = flop * clouds / sec / 1e12
+        peak = peaks["bf16_tflops_sustained"] if pipe == "tensor" else FP32_ALU_TFLOPS
+        out.update({"tflops": tf, "flop_peak": peak, "flop_frac": tf / peak, "pipe": pipe})
+    return out
 
 
 def parse():
@@ -69,6 +94,18 @@ def measured_peaks():
         return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "bf16_tflops": d.get("bf16_tflops", 1590.0),
                 "bf16_tflops_sustained": d.get("bf16_tflops_sustained", 1400.0), "source": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def ncu_traffic(stage):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the stage's kernel, from the committed ncu capture
+    (profiles/traffic.json, written by tools/ncu_traffic.py); None when no capture is on file."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        return json.load(open(p)).get(stage, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 class ClockSampler(object):
@@ -259,18 +296,29 @@ def main():
     top = max(stages.items(), key=lambda kv: kv[1][0])[0]
     top_ms, top_n = stages[top]
     clouds_per_launch = B * K / float(top_n)
+    traffic = ncu_traffic(top)
     roof = {"kernel": top, "share_of_step": top_ms / total_stage_ms, "launches": top_n,
-            "avg_launch_ms": top_ms / top_n, "peak_source": peaks["source"], "traffic": None}
-    if top in FLOPS:
-        ach = FLOPS[top] * clouds_per_launch / (top_ms / top_n * 1e-3) / 1e12
-        roof.update({"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": ach / peaks["bf16_tflops_sustained"],
+            "avg_launch_ms": top_ms / top_n, "peak_source": peaks["source"],
+            "traffic": traffic * 1.0 if traffic is not None else None}
+    r = stage_roofline(top, top_ms, B * K, peaks) if top in STAGE_MODEL else None
+    if r is not None and r.get("pipe") == "tensor" and r["flop_frac"] >= r["hbm_frac"]:
+        roof.update({"bound": "tensor", "achieved": r["tflops"], "peak": r["flop_peak"], "unit": "TFLOP/s", "frac": r["flop_frac"],
                      "note": "algorithmic FLOP of the stage / event-timed duration; peak = measured sustained bf16 cuBLAS"})
-    else:
-        byt = (48 * 1024 + 1024) * clouds_per_launch
-        ach = byt / (top_ms / top_n * 1e-3) / 1e9
-        roof.update({"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"]})
-    stage_table = {k: {"ms_per_cloud": v[0] / (B * K), "share": v[0] / total_stage_ms} for k, v in stages.items()}
+    elif r is not None:
+        roof.update({"bound": "hbm", "achieved": r["hbm_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": r["hbm_frac"],
+                     "algorithmic_bytes_per_launch": STAGE_MODEL[top][1] * clouds_per_launch})
+        if top == "knn":
+            roof["note"] = ("the kNN kernel keeps the whole cloud in shared memory and is bound by FP32-ALU/issue work (distance "
+                            "evaluation + top-20 selection networks), not by HBM: see alt_*; dense-equivalent 8*N^2 FLOP per cloud "
+                            "(exact AABB pruning skips ~84 % of the pairs)")
+            roof.update({"alt_bound": "fp32-alu (dense-equivalent)", "alt_achieved": r["tflops"], "alt_peak": FP32_ALU_TFLOPS,
+                         "alt_unit": "TFLOP/s", "alt_frac": r["flop_frac"]})
+    stage_table = {}
+    for k, v in stages.items():
+        e = {"ms_per_cloud": v[0] / (B * K), "share": v[0] / total_stage_ms}
+        if k in STAGE_MODEL and v[0] > 0:
+            e.update(stage_roofline(k, v[0], B * K, peaks))
+        stage_table[k] = e
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
