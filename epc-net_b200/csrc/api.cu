@@ -623,7 +623,7 @@ int epc_embed(const EpcModel* m, const float* xyz, int B, int N, int knn_arith, 
                                            h.rowss, st))
                     return rc;
             }
-            if (int rc = head_assign_vlad(m, B, N, b0, nbs, h, CONV5_ROWSS_PARTS, st)) return rc;
+            if (int rc = head_assign_vlad(m, B, N, b0, nbs, h, conv5_rowss_parts(), st)) return rc;
             if (feat)
                 if (int rc = export_feat(b0, nbs)) return rc;
         }

@@ -80,6 +80,7 @@ constexpr int VLAD_SPLITK = 2;     // VLAD accumulate split-K slabs
 int tc_conv5_bf16(const __nv_bfloat16* Xc, long long R, int cin, const __nv_bfloat16* W5t, const float* b5,
                   __nv_bfloat16* H, float* rowss, cudaStream_t st);
 constexpr int CONV5_ROWSS_PARTS = 8;   // 1024 / BN(256) N tiles x 2 epilogue warps per lane quarter
+int conv5_rowss_parts();
 int tc_assign(const __nv_bfloat16* H, long long R, const __nv_bfloat16* Wct, const float* rowss, int parts,
               const float* bn_scale, const float* bn_shift, __nv_bfloat16* S, float* a_part, cudaStream_t st);
 int tc_vlad(const __nv_bfloat16* H, const __nv_bfloat16* S, int B, int N, float* V, int splitk, long long slab,

@@ -12,6 +12,7 @@ int tc_conv5_bf16(const __nv_bfloat16* Xc, long long R, int cin, const __nv_bflo
     Operand<__nv_bfloat16> a{Xc, R, cin, cin}, b{W5t, 1024, cin, cin};
     return tc_gemm_bres_launch<__nv_bfloat16, 256, tc::EPI_CONV5_BF16, 8>(a, b, p, st);
 }
+int conv5_rowss_parts() { return 8; }     // 1024 / BN(256) N tiles x 2 epilogue warps per lane quarter
 
 // cluster assignment (loupe.py:255-276): S' = softmax(BN((H Wc)/|H|))/|H| as bf16 [R,64]; a_part [R/128, 64]
 int tc_assign(const __nv_bfloat16* H, long long R, const __nv_bfloat16* Wct, const float* rowss, int parts,
