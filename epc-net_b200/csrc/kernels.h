@@ -9,6 +9,7 @@ namespace epc {
 struct KnnState {          // per-cloud kNN graph in *sorted* (Morton) point order
     float4* sorted;        // [B,N]   (x,y,z,|p|^2)
     int* perm;             // [B,N]   sorted position -> original index
+    uint16_t* perm16;      // [B,N]   the same as u16 (N <= 8192), bulk-copied into the kNN kernel's shared memory
     uint16_t* nbr;         // [B,N,20] neighbour positions (sorted space); those outside the row's 128-point tile come first
     float* kthd;           // [B,N]   20th smallest d
     int* cnt;              // [B,N]   |{j : d_ij <= kthd_i}| (>= 20) in the low 24 bits | (# neighbours outside the row's 128-point tile) << 24
@@ -17,7 +18,7 @@ struct KnnState {          // per-cloud kNN graph in *sorted* (Morton) point ord
 int knn_check_n(int N);
 size_t knn_state_bytes(int B, int N);
 KnnState knn_state_carve(Arena& ar, int B, int N);
-int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sorted, int* perm, float4* aabb, uint16_t* nbr,
+int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sorted, int* perm, uint16_t* perm16, float4* aabb, uint16_t* nbr,
               float* kthd, int* cnt, int32_t* idx_out, float* kth_out, int32_t* count_out, cudaStream_t st);
 int knn_dense(const float* xyz, int B, int N, int arith, const float* kth, float* mask, float* dist, cudaStream_t st);
 int rows_topk_smallest(const float* adj, long long R, int M, int k, int32_t* idx, cudaStream_t st);

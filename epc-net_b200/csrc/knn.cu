@@ -26,7 +26,7 @@ __device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 10 bits -> every t
 
 __global__ void __launch_bounds__(1024) sort_kernel(const float* __restrict__ xyz, int N, int NP,
                                                      float4* __restrict__ sorted, int* __restrict__ perm,
-                                                     float4* __restrict__ aabb) {
+                                                     uint16_t* __restrict__ perm16, float4* __restrict__ aabb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
     __shared__ float red[6][32];
@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(1024) sort_kernel(const float* __restrict__ xy
         const float sq = canon_sq(x, y, z);
         sorted[(size_t)b * N + i] = make_float4(x, y, z, sq);
         perm[(size_t)b * N + i] = src;
+        perm16[(size_t)b * N + i] = (uint16_t)src;      // N <= 8192: the copy the kNN kernel stages in shared memory
         // axis-aligned box (and max |p|^2) of every 32-point block of the sorted order: the kNN kernel's pruning test
         const int nblk = N >> 5;                   // N % 32 == 0 and i ascends by blockDim (a multiple of 32):
         const float lx = warp_min(x), ly = warp_min(y), lz = warp_min(z);      // each warp holds exactly one block
@@ -274,7 +275,7 @@ constexpr int KNN_ROWS_PER_CTA = KNN_ROWS_PER_WARP * KNN_WARPS;
 
 template <int ARITH, bool PRUNE>
 __global__ void __launch_bounds__(KNN_WARPS * 32)
-knn_kernel(const float4* __restrict__ sorted, const int* __restrict__ perm, const float4* __restrict__ aabb, int N,
+knn_kernel(const float4* __restrict__ sorted, const uint16_t* __restrict__ perm16, const float4* __restrict__ aabb, int N,
            uint16_t* __restrict__ nbr, float* __restrict__ kthd, int* __restrict__ cnt, int32_t* __restrict__ idx_out,
            float* __restrict__ kth_out, int32_t* __restrict__ count_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -286,16 +287,31 @@ knn_kernel(const float4* __restrict__ sorted, const int* __restrict__ perm, cons
     float* sbv = reinterpret_cast<float*>(sperm + N);                         // [warps][rows][CAP] candidate values
     uint32_t* sbk = reinterpret_cast<uint32_t*>(sbv + KNN_WARPS * KNN_ROWS_PER_WARP * KNN_CAP);   // ... and keys
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const float4* gp = sorted + (size_t)b * N;
-    const int* gperm = perm + (size_t)b * N;
-    const float4* gbox = aabb + (size_t)b * nblk * 2;
-
-    for (int i = tid; i < N; i += blockDim.x) {
-        spts[i] = gp[i];
-        sperm[i] = (unsigned short)gperm[i];
+    // the whole cloud (points, block boxes, permutation) arrives by three TMA bulk copies issued by one thread
+    uint64_t* ldbar = reinterpret_cast<uint64_t*>(sbk + KNN_WARPS * KNN_ROWS_PER_WARP * KNN_CAP);
+    {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(ldbar);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t b_pts = (uint32_t)N * 16u, b_box = (uint32_t)nblk * 32u, b_perm = (uint32_t)N * 2u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b_pts + b_box + b_perm) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"((uint32_t)__cvta_generic_to_shared(spts)), "l"(sorted + (size_t)b * N), "r"(b_pts), "r"(bar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"((uint32_t)__cvta_generic_to_shared(sblo)), "l"(aabb + (size_t)b * nblk * 2), "r"(b_box), "r"(bar) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"((uint32_t)__cvta_generic_to_shared(sperm)), "l"(perm16 + (size_t)b * N), "r"(b_perm), "r"(bar) : "memory");
+        }
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                         : "=r"(ok) : "r"(bar), "r"(0u) : "memory");
+        }
     }
-    for (int i = tid; i < 2 * nblk; i += blockDim.x) sblo[i] = gbox[i];      // [lo x nblk][hi x nblk]
-    __syncthreads();
 
     const int r0 = blockIdx.x * KNN_ROWS_PER_CTA + wid * KNN_ROWS_PER_WARP;
     if (r0 >= N) return;
@@ -524,7 +540,7 @@ int knn_check_n(int N) {
     return EPC_OK;
 }
 
-int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sorted, int* perm, float4* aabb, uint16_t* nbr,
+int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sorted, int* perm, uint16_t* perm16, float4* aabb, uint16_t* nbr,
               float* kthd, int* cnt, int32_t* idx_out, float* kth_out, int32_t* count_out, cudaStream_t st) {
     if (int rc = knn_check_n(N)) return rc;
     EPC_CHECK_ARG(arith == EPC_KNN_ARITH_MULADD || arith == EPC_KNN_ARITH_FMA, "bad knn arith %d", arith);
@@ -532,7 +548,7 @@ int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sor
     const int NP = next_pow2(N);
     const size_t sort_smem = (size_t)NP * sizeof(unsigned long long);
     static bool attr_done = false;
-    const size_t knn_smem = (size_t)N * 16 + (size_t)(N / 32) * 32 + (size_t)N * 2 + (size_t)KNN_WARPS * KNN_ROWS_PER_WARP * KNN_CAP * 8;
+    const size_t knn_smem = (size_t)N * 16 + (size_t)(N / 32) * 32 + (size_t)N * 2 + (size_t)KNN_WARPS * KNN_ROWS_PER_WARP * KNN_CAP * 8 + 16;
     if (!attr_done) {
         EPC_CUDA(cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         EPC_CUDA(cudaFuncSetAttribute(knn_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -543,7 +559,7 @@ int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sor
     }
     {
         ScopedStage ss(EPC_STAGE_SORT, st);
-        sort_kernel<<<B, 1024, sort_smem, st>>>(xyz, N, NP, sorted, perm, aabb);
+        sort_kernel<<<B, 1024, sort_smem, st>>>(xyz, N, NP, sorted, perm, perm16, aabb);
         EPC_LAUNCH_CHECK();
     }
     ScopedStage ss(EPC_STAGE_KNN, st);
@@ -551,14 +567,14 @@ int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sor
     const int th = KNN_WARPS * 32;
     if (arith == EPC_KNN_ARITH_MULADD) {
         if (prune)
-            knn_kernel<0, true><<<grid, th, knn_smem, st>>>(sorted, perm, aabb, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
+            knn_kernel<0, true><<<grid, th, knn_smem, st>>>(sorted, perm16, aabb, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
         else
-            knn_kernel<0, false><<<grid, th, knn_smem, st>>>(sorted, perm, aabb, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
+            knn_kernel<0, false><<<grid, th, knn_smem, st>>>(sorted, perm16, aabb, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
     } else {
         if (prune)
-            knn_kernel<1, true><<<grid, th, knn_smem, st>>>(sorted, perm, aabb, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
+            knn_kernel<1, true><<<grid, th, knn_smem, st>>>(sorted, perm16, aabb, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
         else
-            knn_kernel<1, false><<<grid, th, knn_smem, st>>>(sorted, perm, aabb, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
+            knn_kernel<1, false><<<grid, th, knn_smem, st>>>(sorted, perm16, aabb, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
     }
     EPC_LAUNCH_CHECK();
     return EPC_OK;
@@ -566,7 +582,7 @@ int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sor
 
 size_t knn_state_bytes(int B, int N) {
     const size_t R = (size_t)B * N;
-    return align_up(R * sizeof(float4)) + align_up(R * sizeof(int)) + align_up(R * KNN_K * sizeof(uint16_t)) +
+    return align_up(R * sizeof(float4)) + align_up(R * sizeof(int)) + align_up(R * sizeof(uint16_t)) + align_up(R * KNN_K * sizeof(uint16_t)) +
            align_up(R * sizeof(float)) + align_up(R * sizeof(int)) + align_up(R / 16 * sizeof(float4));
 }
 
@@ -575,6 +591,7 @@ KnnState knn_state_carve(Arena& ar, int B, int N) {
     KnnState s;
     s.sorted = ar.take<float4>(R);
     s.perm = ar.take<int>(R);
+    s.perm16 = ar.take<uint16_t>(R);
     s.nbr = ar.take<uint16_t>(R * KNN_K);
     s.kthd = ar.take<float>(R);
     s.cnt = ar.take<int>(R);
