@@ -269,6 +269,9 @@ __device__ __forceinline__ void append_hits(RowState& R, unsigned m, float d, in
     R.n += h;
 }
 
+// a row is re-compacted after the index-neighbour blocks only if its buffer holds more than this many candidates
+// (measured: 20 -> 9.11, 32 -> 8.79, 44 -> 8.85, 64 = never -> 8.97 us/cloud)
+constexpr int KNN_STAGE1_MIN = 32;
 constexpr int KNN_ROWS_PER_WARP = 8;
 constexpr int KNN_WARPS = 8;
 constexpr int KNN_ROWS_PER_CTA = KNN_ROWS_PER_WARP * KNN_WARPS;
@@ -425,7 +428,7 @@ knn_kernel(const float4* __restrict__ sorted, const uint16_t* __restrict__ perm1
         }
 #pragma unroll
         for (int r = 0; r < KNN_ROWS_PER_WARP; ++r)
-            if (L[r].n > KNN_K) L[r] = compact(L[r], bv + r * KNN_CAP, bk + r * KNN_CAP);
+            if (L[r].n > (stage == 1 ? KNN_STAGE1_MIN : KNN_K)) L[r] = compact(L[r], bv + r * KNN_CAP, bk + r * KNN_CAP);
     }
 
     // ---- outputs: final compaction; the public idx output is sorted by the full key (tf.nn.top_k order), the internal

@@ -310,8 +310,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const EpiCtx&
                 for (int i = 0; i < 32; ++i) v[32 + i] = t[i];
             }
             float ssq = 0.f;
-            if (m < p.M)
-                for (int i = 0; i < p.rowss_parts; ++i) ssq += p.rowss[(size_t)m * p.rowss_parts + i];
+            if (m < p.M) {
+                if (p.rowss_parts == 8) {            // conv5's partials: one 32-byte row, two vector loads (same summation order)
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(p.rowss + (size_t)m * 8));
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.rowss + (size_t)m * 8) + 1);
+                    ssq = ((((((a.x + a.y) + a.z) + a.w) + b.x) + b.y) + b.z) + b.w;
+                } else {
+                    for (int i = 0; i < p.rowss_parts; ++i) ssq += p.rowss[(size_t)m * p.rowss_parts + i];
+                }
+            }
             const float inv = 1.0f / sqrtf(fmaxf(ssq, L2_EPS));
             float mx = -INFINITY;
     #pragma unroll

@@ -93,19 +93,43 @@ vlad_residual_kernel(const float* __restrict__ V, int nslab, long long slab, con
     __shared__ float s_part[4][64];
     const int b = blockIdx.y, sl = blockIdx.x, tid = threadIdx.x;
     const int c = tid & 63, grp = tid >> 6;
-    float as = 0.f;
-    if (c < K)
-        for (int p = 0; p < a_parts; ++p) as += a_sum[((size_t)b * a_parts + p) * K + c];
+    float as = 0.f;                                  // fixed summation order; the loads are issued eight at a time
+    if (c < K) {
+        for (int p0 = 0; p0 < a_parts; p0 += 8) {
+            float t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = (p0 + u < a_parts) ? __ldg(a_sum + ((size_t)b * a_parts + p0 + u) * K + c) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) as += t[u];
+        }
+    }
     const float* Vb = V + (size_t)b * F * K;
     float* vb = v + (size_t)b * F * K;
     float ss = 0.f;
     if (c < K) {
-        for (int f = sl * VF_ROWS + grp; f < (sl + 1) * VF_ROWS && f < F; f += 4) {
-            float acc = 0.f;
-            for (int s = 0; s < nslab; ++s) acc += Vb[s * slab + (size_t)f * K + c];
-            const float r = acc - as * Wc2[(size_t)f * K + c];
-            vb[(size_t)f * K + c] = r;
-            ss += r * r;
+        const int f0 = sl * VF_ROWS + grp, f1 = min((sl + 1) * VF_ROWS, F);
+        constexpr int U = 8;                       // independent loads in flight per thread (the kernel is pure streaming)
+        for (int fb = f0; fb < f1; fb += 4 * U) {
+            float acc[U], w2[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int f = fb + 4 * u;
+                acc[u] = 0.f;
+                w2[u] = 0.f;
+                if (f < f1) {
+                    for (int s = 0; s < nslab; ++s) acc[u] += __ldg(Vb + s * slab + (size_t)f * K + c);
+                    w2[u] = __ldg(Wc2 + (size_t)f * K + c);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int f = fb + 4 * u;
+                if (f < f1) {
+                    const float r = acc[u] - as * w2[u];
+                    vb[(size_t)f * K + c] = r;
+                    ss += r * r;
+                }
+            }
         }
     }
     s_part[grp][c] = ss;
@@ -121,8 +145,15 @@ vlad_scale_kernel(float* __restrict__ v, const float* __restrict__ colss, int F,
     const int b = blockIdx.y, sl = blockIdx.x, tid = threadIdx.x;
     if (tid < 64) {
         float tot = 0.f;
-        if (tid < K)
-            for (int p = 0; p < (int)gridDim.x; ++p) tot += colss[((size_t)b * gridDim.x + p) * K + tid];
+        if (tid < K) {
+            float t[8];                              // gridDim.x == F / 128 == 8 partials: all loads in flight, fixed order
+            for (int p0 = 0; p0 < (int)gridDim.x; p0 += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] = (p0 + u < (int)gridDim.x) ? __ldg(colss + ((size_t)b * gridDim.x + p0 + u) * K + tid) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) tot += t[u];
+            }
+        }
         const float iv = 1.0f / sqrtf(fmaxf(tot, L2_EPS));
         s_inv[tid] = iv;
         s_g[tid] = (tid < K) ? tot * iv * iv : 0.f;          // squared norm of the normalised column
@@ -165,8 +196,14 @@ __global__ void vlad_tail_kernel(const float* __restrict__ Y, int nslab, size_t 
     float y = 0.f;
     if (d < D) {
         for (int g = 0; g < G; ++g) {
-            float h = 0.f;                    // split-K partial slabs, summed in a fixed order
-            for (int s = 0; s < nslab; ++s) h += Y[s * slab + ((size_t)b * G + g) * D + d];
+            float h = 0.f;                    // split-K partial slabs, summed in a fixed order; loads issued eight at a time
+            for (int s0 = 0; s0 < nslab; s0 += 8) {
+                float t[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] = (s0 + u < nslab) ? __ldg(Y + (s0 + u) * slab + ((size_t)b * G + g) * D + d) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) h += t[u];
+            }
             y += h * bn_scale[d] + bn_shift[d];
         }
         sy[d] = y;
@@ -174,8 +211,16 @@ __global__ void vlad_tail_kernel(const float* __restrict__ Y, int nslab, size_t 
     __syncthreads();
     float z = y;
     if (gating && d < D) {
-        float acc = 0.f;
-        for (int k = 0; k < D; ++k) acc = fmaf(sy[k], Wg[(size_t)k * D + d], acc);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;       // four independent chains: the loop is L2-latency bound
+        int k = 0;
+        for (; k + 4 <= D; k += 4) {
+            a0 = fmaf(sy[k], __ldg(Wg + (size_t)k * D + d), a0);
+            a1 = fmaf(sy[k + 1], __ldg(Wg + (size_t)(k + 1) * D + d), a1);
+            a2 = fmaf(sy[k + 2], __ldg(Wg + (size_t)(k + 2) * D + d), a2);
+            a3 = fmaf(sy[k + 3], __ldg(Wg + (size_t)(k + 3) * D + d), a3);
+        }
+        for (; k < D; ++k) a0 = fmaf(sy[k], __ldg(Wg + (size_t)k * D + d), a0);
+        const float acc = (a0 + a1) + (a2 + a3);
         const float gt = acc * g_scale[d] + g_shift[d];
         z = y * (1.0f / (1.0f + expf(-gt)));
     }
