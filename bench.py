@@ -79,6 +79,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=24, help="clouds in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-retrieval", action="store_true")
+    ap.add_argument("--arch", default=ARCH, choices=["epc-net", "epc-net-l"],
+                    help="epc-net = BASELINE configs[1] (the headline); epc-net-l = configs[2] (lightweight variant)")
     return ap.parse_args()
 
 
@@ -122,7 +124,7 @@ class ClockSampler(object):
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -152,15 +154,15 @@ class ClockSampler(object):
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline(n_sample, V, params):
+def cpu_baseline(n_sample, V, params, arch=ARCH):
     """The reference's CPU path: dense-as-written restatement (oracle), ONE cloud per call like evaluate.py:355."""
     from oracle import epc_oracle
     clouds = make_clouds(n_sample, 4242)
-    epc_oracle.forward(ARCH, clouds[:1][None], V, params)          # warm-up (BLAS thread pools)
+    epc_oracle.forward(arch, clouds[:1][None], V, params)          # warm-up (BLAS thread pools)
     ts = []
     for i in range(n_sample):
         t0 = time.perf_counter()
-        epc_oracle.forward(ARCH, clouds[i:i + 1][None], V, params)
+        epc_oracle.forward(arch, clouds[i:i + 1][None], V, params)
         ts.append(time.perf_counter() - t0)
     return n_sample / float(np.sum(ts)), float(np.median(ts))
 
@@ -225,10 +227,11 @@ def main():
     evaluate = importlib.import_module("epc-net_b200.evaluate")
     models = importlib.import_module("epc-net_b200.models")
 
-    V = variables.synthetic_variables(ARCH, 1)
+    arch = args.arch
+    V = variables.synthetic_variables(arch, 1)
     store = variables.VariableStore(V)
-    params = dict(_data.default_params(ARCH), EMBED_CHUNK=args.chunk, VARIABLES=store)
-    eng = engine_mod.get_engine(ARCH, params, store=store)
+    params = dict(_data.default_params(arch), EMBED_CHUNK=args.chunk, VARIABLES=store)
+    eng = engine_mod.get_engine(arch, params, store=store)
     B, K, W = args.clouds, args.steps, args.warmup
     nbatch = min(K + W, 4)                                         # rotate distinct inputs; intermediates >> L2 anyway
     host_batches = [make_clouds(B, 1000 + 97 * rank + i) for i in range(nbatch)]
@@ -260,7 +263,6 @@ def main():
     launches = lib_mod.launch_count()
     stages = lib_mod.profile_read()
     lib_mod.profile_enable(False)
-    clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -268,7 +270,7 @@ def main():
     value = world * B * K / (ms * 1e-3)
 
     # ---- end to end: host arrays in, host arrays out, through the reference-facing call ---------------------
-    ops = {"MODEL": models.load(ARCH), "params": params}
+    ops = {"MODEL": models.load(arch), "params": params}
     names = {i: {} for i in range(B)}
     for i in range(min(W, 2)):
         evaluate.get_latent_vectors(None, ops, names, host_batches[i % nbatch])
@@ -283,8 +285,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e = world * B * K / e2e_s
+    clocks = sampler.stop() if rank == 0 else None          # sampled across both timed regions
     assert desc.shape == (B, 256) and np.isfinite(desc).all()
 
+    retr = None
+    if not args.no_retrieval:
+        retr = bench_retrieval(evaluate, torch, dist if world > 1 else None, rank, world)      # collective when world > 1
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -323,9 +329,12 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "tensor_operands": "fp16 (ProxyConv 64x64 layers), bf16 (conv5/assignment/VLAD), tf32 (hidden FC; EPC-Net-L conv5); fp32 accumulation",
         "data": "synthetic",
-        "config": {"workload": "EPC-Net (configs/epc-net.yaml: 4 ProxyConv blocks + G_VLAD, 256-d) batch embedding of "
-                               "synthetic uniform(-1,1) 4096-point clouds, seeded random-init weights, batch-sharded",
+        "config": {"workload": ("EPC-Net (configs/epc-net.yaml: 4 ProxyConv blocks + G_VLAD, 256-d)" if arch == "epc-net" else
+                                "EPC-Net-L (configs/epc-net-l.yaml: 2 ProxyConv blocks + max-pool + FC, 256-d)") +
+                               " batch embedding of synthetic uniform(-1,1) 4096-point clouds, seeded random-init weights, "
+                               "batch-sharded",
                    "clouds_per_gpu_per_step": B, "clouds_per_call": args.chunk, "knn_arith": "muladd",
                    "l2": "inputs rotate over %d distinct batches; every call streams >0.5 GB of intermediates "
                          "(>> 126 MB L2)" % nbatch},
@@ -334,9 +343,9 @@ def main():
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "stages": stage_table,
     }
     if not args.no_retrieval:
-        line["retrieval"] = bench_retrieval(evaluate, torch)
+        line["retrieval"] = retr
     if not args.no_cpu_baseline:
-        cps, med = cpu_baseline(args.cpu_sample, V, _data.default_params(ARCH))
+        cps, med = cpu_baseline(args.cpu_sample, V, _data.default_params(arch), arch)
         line["cpu_baseline"] = {"value": cps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                 "sample": "%d clouds, 1 cloud per call (evaluate.py:355), median %.3f s/cloud; numpy/BLAS "
                                           "dense-as-written restatement of the TF-1.12 graph" % (args.cpu_sample, med)}
@@ -345,32 +354,52 @@ def main():
         dist.destroy_process_group()
 
 
-def bench_retrieval(evaluate, torch):
-    """Secondary metrics of BASELINE.json: retrieval queries/s and recall@1 on SURVEY 8d C5 (D=20k, Q=3k, k=25)."""
+def bench_retrieval(evaluate, torch, dist, rank, world):
+    """Secondary metrics of BASELINE.json: retrieval queries/s and recall@1 on SURVEY 8d C5 (D=20k, Q=3k, k=25).
+    With N ranks the database rows are sharded N ways (queries replicated); every rank finds its local top-25 with global
+    row ids, one NCCL all-gather of (distance, index)[Q,25] per rank, then the (distance, index) merge (epc_merge_topk)."""
     from oracle import retrieval_oracle
-    db, q, src = _data.retrieval_problem(D=20000, Q=3000, seed=7)
-    dbt, qt = torch.from_numpy(db).cuda(), torch.from_numpy(q).cuda()
+    D, Q, k = 20000, 3000, 25
+    db, q, src = _data.retrieval_problem(D=D, Q=Q, seed=7)
+    qt = torch.from_numpy(q).cuda()
+    if dist is None:
+        dbt = torch.from_numpy(db).cuda()
+        run = lambda: evaluate.retrieve_topk(dbt, qt, k)
+    else:
+        dmod = importlib.import_module("epc-net_b200.dist")
+        s, e = dmod.shard_range(D, rank, world)
+        dbt = torch.from_numpy(db[s:e]).cuda()
+        run = lambda: dmod.retrieve_sharded(dmod.cuda_local_topk, dmod.cuda_merge, dbt, s, qt, k)
     for _ in range(2):
-        d, i = evaluate.retrieve_topk(dbt, qt, 25)
+        d, i = run()
     torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     reps = 5
     for _ in range(reps):
-        d, i = evaluate.retrieve_topk(dbt, qt, 25)
+        d, i = run()
     e1.record()
     torch.cuda.synchronize()
-    qps = reps * len(q) / (e0.elapsed_time(e1) * 1e-3)
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank != 0:
+        return None
+    qps = reps * Q / (ms * 1e-3)
     idx = i.cpu().numpy()
-    t0 = time.perf_counter()
     n_cpu = 200
-    _, ref = retrieval_oracle.kdtree_knn(db, q[:1], 25)
     from sklearn.neighbors import KDTree
     tree = KDTree(db)
+    tree.query(q[:1], k=k)
     t0 = time.perf_counter()
-    ref = np.stack([tree.query(q[j:j + 1], k=25)[1][0] for j in range(n_cpu)], 0)     # evaluate.py:481, one query per call
+    ref = np.stack([tree.query(q[j:j + 1], k=k)[1][0] for j in range(n_cpu)], 0)     # evaluate.py:481, one query per call
     cpu_qps = n_cpu / (time.perf_counter() - t0)
-    return {"queries_per_s": qps, "recall_at_1": float((idx[:, 0] == src).mean()), "D": 20000, "Q": 3000, "k": 25,
+    return {"queries_per_s": qps, "recall_at_1": float((idx[:, 0] == src).mean()), "D": D, "Q": Q, "k": k,
+            "db_shards": world, "collective": "nccl all_gather of (fp64 dist, int64 idx)[Q,25] per rank + merge" if world > 1 else None,
             "top25_identical_to_kdtree": bool(np.array_equal(idx[:n_cpu], ref)),
             "cpu_kdtree_queries_per_s": cpu_qps, "cpu_sample": "%d queries, sklearn KDTree, 1 query per call" % n_cpu}
 
