@@ -77,39 +77,45 @@ __device__ __forceinline__ void load_bias8(uint32_t addr, float (&b)[8]) {
     b[0] = __uint_as_float(lo.x); b[1] = __uint_as_float(lo.y); b[2] = __uint_as_float(lo.z); b[3] = __uint_as_float(lo.w);
     b[4] = __uint_as_float(hi.x); b[5] = __uint_as_float(hi.y); b[6] = __uint_as_float(hi.z); b[7] = __uint_as_float(hi.w);
 }
-// x0 = relu(BN(p W1 + b1)), cin = 3  (models/epc-net.py:66-69) -> 16-bit [B,N,64].  grid (N*8/256, B)
+// x0 = relu(BN(p W1 + b1)), cin = 3  (models/epc-net.py:66-69) -> 16-bit [B,N,64].  grid (ceil(N / 256), B): a CTA
+// converts 256 points (8 threads per point per pass, 8 passes), so the weight staging is amortised.
+constexpr int CI_POINTS = 256;
 template <int FMT>
-__global__ void conv_in_kernel(const float4* __restrict__ sorted, int N, const float* __restrict__ W,
-                               const float* __restrict__ bias, uint16_t* __restrict__ x, int* __restrict__ flags) {
+__global__ void __launch_bounds__(256) conv_in_kernel(const float4* __restrict__ sorted, int N, const float* __restrict__ W,
+                                                      const float* __restrict__ bias, uint16_t* __restrict__ x, int* __restrict__ flags) {
     const int b = blockIdx.y;
-    if (FMT == FMT_BF16 && flags[b] == 0) return;
-    __shared__ float sW[3 * 64 + 64];
-    for (int i = threadIdx.x; i < 3 * 64 + 64; i += blockDim.x) sW[i] = (i < 192) ? W[i] : bias[i - 192];
+    __shared__ float sW[4][64];                    // rows 0..2: W[k][c]; row 3: bias
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sW[i >> 6][i & 63] = (i < 192) ? W[i] : bias[i - 192];
     __syncthreads();
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = t >> 3;
-    const int c8 = (t & 7) * 8;
-    if (n >= N) return;
-    const size_t r = (size_t)b * N + n;
-    const float4 p = sorted[r];
-    float o[8];
+    const int c8 = (threadIdx.x & 7) * 8;
+    float w0[8], w1[8], w2[8], bb[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int c = c8 + i;
-        float acc = sW[192 + c];
-        acc = fmaf(p.x, sW[c], acc);
-        acc = fmaf(p.y, sW[64 + c], acc);
-        acc = fmaf(p.z, sW[128 + c], acc);
-        o[i] = fmaxf(acc, 0.f);
+        w0[i] = sW[0][c8 + i];
+        w1[i] = sW[1][c8 + i];
+        w2[i] = sW[2][c8 + i];
+        bb[i] = sW[3][c8 + i];
     }
-    if (FMT == FMT_F16 && max8(o) > F16_MAX) flags[b] = 1;
-    *reinterpret_cast<uint4*>(x + r * 64 + c8) = pack8<FMT>(o);
+    bool over = false;
+#pragma unroll 2
+    for (int pass = 0; pass < CI_POINTS / 32; ++pass) {
+        const int n = blockIdx.x * CI_POINTS + pass * 32 + (threadIdx.x >> 3);
+        if (n >= N) break;
+        const size_t r = (size_t)b * N + n;
+        const float4 p = __ldg(sorted + r);
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaxf(fmaf(p.z, w2[i], fmaf(p.y, w1[i], fmaf(p.x, w0[i], bb[i]))), 0.f);
+        if (FMT == FMT_F16) over |= (max8(o) > F16_MAX);
+        *reinterpret_cast<uint4*>(x + r * 64 + c8) = pack8<FMT>(o);
+    }
+    if (FMT == FMT_F16 && over) flags[b] = 1;
 }
 
 int conv_in(const float4* sorted, int B, int N, const DenseDev& L, uint16_t* x, int* flags, cudaStream_t st) {
     EPC_CHECK_ARG(L.cin == 3 && L.cout == 64, "conv_in expects a 3->64 layer, got %d->%d", L.cin, L.cout);
     if (B == 0) return EPC_OK;
-    dim3 grid((N * 8 + 255) / 256, B);
+    dim3 grid((N + CI_POINTS - 1) / CI_POINTS, B);
     conv_in_kernel<FMT_F16><<<grid, 256, 0, st>>>(sorted, N, L.W, L.b, x, flags);
     EPC_LAUNCH_CHECK();
     return EPC_OK;

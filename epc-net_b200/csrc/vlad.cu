@@ -87,8 +87,9 @@ int assign_softmax(const float* logits, const float* inv, const float* bn_scale,
 //   pass 2: every CTA re-derives the 64 column scales and the global scale from colss (fixed order) and scales its slice.
 constexpr int VF_ROWS = 128;
 
+template <int NSLAB>
 __global__ void __launch_bounds__(256)
-vlad_residual_kernel(const float* __restrict__ V, int nslab, long long slab, const float* __restrict__ a_sum, int a_parts,
+vlad_residual_kernel(const float* __restrict__ V, long long slab, const float* __restrict__ a_sum, int a_parts,
                      const float* __restrict__ Wc2, int F, int K, float* __restrict__ v, float* __restrict__ colss) {
     __shared__ float s_part[4][64];
     const int b = blockIdx.y, sl = blockIdx.x, tid = threadIdx.x;
@@ -110,14 +111,16 @@ vlad_residual_kernel(const float* __restrict__ V, int nslab, long long slab, con
         const int f0 = sl * VF_ROWS + grp, f1 = min((sl + 1) * VF_ROWS, F);
         constexpr int U = 8;                       // independent loads in flight per thread (the kernel is pure streaming)
         for (int fb = f0; fb < f1; fb += 4 * U) {
-            float acc[U], w2[U];
+            float part[U][NSLAB], w2[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int f = fb + 4 * u;
-                acc[u] = 0.f;
                 w2[u] = 0.f;
+#pragma unroll
+                for (int s = 0; s < NSLAB; ++s) part[u][s] = 0.f;
                 if (f < f1) {
-                    for (int s = 0; s < nslab; ++s) acc[u] += __ldg(Vb + s * slab + (size_t)f * K + c);
+#pragma unroll
+                    for (int s = 0; s < NSLAB; ++s) part[u][s] = __ldg(Vb + s * slab + (size_t)f * K + c);
                     w2[u] = __ldg(Wc2 + (size_t)f * K + c);
                 }
             }
@@ -125,7 +128,10 @@ vlad_residual_kernel(const float* __restrict__ V, int nslab, long long slab, con
             for (int u = 0; u < U; ++u) {
                 const int f = fb + 4 * u;
                 if (f < f1) {
-                    const float r = acc[u] - as * w2[u];
+                    float acc = 0.f;                 // split-K slabs summed in a fixed order
+#pragma unroll
+                    for (int s = 0; s < NSLAB; ++s) acc += part[u][s];
+                    const float r = acc - as * w2[u];
                     vb[(size_t)f * K + c] = r;
                     ss += r * r;
                 }
@@ -177,7 +183,16 @@ int vlad_finalize(const float* V, int nslab, long long slab, const float* a_sum,
     EPC_CHECK_ARG(K >= 1 && K <= 64, "vlad_finalize: cluster_size=%d unsupported (1..64)", K);
     if (B == 0) return EPC_OK;
     dim3 grid((F + VF_ROWS - 1) / VF_ROWS, B);
-    vlad_residual_kernel<<<grid, 256, 0, st>>>(V, nslab, slab, a_sum, a_parts, Wc2, F, K, v, colss);
+    if (nslab == 1)
+        vlad_residual_kernel<1><<<grid, 256, 0, st>>>(V, slab, a_sum, a_parts, Wc2, F, K, v, colss);
+    else if (nslab == 2)
+        vlad_residual_kernel<2><<<grid, 256, 0, st>>>(V, slab, a_sum, a_parts, Wc2, F, K, v, colss);
+    else if (nslab == 4)
+        vlad_residual_kernel<4><<<grid, 256, 0, st>>>(V, slab, a_sum, a_parts, Wc2, F, K, v, colss);
+    else {
+        set_error("vlad_finalize: %d split-K slabs unsupported (1, 2 or 4)", nslab);
+        return EPC_EUNSUPPORTED;
+    }
     EPC_LAUNCH_CHECK();
     vlad_scale_kernel<<<grid, 256, 0, st>>>(v, colss, F, K);
     EPC_LAUNCH_CHECK();
