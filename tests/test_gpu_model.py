@@ -106,6 +106,23 @@ def test_batch_independence_and_determinism(pkg):
     assert torch.equal(a, b) and torch.equal(a[2:3], c) and torch.equal(a, e_big.embed(x))
 
 
+def test_fp16_range_fallback_is_per_cloud(pkg):
+    """The ProxyConv chain runs in fp16 and re-runs in fp32 every cloud whose activations left the fp16 range (the all-zero
+    "fake" clouds of evaluate.py:425-430 grow by N/20 per block).  The fallback must (a) reproduce the oracle for the
+    degenerate cloud and (b) leave the other clouds of the batch bit-identical to a batch without it."""
+    for arch in ("epc-net", "epc-net-l"):
+        V = pkg.variables.synthetic_variables(arch, 8)
+        params = dict(_data.default_params(arch), VARIABLES=pkg.variables.VariableStore(V))
+        normal = np.stack([_data.cloud("uniform", 300 + i, 4096) for i in range(3)], 0)
+        mixed = np.concatenate([normal[:1], np.zeros((1, 4096, 3), np.float32), normal[1:]], 0)
+        f = pkg.models.load(arch).forward
+        a = f(torch.from_numpy(normal[None]).cuda(), False, params=params)[0]
+        b = f(torch.from_numpy(mixed[None]).cuda(), False, params=params)[0]
+        assert torch.equal(a, b[[0, 2, 3]]), arch
+        ref = epc_oracle.forward(arch, mixed[None, 1:2], V, params)
+        _check_desc(b[1:2].cpu().numpy(), ref, arch + " zero cloud")
+
+
 def test_point_permutation_invariance(pkg):
     """Full-size property: descriptors do not depend on the order of the points of a cloud (kNN sets, max-pool and
     VLAD sums are permutation invariant; only fp32 summation order moves)."""
