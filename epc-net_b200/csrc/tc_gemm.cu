@@ -1,4 +1,5 @@
 // Instantiations of the tcgen05 GEMM template (tc_gemm.cuh) for the dense contractions of the EPC-Net head.
+#include <stdlib.h>
 #include "tc_gemm.cuh"
 #include "kernels.h"
 
@@ -10,6 +11,11 @@ int tc_conv5_bf16(const __nv_bfloat16* Xc, long long R, int cin, const __nv_bflo
     tc::GemmParams p = {};
     p.M = (int)R; p.N = 1024; p.K = cin; p.splitk = 1; p.C = H; p.ldc = 1024; p.bias = b5; p.relu = 1; p.aux = rowss;
     Operand<__nv_bfloat16> a{Xc, R, cin, cin}, b{W5t, 1024, cin, cin};
+    // Variant with the A tiles TMA-multicast to a cluster of the 4 N-tile CTAs (L2->SM operand traffic / 4): correct, but
+    // measured slower on B200 (2.72 vs 2.47 us/cloud) -- the kernel is bound by the 8 MiB/cloud H write, not by operand
+    // reads, and the cluster couples four CTAs' pipelines.  Kept selectable for experiments.
+    static const bool mc = getenv("EPC_CONV5_MULTICAST") != nullptr;
+    if (mc) return tc_gemm_bres_launch<__nv_bfloat16, 256, tc::EPI_CONV5_BF16, 8, 4>(a, b, p, st);
     return tc_gemm_bres_launch<__nv_bfloat16, 256, tc::EPI_CONV5_BF16, 8>(a, b, p, st);
 }
 int conv5_rowss_parts() { return 8; }     // 1024 / BN(256) N tiles x 2 epilogue warps per lane quarter

@@ -54,6 +54,27 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// 2-D TMA tile load multicast to every CTA of the cluster named in cta_mask: the tile lands at the same shared-memory
+// offset in each of them and completes (bytes) on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
+// arrive (once all previously issued MMAs of this thread completed) on the mbarrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
@@ -487,7 +508,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //   warps 2-5  epilogue of tile i while the tensor core already works on tile i+1
 // grid.x = (#CTAs, a multiple of N/BN); CTA c: N tile c % (N/BN), row tiles c / (N/BN), + gridDim.x / (N/BN), ...
 // ---------------------------------------------------------------------------------------------------------
-template <typename T, int BN, int EPI, int EW /*epilogue warps: 4, or 8 = two per TMEM lane quarter*/>
+template <typename T, int BN, int EPI, int EW /*epilogue warps: 4, or 8 = two per TMEM lane quarter*/,
+          int CL = 1 /*cluster size: CL > 1 = the N/BN == CL CTAs of a cluster share every A tile by TMA multicast*/>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p,
                     const int a_stages) {
@@ -511,8 +533,11 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NT = p.N / BN;
-    const int n_tile = blockIdx.x % NT, cta_m = blockIdx.x / NT, m_stride = gridDim.x / NT;
+    // CL > 1: cluster = the NT (== CL) N tiles of one M-tile stream; rank in cluster = N tile
+    const int n_tile = (CL > 1) ? (int)cluster_ctarank() : (int)(blockIdx.x % NT);
+    const int cta_m = blockIdx.x / NT, m_stride = gridDim.x / NT;
     const int n0 = n_tile * BN;
+    constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1u);
     const int num_m_tiles = (p.M + TC_BM - 1) / TC_BM;
     constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
 
@@ -521,7 +546,7 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < a_stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], CL);          // every CTA of the cluster frees the slot (multicast commit)
         }
         mbar_init(b_full, 1);
         for (int i = 0; i < 2; ++i) {
@@ -538,6 +563,7 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int i = threadIdx.x; i < BN; i += blockDim.x) sBias[i] = p.bias[n0 + i];
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync();                // peers' barriers are initialised before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -552,7 +578,10 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const uint32_t ph = (it / a_stages) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
                     mbar_expect_tx(&full[s], A_BYTES);
-                    tma_load_2d(sA + (size_t)s * A_BYTES, &tmA, &full[s], kb * BK, mt * TC_BM);
+                    if (CL == 1)
+                        tma_load_2d(sA + (size_t)s * A_BYTES, &tmA, &full[s], kb * BK, mt * TC_BM);
+                    else if (kb % CL == n_tile)    // this CTA's share of the tile, delivered to the whole cluster
+                        tma_load_2d_mc(sA + (size_t)s * A_BYTES, &tmA, &full[s], kb * BK, mt * TC_BM, CL_MASK);
                 }
             }
         }
@@ -579,7 +608,10 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const uint64_t db = smem_desc_sw128(b_addr + kk * 32, 16, 1024);
                         mma_ss<Tr::F16>(tmem_d, da, db, idesc, (kb | kk) != 0);
                     }
-                    mma_commit(&empty[s]);
+                    if (CL == 1)
+                        mma_commit(&empty[s]);
+                    else
+                        mma_commit_mc(&empty[s], CL_MASK);
                 }
                 mma_commit(&tfull[buf]);
             }
@@ -609,6 +641,7 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync();                // no CTA leaves while a peer may still multicast into it
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -716,7 +749,7 @@ inline int sm_count() {
 }
 
 // Persistent B-resident launch: A [M,K], B [N,K] both K-major; one CTA per SM (rounded to a multiple of N/BN).
-template <typename T, int BN, int EPI, int EW = 4>
+template <typename T, int BN, int EPI, int EW = 4, int CL = 1>
 inline int tc_gemm_bres_launch(const Operand<T>& A, const Operand<T>& B, const tc::GemmParams& p, cudaStream_t st) {
     constexpr int BK = tc::ElemTraits<T>::PER128;
     constexpr size_t A_BYTES = tc::TC_BM * 128, B_BYTES = BN * 128;
@@ -736,7 +769,7 @@ inline int tc_gemm_bres_launch(const Operand<T>& A, const Operand<T>& B, const t
     if (int rc = make_tmap_2d(&tmA, A.ptr, A.rows, A.cols, A.ld, BK, tc::TC_BM)) return rc;
     if (int rc = make_tmap_2d(&tmB, B.ptr, B.rows, B.cols, B.ld, BK, BN)) return rc;
     static_assert(EW == 4 || (EW == 8 && EPI != tc::EPI_ASSIGN && BN >= 64), "8 epilogue warps split the tile's columns");
-    auto kern = tc::tc_gemm_bres_kernel<T, BN, EPI, EW>;
+    auto kern = tc::tc_gemm_bres_kernel<T, BN, EPI, EW, CL>;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
         EPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -744,6 +777,29 @@ inline int tc_gemm_bres_launch(const Operand<T>& A, const Operand<T>& B, const t
     }
     const int NT = p.N / BN;
     const int m_tiles = (p.M + tc::TC_BM - 1) / tc::TC_BM;
+    if (CL > 1) {
+        // one cluster = the NT N tiles of an M-tile stream; as many clusters as fit on the device at once (persistent)
+        EPC_CHECK_ARG(NT == CL, "tc_gemm_bres: cluster size %d needs N/BN == %d, got %d", CL, CL, NT);
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3(CL, 1, 1); cfg.blockDim = dim3(64 + 32 * EW, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        static int max_clusters = 0;
+        if (!max_clusters) {
+            cfg.gridDim = dim3(CL * (sm_count() / CL), 1, 1);
+            int n = 0;
+            EPC_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+            EPC_CHECK_ARG(n >= 1, "tc_gemm_bres: no cluster of %d CTAs fits on this device", CL);
+            max_clusters = n;
+        }
+        const int clusters = max_clusters < m_tiles ? max_clusters : m_tiles;
+        cfg.gridDim = dim3(clusters * CL, 1, 1);
+        EPC_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p, a_stages));
+        count_launch();
+        return EPC_OK;
+    }
     int per_nt = sm_count() / NT;
     if (per_nt < 1) per_nt = 1;
     if (per_nt > m_tiles) per_nt = m_tiles;
