@@ -68,12 +68,9 @@ int sgemm(const GemmArgs& g, cudaStream_t st);
 
 // ---- vlad.cu -----------------------------------------------------------------------------------
 int row_inv_norm(const float* X, long long R, int F, float* inv, cudaStream_t st);
-int assign_softmax(const float* logits, const float* inv, const float* bn_scale, const float* bn_shift, int B, int N,
-                   int K, float* S, float* a_sum, cudaStream_t st);
 // V: nslab split-K slabs of [B,F,K] (slab elements apart); a_sum: [B, a_parts, K] partial column sums
 int vlad_finalize(const float* V, int nslab, long long slab, const float* a_sum, int a_parts, const float* Wc2, int B,
                   int F, int K, float* v, float* colss /*[B, F/128, K] scratch*/, cudaStream_t st);
-constexpr int ASSIGN_PARTS = 16;   // FFMA assign path: a_sum is produced as [B, ASSIGN_PARTS, K] partials
 constexpr int HIDDEN_SPLITK = 32;  // hidden FC split-K slabs [HIDDEN_SPLITK, B*G, D]
 constexpr int VLAD_SPLITK = 2;     // VLAD accumulate split-K slabs
 

@@ -29,58 +29,6 @@ int row_inv_norm(const float* X, long long R, int F, float* inv, cudaStream_t st
     return EPC_OK;
 }
 
-// Soft assignment (loupe.py:255-276): logits are the RAW products H.Wc of un-normalised rows; the row
-// scale inv[n] = 1/|H_n| is applied here (exact: the product is linear in the row).
-//   act = softmax_c( BN(logit * inv) );  S'[n,c] = act * inv  (so that sum_n S'[n,c] H[n,f] = sum_n act X[n,f]);
-//   a_sum[b,c] += act.
-// One warp per point; K <= 64 (lane handles c = lane and lane + 32).
-__global__ void assign_softmax_kernel(const float* __restrict__ logits, const float* __restrict__ inv,
-                                      const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, int N,
-                                      int K, float* __restrict__ S, float* __restrict__ a_sum) {
-    __shared__ float s_part[8][64];
-    const int b = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    const int c0 = lane, c1 = lane + 32;
-    const float sc0 = (c0 < K) ? bn_scale[c0] : 0.f, sh0 = (c0 < K) ? bn_shift[c0] : 0.f;
-    const float sc1 = (c1 < K) ? bn_scale[c1] : 0.f, sh1 = (c1 < K) ? bn_shift[c1] : 0.f;
-    float acc0 = 0.f, acc1 = 0.f;
-    const int per = (N + gridDim.x - 1) / gridDim.x;
-    const int n_begin = blockIdx.x * per, n_end = min(N, n_begin + per);
-    for (int n = n_begin + warp; n < n_end; n += nwarp) {
-        const size_t row = (size_t)b * N + n;
-        const float iv = inv ? inv[row] : 1.0f;      // inv == nullptr: rows are used as given (loupe API)
-        const float l0 = (c0 < K) ? (logits[row * K + c0] * iv) * sc0 + sh0 : -INFINITY;
-        const float l1 = (c1 < K) ? (logits[row * K + c1] * iv) * sc1 + sh1 : -INFINITY;
-        const float mx = warp_max(fmaxf(l0, l1));
-        const float e0 = (c0 < K) ? expf(l0 - mx) : 0.f;
-        const float e1 = (c1 < K) ? expf(l1 - mx) : 0.f;
-        const float den = warp_sum(e0 + e1);
-        const float a0 = e0 / den, a1 = e1 / den;
-        if (c0 < K) S[row * K + c0] = a0 * iv;
-        if (c1 < K) S[row * K + c1] = a1 * iv;
-        acc0 += a0;
-        acc1 += a1;
-    }
-    s_part[warp][c0] = acc0;
-    s_part[warp][c1] = acc1;
-    __syncthreads();
-    if (threadIdx.x < K) {     // fixed summation order => bit-reproducible; a_sum is [B, ASSIGN_PARTS, K] partials
-        float t = 0.f;
-        for (int w = 0; w < nwarp; ++w) t += s_part[w][threadIdx.x];
-        a_sum[((size_t)b * gridDim.x + blockIdx.x) * K + threadIdx.x] = t;
-    }
-}
-
-int assign_softmax(const float* logits, const float* inv, const float* bn_scale, const float* bn_shift, int B, int N,
-                   int K, float* S, float* a_sum, cudaStream_t st) {
-    EPC_CHECK_ARG(K >= 1 && K <= 64, "assign_softmax: cluster_size=%d unsupported (1..64)", K);
-    if (B == 0) return EPC_OK;
-    dim3 grid(ASSIGN_PARTS, B);
-    assign_softmax_kernel<<<grid, 256, 0, st>>>(logits, inv, bn_scale, bn_shift, N, K, S, a_sum);
-    EPC_LAUNCH_CHECK();
-    return EPC_OK;
-}
-
 // VLAD finalise (loupe.py:284-298): r[f,c] = V[f,c] - a_sum[c] * Wc2[f,c]; L2 over f per (b,c); flatten f-major
 // (index f*K + c); global L2.  Two passes over (cloud, 128-feature slice) CTAs:
 //   pass 1: r -> v (unnormalised), partial column sums of squares -> colss [B, F/128, K]

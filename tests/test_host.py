@@ -163,3 +163,29 @@ def test_sharded_retrieval_and_embedding_world2_gloo():
         p.join(60)
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(r[1] and r[2] for r in res), res
+
+
+def test_loading_pointclouds_wire_formats(tmp_path):
+    """.bin float64 clouds (utils/loading_pointclouds.py:26-65) and the evaluation pickles."""
+    import pickle
+    lp = importlib.import_module("epc-net_b200.utils.loading_pointclouds")
+    rng = np.random.default_rng(0)
+    good = rng.uniform(-1, 1, (4096, 3))
+    good.astype(np.float64).tofile(tmp_path / "a.bin")
+    rng.uniform(-1, 1, (100, 3)).tofile(tmp_path / "short.bin")
+    pc = lp.load_pc_file("a.bin", str(tmp_path))
+    assert pc.dtype == np.float64 and pc.shape == (4096, 3) and np.array_equal(pc, good)
+    assert not lp.load_pc_file("short.bin", str(tmp_path)).any()                    # wrong size -> zeros (:33-38)
+    assert lp.load_pc_files(["a.bin", "short.bin"], str(tmp_path)).shape == (2, 4096, 3)
+    runs = [{0: {"query": "a.bin", "northing": 1.0, "easting": 2.0, 1: [0]}, 1: {"query": "short.bin", "northing": 3.0, "easting": 4.0}},
+            {0: {"query": "a.bin", "northing": 1.5, "easting": 2.5, 0: [0, 1]}}]
+    with open(tmp_path / "db.pickle", "wb") as f:
+        pickle.dump(runs, f)
+    sets = lp.get_sets_dict(str(tmp_path / "db.pickle"))
+    data = lp.load_pc_data_set(sets, str(tmp_path))
+    assert [d.shape for d in data] == [(2, 4096, 3), (1, 4096, 3)] and data[0].dtype == np.float32
+    assert np.array_equal(data[0][0], good.astype(np.float32)) and not data[0][1].any()
+    feat = rng.uniform(0, 5, (4096, 13))
+    feat.tofile(tmp_path / "f.bin")
+    p13 = lp.load_pc_file("f.bin", str(tmp_path), input_dim=13)
+    assert p13.shape == (4096, 13) and p13[:, 3:12].min() >= 0 and p13[:, 3:12].max() <= 1 and np.array_equal(p13[:, :3], feat[:, :3])
