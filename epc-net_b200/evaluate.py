@@ -73,6 +73,17 @@ def retrieve_topk(database_output, queries_output, k, id_offset=0):
     return dist, idx
 
 
+def get_random_hard_negatives(query_vec, random_negs, num_to_take, training_latent_vectors):
+    """train.py:857-869: the ``num_to_take`` candidates of ``random_negs`` whose cached descriptors are
+    nearest to ``query_vec`` -- the reference builds a KDTree over ``TRAINING_LATENT_VECTORS[random_negs]`` per query;
+    here it is one exact GPU k-NN (same indices).  ``training_latent_vectors`` replaces the reference's global."""
+    random_negs = np.asarray(random_negs)
+    latent_vecs = np.asarray(training_latent_vectors, dtype=np.float32)[random_negs]
+    _, indices = retrieve_topk(latent_vecs, np.asarray(query_vec, dtype=np.float32)[None], int(num_to_take))
+    hard_negs = np.squeeze(random_negs[indices[0].cpu().numpy()])
+    return hard_negs.tolist()
+
+
 def recall_from_neighbors(indices, valid, true_neighbors_list, queries_output, database_output, num_db,
                           num_neighbors=NUM_NEIGHBORS):
     """The bookkeeping of evaluate.py:466-530 given the retrieved ``indices`` (one row per evaluated query)."""

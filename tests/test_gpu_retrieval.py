@@ -87,3 +87,16 @@ def test_get_recall_flow(ev):
             oprs.append(opr)
     ave, avs, avo = R.evaluate_pairs(dbv, qv, qsets)
     assert np.allclose(tot / cnt, ave) and np.isclose(np.mean(sims), avs) and np.isclose(np.mean(oprs), avo)
+
+
+def test_get_random_hard_negatives_matches_kdtree(ev):
+    """train.py:857-869 through the GPU k-NN: same picks as the reference's per-query KDTree."""
+    from sklearn.neighbors import KDTree
+    rng = np.random.default_rng(11)
+    latent = rng.standard_normal((4000, 256)).astype(np.float32)
+    latent /= np.linalg.norm(latent, axis=1, keepdims=True)
+    random_negs = rng.choice(4000, 2000, replace=False)
+    q = latent[17] + 0.1 * rng.standard_normal(256).astype(np.float32)
+    got = ev.get_random_hard_negatives(q, random_negs.tolist(), 10, latent)
+    _, ind = KDTree(latent[random_negs]).query(np.array([q]), k=10)
+    assert got == np.squeeze(random_negs[ind[0]]).tolist()
