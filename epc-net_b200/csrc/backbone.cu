@@ -209,6 +209,7 @@ struct PbArgs {
     const uint16_t* nbr;      // [B,N,20] neighbour positions, out-of-tile ones first
     const float* kthd;        // [B,N]
     const int* cnt;           // [B,N]  |thresholded set| | (#out-of-tile neighbours << 24)
+    const uint32_t* tie;      // [B][TIE_WORDS] set members beyond the 20 listed ones (kernels.h)
     const float4* sorted;     // [B,N]
     int* flags;               // [B]  cloud left the fp16 range
     int N, arith, tiles_per_cloud, num_tiles;
@@ -358,17 +359,46 @@ __global__ void __launch_bounds__(PB_THREADS, 1) proxy_block_kernel(const PbArgs
                 const unsigned tie_mask = __ballot_sync(FULL, count != KNN_K);
                 if (tie_mask) {
                     const size_t row_tile = (size_t)b * N + tile0;
+                    const uint32_t* tl = p.tie + (size_t)b * TIE_WORDS;
+                    const uint32_t n_tie = __ldg(tl);
                     for (int g = 0; g < 4; ++g) {
                         if (!((tie_mask >> (8 * g)) & 1u)) continue;                    // warp-uniform
                         const size_t trow = row_tile + (pl - grp) + g;
                         const float thr = __ldg(p.kthd + trow);
-                        const float4 qp = p.sorted[trow];
-                        const float4* sp = p.sorted + (size_t)b * N;
+                        const int want = (__shfl_sync(FULL, count, 8 * g) & 0xffffff) - KNN_K;     // members beyond the listed 20
+                        // (a) the kNN kernel logged them in the cloud's tie list: add exactly those
+                        int found = 0;
                         float a2[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) a2[i] = 0.f;
-                        // N is a multiple of 128: four 32-point blocks per step, their loads in flight together (one warp
-                        // re-scans the cloud while its CTA waits: latency, not throughput, is what matters here)
+                        if (n_tie <= TIE_CAP) {
+                            const uint32_t tag = (uint32_t)(tile0 + (pl - grp) + g);
+                            for (uint32_t e0 = 0; e0 < n_tie; e0 += 32) {
+                                uint2 ent = make_uint2(0xffffffffu, 0u);
+                                if (e0 + lane < n_tie) ent = __ldg(reinterpret_cast<const uint2*>(tl + 2) + e0 + lane);
+                                unsigned mk = __ballot_sync(FULL, (ent.x >> 16) == tag && ent.y == __float_as_uint(thr));
+                                found += __popc(mk);
+                                while (mk) {
+                                    const int src = __ffs(mk) - 1;
+                                    mk &= mk - 1;
+                                    const uint32_t j = __shfl_sync(FULL, ent.x, src) & 0xffffu;
+                                    if (grp == g) add8<FMT>(a2, __ldg(reinterpret_cast<const uint4*>(xb + (size_t)j * 128)));
+                                }
+                            }
+                        }
+                        if (n_tie <= TIE_CAP && found == want) {
+                            if (grp == g) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) acc[i] += a2[i];
+                            }
+                            continue;
+                        }
+                        // (b) list overflow (degenerate clouds): exact re-scan of the cloud
+                        const float4 qp = p.sorted[trow];
+                        const float4* sp = p.sorted + (size_t)b * N;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) a2[i] = 0.f;
+                        // N is a multiple of 128: four 32-point blocks per step, their loads in flight together
                         for (int j0 = 0; j0 < N; j0 += 128) {
                             float4 pj[4];
 #pragma unroll
@@ -566,7 +596,7 @@ int proxy_block(const uint16_t* x, const KnnState& g, int B, int N, int arith, f
     }
     auto img = [&](const DenseDev& L) { return reinterpret_cast<const uint4*>(L.Wimg); };
     PbArgs a = {};
-    a.x = x; a.nbr = g.nbr; a.kthd = g.kthd; a.cnt = g.cnt; a.sorted = g.sorted; a.flags = flags;
+    a.x = x; a.nbr = g.nbr; a.kthd = g.kthd; a.cnt = g.cnt; a.tie = g.tie; a.sorted = g.sorted; a.flags = flags;
     a.N = N; a.arith = arith; a.tiles_per_cloud = N / PB_TILE; a.num_tiles = B * (N / PB_TILE);
     a.inv_div = 1.0f / divisor;                           // one rounding away from a true division by float(k)
     a.Wa_img = img(conv_a); a.ba = conv_a.b;

@@ -14,11 +14,15 @@ struct KnnState {          // per-cloud kNN graph in *sorted* (Morton) point ord
     float* kthd;           // [B,N]   20th smallest d
     int* cnt;              // [B,N]   |{j : d_ij <= kthd_i}| (>= 20) in the low 24 bits | (# neighbours outside the row's 128-point tile) << 24
     float4* aabb;          // [B][2][N/32] per 32-point block: (lo.xyz, max |p|^2), then (hi.xyz, -)
+    uint32_t* tie;         // [B][TIE_WORDS] per cloud: count, pad, then up to TIE_CAP entries (row << 16 | neighbour, d bits):
+                           // the members of thresholded sets beyond the 20 listed ones (ties at the 20th distance)
 };
+constexpr uint32_t TIE_CAP = 510;                  // entries per cloud; more (degenerate clouds) -> the gather re-scans the cloud
+constexpr uint32_t TIE_WORDS = 2 + 2 * TIE_CAP;    // 4 KB per cloud
 int knn_check_n(int N);
 size_t knn_state_bytes(int B, int N);
 KnnState knn_state_carve(Arena& ar, int B, int N);
-int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sorted, int* perm, uint16_t* perm16, float4* aabb, uint16_t* nbr,
+int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sorted, int* perm, uint16_t* perm16, float4* aabb, uint32_t* tie, uint16_t* nbr,
               float* kthd, int* cnt, int32_t* idx_out, float* kth_out, int32_t* count_out, cudaStream_t st);
 int knn_dense(const float* xyz, int B, int N, int arith, const float* kth, float* mask, float* dist, cudaStream_t st);
 int rows_topk_smallest(const float* adj, long long R, int M, int k, int32_t* idx, cudaStream_t st);

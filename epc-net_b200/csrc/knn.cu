@@ -133,6 +133,10 @@ struct RowState {
 };
 constexpr uint32_t KEY_EMPTY = 0xffffffffu;
 constexpr int KNN_CAP = 64;      // buffer entries per row = two per lane during a compaction
+constexpr int KNN_ROWS_PER_WARP = 8;
+constexpr int KNN_WARPS = 8;
+constexpr int KNN_ROWS_PER_CTA = KNN_ROWS_PER_WARP * KNN_WARPS;
+constexpr size_t KNN_BUF_BYTES = (size_t)KNN_ROWS_PER_CTA * KNN_CAP * 8;     // candidate values + keys: the first bytes of the dynamic smem
 
 __device__ __forceinline__ bool key_lt(float av, uint32_t ak, float bv, uint32_t bk) {
     return (av < bv) || (av == bv && ak < bk);
@@ -220,6 +224,23 @@ __device__ __noinline__ RowState compact(RowState R, float* __restrict__ bv, uin
             if (t0 && k0 == best) { t0 = false; keep0 = true; }
             if (t1 && k1 == best) { t1 = false; keep1 = true; }
         }
+        // The dropped tied candidates belong to the row's thresholded set if thr_new turns out to be its final threshold:
+        // log them (row, position, value) in the cloud's tie list so that the ProxyConv gather can add them without
+        // re-scanning the cloud.  An overflowing list (degenerate clouds) makes the gather fall back to the re-scan.
+        // (row and list are recovered from the buffer address: the candidate buffers open the dynamic shared memory and
+        // the kernel leaves the list pointer right behind them -- extra arguments would cost this call's ABI registers)
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        const uint32_t row_pos = blockIdx.x * KNN_ROWS_PER_CTA + (uint32_t)((bv - reinterpret_cast<float*>(smem_raw)) / KNN_CAP);
+        uint32_t* tie = *reinterpret_cast<uint32_t**>(smem_raw + KNN_BUF_BYTES);
+        const bool room = *reinterpret_cast<volatile uint32_t*>(tie) <= TIE_CAP;      // stop counting once the list has overflowed
+        if (t0 && room) {
+            const uint32_t slot = atomicAdd(tie, 1u);
+            if (slot < TIE_CAP) reinterpret_cast<uint2*>(tie + 2)[slot] = make_uint2((row_pos << 16) | (k0 & 0xffffu), __float_as_uint(o0));
+        }
+        if (t1 && room) {
+            const uint32_t slot = atomicAdd(tie, 1u);
+            if (slot < TIE_CAP) reinterpret_cast<uint2*>(tie + 2)[slot] = make_uint2((row_pos << 16) | (k1 & 0xffffu), __float_as_uint(o1));
+        }
     }
     R.extra = ((thr_new == R.thr) ? R.extra : 0) + (c_eq - need_eq);
     R.thr = thr_new;
@@ -272,29 +293,29 @@ __device__ __forceinline__ void append_hits(RowState& R, unsigned m, float d, in
 // a row is re-compacted after the index-neighbour blocks only if its buffer holds more than this many candidates
 // (measured: 20 -> 9.11, 32 -> 8.79, 44 -> 8.85, 64 = never -> 8.97 us/cloud)
 constexpr int KNN_STAGE1_MIN = 32;
-constexpr int KNN_ROWS_PER_WARP = 8;
-constexpr int KNN_WARPS = 8;
-constexpr int KNN_ROWS_PER_CTA = KNN_ROWS_PER_WARP * KNN_WARPS;
 
 template <int ARITH, bool PRUNE>
-__global__ void __launch_bounds__(KNN_WARPS * 32)
-knn_kernel(const float4* __restrict__ sorted, const uint16_t* __restrict__ perm16, const float4* __restrict__ aabb, int N,
+__global__ void __launch_bounds__(KNN_WARPS * 32, 2)
+knn_kernel(const float4* __restrict__ sorted, const uint16_t* __restrict__ perm16, const float4* __restrict__ aabb,
+           uint32_t* __restrict__ tie_all, int N,
            uint16_t* __restrict__ nbr, float* __restrict__ kthd, int* __restrict__ cnt, int32_t* __restrict__ idx_out,
            float* __restrict__ kth_out, int32_t* __restrict__ count_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nblk = N >> 5;
-    float4* spts = reinterpret_cast<float4*>(smem_raw);   // [N]   (x,y,z,s)
+    float* sbv = reinterpret_cast<float*>(smem_raw);                          // [warps][rows][CAP] candidate values (compact() relies on offset 0)
+    uint32_t* sbk = reinterpret_cast<uint32_t*>(sbv + KNN_WARPS * KNN_ROWS_PER_WARP * KNN_CAP);   // ... and keys
+    uint32_t** stie = reinterpret_cast<uint32_t**>(smem_raw + KNN_BUF_BYTES);                     // this cloud's tie list (for compact())
+    uint64_t* ldbar = reinterpret_cast<uint64_t*>(stie + 1);
+    float4* spts = reinterpret_cast<float4*>(smem_raw + KNN_BUF_BYTES + 16);   // [N]   (x,y,z,s)
     float4* sblo = spts + N;                              // [nblk] (lo.xyz, max s)
     float4* sbhi = sblo + nblk;                           // [nblk] (hi.xyz, -)
     unsigned short* sperm = reinterpret_cast<unsigned short*>(sbhi + nblk);   // [N] sorted position -> original index
-    float* sbv = reinterpret_cast<float*>(sperm + N);                         // [warps][rows][CAP] candidate values
-    uint32_t* sbk = reinterpret_cast<uint32_t*>(sbv + KNN_WARPS * KNN_ROWS_PER_WARP * KNN_CAP);   // ... and keys
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // the whole cloud (points, block boxes, permutation) arrives by three TMA bulk copies issued by one thread
-    uint64_t* ldbar = reinterpret_cast<uint64_t*>(sbk + KNN_WARPS * KNN_ROWS_PER_WARP * KNN_CAP);
     {
         const uint32_t bar = (uint32_t)__cvta_generic_to_shared(ldbar);
         if (tid == 0) {
+            *stie = tie_all + (size_t)blockIdx.y * TIE_WORDS;
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -543,7 +564,7 @@ int knn_check_n(int N) {
     return EPC_OK;
 }
 
-int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sorted, int* perm, uint16_t* perm16, float4* aabb, uint16_t* nbr,
+int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sorted, int* perm, uint16_t* perm16, float4* aabb, uint32_t* tie, uint16_t* nbr,
               float* kthd, int* cnt, int32_t* idx_out, float* kth_out, int32_t* count_out, cudaStream_t st) {
     if (int rc = knn_check_n(N)) return rc;
     EPC_CHECK_ARG(arith == EPC_KNN_ARITH_MULADD || arith == EPC_KNN_ARITH_FMA, "bad knn arith %d", arith);
@@ -565,19 +586,20 @@ int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sor
         sort_kernel<<<B, 1024, sort_smem, st>>>(xyz, N, NP, sorted, perm, perm16, aabb);
         EPC_LAUNCH_CHECK();
     }
+    EPC_CUDA(cudaMemsetAsync(tie, 0, (size_t)B * TIE_WORDS * sizeof(uint32_t), st));      // counters (and stale entries)
     ScopedStage ss(EPC_STAGE_KNN, st);
     dim3 grid((N + KNN_ROWS_PER_CTA - 1) / KNN_ROWS_PER_CTA, B);
     const int th = KNN_WARPS * 32;
     if (arith == EPC_KNN_ARITH_MULADD) {
         if (prune)
-            knn_kernel<0, true><<<grid, th, knn_smem, st>>>(sorted, perm16, aabb, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
+            knn_kernel<0, true><<<grid, th, knn_smem, st>>>(sorted, perm16, aabb, tie, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
         else
-            knn_kernel<0, false><<<grid, th, knn_smem, st>>>(sorted, perm16, aabb, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
+            knn_kernel<0, false><<<grid, th, knn_smem, st>>>(sorted, perm16, aabb, tie, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
     } else {
         if (prune)
-            knn_kernel<1, true><<<grid, th, knn_smem, st>>>(sorted, perm16, aabb, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
+            knn_kernel<1, true><<<grid, th, knn_smem, st>>>(sorted, perm16, aabb, tie, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
         else
-            knn_kernel<1, false><<<grid, th, knn_smem, st>>>(sorted, perm16, aabb, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
+            knn_kernel<1, false><<<grid, th, knn_smem, st>>>(sorted, perm16, aabb, tie, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
     }
     EPC_LAUNCH_CHECK();
     return EPC_OK;
@@ -585,13 +607,14 @@ int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sor
 
 size_t knn_state_bytes(int B, int N) {
     const size_t R = (size_t)B * N;
-    return align_up(R * sizeof(float4)) + align_up(R * sizeof(int)) + align_up(R * sizeof(uint16_t)) + align_up(R * KNN_K * sizeof(uint16_t)) +
+    return align_up((size_t)B * TIE_WORDS * sizeof(uint32_t)) + align_up(R * sizeof(float4)) + align_up(R * sizeof(int)) + align_up(R * sizeof(uint16_t)) + align_up(R * KNN_K * sizeof(uint16_t)) +
            align_up(R * sizeof(float)) + align_up(R * sizeof(int)) + align_up(R / 16 * sizeof(float4));
 }
 
 KnnState knn_state_carve(Arena& ar, int B, int N) {
     const size_t R = (size_t)B * N;
     KnnState s;
+    s.tie = ar.take<uint32_t>((size_t)B * TIE_WORDS);
     s.sorted = ar.take<float4>(R);
     s.perm = ar.take<int>(R);
     s.perm16 = ar.take<uint16_t>(R);
