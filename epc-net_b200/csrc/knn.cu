@@ -24,6 +24,77 @@ __device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 10 bits -> every t
     return v;
 }
 
+// Bitonic sort of E*1024 unique 64-bit keys by 1024 threads.  Element e = slot*1024 + tid lives in register k[slot]:
+// compare-exchange distances j >= 1024 stay inside the thread, j < 32 are warp shuffles, and only 32 <= j <= 512 go
+// through shared memory (one barrier per pass, plus one to spill and one to reload) -- 32 barriers instead of 78 at N=4096.
+template <int E>
+__device__ __forceinline__ void bitonic_regs(unsigned long long* __restrict__ keys, int tid) {
+    unsigned long long k[E];
+#pragma unroll
+    for (int s = 0; s < E; ++s) k[s] = keys[s * 1024 + tid];
+    __syncthreads();
+    for (int K = 2; K <= E * 1024; K <<= 1) {
+        int j = K >> 1;
+        // distances >= 1024: both elements in this thread
+#pragma unroll
+        for (int js = E >> 1; js > 0; js >>= 1) {
+            if (j == js * 1024) {
+#pragma unroll
+                for (int s = 0; s < E; ++s) {
+                    const int t = s ^ js;
+                    if (s < t) {
+                        const bool up = (((s * 1024 + tid) & K) == 0);
+                        const unsigned long long a = k[s], c = k[t];
+                        if ((a > c) == up) {
+                            k[s] = c;
+                            k[t] = a;
+                        }
+                    }
+                }
+                j >>= 1;
+            }
+        }
+        // distances 512..32: through shared memory
+        if (j >= 32) {
+#pragma unroll
+            for (int s = 0; s < E; ++s) keys[s * 1024 + tid] = k[s];
+            __syncthreads();
+            for (; j >= 32; j >>= 1) {
+#pragma unroll
+                for (int s = 0; s < E; ++s) {
+                    const int i = s * 1024 + tid, ixj = i ^ j;
+                    if (ixj > i) {
+                        const unsigned long long a = keys[i], c = keys[ixj];
+                        const bool up = ((i & K) == 0);
+                        if ((a > c) == up) {
+                            keys[i] = c;
+                            keys[ixj] = a;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int s = 0; s < E; ++s) k[s] = keys[s * 1024 + tid];
+        }
+        // distances 16..1: warp shuffles
+        for (; j > 0; j >>= 1) {
+            const bool lower = ((tid & j) == 0);
+#pragma unroll
+            for (int s = 0; s < E; ++s) {
+                const bool up = (((s * 1024 + tid) & K) == 0);
+                const unsigned long long o = __shfl_xor_sync(FULL, k[s], j);
+                const bool take_min = (lower == up);
+                k[s] = take_min ? (o < k[s] ? o : k[s]) : (o > k[s] ? o : k[s]);
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < E; ++s) keys[s * 1024 + tid] = k[s];
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(1024) sort_kernel(const float* __restrict__ xyz, int N, int NP,
                                                      float4* __restrict__ sorted, int* __restrict__ perm,
                                                      uint16_t* __restrict__ perm16, float4* __restrict__ aabb) {
@@ -82,20 +153,27 @@ __global__ void __launch_bounds__(1024) sort_kernel(const float* __restrict__ xy
     }
     __syncthreads();
     // bitonic sort, ascending
-    for (int k = 2; k <= NP; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < NP; i += blockDim.x) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    unsigned long long a = keys[i], c = keys[ixj];
-                    bool up = ((i & k) == 0);
-                    if ((a > c) == up) {
-                        keys[i] = c;
-                        keys[ixj] = a;
+    if (NP >= 1024) {
+        if (NP == 1024) bitonic_regs<1>(keys, tid);
+        else if (NP == 2048) bitonic_regs<2>(keys, tid);
+        else if (NP == 4096) bitonic_regs<4>(keys, tid);
+        else bitonic_regs<8>(keys, tid);
+    } else {
+        for (int k = 2; k <= NP; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < NP; i += blockDim.x) {
+                    int ixj = i ^ j;
+                    if (ixj > i) {
+                        unsigned long long a = keys[i], c = keys[ixj];
+                        bool up = ((i & k) == 0);
+                        if ((a > c) == up) {
+                            keys[i] = c;
+                            keys[ixj] = a;
+                        }
                     }
                 }
+                __syncthreads();
             }
-            __syncthreads();
         }
     }
     for (int i = tid; i < N; i += blockDim.x) {
