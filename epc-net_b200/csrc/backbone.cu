@@ -137,7 +137,11 @@ int conv_in(const float4* sorted, int B, int N, const DenseDev& L, uint16_t* x, 
 // Shared memory: 3 weight images (8 KB each, pre-swizzled at model creation) + 4 stages x (A 16 KB + m 16 KB + window 16 KB).
 // ------------------------------------------------------------------------------------------------
 constexpr int PB_TILE = 128;
-constexpr int PB_CONS_WARPS = 8;                 // 2 groups x 4
+#ifndef PB_GROUPS
+#define PB_GROUPS 2
+#endif
+constexpr int PB_CONS_GROUPS = PB_GROUPS;        // consumer groups of 4 warps, taking tiles in turn
+constexpr int PB_CONS_WARPS = 4 * PB_CONS_GROUPS;
 constexpr int PB_GATHER_WARPS = 16;
 constexpr int PB_THREADS = 32 * (PB_CONS_WARPS + PB_GATHER_WARPS);
 constexpr int PB_STAGES = 4;                     // A/M ring (gather -> consumers)
@@ -459,7 +463,7 @@ __global__ void __launch_bounds__(PB_THREADS, 1) proxy_block_kernel(const PbArgs
         uint32_t mma_phase = 0;
         int u = 0;
         for (int it = next_active(-1); it < n_local; it = next_active(it), ++u) {
-            if ((u & 1) != group) continue;
+            if ((u % PB_CONS_GROUPS) != group) continue;
             const int tile = blockIdx.x + it * gridDim.x;
             const int b = tile / p.tiles_per_cloud;
             const int s = u % PB_STAGES;
