@@ -142,7 +142,10 @@ constexpr int PB_TILE = 128;
 #endif
 constexpr int PB_CONS_GROUPS = PB_GROUPS;        // consumer groups of 4 warps, taking tiles in turn
 constexpr int PB_CONS_WARPS = 4 * PB_CONS_GROUPS;
-constexpr int PB_GATHER_WARPS = 16;
+#ifndef PB_GWARPS
+#define PB_GWARPS 16
+#endif
+constexpr int PB_GATHER_WARPS = PB_GWARPS;         // the 32 quads (4 points) of a tile are dealt round-robin, continuing across tiles
 constexpr int PB_THREADS = 32 * (PB_CONS_WARPS + PB_GATHER_WARPS);
 constexpr int PB_STAGES = 4;                     // A/M ring (gather -> consumers)
 constexpr int PB_WSTAGES = 3;                    // window ring (TMA -> gather), filled two tiles ahead
@@ -161,6 +164,7 @@ constexpr uint32_t PB_OFF_BAR = PB_OFF_BIAS + 3 * 64 * 4;          // full[S] em
 constexpr uint32_t PB_OFF_TMEM = PB_OFF_BAR + (2 * PB_STAGES + 2 * PB_WSTAGES + 2) * 8;
 constexpr size_t PB_SMEM = 1024 + PB_OFF_TMEM + 16;
 static_assert(PB_SMEM <= 227 * 1024, "proxy_block shared memory");
+static_assert(PB_GATHER_WARPS <= PB_TILE / 4, "every gather warp must own at least one quad of every tile (barrier counts)");
 static_assert(PB_STAGE_BYTES % 1024 == 0 && PB_OFF_STAGE % 1024 == 0, "UMMA SW128 tiles must be 1024-byte aligned");
 // per stage
 constexpr uint32_t PB_ST_A = 0, PB_ST_M = PB_A_BYTES;
@@ -317,9 +321,11 @@ __global__ void __launch_bounds__(PB_THREADS, 1) proxy_block_kernel(const PbArgs
             if (elected && it2 < n_local) issue_window(it2, u + 2);
             __syncwarp();
             bar_wait_backoff(bar_wfull + 8 * ws, wuse & 1u);
+            bool first = true;
 #pragma unroll 1
-            for (int sub = 0; sub < 2; ++sub) {
-                const int pl = (gw + sub * PB_GATHER_WARPS) * 4 + grp;      // this lane group's point within the tile
+            for (int quad = (gw + PB_GATHER_WARPS - (u * (PB_TILE / 4)) % PB_GATHER_WARPS) % PB_GATHER_WARPS; quad < PB_TILE / 4;
+                 quad += PB_GATHER_WARPS) {
+                const int pl = quad * 4 + grp;      // this lane group's point within the tile
                 uint32_t idx[10];
                 {
                     const uint32_t ia = wst + PB_WS_NBR + (uint32_t)pl * (KNN_K * 2);
@@ -435,7 +441,8 @@ __global__ void __launch_bounds__(PB_THREADS, 1) proxy_block_kernel(const PbArgs
                     t[i] = m[i] - xs[i];                 // t1 = x1 - x                       (:72)
                 }
                 if (FMT == FMT_F16 && max8(m) > F16_MAX) p.flags[b] = 1;     // x >= 0, so |t| <= max(m, x)
-                if (sub == 0) bar_wait_backoff(bar_empty + 8 * s, (use & 1u) ^ 1u);      // the consumers have released this A/M stage
+                if (first) bar_wait_backoff(bar_empty + 8 * s, (use & 1u) ^ 1u);      // the consumers have released this A/M stage
+                first = false;
                 const uint32_t off = sw128_off(pl, c);
                 sts128(st + PB_ST_M + off, pack8<FMT>(m));
                 sts128(st + PB_ST_A + off, pack8<FMT>(t));
