@@ -2,7 +2,8 @@
 // Replaces `KDTree(database_output).query(q, k=25)` of evaluate.get_recall (evaluate.py:463,481), which
 // evaluates float64 Euclidean distances on the fp32 descriptors one query at a time on the CPU.
 //
-//   1. fp32 scoring  s_ij = (|q_i|^2 + |d_j|^2) - 2 q_i.d_j     (GEMM + norms)
+//   1. fp32-accurate scoring  s_ij = (|q_i|^2 + |d_j|^2) - 2 q_i.d_j: the GEMM runs on TF32 tensor cores with the 3xTF32
+//      operand split (q = qh + ql, d = dh + dl; qh.dh + qh.dl + ql.dh as ONE GEMM with K = 3 dim), FFMA when dim % 32 != 0
 //   2. per query: the 32 smallest scores (warp-distributed list)            -> candidates
 //   3. float64 re-rank of the candidates, sequential sum_k (q_k - d_k)^2    -> top-k, ascending (dist, index)
 //   4. proof of exactness per query: every non-candidate has score >= a32 (the 32nd candidate's score),
@@ -29,6 +30,24 @@ __global__ void sq_norm_kernel(const float* __restrict__ X, int R, int dim, floa
     if (lane == 0) out[r] = ss;
 }
 
+// 3xTF32 operand split of X [R, dim] -> out [Rpad, 3 dim]: (hi | hi | lo) for the queries, (hi | lo | hi) for the database,
+// hi = tf32(x), lo = tf32(x - hi); rows >= R are zero (N padding of the GEMM)
+__global__ void split3_kernel(const float* __restrict__ X, int R, int Rpad, int dim, int db_side, float* __restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)Rpad * dim) return;
+    const int r = (int)(t / dim), c = (int)(t - (long long)r * dim);
+    float hi = 0.f, lo = 0.f;
+    if (r < R) {
+        const float x = X[t];
+        hi = round_tf32(x);
+        lo = round_tf32(x - hi);
+    }
+    float* o = out + (size_t)r * 3 * dim + c;
+    o[0] = hi;
+    o[dim] = db_side ? lo : hi;
+    o[2 * dim] = db_side ? hi : lo;
+}
+
 // lexicographic (value, index) "a before b"
 __device__ __forceinline__ bool key_less(double av, long long ai, double bv, long long bi) {
     return (av < bv) || (av == bv && ai < bi);
@@ -36,40 +55,50 @@ __device__ __forceinline__ bool key_less(double av, long long ai, double bv, lon
 
 // One warp per query: 32 smallest of score_j = (qn + dn[j]) - 2 dot[j], ascending; columns ascend so ties keep
 // the lower index.
-__global__ void candidates_kernel(const float* __restrict__ dots, const float* __restrict__ qn,
+__global__ void candidates_kernel(const float* __restrict__ dots, int ld, const float* __restrict__ qn,
                                   const float* __restrict__ dn, int Qt, int D, int* __restrict__ cand,
                                   float* __restrict__ a32) {
     const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (qi >= Qt) return;
-    const float* row = dots + (size_t)qi * D;
+    const float* row = dots + (size_t)qi * ld;
     const float qq = qn[qi];
     float val = INFINITY;
     int vi = -1;
     int filled = 0;
     float thr = INFINITY;
-    for (int j0 = 0; j0 < D; j0 += 32) {
-        const int j = j0 + lane;
-        const float s = (j < D) ? fmaf(-2.0f, __ldg(row + j), qq + __ldg(dn + j)) : INFINITY;
-        unsigned m = __ballot_sync(FULL, (j < D) && (filled < RC || s < thr));
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const float c = __shfl_sync(FULL, s, src);
-            const bool before = (lane < filled) && (val <= c);
-            const int pos = __popc(__ballot_sync(FULL, before));
-            if (pos < RC) {
-                const float upv = __shfl_up_sync(FULL, val, 1);
-                const int upi = __shfl_up_sync(FULL, vi, 1);
-                if (lane == pos) {
-                    val = c;
-                    vi = j0 + src;
-                } else if (lane > pos) {
-                    val = upv;
-                    vi = upi;
+    constexpr int U = 8;                              // 32-column blocks loaded together: the scan is latency-bound otherwise
+    for (int jb = 0; jb < D; jb += 32 * U) {
+        float sv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = jb + 32 * u + lane;
+            sv[u] = (j < D) ? fmaf(-2.0f, __ldg(row + j), qq + __ldg(dn + j)) : INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j0 = jb + 32 * u;
+            const float s = sv[u];
+            unsigned m = __ballot_sync(FULL, (j0 + lane < D) && (filled < RC || s < thr));
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const float c = __shfl_sync(FULL, s, src);
+                const bool before = (lane < filled) && (val <= c);
+                const int pos = __popc(__ballot_sync(FULL, before));
+                if (pos < RC) {
+                    const float upv = __shfl_up_sync(FULL, val, 1);
+                    const int upi = __shfl_up_sync(FULL, vi, 1);
+                    if (lane == pos) {
+                        val = c;
+                        vi = j0 + src;
+                    } else if (lane > pos) {
+                        val = upv;
+                        vi = upi;
+                    }
+                    filled = min(filled + 1, RC);
+                    thr = (filled == RC) ? __shfl_sync(FULL, val, RC - 1) : INFINITY;
                 }
-                filled = min(filled + 1, RC);
-                thr = (filled == RC) ? __shfl_sync(FULL, val, RC - 1) : INFINITY;
             }
         }
     }
@@ -79,9 +108,32 @@ __global__ void candidates_kernel(const float* __restrict__ dots, const float* _
 
 __device__ __forceinline__ double exact_d2(const float* __restrict__ q, const float* __restrict__ d, int dim) {
     double acc = 0.0;
-    for (int k = 0; k < dim; ++k) {
+    int k = 0;
+    if ((dim & 3) == 0 && ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(d)) & 15) == 0) {
+        // same sequential order, operands fetched 16 bytes at a time with a batch of loads in flight
+        const float4* q4 = reinterpret_cast<const float4*>(q);
+        const float4* d4 = reinterpret_cast<const float4*>(d);
+        for (; k + 16 <= dim; k += 16) {
+            float4 a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                a[u] = __ldg(q4 + (k >> 2) + u);
+                b[u] = __ldg(d4 + (k >> 2) + u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double t0 = (double)a[u].x - (double)b[u].x, t1 = (double)a[u].y - (double)b[u].y;
+                const double t2 = (double)a[u].z - (double)b[u].z, t3 = (double)a[u].w - (double)b[u].w;
+                acc = __dadd_rn(acc, __dmul_rn(t0, t0));   // no FMA contraction: sklearn's rdist loop is mul then add
+                acc = __dadd_rn(acc, __dmul_rn(t1, t1));
+                acc = __dadd_rn(acc, __dmul_rn(t2, t2));
+                acc = __dadd_rn(acc, __dmul_rn(t3, t3));
+            }
+        }
+    }
+    for (; k < dim; ++k) {
         const double t = (double)q[k] - (double)d[k];
-        acc = __dadd_rn(acc, __dmul_rn(t, t));   // no FMA contraction: sklearn's rdist loop is mul then add
+        acc = __dadd_rn(acc, __dmul_rn(t, t));
     }
     return acc;
 }
@@ -108,7 +160,7 @@ __device__ __forceinline__ void warp_sort_pairs(double& v, long long& i, int lan
 __global__ void rerank_kernel(const float* __restrict__ db, const float* __restrict__ q, const int* __restrict__ cand,
                               const float* __restrict__ a32, const float* __restrict__ qn, const float* __restrict__ dn_max_p, int Qt, int dim,
                               int k, long long id_offset, int64_t* __restrict__ idx, double* __restrict__ dist,
-                              int* __restrict__ flags) {
+                              int* __restrict__ flags, float err_unit) {
     const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (qi >= Qt) return;
@@ -126,8 +178,10 @@ __global__ void rerank_kernel(const float* __restrict__ db, const float* __restr
     }
     const double kth = __shfl_sync(FULL, v, k - 1);
     if (lane == 0) {
-        // fp32 scoring error bound: |score - exact d^2| <= err  (dim-term FMA chain + norm sums), generous
-        const float err = 6e-8f * (float)(dim + 8) * (qn[qi] + *dn_max_p) * 2.0f;
+        // scoring error bound: |score - exact d^2| <= err = err_unit (|q|^2 + max|d|^2).  FFMA path: dim-term FMA chain + norm
+        // sums, 1.2e-7 (dim + 8).  3xTF32 path: products exact in fp32, dropped ql.dl and split residues 3 x 2^-22, accumulation
+        // of 3 dim terms at <= 2^-22 each (the tensor core may truncate): 2.4e-7 (3 dim + 8) -- both generous.
+        const float err = err_unit * (qn[qi] + *dn_max_p);
         const float a = a32[qi];
         flags[qi] = (a == INFINITY) ? 0 : !((float)kth * (1.0f + 2e-7f) < a - err);
     }
@@ -196,12 +250,15 @@ static int query_tile(int D, int Q) {
     return (int)(qt > 0 ? qt : 1);
 }
 
+static int pad256(int D) { return (D + 255) / 256 * 256; }
+
 size_t retrieve_workspace_bytes(int D, int Q, int dim, int k) {
-    (void)dim;
     (void)k;
-    const int qt = query_tile(D, Q);
-    return align_up((size_t)D * 4) + align_up((size_t)Q * 4) + align_up((size_t)qt * D * 4) +
-           align_up((size_t)qt * RC * 4) + align_up((size_t)qt * 4) + align_up((size_t)qt * 4) + 256;
+    const int Dp = pad256(D);
+    const int qt = query_tile(Dp, Q);
+    return align_up((size_t)D * 4) + align_up((size_t)Q * 4) + align_up((size_t)qt * Dp * 4) +
+           align_up((size_t)qt * RC * 4) + align_up((size_t)qt * 4) + align_up((size_t)qt * 4) +
+           align_up((size_t)Dp * 3 * dim * 4) + align_up((size_t)qt * 3 * dim * 4) + 512;
 }
 
 int retrieve_topk(const float* db, int D, const float* q, int Q, int dim, int k, long long id_offset, int64_t* idx,
@@ -213,15 +270,27 @@ int retrieve_topk(const float* db, int D, const float* q, int Q, int dim, int k,
         set_error("retrieve_topk: workspace %zu < required %zu", ws_bytes, retrieve_workspace_bytes(D, Q, dim, k));
         return EPC_EWORKSPACE;
     }
-    const int qt = query_tile(D, Q);
+    const int Dp = pad256(D);
+    const int qt = query_tile(Dp, Q);
+    const bool tensor = (dim % 32 == 0);            // 3 dim must be a multiple of the TF32 k-block (32)
+    const int ld = tensor ? Dp : D;
     Arena ar(ws, ws_bytes);
     float* dn = ar.take<float>(D);
     float* qn = ar.take<float>(Q);
-    float* dots = ar.take<float>((size_t)qt * D);
+    float* dots = ar.take<float>((size_t)qt * Dp);
     int* cand = ar.take<int>((size_t)qt * RC);
     float* a32 = ar.take<float>(qt);
     int* flags = ar.take<int>(qt);
     float* dn_max_dev = ar.take<float>(1);
+    float* db3 = ar.take<float>((size_t)Dp * 3 * dim);
+    float* q3 = ar.take<float>((size_t)qt * 3 * dim);
+    const float err_unit = tensor ? 2.4e-7f * (float)(3 * dim + 8) : 1.2e-7f * (float)(dim + 8);
+    if (tensor) {
+        ScopedStage ss(EPC_STAGE_RETRIEVE_SCORE, st);
+        const long long n = (long long)Dp * dim;
+        split3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(db, D, Dp, dim, 1, db3);
+        EPC_LAUNCH_CHECK();
+    }
 
     sq_norm_kernel<<<(D + 7) / 8, 256, 0, st>>>(db, D, dim, dn);
     EPC_LAUNCH_CHECK();
@@ -238,16 +307,23 @@ int retrieve_topk(const float* db, int D, const float* q, int Q, int dim, int k,
         g.C = dots; g.ldc = D; g.M = nq; g.N = D; g.K = dim; g.batch = 1; g.splitk = 1;
         {
             ScopedStage ss(EPC_STAGE_RETRIEVE_SCORE, st);
-            if (int rc = sgemm(g, st)) return rc;
+            if (tensor) {
+                const long long n = (long long)nq * dim;
+                split3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q + (size_t)q0 * dim, nq, nq, dim, 0, q3);
+                EPC_LAUNCH_CHECK();
+                if (int rc = tc_scores(q3, nq, db3, Dp, 3 * dim, dots, st)) return rc;
+            } else {
+                if (int rc = sgemm(g, st)) return rc;
+            }
         }
         {
             ScopedStage ss(EPC_STAGE_RETRIEVE_SELECT, st);
-            candidates_kernel<<<(nq + 7) / 8, 256, 0, st>>>(dots, qn + q0, dn, nq, D, cand, a32);
+            candidates_kernel<<<(nq + 7) / 8, 256, 0, st>>>(dots, ld, qn + q0, dn, nq, D, cand, a32);
             EPC_LAUNCH_CHECK();
         }
         ScopedStage ss(EPC_STAGE_RETRIEVE_RERANK, st);
         rerank_kernel<<<(nq + 7) / 8, 256, 0, st>>>(db, q + (size_t)q0 * dim, cand, a32, qn + q0, dn_max_dev, nq, dim, k,
-                                                    id_offset, idx + (size_t)q0 * k, dist + (size_t)q0 * k, flags);
+                                                    id_offset, idx + (size_t)q0 * k, dist + (size_t)q0 * k, flags, err_unit);
         EPC_LAUNCH_CHECK();
         exact_fallback_kernel<<<(nq + 7) / 8, 256, 0, st>>>(db, q + (size_t)q0 * dim, flags, nq, D, dim, k, id_offset,
                                                             idx + (size_t)q0 * k, dist + (size_t)q0 * k);

@@ -69,4 +69,13 @@ int tc_hidden(const float* v, int rows, int hidden_in, const float* Wht /*[D, hi
     return tc_gemm_launch<float, 256, false, false, tc::EPI_STORE_F32>(a, b, p, 1, st, 1);
 }
 
+// retrieval scores (retrieval.cu): dots[nq, Dpad] = Q3[nq, K3] . DB3[Dpad, K3]^T on TF32 tensor cores; Q3/DB3 hold the
+// 3xTF32 split of the fp32 operands (hi|hi|lo vs hi|lo|hi), so the sum is q.d to ~2^-21 relative
+int tc_scores(const float* q3, int nq, const float* db3, int Dpad, int K3, float* dots, cudaStream_t st) {
+    tc::GemmParams p = {};
+    p.M = nq; p.N = Dpad; p.K = K3; p.splitk = 1; p.C = dots; p.ldc = Dpad;
+    Operand<float> a{q3, nq, K3, K3}, b{db3, Dpad, K3, K3};
+    return tc_gemm_launch<float, 256, false, false, tc::EPI_STORE_F32>(a, b, p, 1, st, 1);
+}
+
 }  // namespace epc
