@@ -83,6 +83,7 @@ struct EpcModel {
                 *hbn_scale = nullptr, *hbn_shift = nullptr, *Wg = nullptr, *gbn_scale = nullptr, *gbn_shift = nullptr;
     int hidden_in = 0;                // rows of hidden1_weights
     DenseDev fc1;
+    const float* fc1_Wt = nullptr;      // fc1 weights transposed [D, 1024], TF32-rounded: K-major B operand of the tensor-core FC
 };
 
 namespace {
@@ -353,7 +354,7 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
     offW[12] = pk.add(W5t); offb[12] = pk.add(b);
     std::vector<__nv_bfloat16> h16;                              // bf16 operands (EPC-Net head)
     size_t o16_W5 = 0, o16_Wc = 0;
-    size_t oCs = 0, oCh = 0, oWc2 = 0, oWh = 0, oHs = 0, oHh = 0, oWg = 0, oGs = 0, oGh = 0, oFW = 0, oFb = 0;
+    size_t oCs = 0, oCh = 0, oWc2 = 0, oWh = 0, oHs = 0, oHh = 0, oWg = 0, oGs = 0, oGh = 0, oFW = 0, oFb = 0, oFWt = 0;
     if (vlad) {
         const int K = w->cluster_size, D = w->output_dim;
         if (K != 64) { delete m; set_error("cluster_size=%d unsupported: the tensor-core assignment kernel is built for 64", K); return EPC_EUNSUPPORTED; }
@@ -390,6 +391,13 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
         }
         fold_dense(w->fc1, W, b);
         oFW = pk.add(W); oFb = pk.add(b);
+        {
+            const int D = w->output_dim;
+            std::vector<float> Wt((size_t)D * 1024);
+            for (int k = 0; k < 1024; ++k)
+                for (int n = 0; n < D; ++n) Wt[(size_t)n * 1024 + k] = host_round_tf32(W[(size_t)k * D + n]);
+            oFWt = pk.add(Wt);
+        }
     }
     cudaError_t e = cudaMalloc(&m->blob, pk.host.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(m->blob, pk.host.data(), pk.host.size() * sizeof(float), cudaMemcpyHostToDevice);
@@ -416,6 +424,7 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
         if (w->gating) { m->Wg = m->blob + oWg; m->gbn_scale = m->blob + oGs; m->gbn_shift = m->blob + oGh; }
     } else {
         m->fc1 = DenseDev{m->blob + oFW, m->blob + oFb, 1024, w->output_dim, nullptr, nullptr};
+        m->fc1_Wt = m->blob + oFWt;
     }
     *out = m;
     return EPC_OK;
@@ -637,11 +646,15 @@ int epc_embed(const EpcModel* m, const float* xyz, int B, int N, int knn_arith, 
         }
         {
             ScopedStage ss(EPC_STAGE_FC, st);
-            GemmArgs g = {};
-            g.A = gmax; g.sAm = 1024; g.sAk = 1;
-            g.B = m->fc1.W; g.sBk = m->D; g.sBn = 1;
-            g.C = o; g.ldc = m->D; g.M = B; g.N = m->D; g.K = 1024; g.bias = m->fc1.b; g.relu = 1; g.batch = 1; g.splitk = 1;
-            if (int rc = sgemm(g, st)) return rc;
+            if (m->D == 256) {
+                if (int rc = tc_fc_relu(gmax, B, 1024, m->fc1_Wt, m->fc1.b, m->D, o, st)) return rc;
+            } else {
+                GemmArgs g = {};
+                g.A = gmax; g.sAm = 1024; g.sAk = 1;
+                g.B = m->fc1.W; g.sBk = m->D; g.sBn = 1;
+                g.C = o; g.ldc = m->D; g.M = B; g.N = m->D; g.K = 1024; g.bias = m->fc1.b; g.relu = 1; g.batch = 1; g.splitk = 1;
+                if (int rc = sgemm(g, st)) return rc;
+            }
             if (int rc = row_l2_normalize(o, B, m->D, out, st)) return rc;
         }
         if (feat)

@@ -69,6 +69,14 @@ int tc_hidden(const float* v, int rows, int hidden_in, const float* Wht /*[D, hi
     return tc_gemm_launch<float, 256, false, false, tc::EPI_STORE_F32>(a, b, p, 1, st, 1);
 }
 
+// EPC-Net-L head FC (models/epc-net-l.py:95): o[B, D] = relu(g[B,1024] . Wfc + b) on TF32 tensor cores (BN folded into W, b)
+int tc_fc_relu(const float* g, int rows, int K, const float* Wt /*[D, K]*/, const float* bias, int D, float* out, cudaStream_t st) {
+    tc::GemmParams p = {};
+    p.M = rows; p.N = D; p.K = K; p.splitk = 1; p.C = out; p.ldc = D; p.bias = bias; p.relu = 1;
+    Operand<float> a{g, rows, K, K}, b{Wt, D, K, K};
+    return tc_gemm_launch<float, 256, false, false, tc::EPI_STORE_F32>(a, b, p, 1, st, 1);
+}
+
 // retrieval scores (retrieval.cu): dots[nq, Dpad] = Q3[nq, K3] . DB3[Dpad, K3]^T on TF32 tensor cores; Q3/DB3 hold the
 // 3xTF32 split of the fp32 operands (hi|hi|lo vs hi|lo|hi), so the sum is q.d to ~2^-21 relative
 int tc_scores(const float* q3, int nq, const float* db3, int Dpad, int K3, float* dots, cudaStream_t st) {
