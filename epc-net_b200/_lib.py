@@ -74,6 +74,8 @@ PROTOTYPES = {
     "epc_retrieve_topk": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_longlong, c_void_p, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),
     "epc_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "epc_radius_count": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p]),
+    "epc_radius_fill": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

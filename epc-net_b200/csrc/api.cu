@@ -709,6 +709,19 @@ int epc_retrieve_topk(const float* db, int D, const float* q, int Q, int dim, in
                          static_cast<cudaStream_t>(stream));
 }
 
+int epc_radius_count(const double* db, int D, const double* q, int Q, int dim, double r, int32_t* counts, void* stream) {
+    EPC_CHECK_ARG(db && (q || Q == 0) && counts, "epc_radius_count: NULL argument");
+    if (int rc = ensure_device(db)) return rc;
+    return radius_search(db, D, q, Q, dim, r, counts, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int epc_radius_fill(const double* db, int D, const double* q, int Q, int dim, double r, const int64_t* offsets, int32_t* indices,
+                    void* stream) {
+    EPC_CHECK_ARG(db && (q || Q == 0) && offsets && indices, "epc_radius_fill: NULL argument");
+    if (int rc = ensure_device(db)) return rc;
+    return radius_search(db, D, q, Q, dim, r, nullptr, offsets, indices, static_cast<cudaStream_t>(stream));
+}
+
 int epc_merge_topk(const double* dist, const int64_t* idx, int R, int Q, int k, double* out_dist, int64_t* out_idx,
                    void* stream) {
     EPC_CHECK_ARG(dist && idx && out_dist && out_idx, "epc_merge_topk: NULL argument");

@@ -104,6 +104,8 @@ int kd_feat(const float* H, const float* inv, const int* perm, int B, int N, int
 size_t retrieve_workspace_bytes(int D, int Q, int dim, int k);
 int retrieve_topk(const float* db, int D, const float* q, int Q, int dim, int k, long long id_offset, int64_t* idx,
                   double* dist, void* ws, size_t ws_bytes, cudaStream_t st);
+int radius_search(const double* db, int D, const double* q, int Q, int dim, double r, int32_t* counts, const int64_t* offsets,
+                  int32_t* indices, cudaStream_t st);
 int merge_topk(const double* dist, const int64_t* idx, int R, int Q, int k, double* out_dist, int64_t* out_idx,
                cudaStream_t st);
 

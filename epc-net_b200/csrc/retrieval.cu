@@ -332,6 +332,49 @@ int retrieve_topk(const float* db, int D, const float* q, int Q, int dim, int k,
     return EPC_OK;
 }
 
+// Radius search: the reference builds its evaluation pickles with sklearn's
+// KDTree(db[['northing','easting']]).query_radius(coor, r=25) (generating_queries/generate_test_sets.py:70-104), one query per
+// call.  Here: one warp per query, float64 (UTM coordinates need it), membership d^2 = sum_k (q_k - d_k)^2 <= r^2 evaluated in
+// sklearn's order; two passes (count, then fill at the caller's exclusive offsets), indices ascending.
+template <bool FILL>
+__global__ void radius_kernel(const double* __restrict__ db, int D, const double* __restrict__ q, int Q, int dim, double r2,
+                              int32_t* __restrict__ counts, const int64_t* __restrict__ offsets, int32_t* __restrict__ indices) {
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (qi >= Q) return;
+    const double* qq = q + (size_t)qi * dim;
+    int n = 0;
+    for (int j0 = 0; j0 < D; j0 += 32) {
+        const int j = j0 + lane;
+        bool in = false;
+        if (j < D) {
+            double acc = 0.0;
+            for (int k = 0; k < dim; ++k) {
+                const double t = qq[k] - db[(size_t)j * dim + k];
+                acc = __dadd_rn(acc, __dmul_rn(t, t));
+            }
+            in = (acc <= r2);
+        }
+        const unsigned m = __ballot_sync(FULL, in);
+        if (FILL && in) indices[offsets[qi] + n + __popc(m & ((1u << lane) - 1u))] = j;
+        n += __popc(m);
+    }
+    if (!FILL && lane == 0) counts[qi] = n;
+}
+
+int radius_search(const double* db, int D, const double* q, int Q, int dim, double r, int32_t* counts, const int64_t* offsets,
+                  int32_t* indices, cudaStream_t st) {
+    EPC_CHECK_ARG(D >= 0 && Q >= 0 && dim >= 1 && r >= 0.0, "radius_search: bad sizes D=%d Q=%d dim=%d r=%g", D, Q, dim, r);
+    if (Q == 0) return EPC_OK;
+    const double r2 = r * r;
+    if (indices)
+        radius_kernel<true><<<(Q + 7) / 8, 256, 0, st>>>(db, D, q, Q, dim, r2, nullptr, offsets, indices);
+    else
+        radius_kernel<false><<<(Q + 7) / 8, 256, 0, st>>>(db, D, q, Q, dim, r2, counts, nullptr, nullptr);
+    EPC_LAUNCH_CHECK();
+    return EPC_OK;
+}
+
 // Merge R shard lists per query by (distance, index): one warp per query, lists staged in shared memory.
 __global__ void merge_topk_kernel(const double* __restrict__ dist, const int64_t* __restrict__ idx, int R, int Q, int k,
                                   double* __restrict__ out_dist, int64_t* __restrict__ out_idx) {

@@ -73,6 +73,33 @@ def retrieve_topk(database_output, queries_output, k, id_offset=0):
     return dist, idx
 
 
+def query_radius(database_coords, query_coords, r):
+    """``KDTree(database_coords).query_radius(query_coords, r)`` (generating_queries/generate_test_sets.py:70-104: r = 25 m
+    on (northing, easting); generate_training_tuples_baseline.py:52-62: r = 10 / 50) as one exact GPU search in float64.
+    Returns a list with one ascending int64 index array per query (sklearn returns the same sets in tree order)."""
+    _engine._require_cuda()
+    lib = _lib.load()
+    db = torch.as_tensor(np.ascontiguousarray(database_coords, dtype=np.float64)).cuda()
+    q = torch.as_tensor(np.ascontiguousarray(query_coords, dtype=np.float64)).cuda()
+    if db.dim() != 2 or q.dim() != 2 or db.shape[1] != q.shape[1]:
+        raise ValueError("query_radius expects (D, dim) and (Q, dim) arrays")
+    D, dim = db.shape
+    Q = q.shape[0]
+    if Q == 0:
+        return []
+    counts = torch.zeros((Q,), dtype=torch.int32, device=db.device)
+    with torch.cuda.device(db.device):
+        _lib.check(lib.epc_radius_count(_ptr(db), D, _ptr(q), Q, dim, float(r), _ptr(counts), _stream()))
+        offsets = torch.cumsum(counts.to(torch.int64), 0) - counts.to(torch.int64)
+        total = int(counts.sum().item())
+        indices = torch.empty((max(total, 1),), dtype=torch.int32, device=db.device)
+        _lib.check(lib.epc_radius_fill(_ptr(db), D, _ptr(q), Q, dim, float(r), _ptr(offsets), _ptr(indices), _stream()))
+    ind = indices[:total].cpu().numpy().astype(np.int64)
+    off = offsets.cpu().numpy()
+    cnt = counts.cpu().numpy()
+    return [ind[off[i]:off[i] + cnt[i]] for i in range(Q)]
+
+
 def get_random_hard_negatives(query_vec, random_negs, num_to_take, training_latent_vectors):
     """train.py:857-869: the ``num_to_take`` candidates of ``random_negs`` whose cached descriptors are
     nearest to ``query_vec`` -- the reference builds a KDTree over ``TRAINING_LATENT_VECTORS[random_negs]`` per query;

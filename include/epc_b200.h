@@ -208,6 +208,20 @@ int epc_retrieve_topk(const float* db /*[D,dim]*/, int D, const float* q /*[Q,di
 int epc_merge_topk(const double* dist /*[R,Q,k]*/, const int64_t* idx /*[R,Q,k]*/, int R, int Q, int k,
                    double* out_dist /*[Q,k]*/, int64_t* out_idx /*[Q,k]*/, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Radius search  (replaces KDTree(db[['northing','easting']]).query_radius(coor, r) of
+ * generating_queries/generate_test_sets.py:70-104 and generate_training_tuples_baseline.py:52-62, which
+ * build the true_neighbors lists consumed by evaluate.get_recall)
+ *
+ * All rows j of db [D,dim] (float64) with sum_k (q_k - d_k)^2 <= r^2, per query, as a CSR pair: first
+ * epc_radius_count -> counts [Q]; the caller turns them into exclusive offsets [Q] (int64) and sizes
+ * `indices`; then epc_radius_fill writes each query's row ids in ascending order.
+ * ------------------------------------------------------------------------------------------- */
+int epc_radius_count(const double* db /*[D,dim]*/, int D, const double* q /*[Q,dim]*/, int Q, int dim, double r,
+                     int32_t* counts /*[Q]*/, void* stream);
+int epc_radius_fill(const double* db, int D, const double* q, int Q, int dim, double r, const int64_t* offsets /*[Q]*/,
+                    int32_t* indices, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

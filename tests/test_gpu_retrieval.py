@@ -100,3 +100,18 @@ def test_get_random_hard_negatives_matches_kdtree(ev):
     got = ev.get_random_hard_negatives(q, random_negs.tolist(), 10, latent)
     _, ind = KDTree(latent[random_negs]).query(np.array([q]), k=10)
     assert got == np.squeeze(random_negs[ind[0]]).tolist()
+
+
+def test_query_radius_matches_kdtree(ev):
+    """generating_queries/generate_test_sets.py:95-104: KDTree(...).query_radius(coor, r=25) on UTM-sized float64 coordinates."""
+    from sklearn.neighbors import KDTree
+    rng = np.random.default_rng(3)
+    db = np.stack([5735000.0 + rng.uniform(0, 600, 500), 620000.0 + rng.uniform(0, 600, 500)], 1)
+    q = np.stack([5735000.0 + rng.uniform(0, 600, 130), 620000.0 + rng.uniform(0, 600, 130)], 1)
+    q[0] = db[7]                                                     # an exact hit
+    got = ev.query_radius(db, q, 25)
+    ref = KDTree(db).query_radius(q, r=25)
+    assert len(got) == len(ref)
+    for g, r in zip(got, ref):
+        assert np.array_equal(g, np.sort(r))
+    assert ev.query_radius(db, q[:0], 25) == []
