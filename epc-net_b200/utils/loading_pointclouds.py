@@ -32,32 +32,31 @@ def get_sets_dict(filename):
         return pickle.load(handle)
 
 
+def _read_cloud(path, columns):
+    """Raw float64 records -> (NUM_POINTS, columns), or None when the file does not hold exactly that many values."""
+    flat = np.fromfile(path, dtype="<f8")
+    return flat.reshape(NUM_POINTS, columns) if flat.size == NUM_POINTS * columns else None
+
+
 def load_pc_file(filename, dataset_folder, input_dim=3):
-    """:26-53.  A file of the wrong size yields an all-zero cloud (the reference prints an error and does the same)."""
-    pc = np.fromfile(os.path.join(dataset_folder, filename), dtype=np.float64)
-    if input_dim == 3:
-        if pc.shape[0] != NUM_POINTS * 3:
-            return np.zeros([NUM_POINTS, 3])
-        return np.reshape(pc, (pc.shape[0] // 3, 3))
-    if pc.shape[0] != NUM_POINTS * 13:
-        return np.zeros([NUM_POINTS, 13])
-    pc = np.reshape(pc, (pc.shape[0] // 13, 13))
-    with np.errstate(divide="ignore", invalid="ignore"):
-        pc[:, 3:12] = ((pc - pc.min(axis=0)) / (pc.max(axis=0) - pc.min(axis=0)))[:, 3:12]      # :47
-    pc[np.isnan(pc)] = 0.0
-    pc[np.isinf(pc)] = 1.0
-    return pc
+    """:26-53.  A file of the wrong size yields an all-zero cloud (the reference prints an error and does the same).
+    With the 13-column layout, columns 3..11 are min-max scaled per cloud, NaN -> 0 and inf -> 1 (:47-51)."""
+    columns = 3 if input_dim == 3 else 13
+    cloud = _read_cloud(os.path.join(dataset_folder, filename), columns)
+    if cloud is None:
+        return np.zeros((NUM_POINTS, columns))
+    if columns == 13:
+        lo, hi = cloud.min(axis=0), cloud.max(axis=0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            cloud[:, 3:12] = ((cloud - lo) / (hi - lo))[:, 3:12]
+        np.nan_to_num(cloud, copy=False, nan=0.0, posinf=1.0, neginf=1.0)
+    return cloud
 
 
 def load_pc_files(filenames, dataset_folder, input_dim=3):
     """:56-65 -- stacks the clouds that have 4096 points."""
-    pcs = []
-    for filename in filenames:
-        pc = load_pc_file(filename, dataset_folder, input_dim)
-        if pc.shape[0] != NUM_POINTS:
-            continue
-        pcs.append(pc)
-    return np.array(pcs)
+    clouds = (load_pc_file(name, dataset_folder, input_dim) for name in filenames)
+    return np.array([c for c in clouds if c.shape[0] == NUM_POINTS])
 
 
 def load_pc_data(data, dataset_folder, input_dim=3, out=None):
