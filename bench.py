@@ -251,8 +251,6 @@ def main():
     if rank == 0:
         sampler.start()
     lib_mod.launch_count_reset()
-    lib_mod.profile_reset()
-    lib_mod.profile_enable(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(K):
@@ -261,6 +259,12 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = lib_mod.launch_count()
+    # the same K steps once more with the per-stage event brackets on (they cost ~1 %, so they stay out of `value`)
+    lib_mod.profile_reset()
+    lib_mod.profile_enable(True)
+    for i in range(K):
+        eng.embed(dev_batches[(W + i) % nbatch], out=out)
+    torch.cuda.synchronize()
     stages = lib_mod.profile_read()
     lib_mod.profile_enable(False)
     if world > 1:
@@ -270,14 +274,18 @@ def main():
     value = world * B * K / (ms * 1e-3)
 
     # ---- end to end: host arrays in, host arrays out, through the reference-facing call ---------------------
+    # One get_latent_vectors call over the K steps' clouds, the way evaluate.py:283-293 calls it on a whole database set
+    # (hundreds of clouds): every step's 128 clouds are staged through pinned memory, copied H2D, embedded, and the
+    # descriptors copied back -- all inside the timed region; the engine overlaps step i+1's copy with step i's compute.
     ops = {"MODEL": models.load(arch), "params": params}
-    names = {i: {} for i in range(B)}
-    for i in range(min(W, 2)):
-        evaluate.get_latent_vectors(None, ops, names, host_batches[i % nbatch])
+    big = np.concatenate([host_batches[(W + i) % nbatch] for i in range(K)], 0)
+    names = {i: {} for i in range(len(big))}
+    warm = np.concatenate([host_batches[i % nbatch] for i in range(max(2, min(W, 3)))], 0)
+    evaluate.get_latent_vectors(None, ops, {i: {} for i in range(len(warm))}, warm)
+    evaluate.get_latent_vectors(None, ops, names, big)                  # sizes the staging buffers for the timed call
     barrier()
     t0 = time.perf_counter()
-    for i in range(K):
-        desc = evaluate.get_latent_vectors(None, ops, names, host_batches[(W + i) % nbatch])
+    desc = evaluate.get_latent_vectors(None, ops, names, big)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -286,7 +294,7 @@ def main():
         e2e_s = float(t.item())
     e2e = world * B * K / e2e_s
     clocks = sampler.stop() if rank == 0 else None          # sampled across both timed regions
-    assert desc.shape == (B, 256) and np.isfinite(desc).all()
+    assert desc.shape == (B * K, 256) and np.isfinite(desc).all()
 
     retr = None
     if not args.no_retrieval:
@@ -339,7 +347,7 @@ def main():
                    "l2": "inputs rotate over %d distinct batches; every call streams >0.5 GB of intermediates "
                          "(>> 126 MB L2)" % nbatch},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * N_POINTS * 3 * 4, "d2h_bytes_per_step": B * 256 * 4,
-                "api": "evaluate.get_latent_vectors(host ndarray) -> host ndarray"},
+                "api": "one evaluate.get_latent_vectors(host ndarray of steps x clouds) -> host ndarray call; per-step pinned staging, H2D and D2H inside"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "stages": stage_table,
     }
     if not args.no_retrieval:
