@@ -6,6 +6,7 @@ the C ABI of libepc_b200.so (``_lib``).
 from __future__ import annotations
 
 import ctypes
+import os
 import threading
 
 import numpy as np
@@ -29,6 +30,9 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_POISON = int(os.environ["EPC_POISON_WORKSPACE"], 0) if os.environ.get("EPC_POISON_WORKSPACE") else None
+
+
 class _Workspaces(object):
     """One grow-only byte buffer per (device, stream)."""
 
@@ -45,6 +49,8 @@ class _Workspaces(object):
                 self._buf.pop(key, None)
                 b = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device="cuda")
                 self._buf[key] = b
+            if _POISON is not None:      # debugging aid: EPC_POISON_WORKSPACE=<byte> refills the scratch before every call
+                b.fill_(_POISON)
             return b
 
     def clear(self):
