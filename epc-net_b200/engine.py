@@ -258,6 +258,7 @@ class Engine(object):
 # ---- engine cache keyed like a TF graph: (store, scope, arch, head options, device) -------------------
 _engines = {}
 _engines_lock = threading.Lock()
+_ENGINE_CACHE_MAX = 16        # each engine owns a device weight blob (~6 MB)
 
 
 def get_engine(arch: str, params: dict, scope: str = None, store: variables.VariableStore = None,
@@ -265,14 +266,16 @@ def get_engine(arch: str, params: dict, scope: str = None, store: variables.Vari
     _require_cuda()
     scope = variables.current_scope("query_triplets") if scope is None else scope
     store = variables.default_store() if store is None else store
-    key = (id(store), store.version, scope, arch, pooling, gating, torch.cuda.current_device(),
+    key = (store.uid, store.version, scope, arch, pooling, gating, torch.cuda.current_device(),
            int(params.get("CLUSTER_SIZE", 64)), int(params.get("FEATURE_OUTPUT_DIM", 256)), int(params.get("GROUPS", 4)),
            int(params.get("KNN", 20)), str(params.get("KNN_ARITH", "muladd")), int(params.get("EMBED_CHUNK", 32)))
     with _engines_lock:
-        eng = _engines.get(key)
+        eng = _engines.pop(key, None)
         if eng is None:
             eng = Engine(arch, store, scope, params, pooling=pooling, gating=gating)
-            _engines[key] = eng
+            while len(_engines) >= _ENGINE_CACHE_MAX:         # least recently used first (dicts keep insertion order)
+                _engines.pop(next(iter(_engines)))
+        _engines[key] = eng                                   # (re-)insert as the most recently used
         return eng
 
 

@@ -46,13 +46,15 @@ class PoolingBaseModel(object):
         params = {"CLUSTER_SIZE": self.cluster_size, "FEATURE_OUTPUT_DIM": self.output_dim, "GROUPS": groups,
                   "KNN": 20, "INPUT_DIM": 3}
         store = getattr(self, "variables", None) or variables.default_store()
-        key = ("loupe", id(store), store.version, scope, pooling, self.gating, self.cluster_size, self.output_dim, groups,
+        key = ("loupe", store.uid, store.version, scope, pooling, self.gating, self.cluster_size, self.output_dim, groups,
                torch.cuda.current_device() if torch.cuda.is_available() else -1)
-        eng = _ENGINES.get(key)
+        eng = _ENGINES.pop(key, None)
         if eng is None:
             eng = _engine.Engine("epc-net", store, scope, params, pooling=pooling, gating=self.gating, head_only=True,
                                  vlad_prefix=scope + "/")
-            _ENGINES[key] = eng
+            while len(_ENGINES) >= 16:                        # least recently used first
+                _ENGINES.pop(next(iter(_ENGINES)))
+        _ENGINES[key] = eng
         return eng.vlad(reshaped_input, self.max_samples)
 
 

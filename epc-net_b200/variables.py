@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import contextlib
 import threading
+import itertools
 from collections import OrderedDict
 
 import numpy as np
@@ -137,8 +138,11 @@ def synthetic_variables(arch: str, seed: int = 0, scope: str = "query_triplets",
 class VariableStore(object):
     """name -> np.float32 array; the stand-in for the TF variable collection + Saver."""
 
+    _uids = itertools.count(1)
+
     def __init__(self, values=None):
         self._v = OrderedDict()
+        self.uid = next(VariableStore._uids)     # process-unique, never reused (id() is, once a store is collected)
         self.version = 0
         if values:
             self.update(values)

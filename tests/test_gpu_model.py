@@ -123,6 +123,25 @@ def test_fp16_range_fallback_is_per_cloud(pkg):
         _check_desc(b[1:2].cpu().numpy(), ref, arch + " zero cloud")
 
 
+def test_engine_cache_is_keyed_by_store_identity_not_address(pkg):
+    """A collected VariableStore's address is reused by the next one: the plugin must not serve the engine (weights) of
+    the dead store.  Each round builds a fresh store with different weights at (very likely) the same address."""
+    import gc
+    arch = "epc-net-l"
+    x = torch.from_numpy(np.stack([_data.cloud("uniform", 40, 512)], 0)[None]).cuda()
+    outs = []
+    for seed in (1, 2, 3, 1):
+        store = pkg.variables.VariableStore(pkg.variables.synthetic_variables(arch, seed))
+        params = dict(_data.default_params(arch), NUM_POINTS=512, VARIABLES=store)
+        got = pkg.models.load(arch).forward(x, False, params=params)[0]
+        want = pkg.engine.Engine(arch, store, "query_triplets", params).embed(x[0])
+        assert torch.equal(got, want), "seed %d served by a stale engine" % seed
+        outs.append(got.cpu().numpy())
+        del store, params
+        gc.collect()
+    assert not np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[3])
+
+
 def test_point_permutation_invariance(pkg):
     """Full-size property: descriptors do not depend on the order of the points of a cloud (kNN sets, max-pool and
     VLAD sums are permutation invariant; only fp32 summation order moves)."""

@@ -189,3 +189,16 @@ def test_loading_pointclouds_wire_formats(tmp_path):
     feat.tofile(tmp_path / "f.bin")
     p13 = lp.load_pc_file("f.bin", str(tmp_path), input_dim=13)
     assert p13.shape == (4096, 13) and p13[:, 3:12].min() >= 0 and p13[:, 3:12].max() <= 1 and np.array_equal(p13[:, :3], feat[:, :3])
+
+
+def test_variable_store_uids_are_never_reused():
+    """Engine caches key on VariableStore.uid: id() of a collected store is handed to the next one."""
+    import gc
+    variables = importlib.import_module("epc-net_b200.variables")
+    seen = set()
+    for _ in range(64):
+        s = variables.VariableStore({"a": np.zeros(1, np.float32)})
+        assert s.uid not in seen
+        seen.add(s.uid)
+        del s
+        gc.collect()
