@@ -74,8 +74,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--clouds", type=int, default=128, help="clouds per GPU per step")
+    ap.add_argument("--clouds", type=int, default=256, help="clouds per GPU per step")
     ap.add_argument("--chunk", type=int, default=128, help="clouds per library call")
+    ap.add_argument("--streams", type=int, default=2, help="CUDA streams the calls of one step alternate over")
     ap.add_argument("--cpu-sample", type=int, default=24, help="clouds in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-retrieval", action="store_true")
@@ -230,8 +231,9 @@ def main():
     arch = args.arch
     V = variables.synthetic_variables(arch, 1)
     store = variables.VariableStore(V)
-    params = dict(_data.default_params(arch), EMBED_CHUNK=args.chunk, VARIABLES=store)
+    params = dict(_data.default_params(arch), EMBED_CHUNK=args.chunk, EMBED_STREAMS=args.streams, VARIABLES=store)
     eng = engine_mod.get_engine(arch, params, store=store)
+    eng_serial = engine_mod.get_engine(arch, dict(params, EMBED_STREAMS=1), store=store)      # per-stage timing pass only
     B, K, W = args.clouds, args.steps, args.warmup
     nbatch = min(K + W, 4)                                         # rotate distinct inputs; intermediates >> L2 anyway
     host_batches = [make_clouds(B, 1000 + 97 * rank + i) for i in range(nbatch)]
@@ -259,11 +261,12 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = lib_mod.launch_count()
-    # the same K steps once more with the per-stage event brackets on (they cost ~1 %, so they stay out of `value`)
+    # the same K steps once more with the per-stage event brackets on, on ONE stream (brackets of concurrent streams would
+    # time each other's kernels); they stay out of `value`
     lib_mod.profile_reset()
     lib_mod.profile_enable(True)
     for i in range(K):
-        eng.embed(dev_batches[(W + i) % nbatch], out=out)
+        eng_serial.embed(dev_batches[(W + i) % nbatch], out=out)
     torch.cuda.synchronize()
     stages = lib_mod.profile_read()
     lib_mod.profile_enable(False)
@@ -343,7 +346,7 @@ def main():
                                 "EPC-Net-L (configs/epc-net-l.yaml: 2 ProxyConv blocks + max-pool + FC, 256-d)") +
                                " batch embedding of synthetic uniform(-1,1) 4096-point clouds, seeded random-init weights, "
                                "batch-sharded",
-                   "clouds_per_gpu_per_step": B, "clouds_per_call": args.chunk, "knn_arith": "muladd",
+                   "clouds_per_gpu_per_step": B, "clouds_per_call": args.chunk, "streams": args.streams, "knn_arith": "muladd",
                    "l2": "inputs rotate over %d distinct batches; every call streams >0.5 GB of intermediates "
                          "(>> 126 MB L2)" % nbatch},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * N_POINTS * 3 * 4, "d2h_bytes_per_step": B * 256 * 4,

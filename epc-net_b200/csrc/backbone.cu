@@ -615,7 +615,8 @@ int proxy_block(const uint16_t* x, const KnnState& g, int B, int N, int arith, f
     a.Wn_img = conv_next ? img(*conv_next) : nullptr;
     a.bn = conv_next ? conv_next->b : nullptr;
     a.concat32 = concat; a.concat16 = concat16; a.ctot = ctot; a.coff = coff; a.xnext = xnext;
-    const int grid = a.num_tiles < sm_count() ? a.num_tiles : sm_count();
+    const int ctas = persistent_ctas("EPC_BLOCK_CTAS");
+    const int grid = a.num_tiles < ctas ? a.num_tiles : ctas;
     if (conv_next)
         proxy_block_kernel<true, FMT_F16><<<grid, PB_THREADS, PB_SMEM, st>>>(a);
     else

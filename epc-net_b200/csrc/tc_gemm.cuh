@@ -748,6 +748,14 @@ inline int sm_count() {
     return n;
 }
 
+// Number of CTAs a persistent kernel launches: one per SM, or fewer when `env` says so (leaves SMs to kernels of other
+// streams: Engine EMBED_STREAMS overlaps the ALU-bound kNN of one chunk with the HBM-bound head of another).
+inline int persistent_ctas(const char* env) {
+    const char* e = getenv(env);
+    const int n = e ? atoi(e) : 0;
+    return (n > 0 && n < sm_count()) ? n : sm_count();
+}
+
 // Persistent B-resident launch: A [M,K], B [N,K] both K-major; one CTA per SM (rounded to a multiple of N/BN).
 template <typename T, int BN, int EPI, int EW = 4, int CL = 1>
 inline int tc_gemm_bres_launch(const Operand<T>& A, const Operand<T>& B, const tc::GemmParams& p, cudaStream_t st) {
@@ -800,7 +808,7 @@ inline int tc_gemm_bres_launch(const Operand<T>& A, const Operand<T>& B, const t
         count_launch();
         return EPC_OK;
     }
-    int per_nt = sm_count() / NT;
+    int per_nt = persistent_ctas("EPC_HEAD_CTAS") / NT;
     if (per_nt < 1) per_nt = 1;
     if (per_nt > m_tiles) per_nt = m_tiles;
     kern<<<per_nt * NT, 64 + 32 * EW, smem, st>>>(tmA, tmB, p, a_stages);

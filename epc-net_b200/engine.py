@@ -60,6 +60,18 @@ class _Workspaces(object):
 
 workspaces = _Workspaces()
 
+_side_pool = {}
+
+
+def side_streams(n: int):
+    """The process-wide side streams of the current device (shared by every engine, so that the per-stream workspaces stay
+    bounded however many engines come and go)."""
+    dev = torch.cuda.current_device()
+    pool = _side_pool.setdefault(dev, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream())
+    return pool[:n]
+
 
 def _np_ptr(a):
     return a.ctypes.data_as(_fp)
@@ -84,6 +96,9 @@ class Engine(object):
         self.num_points = int(params.get("NUM_POINTS", 4096))
         self.is_vlad = head == "gvlad"
         self.chunk = int(params.get("EMBED_CHUNK", 32))
+        # chunks of one call may alternate over this many side streams (own workspace each): the ALU-bound kNN of one chunk
+        # then overlaps the HBM-bound head GEMMs of another
+        self.nstreams = max(1, int(params.get("EMBED_STREAMS", os.environ.get("EPC_EMBED_STREAMS", 2))))
         self.knn_arith = _lib.KNN_ARITH[str(params.get("KNN_ARITH", "muladd"))]
         if int(params.get("INPUT_DIM", 3)) != 3:
             raise ValueError("INPUT_DIM must be 3 (xyz): conv1 of the shipped checkpoints is [1,3,64]")
@@ -176,14 +191,25 @@ class Engine(object):
             raise ValueError("out must be a contiguous CUDA fp32 tensor [B,%d]" % self.output_dim)
         feat = torch.empty((B * N, 1024), dtype=torch.float32, device=xyz.device) if want_feat else None
         with torch.cuda.device(xyz.device):
-            for s in range(0, B, self.chunk):
+            starts = list(range(0, B, self.chunk))
+            fan = min(self.nstreams, len(starts))
+            main = torch.cuda.current_stream()
+            side = side_streams(fan) if fan > 1 else None
+            if fan > 1:
+                for st in side:
+                    st.wait_stream(main)
+            for ci, s in enumerate(starts):
                 e = min(B, s + self.chunk)
                 nb = e - s
-                need = self.lib.epc_embed_workspace_bytes(self._h, nb, N)
-                ws = workspaces.get(need)
-                f = feat[s * N:e * N] if want_feat else None
-                _lib.check(self.lib.epc_embed(self._h, _ptr(xyz[s:e]), nb, N, self.knn_arith, _ptr(out[s:e]), _ptr(f),
-                                              _ptr(ws), ws.numel(), _stream()))
+                with torch.cuda.stream(side[ci % fan] if fan > 1 else main):
+                    need = self.lib.epc_embed_workspace_bytes(self._h, nb, N)
+                    ws = workspaces.get(need)              # one grow-only buffer per stream
+                    f = feat[s * N:e * N] if want_feat else None
+                    _lib.check(self.lib.epc_embed(self._h, _ptr(xyz[s:e]), nb, N, self.knn_arith, _ptr(out[s:e]), _ptr(f),
+                                                  _ptr(ws), ws.numel(), _stream()))
+            if fan > 1:
+                for st in side:
+                    main.wait_stream(st)
         return (out, feat) if want_feat else out
 
     def vlad(self, X: torch.Tensor, max_samples: int):
@@ -216,39 +242,50 @@ class Engine(object):
         if n == 0:
             return out
         with torch.cuda.device(self.device):
+            starts = list(range(0, n, chunk))
+            fan = min(self.nstreams, len(starts))          # compute streams the chunks alternate over
+            slots = fan + 1                                # staging slots: one being filled while `fan` are in use
             # staging buffers are cached: pinning host memory costs far more than the copy itself
             st = getattr(self, "_staging", None)
-            if st is None or st["chunk"] != chunk or st["N"] != N or st["n"] < n:
-                st = {"chunk": chunk, "N": N, "n": n,
-                      "pin_in": [torch.empty((chunk, N, 3), dtype=torch.float32).pin_memory() for _ in range(2)],
+            if st is None or st["chunk"] != chunk or st["N"] != N or st["n"] < n or st["slots"] < slots:
+                st = {"chunk": chunk, "N": N, "n": n, "slots": slots,
+                      "pin_in": [torch.empty((chunk, N, 3), dtype=torch.float32).pin_memory() for _ in range(slots)],
                       "pin_out": torch.empty((n, D), dtype=torch.float32).pin_memory(),
-                      "dev_in": [torch.empty((chunk, N, 3), dtype=torch.float32, device=self.device) for _ in range(2)],
+                      "dev_in": [torch.empty((chunk, N, 3), dtype=torch.float32, device=self.device) for _ in range(slots)],
                       "dev_out": torch.empty((n, D), dtype=torch.float32, device=self.device),
                       "copy_stream": torch.cuda.Stream()}
                 self._staging = st
             pin_in, dev_in, copy_stream = st["pin_in"], st["dev_in"], st["copy_stream"]
             pin_out, dev_out = st["pin_out"][:n], st["dev_out"][:n]
             main = torch.cuda.current_stream()
+            compute = side_streams(fan) if fan > 1 else [main]
             copy_stream.wait_stream(main)
-            in_ready = [torch.cuda.Event() for _ in range(2)]
-            in_free = [torch.cuda.Event() for _ in range(2)]
-            starts = list(range(0, n, chunk))
-            host_free = [None, None]
+            for cs in compute:
+                if cs is not main:
+                    cs.wait_stream(main)
+            in_ready = [torch.cuda.Event() for _ in range(slots)]
+            in_free = [torch.cuda.Event() for _ in range(slots)]
+            host_free = [None] * slots
             for i, s in enumerate(starts):
                 e = min(n, s + chunk)
-                slot = i & 1
+                slot = i % slots
+                cs = compute[i % fan]
                 if host_free[slot] is not None:
                     host_free[slot].synchronize()        # the H2D that last read this pinned slot is done
                 pin_in[slot][:e - s].copy_(torch.from_numpy(clouds[s:e]))
                 with torch.cuda.stream(copy_stream):
-                    if i >= 2:
-                        copy_stream.wait_event(in_free[slot])      # compute of chunk i-2 released the device slot
+                    if i >= slots:
+                        copy_stream.wait_event(in_free[slot])      # compute of chunk i-slots released the device slot
                     dev_in[slot][:e - s].copy_(pin_in[slot][:e - s], non_blocking=True)
                     in_ready[slot].record(copy_stream)
                     host_free[slot] = in_ready[slot]
-                main.wait_event(in_ready[slot])
-                self.embed(dev_in[slot][:e - s], out=dev_out[s:e])
-                in_free[slot].record(main)
+                cs.wait_event(in_ready[slot])
+                with torch.cuda.stream(cs):
+                    self.embed(dev_in[slot][:e - s], out=dev_out[s:e])       # one chunk: runs on `cs`
+                in_free[slot].record(cs)
+            for cs in compute:
+                if cs is not main:
+                    main.wait_stream(cs)
             pin_out.copy_(dev_out, non_blocking=True)
             main.synchronize()
         out[...] = pin_out.numpy()
@@ -268,7 +305,8 @@ def get_engine(arch: str, params: dict, scope: str = None, store: variables.Vari
     store = variables.default_store() if store is None else store
     key = (store.uid, store.version, scope, arch, pooling, gating, torch.cuda.current_device(),
            int(params.get("CLUSTER_SIZE", 64)), int(params.get("FEATURE_OUTPUT_DIM", 256)), int(params.get("GROUPS", 4)),
-           int(params.get("KNN", 20)), str(params.get("KNN_ARITH", "muladd")), int(params.get("EMBED_CHUNK", 32)))
+           int(params.get("KNN", 20)), str(params.get("KNN_ARITH", "muladd")), int(params.get("EMBED_CHUNK", 32)),
+           int(params.get("EMBED_STREAMS", os.environ.get("EPC_EMBED_STREAMS", 2))))
     with _engines_lock:
         eng = _engines.pop(key, None)
         if eng is None:

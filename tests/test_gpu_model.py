@@ -233,3 +233,8 @@ def test_get_latent_vectors_host_path(pkg):
     assert got.shape == (11, 256)
     _check_desc(got, ref, "get_latent_vectors")
     assert pkg.evaluate.get_latent_vectors(None, ops, {}, np.zeros((0, N, 3), np.float32)).shape == (0, 256)
+    # chunks alternate over EMBED_STREAMS side streams (default 2): same bits on one stream and on three, called twice
+    for streams in (1, 3):
+        ops_s = {"MODEL": ops["MODEL"], "params": dict(params, EMBED_STREAMS=streams)}
+        for _ in range(2):
+            assert np.array_equal(pkg.evaluate.get_latent_vectors(None, ops_s, {i: {} for i in range(11)}, data), got), streams
