@@ -8,7 +8,7 @@ timeout 1500 python -m pytest tests -m gpu -q --tb=line -p no:cacheprovider 2>&1
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4 | tee gpurun_out/smoke_${tag}.log
 timeout 900 python bench.py 2> gpurun_out/bench.err | tee gpurun_out/bench_${tag}.json | cut -c1-300
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>> gpurun_out/bench.err | tee gpurun_out/bench_ref_${tag}.json | cut -c1-200
-timeout 600 python bench.py --arch epc-net-l --clouds 256 --chunk 256 --no-retrieval --cpu-sample 12 2>> gpurun_out/bench.err | tee gpurun_out/bench_l_${tag}.json | cut -c1-200
+timeout 600 python bench.py --arch epc-net-l --clouds 512 --chunk 256 --no-retrieval --cpu-sample 12 2>> gpurun_out/bench.err | tee gpurun_out/bench_l_${tag}.json | cut -c1-200
 echo "== ncu launch list (same command, short)"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${tag}.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-retrieval > gpurun_out/ncu_launch.log 2>&1
