@@ -10,7 +10,7 @@ tfu = importlib.import_module("epc-net_b200.utils.tf_util")
 kinds = ["uniform", "clustered", "coarse", "duplicated", "planar", "zeros"]
 rng = np.random.default_rng(123)
 worst = 0.0
-for trial in range(10):
+for trial in range(int(sys.argv[1]) if len(sys.argv) > 1 else 10):
     N = int(rng.choice([128, 256, 512, 1024, 2048]))
     B = int(rng.integers(1, 9))
     arch = ["epc-net", "epc-net-l", "kd_epc-net"][trial % 3]
@@ -20,7 +20,8 @@ for trial in range(10):
     oi, ok, oc = knn_c.knn(clouds)
     assert np.array_equal(kth.cpu().numpy().view(np.uint32), ok.view(np.uint32)) and np.array_equal(cnt.cpu().numpy(), oc) and np.array_equal(idx.cpu().numpy(), oi), ("knn", trial, N, ks)
     V = variables.synthetic_variables(arch, 100 + trial)
-    params = dict(_data.default_params(arch), NUM_POINTS=N, VARIABLES=variables.VariableStore(V))
+    params = dict(_data.default_params(arch), NUM_POINTS=N, EMBED_CHUNK=int(rng.choice([1, 3, 32])), EMBED_STREAMS=int(rng.choice([1, 2, 3])),
+                  VARIABLES=variables.VariableStore(V))
     res = models.load(arch).forward(torch.from_numpy(clouds[None]).cuda(), False, params=params)
     out = res[1] if arch.startswith("kd_") else res
     ref = epc_oracle.forward(arch, clouds[None], V, params)
