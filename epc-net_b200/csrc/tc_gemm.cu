@@ -26,6 +26,7 @@ int tc_assign(const __nv_bfloat16* H, long long R, const __nv_bfloat16* Wct, con
     tc::GemmParams p = {};
     p.M = (int)R; p.N = 64; p.K = 1024; p.splitk = 1; p.C = S; p.ldc = 64; p.aux = a_part; p.rowss = rowss;
     p.rowss_parts = parts; p.bn_scale = bn_scale; p.bn_shift = bn_shift;
+    p.reverse_m = getenv("EPC_ASSIGN_FORWARD") ? 0 : 1;     // conv5 wrote the last rows of H last: start with what is still in L2
     Operand<__nv_bfloat16> a{H, R, 1024, 1024}, b{Wct, 64, 1024, 1024};
     return tc_gemm_bres_launch<__nv_bfloat16, 64, tc::EPI_ASSIGN>(a, b, p, st);
 }

@@ -187,6 +187,8 @@ struct GemmParams {
     const float* bn_scale;    // ASSIGN: cluster_bn affine [64]
     const float* bn_shift;
     int rows_per_cloud;       // COLMAX: N points per cloud
+    int reverse_m;            // persistent kernels: walk the row tiles from the last to the first (the producer kernel wrote
+                              // the last tiles most recently: they are the ones still in L2)
 };
 
 template <typename T> struct ElemTraits;
@@ -539,6 +541,7 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int n0 = n_tile * BN;
     constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1u);
     const int num_m_tiles = (p.M + TC_BM - 1) / TC_BM;
+    auto tile_of = [&](int mt) { return p.reverse_m ? num_m_tiles - 1 - mt : mt; };
     constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
 
     if (warp == 0 && lane == 0) {
@@ -579,9 +582,9 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     mbar_wait(&empty[s], ph ^ 1);
                     mbar_expect_tx(&full[s], A_BYTES);
                     if (CL == 1)
-                        tma_load_2d(sA + (size_t)s * A_BYTES, &tmA, &full[s], kb * BK, mt * TC_BM);
+                        tma_load_2d(sA + (size_t)s * A_BYTES, &tmA, &full[s], kb * BK, tile_of(mt) * TC_BM);
                     else if (kb % CL == n_tile)    // this CTA's share of the tile, delivered to the whole cluster
-                        tma_load_2d_mc(sA + (size_t)s * A_BYTES, &tmA, &full[s], kb * BK, mt * TC_BM, CL_MASK);
+                        tma_load_2d_mc(sA + (size_t)s * A_BYTES, &tmA, &full[s], kb * BK, tile_of(mt) * TC_BM, CL_MASK);
                 }
             }
         }
@@ -626,7 +629,7 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_after();
             EpiCtx c;
             c.trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
-            c.m0 = mt * TC_BM; c.m = c.m0 + row; c.row = row; c.lane = lane; c.n0 = n0; c.mtile = mt;
+            c.m0 = tile_of(mt) * TC_BM; c.m = c.m0 + row; c.row = row; c.lane = lane; c.n0 = n0; c.mtile = tile_of(mt);
             c.c_off = 0; c.scratch = scratch; c.epi_tid = threadIdx.x - 64;
             c.bias = p.bias ? sBias : nullptr;
             constexpr int SPLIT = EW / 4;                       // warps per lane quarter
