@@ -95,7 +95,8 @@ class Engine(object):
         self.knn_k = int(params.get("KNN", 20))
         self.num_points = int(params.get("NUM_POINTS", 4096))
         self.is_vlad = head == "gvlad"
-        self.chunk = int(params.get("EMBED_CHUNK", 32))
+        # clouds per epc_embed call; unset: as large as 128, but at least `EMBED_STREAMS` chunks per call so that they overlap
+        self.chunk = int(params["EMBED_CHUNK"]) if params.get("EMBED_CHUNK") else None
         # chunks of one call may alternate over this many side streams (own workspace each): the ALU-bound kNN of one chunk
         # then overlaps the HBM-bound head GEMMs of another
         self.nstreams = max(1, int(params.get("EMBED_STREAMS", os.environ.get("EPC_EMBED_STREAMS", 2))))
@@ -178,6 +179,11 @@ class Engine(object):
                 pass
             self._h = None
 
+    def _chunk_for(self, n: int) -> int:
+        if self.chunk:
+            return self.chunk
+        return max(1, min(128, -(-n // self.nstreams)))
+
     # ---- device-resident API ------------------------------------------------------------------
     def embed(self, xyz: torch.Tensor, want_feat: bool = False, out: torch.Tensor = None):
         """xyz [B,N,3] fp32 CUDA tensor -> descriptors [B,D] (and KD features [B*N,1024])."""
@@ -191,7 +197,8 @@ class Engine(object):
             raise ValueError("out must be a contiguous CUDA fp32 tensor [B,%d]" % self.output_dim)
         feat = torch.empty((B * N, 1024), dtype=torch.float32, device=xyz.device) if want_feat else None
         with torch.cuda.device(xyz.device):
-            starts = list(range(0, B, self.chunk))
+            chunk = self._chunk_for(B)
+            starts = list(range(0, B, chunk))
             fan = min(self.nstreams, len(starts))
             main = torch.cuda.current_stream()
             side = side_streams(fan) if fan > 1 else None
@@ -199,7 +206,7 @@ class Engine(object):
                 for st in side:
                     st.wait_stream(main)
             for ci, s in enumerate(starts):
-                e = min(B, s + self.chunk)
+                e = min(B, s + chunk)
                 nb = e - s
                 with torch.cuda.stream(side[ci % fan] if fan > 1 else main):
                     need = self.lib.epc_embed_workspace_bytes(self._h, nb, N)
@@ -222,8 +229,9 @@ class Engine(object):
         B = X.shape[0] // max_samples
         out = torch.empty((B, self.output_dim), dtype=torch.float32, device=X.device)
         with torch.cuda.device(X.device):
-            for s in range(0, B, self.chunk):
-                e = min(B, s + self.chunk)
+            chunk = self._chunk_for(B)
+            for s in range(0, B, chunk):
+                e = min(B, s + chunk)
                 need = self.lib.epc_vlad_workspace_bytes(self._h, e - s, max_samples)
                 ws = workspaces.get(need)
                 _lib.check(self.lib.epc_vlad_forward(self._h, _ptr(X[s * max_samples:e * max_samples]), e - s, max_samples,
@@ -235,7 +243,7 @@ class Engine(object):
         """clouds [n,N,3] host array -> [n,D] host array.  H2D of chunk i+1 overlaps compute of chunk i."""
         clouds = np.ascontiguousarray(clouds, dtype=np.float32)
         n, N, _ = clouds.shape
-        chunk = pipeline_chunk or self.chunk
+        chunk = pipeline_chunk or self._chunk_for(n)
         D = self.output_dim
         if out is None:
             out = np.empty((n, D), np.float32)
@@ -247,7 +255,7 @@ class Engine(object):
             slots = fan + 1                                # staging slots: one being filled while `fan` are in use
             # staging buffers are cached: pinning host memory costs far more than the copy itself
             st = getattr(self, "_staging", None)
-            if st is None or st["chunk"] != chunk or st["N"] != N or st["n"] < n or st["slots"] < slots:
+            if st is None or st["chunk"] < chunk or st["N"] != N or st["n"] < n or st["slots"] < slots:
                 st = {"chunk": chunk, "N": N, "n": n, "slots": slots,
                       "pin_in": [torch.empty((chunk, N, 3), dtype=torch.float32).pin_memory() for _ in range(slots)],
                       "pin_out": torch.empty((n, D), dtype=torch.float32).pin_memory(),
@@ -305,7 +313,7 @@ def get_engine(arch: str, params: dict, scope: str = None, store: variables.Vari
     store = variables.default_store() if store is None else store
     key = (store.uid, store.version, scope, arch, pooling, gating, torch.cuda.current_device(),
            int(params.get("CLUSTER_SIZE", 64)), int(params.get("FEATURE_OUTPUT_DIM", 256)), int(params.get("GROUPS", 4)),
-           int(params.get("KNN", 20)), str(params.get("KNN_ARITH", "muladd")), int(params.get("EMBED_CHUNK", 32)),
+           int(params.get("KNN", 20)), str(params.get("KNN_ARITH", "muladd")), int(params.get("EMBED_CHUNK") or 0),
            int(params.get("EMBED_STREAMS", os.environ.get("EPC_EMBED_STREAMS", 2))))
     with _engines_lock:
         eng = _engines.pop(key, None)
