@@ -238,3 +238,27 @@ def test_get_latent_vectors_host_path(pkg):
         ops_s = {"MODEL": ops["MODEL"], "params": dict(params, EMBED_STREAMS=streams)}
         for _ in range(2):
             assert np.array_equal(pkg.evaluate.get_latent_vectors(None, ops_s, {i: {} for i in range(11)}, data), got), streams
+
+
+def test_train_side_callers(pkg):
+    """train.py:857-965 mirrors: same rows as the evaluate path, the reference's result shapes (flat vector for one cloud,
+    empty array for none) and hard negatives picked from the cached descriptors."""
+    from sklearn.neighbors import KDTree
+    train = importlib.import_module("epc-net_b200.train")
+    arch, N = "epc-net-l", 256
+    V = pkg.variables.synthetic_variables(arch, 12)
+    params = dict(_data.default_params(arch), NUM_POINTS=N, VARIABLES=pkg.variables.VariableStore(V))
+    ops = {"MODEL": pkg.models.load(arch), "params": params}
+    data = np.stack([_data.cloud("uniform", 2100 + i, N) for i in range(9)], 0)
+    train.train_data = data
+    allv = train.get_latent_vectors(None, ops, {i: {} for i in range(9)})
+    assert allv.shape == (9, 256)
+    assert np.array_equal(allv, pkg.evaluate.get_latent_vectors(None, ops, {i: {} for i in range(9)}, data))
+    one = train.get_latent_vectors(None, ops, {0: {}})
+    assert one.shape == (256,) and np.array_equal(one, allv[0])
+    assert train.get_latent_vectors(None, ops, {}).shape == (0,)
+    train.TRAINING_LATENT_VECTORS = allv
+    negs = [8, 1, 5, 3, 7, 2]
+    got = train.get_random_hard_negatives(allv[0], negs, 3)
+    _, ind = KDTree(allv[negs]).query(np.array([allv[0]]), k=3)
+    assert got == np.squeeze(np.array(negs)[ind[0]]).tolist()
