@@ -99,6 +99,15 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def ncu_warp_instructions(stage):
+    """smsp__inst_executed.sum per launch of the stage's kernel at 128 clouds per call, from the same committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get(stage, {}).get("warp_instructions_per_launch")
+    except Exception:
+        return None
+
+
 def ncu_traffic(stage):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the stage's kernel, from the committed ncu capture
     (profiles/traffic.json, written by tools/ncu_traffic.py); None when no capture is on file."""
@@ -330,6 +339,15 @@ def main():
                             "(exact AABB pruning skips ~84 % of the pairs)")
             roof.update({"alt_bound": "fp32-alu (dense-equivalent)", "alt_achieved": r["tflops"], "alt_peak": FP32_ALU_TFLOPS,
                          "alt_unit": "TFLOP/s", "alt_frac": r["flop_frac"]})
+            inst = ncu_warp_instructions(top)
+            if inst and clocks and clocks.get("sm_mhz") and abs(clouds_per_launch - 128) < 1e-6:
+                # what actually bounds it: warp-instruction issue (4 schedulers per SM, one instruction per clock each)
+                ach = inst / (top_ms / top_n * 1e-3) / 1e9
+                peak = torch.cuda.get_device_properties(local).multi_processor_count * 4 * clocks["sm_mhz"] * 1e6 / 1e9
+                roof.update({"issue_bound": "warp-instruction issue slots", "issue_achieved": ach, "issue_peak": peak,
+                             "issue_unit": "G warp-instr/s", "issue_frac": ach / peak,
+                             "issue_note": "instructions per 128-cloud launch from the committed ncu capture (profiles/traffic.json), "
+                                           "launch duration event-timed here"})
     stage_table = {}
     for k, v in stages.items():
         e = {"ms_per_cloud": v[0] / (B * K), "share": v[0] / total_stage_ms}

@@ -13,18 +13,21 @@ for rep in sys.argv[1:]:
     rows = list(csv.reader(io.StringIO(txt)))
     h, units = rows[0], rows[1]
     ik, ir, iw, it = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("gpu__time_duration.sum")
+    ii = h.index("smsp__inst_executed.sum")
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     acc = {}
     for r in rows[2:]:
         for pat, st in STAGE_OF:
             if pat in r[ik]:
                 b = float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
-                a = acc.setdefault(st, [0.0, 0, r[ik].split("(")[0]])
+                a = acc.setdefault(st, [0.0, 0, r[ik].split("(")[0], 0.0])
                 a[0] += b
                 a[1] += 1
+                a[3] += float(r[ii].replace(",", ""))
                 break
-    for st, (b, n, name) in acc.items():
-        out[st] = {"dram_bytes_per_launch": b / n, "launches_profiled": n, "kernel": name, "report": os.path.basename(rep),
+    for st, (b, n, name, inst) in acc.items():
+        out[st] = {"dram_bytes_per_launch": b / n, "warp_instructions_per_launch": inst / n, "launches_profiled": n, "kernel": name,
+                   "report": os.path.basename(rep),
                    "note": "ncu replays each launch with cold caches; batch = the bench's 128 clouds per call"}
 json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", "traffic.json"), "w"), indent=1)
 print(json.dumps(out, indent=1))
