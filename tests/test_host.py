@@ -202,3 +202,18 @@ def test_variable_store_uids_are_never_reused():
         seen.add(s.uid)
         del s
         gc.collect()
+
+
+def test_train_mirror_surface():
+    """train.py:857-965 mirrors: the reference's names and module globals; no CUDA needed for the empty cases."""
+    train = importlib.import_module("epc-net_b200.train")
+    assert hasattr(train, "TRAINING_LATENT_VECTORS") and hasattr(train, "train_data")
+    saved = train.train_data
+    try:
+        train.train_data = None
+        with pytest.raises(RuntimeError):
+            train.get_latent_vectors(None, {}, {0: {}})
+        train.train_data = np.zeros((0, 128, 3), np.float32)
+        assert train.get_latent_vectors(None, {}, {}).shape == (0,)
+    finally:
+        train.train_data = saved
