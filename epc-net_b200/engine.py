@@ -61,16 +61,18 @@ class _Workspaces(object):
 workspaces = _Workspaces()
 
 _side_pool = {}
+_side_lock = threading.Lock()
 
 
 def side_streams(n: int):
     """The process-wide side streams of the current device (shared by every engine, so that the per-stream workspaces stay
     bounded however many engines come and go)."""
     dev = torch.cuda.current_device()
-    pool = _side_pool.setdefault(dev, [])
-    while len(pool) < n:
-        pool.append(torch.cuda.Stream())
-    return pool[:n]
+    with _side_lock:
+        pool = _side_pool.setdefault(dev, [])
+        while len(pool) < n:
+            pool.append(torch.cuda.Stream())
+        return pool[:n]
 
 
 def _np_ptr(a):
