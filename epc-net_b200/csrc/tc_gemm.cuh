@@ -223,7 +223,7 @@ struct EpiCtx {
     int mtile;          // index of the 128-row tile (ASSIGN: a_part row)
     int nparts, npart;  // CONV5: number / index of the N tile (rowss partials)
     long long c_off;    // STORE_F32: element offset of this batch / split-K slab in C
-    float* scratch;     // ASSIGN: [128][65] fp32 shared-memory scratch
+    float* scratch;     // ASSIGN: [4][64] fp32 column-sum partials of the four epilogue warps
     int epi_tid;        // 0..127 within the epilogue warps
     const float* bias;  // bias of this N tile (global or shared), indexed by the column within the tile; may be nullptr
     int col_begin, col_end;   // columns of the tile this warp drains (two warps per lane quarter split the tile)
@@ -356,13 +356,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const EpiCtx&
                 den += v[i];
             }
             const float rden = 1.0f / den;
-            // column sums of the soft assignment over this tile: stage through (now idle) pipeline smem
-            float* sS = c.scratch;        // [128][65]
     #pragma unroll
-            for (int i = 0; i < 64; ++i) {
-                v[i] *= rden;
-                sS[row * 65 + i] = (m < p.M) ? v[i] : 0.f;
-            }
+            for (int i = 0; i < 64; ++i) v[i] *= rden;
             if (m < p.M) {
                 uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)m * 64);
     #pragma unroll
@@ -375,14 +370,32 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const EpiCtx&
                     }
                     dst[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
+            } else {
+    #pragma unroll
+                for (int i = 0; i < 64; ++i) v[i] = 0.f;
             }
+            // column sums of the soft assignment over this tile (a_sum partials, loupe.py:276): transpose-reduce across the
+            // warp's 32 rows -- each step a lane hands half of its columns to its partner and adds the partner's other half
+            // (62 shuffles for 64 columns) -- then the four warps' partials meet in 1 KB of shared memory.  Fixed order.
+    #pragma unroll
+            for (int h = 32, bit = 16; h >= 2; h >>= 1, bit >>= 1) {
+                const bool up = (c.lane & bit) != 0;
+    #pragma unroll
+                for (int i = 0; i < h; ++i) {
+                    const float keep = up ? v[i + h] : v[i];
+                    const float send = up ? v[i] : v[i + h];
+                    v[i] = keep + __shfl_xor_sync(FULL, send, bit);
+                }
+            }
+            // lane l now holds the warp's sums of columns 2l and 2l+1 (lane bit 16 chose the upper 32 columns, bit 8 the upper 16, ...)
+            const int col0 = 2 * c.lane;      // 32*b16 + 16*b8 + 8*b4 + 4*b2 + 2*b1
+            float* sS = c.scratch;        // [4 warps][64]
+            const int wq = c.row >> 5;
+            sS[wq * 64 + col0] = v[0];
+            sS[wq * 64 + col0 + 1] = v[1];
             asm volatile("bar.sync 1, 128;" ::: "memory");     // the four epilogue warps only
             const int t = c.epi_tid;
-            if (t < 64) {
-                float a = 0.f;
-                for (int r = 0; r < TC_BM; ++r) a += sS[r * 65 + t];
-                p.aux[(size_t)c.mtile * 64 + t] = a;
-            }
+            if (t < 64) p.aux[(size_t)c.mtile * 64 + t] = ((sS[t] + sS[64 + t]) + sS[128 + t]) + sS[192 + t];
             asm volatile("bar.sync 1, 128;" ::: "memory");     // scratch may be rewritten by the next tile (persistent kernel)
         }
 }
@@ -518,7 +531,7 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     using Tr = ElemTraits<T>;
     constexpr int BK = Tr::PER128;
     constexpr uint32_t A_BYTES = TC_BM * 128, B_BYTES = BN * 128;
-    constexpr size_t SCRATCH = (EPI == EPI_ASSIGN) ? (size_t)TC_BM * 65 * 4 : (EPI == EPI_CONV5_BF16) ? (size_t)EW * 4096 : 0;
+    constexpr size_t SCRATCH = (EPI == EPI_ASSIGN) ? (size_t)4 * 64 * 4 : (EPI == EPI_CONV5_BF16) ? (size_t)EW * 4096 : 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int nkb = p.K / BK;
@@ -764,7 +777,7 @@ template <typename T, int BN, int EPI, int EW = 4, int CL = 1>
 inline int tc_gemm_bres_launch(const Operand<T>& A, const Operand<T>& B, const tc::GemmParams& p, cudaStream_t st) {
     constexpr int BK = tc::ElemTraits<T>::PER128;
     constexpr size_t A_BYTES = tc::TC_BM * 128, B_BYTES = BN * 128;
-    constexpr size_t SCRATCH = (EPI == tc::EPI_ASSIGN) ? (size_t)tc::TC_BM * 65 * 4 : (EPI == tc::EPI_CONV5_BF16) ? (size_t)EW * 4096 : 0;
+    constexpr size_t SCRATCH = (EPI == tc::EPI_ASSIGN) ? (size_t)4 * 64 * 4 : (EPI == tc::EPI_CONV5_BF16) ? (size_t)EW * 4096 : 0;
     EPC_CHECK_ARG(p.K % BK == 0 && p.K >= BK && p.N % BN == 0 && p.splitk == 1, "tc_gemm_bres: bad shape K=%d N=%d", p.K, p.N);
     EPC_CHECK_ARG((reinterpret_cast<uintptr_t>(A.ptr) & 15) == 0 && (reinterpret_cast<uintptr_t>(B.ptr) & 15) == 0 &&
                       (A.ld * sizeof(T)) % 16 == 0 && (B.ld * sizeof(T)) % 16 == 0,
