@@ -245,6 +245,24 @@ def forward(arch, point_cloud, V, params, scope="query_triplets", mask=None, ari
     return res
 
 
+def forward_f64(arch, point_cloud, V, params, scope="query_triplets", mask=None, arith="muladd"):
+    """fp64 shadow of ``forward``: the same graph evaluated in float64 on the SAME neighbour mask (the mask is
+    a discrete decision and stays pinned to the canonical fp32 arithmetic).  It bounds the fp32 restatement's own rounding
+    error, so that a CUDA-vs-oracle difference can be split into "oracle noise" and "kernel error"."""
+    global F32
+    pc32 = np.asarray(point_cloud, dtype=np.float32)
+    Bq, P, N, dim = pc32.shape
+    if mask is None:
+        mask = pairwise_distance_mask(pc32.reshape(Bq * P, N, dim), k=params.get("KNN", 20), arith=arith)
+    saved = F32
+    F32 = np.float64
+    try:
+        V64 = {k: np.asarray(v, dtype=np.float64) for k, v in V.items()}
+        return forward(arch, pc32.astype(np.float64), V64, params, scope=scope, mask=np.asarray(mask, dtype=np.float64))
+    finally:
+        F32 = saved
+
+
 # ------------------------------------------------------------------------------------------------
 # evaluate.py
 # ------------------------------------------------------------------------------------------------

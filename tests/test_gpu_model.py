@@ -88,6 +88,11 @@ def test_forward_matches_oracle_small(pkg, arch, arith):
     ref = epc_oracle.forward(arch, clouds, V, params, mask=mask)
     assert tuple(out.shape) == (2, 3, 256)
     _check_desc(out.cpu().numpy(), ref, "%s/%s" % (arch, arith))
+    # the float64 shadow of the same graph on the same mask: the fp32 restatement's own noise (~1e-6) is not what the
+    # tolerance is spent on
+    ref64 = epc_oracle.forward_f64(arch, clouds, V, params, mask=mask)
+    assert np.abs(ref - ref64).max() <= 1e-5
+    _check_desc(out.cpu().numpy(), ref64.astype(np.float32), "%s/%s vs fp64 shadow" % (arch, arith))
 
 
 def test_batch_independence_and_determinism(pkg):

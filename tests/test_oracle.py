@@ -104,3 +104,19 @@ def test_get_latent_vectors_batching_is_transparent():
     a = O.get_latent_vectors(arch, V, p, data, batch_num_queries=1)
     b = O.get_latent_vectors(arch, V, p, data, batch_num_queries=2, positives=1, negatives=0)
     assert a.shape == (5, 256) and np.abs(a - b).max() <= 1e-6
+
+
+@pytest.mark.parametrize("arch", ["epc-net", "epc-net-l"])
+def test_fp64_shadow_bounds_the_restatement(arch):
+    """the fp32 restatement against its float64 shadow on the same neighbour mask -- the oracle's own rounding
+    noise is two orders of magnitude below the 1e-3 descriptor tolerance the CUDA path is held to."""
+    variables = importlib.import_module("epc-net_b200.variables")
+    N = 256
+    clouds = np.stack([_data.cloud(k, 810 + i, N) for i, k in enumerate(["uniform", "clustered", "coarse"])], 0)[None]
+    V = variables.synthetic_variables(arch, 5)
+    params = dict(_data.default_params(arch), NUM_POINTS=N)
+    o32 = O.forward(arch, clouds, V, params)
+    o64 = O.forward_f64(arch, clouds, V, params)
+    assert o64.dtype == np.float64 and o32.dtype == np.float32
+    assert np.abs(o32 - o64).max() <= 1e-5
+    assert O.F32 is np.float32          # the shadow restores the working precision
