@@ -80,6 +80,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=24, help="clouds in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-retrieval", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-run oracle check of the timed outputs")
     ap.add_argument("--arch", default=ARCH, choices=["epc-net", "epc-net-l"],
                     help="epc-net = BASELINE configs[1] (the headline); epc-net-l = configs[2] (lightweight variant)")
     return ap.parse_args()
@@ -175,6 +176,19 @@ def cpu_baseline(n_sample, V, params, arch=ARCH):
         epc_oracle.forward(arch, clouds[i:i + 1][None], V, params)
         ts.append(time.perf_counter() - t0)
     return n_sample / float(np.sum(ts)), float(np.median(ts))
+
+
+def parity_check(got, clouds, rows, V, arch):
+    """max-abs / min cosine of the given descriptor rows against the oracle's forward on the same clouds."""
+    from oracle import epc_oracle
+    params = _data.default_params(arch)
+    worst_abs, worst_cos = 0.0, 1.0
+    for r in rows:
+        ref = epc_oracle.forward(arch, clouds[r:r + 1][None], V, params).reshape(-1)
+        g = got[r]
+        worst_abs = max(worst_abs, float(np.abs(g - ref).max()))
+        worst_cos = min(worst_cos, float((g * ref).sum() / max(np.linalg.norm(g) * np.linalg.norm(ref), 1e-30)))
+    return worst_abs, worst_cos
 
 
 def run_reference(args):
@@ -307,6 +321,19 @@ def main():
     e2e = world * B * K / e2e_s
     clocks = sampler.stop() if rank == 0 else None          # sampled across both timed regions
     assert desc.shape == (B * K, 256) and np.isfinite(desc).all()
+    # parity of what was just timed: first/last descriptor of each library call of the last device-resident step and of the
+    # end-to-end result against the CPU oracle (the checker, never the thing measured)
+    parity = None
+    if rank == 0 and not args.no_parity:
+        last = host_batches[(W + K - 1) % nbatch]
+        rows = sorted({0, min(args.chunk, B) - 1, min(args.chunk, B - 1), B - 1})
+        p1 = parity_check(out.cpu().numpy(), last, rows, V, arch)
+        rows2 = sorted({0, B - 1, (K - 1) * B, K * B - 1})
+        p2 = parity_check(desc, big, rows2, V, arch)
+        parity = {"parity_checked": True, "max_abs": max(p1[0], p2[0]), "min_cos": min(p1[1], p2[1]),
+                  "rows_checked": len(rows) + len(rows2), "tolerance": {"max_abs": 1e-3, "min_cos": 0.9999},
+                  "against": "oracle/epc_oracle.forward (dense-as-written restatement of models/epc-net.py:29-157)"}
+        assert parity["max_abs"] <= 1e-3 and parity["min_cos"] >= 0.9999, parity
 
     retr = None
     if not args.no_retrieval:
@@ -371,6 +398,8 @@ def main():
                 "api": "one evaluate.get_latent_vectors(host ndarray of steps x clouds) -> host ndarray call; per-step pinned staging, H2D and D2H inside"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "stages": stage_table,
     }
+    if parity is not None:
+        line.update(parity)
     if not args.no_retrieval:
         line["retrieval"] = retr
     if not args.no_cpu_baseline:

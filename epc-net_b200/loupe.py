@@ -11,8 +11,19 @@ from __future__ import annotations
 
 import torch
 
-from . import engine as _engine
-from . import variables
+if __package__:
+    from . import engine as _engine
+    from . import variables
+else:
+    # imported the reference's way -- `import loupe as lp` with the package directory on sys.path (models/epc-net.py:13-16)
+    import importlib as _il
+    import os as _os
+    import sys as _sys
+    _root = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+    if _root not in _sys.path:
+        _sys.path.insert(0, _root)
+    _engine = _il.import_module("epc-net_b200.engine")
+    variables = _il.import_module("epc-net_b200.variables")
 
 
 class PoolingBaseModel(object):

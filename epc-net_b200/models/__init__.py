@@ -1,7 +1,9 @@
 """The reference's model plugins (``MODEL = importlib.import_module(args["ARCH"])``, evaluate.py:119).
 
-``load(arch)`` returns the module for a yaml ``ARCH`` value; the hyphenated file names are kept so that
-adding this directory to ``sys.path`` lets the reference's own import statement find them.
+``load(arch)`` returns the module for a yaml ``ARCH`` value.  The hyphenated file names are kept and every plugin also
+imports as a TOP-LEVEL module: with this directory on ``sys.path`` (the reference appends its own ``models`` directory,
+evaluate.py:11-13) the reference's unmodified ``importlib.import_module(args["ARCH"])`` finds them
+(tests/test_host.py::test_reference_style_plugin_import).
 """
 import importlib
 

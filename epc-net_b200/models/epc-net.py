@@ -6,7 +6,17 @@ Same plugin surface as the reference module of the same name: ``placeholder_inpu
 TensorFlow names in ``params["VARIABLES"]`` or the default ``variables`` store under the current
 ``variables.variable_scope``.  The whole forward is one call into libepc_b200 (epc_embed).
 """
-from . import _common
+if __package__:
+    from . import _common
+else:
+    # imported the reference's way -- sys.path.append(<models dir>); importlib.import_module(args["ARCH"]) (evaluate.py:11-13,119)
+    import importlib as _il
+    import os as _os
+    import sys as _sys
+    _root = _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+    if _root not in _sys.path:
+        _sys.path.insert(0, _root)
+    _common = _il.import_module("epc-net_b200.models._common")
 
 ARCH = "epc-net"
 placeholder_inputs = _common.placeholder_inputs

@@ -13,8 +13,21 @@ import ctypes
 import numpy as np
 import torch
 
-from .. import _lib, variables
-from ..engine import _ptr, _require_cuda, _stream, workspaces
+if __package__:
+    from .. import _lib, variables
+    from ..engine import _ptr, _require_cuda, _stream, workspaces
+else:
+    # imported the reference's way -- `import tf_util` with the utils directory on sys.path (models/epc-net.py:11-14)
+    import importlib as _il
+    import os as _os
+    import sys as _sys
+    _root = _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+    if _root not in _sys.path:
+        _sys.path.insert(0, _root)
+    _lib = _il.import_module("epc-net_b200._lib")
+    variables = _il.import_module("epc-net_b200.variables")
+    _eng = _il.import_module("epc-net_b200.engine")
+    _ptr, _require_cuda, _stream, workspaces = _eng._ptr, _eng._require_cuda, _eng._stream, _eng.workspaces
 
 _fp = ctypes.POINTER(ctypes.c_float)
 

@@ -267,3 +267,36 @@ def test_train_side_callers(pkg):
     got = train.get_random_hard_negatives(allv[0], negs, 3)
     _, ind = KDTree(allv[negs]).query(np.array([allv[0]]), k=3)
     assert got == np.squeeze(np.array(negs)[ind[0]]).tolist()
+
+
+@pytest.mark.parametrize("arch,scope", [("epc-net", "query_triplets"), ("kd_epc-net-l", "student/query_triplets")])
+def test_checkpoint_restore_then_forward(pkg, arch, scope, tmp_path):
+    """evaluate.py:262-266 (saver.restore) -> forward: weights written as a TF V2 bundle, restored by name through
+    VariableStore.restore (tf_bundle.py) and embedded, give the very descriptors of the in-memory store."""
+    tf_bundle = importlib.import_module("epc-net_b200.tf_bundle")
+    V = pkg.variables.synthetic_variables(arch, 17, scope)
+    prefix = str(tmp_path / "model_epoch1_iter101.ckpt")
+    extra = dict(V)
+    extra["Variable"] = np.array(101, np.int32)                         # global step + an Adam slot, as in the shipped bundles
+    extra[next(iter(V)) + "/Adam"] = np.zeros_like(V[next(iter(V))])
+    tf_bundle.write_checkpoint(prefix, extra)
+    restored = pkg.variables.VariableStore()
+    restored.restore(prefix)
+    direct = pkg.variables.VariableStore(V)
+    clouds = np.stack([_data.cloud(k, 60 + i, 1024) for i, k in enumerate(["uniform", "clustered", "coarse"])], 0)
+    x = torch.from_numpy(clouds[None]).cuda()
+    outer, inner = scope.split("/", 1) if "/" in scope else (None, scope)
+    outs = []
+    for store in (restored, direct):
+        params = dict(_data.default_params(arch), NUM_POINTS=1024, VARIABLES=store)
+        if outer:
+            with pkg.variables.variable_scope(outer), pkg.variables.variable_scope(inner):
+                res = pkg.models.load(arch).forward(x, False, params=params)
+        else:
+            with pkg.variables.variable_scope(scope):
+                res = pkg.models.load(arch).forward(x, False, params=params)
+        outs.append(res[1] if arch.startswith("kd_") else res)
+    assert torch.equal(outs[0], outs[1])
+    ref = epc_oracle.forward(arch, clouds[None], V, dict(_data.default_params(arch), NUM_POINTS=1024), scope=scope)
+    ref = ref[1] if isinstance(ref, tuple) else ref
+    _check_desc(outs[0].cpu().numpy(), ref, arch + " restored checkpoint")

@@ -217,3 +217,51 @@ def test_train_mirror_surface():
         assert train.get_latent_vectors(None, {}, {}).shape == (0,)
     finally:
         train.train_data = saved
+
+
+def test_reference_style_plugin_import():
+    """evaluate.py:11-13,119 verbatim: the reference appends its `models` (and `utils`) directory to sys.path and imports the
+    yaml ARCH value as a TOP-LEVEL module.  With our directories in their place the unmodified statements must work."""
+    import subprocess
+    code = r'''
+import importlib, os, sys
+BASE_DIR = %r
+sys.path.append(BASE_DIR)
+sys.path.append(os.path.join(BASE_DIR, 'models'))
+sys.path.append(os.path.join(BASE_DIR, 'utils'))
+from loading_pointclouds import get_sets_dict, load_pc_file, load_pc_files
+import tf_util
+import loupe as lp
+for arch in ("epc-net", "epc-net-l", "kd_epc-net", "kd_epc-net-l"):
+    MODEL = importlib.import_module(arch)
+    assert callable(MODEL.forward) and callable(MODEL.placeholder_inputs) and MODEL.ARCH == arch
+assert callable(tf_util.pairwise_distance_mask) and callable(tf_util.conv1d) and callable(lp.G_VLAD) and callable(lp.NetVLAD)
+print("ok")
+''' % os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "epc-net_b200")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=tempfile.gettempdir())
+    assert res.returncode == 0 and res.stdout.strip().endswith("ok"), res.stderr[-2000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted (GPU box)")
+@pytest.mark.parametrize("cfg", ["epc-net.yaml", "epc-net-l.yaml", "epc-net-l-d.yaml"])
+def test_reference_yaml_configs_feed_the_plugin(cfg):
+    """configs/*.yaml through yaml.safe_load (evaluate.py:37-82) give a params dict the plugin accepts as it is: the ARCH
+    value names a plugin module, every key forward() reads is present, and the values are the ones the kernels are built for."""
+    import yaml
+    models = importlib.import_module("epc-net_b200.models")
+    args = yaml.safe_load(open(os.path.join(REF, "configs", cfg)))
+    archs = [args[k] for k in ("ARCH", "ARCH_TEACHER", "ARCH_STUDENT") if k in args]
+    assert archs
+    for arch in archs:
+        mod = models.load(arch)
+        assert mod.ARCH == arch
+        for key in ("CLUSTER_SIZE", "FEATURE_OUTPUT_DIM", "KNN", "INPUT_DIM", "NUM_POINTS"):
+            assert key in args, key
+        assert (args["NUM_POINTS"], args["INPUT_DIM"], args["CLUSTER_SIZE"], args["FEATURE_OUTPUT_DIM"], args["KNN"]) == \
+               (4096, 3, 64, 256, 20)
+        # parameter validation happens before any device work: a training-mode call and a missing key fail like the reference
+        with pytest.raises(NotImplementedError):
+            mod.forward(np.zeros((1, 1, 4096, 3), np.float32), True, params=args)
+        bad = {k: v for k, v in args.items() if k != "KNN"}
+        with pytest.raises(KeyError):
+            mod.forward(np.zeros((1, 1, 4096, 3), np.float32), False, params=bad)
