@@ -599,12 +599,9 @@ int proxy_block(const uint16_t* x, const KnnState& g, int B, int N, int arith, f
     EPC_CHECK_ARG(conv_a.Wimg && conv_b.Wimg && (!conv_next || conv_next->Wimg), "proxy_block: missing swizzled weight images");
     EPC_CHECK_ARG(ctot % 8 == 0 && coff % 8 == 0, "proxy_block: concat slice must be 16-byte aligned");
     if (B == 0) return EPC_OK;
-    static bool attr_done = false;
-    if (!attr_done) {
-        EPC_CUDA(cudaFuncSetAttribute(proxy_block_kernel<true, FMT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM));
-        EPC_CUDA(cudaFuncSetAttribute(proxy_block_kernel<false, FMT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM));
-        attr_done = true;
-    }
+    static PerDeviceSize attr_a, attr_b;
+    EPC_CUDA(ensure_dyn_smem(proxy_block_kernel<true, FMT_F16>, PB_SMEM, attr_a));
+    EPC_CUDA(ensure_dyn_smem(proxy_block_kernel<false, FMT_F16>, PB_SMEM, attr_b));
     auto img = [&](const DenseDev& L) { return reinterpret_cast<const uint4*>(L.Wimg); };
     PbArgs a = {};
     a.x = x; a.nbr = g.nbr; a.kthd = g.kthd; a.cnt = g.cnt; a.tie = g.tie; a.sorted = g.sorted; a.flags = flags;

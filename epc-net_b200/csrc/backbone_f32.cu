@@ -346,12 +346,9 @@ int proxy_block_f32(const int* flags, const float* x, const KnnState& g, int B, 
     EPC_CHECK_ARG(N % PB_TILE == 0, "proxy_block: N=%d must be a multiple of %d", N, PB_TILE);
     EPC_CHECK_ARG(conv_a.Wimg32 && conv_b.Wimg32 && (!conv_next || conv_next->Wimg32), "proxy_block: missing swizzled weight images");
     if (B == 0) return EPC_OK;
-    static bool attr_done = false;
-    if (!attr_done) {
-        EPC_CUDA(cudaFuncSetAttribute(proxy_block_f32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM));
-        EPC_CUDA(cudaFuncSetAttribute(proxy_block_f32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM));
-        attr_done = true;
-    }
+    static PerDeviceSize attr_a, attr_b;
+    EPC_CUDA(ensure_dyn_smem(proxy_block_f32_kernel<true>, PB_SMEM, attr_a));
+    EPC_CUDA(ensure_dyn_smem(proxy_block_f32_kernel<false>, PB_SMEM, attr_b));
     dim3 grid(N / PB_TILE, B < SAFE_SLOTS ? B : SAFE_SLOTS);
     if (conv_next) {
         proxy_block_f32_kernel<true><<<grid, PB_THREADS, PB_SMEM, st>>>(flags, B, x, g.nbr, g.kthd, g.cnt, g.sorted, N, arith, divisor,

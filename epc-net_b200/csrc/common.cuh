@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include "../../include/epc_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -57,6 +58,29 @@ struct ScopedStage {
     } while (0)
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Function attributes (opt-in dynamic shared memory), SM counts and cluster occupancies are PER DEVICE, and one process may
+// drive several devices (Engine(device=...), ensure_device()): every such cache is an array indexed by the current device,
+// with atomics because the C ABI is called from threads that run with the GIL released.
+constexpr int EPC_MAX_DEVICES = 64;
+inline int current_device_slot() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0) d = 0;
+    return d % EPC_MAX_DEVICES;
+}
+struct PerDeviceSize {
+    std::atomic<size_t> v[EPC_MAX_DEVICES];
+    PerDeviceSize() { for (auto& x : v) x.store(0, std::memory_order_relaxed); }
+};
+// raise cudaFuncAttributeMaxDynamicSharedMemorySize of `kern` on the current device to at least `bytes` (idempotent, cheap)
+template <typename K>
+inline cudaError_t ensure_dyn_smem(K kern, size_t bytes, PerDeviceSize& cache) {
+    std::atomic<size_t>& c = cache.v[current_device_slot()];
+    if (bytes <= c.load(std::memory_order_acquire)) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) c.store(bytes, std::memory_order_release);
+    return e;
+}
 
 // Bump allocator over the caller's workspace.
 struct Arena {

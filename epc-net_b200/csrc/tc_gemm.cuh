@@ -741,11 +741,8 @@ inline int tc_gemm_launch(const Operand<T>& A, const Operand<T>& B, const tc::Ge
     if (stages > nkb) stages = nkb < 2 ? 2 : nkb;
     const size_t smem = Cfg::smem(stages);
     auto kern = tc::tc_gemm_kernel<T, BN, A_MN, B_MN, EPI>;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        EPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem(Cfg::STAGES)));
-        attr_smem = Cfg::smem(Cfg::STAGES);
-    }
+    static PerDeviceSize attr_smem;
+    EPC_CUDA(ensure_dyn_smem(kern, Cfg::smem(Cfg::STAGES), attr_smem));
     dim3 grid((p.M + tc::TC_BM - 1) / tc::TC_BM, p.N / BN, batch * p.splitk);
     kern<<<grid, 192, smem, st>>>(tmA, tmB, p, stages);
     EPC_LAUNCH_CHECK();
@@ -754,14 +751,17 @@ inline int tc_gemm_launch(const Operand<T>& A, const Operand<T>& B, const tc::Ge
 
 
 inline int sm_count() {
-    static int n = 0;
+    static PerDeviceSize cache;
+    std::atomic<size_t>& c = cache.v[current_device_slot()];
+    size_t n = c.load(std::memory_order_acquire);
     if (!n) {
-        int dev = 0;
+        int dev = 0, v = 0;
         cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        n = v > 0 ? (size_t)v : 148;
+        c.store(n, std::memory_order_release);
     }
-    return n;
+    return (int)n;
 }
 
 // Number of CTAs a persistent kernel launches: one per SM, or fewer when `env` says so (leaves SMs to kernels of other
@@ -794,11 +794,8 @@ inline int tc_gemm_bres_launch(const Operand<T>& A, const Operand<T>& B, const t
     if (int rc = make_tmap_2d(&tmB, B.ptr, B.rows, B.cols, B.ld, BK, BN)) return rc;
     static_assert(EW == 4 || (EW == 8 && EPI != tc::EPI_ASSIGN && BN >= 64), "8 epilogue warps split the tile's columns");
     auto kern = tc::tc_gemm_bres_kernel<T, BN, EPI, EW, CL>;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        EPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
+    static PerDeviceSize attr_smem;
+    EPC_CUDA(ensure_dyn_smem(kern, smem, attr_smem));
     const int NT = p.N / BN;
     const int m_tiles = (p.M + tc::TC_BM - 1) / tc::TC_BM;
     if (CL > 1) {
@@ -810,13 +807,16 @@ inline int tc_gemm_bres_launch(const Operand<T>& A, const Operand<T>& B, const t
         attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.gridDim = dim3(CL, 1, 1); cfg.blockDim = dim3(64 + 32 * EW, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        static int max_clusters = 0;
+        static PerDeviceSize max_clusters_cache;
+        std::atomic<size_t>& mc = max_clusters_cache.v[current_device_slot()];
+        int max_clusters = (int)mc.load(std::memory_order_acquire);
         if (!max_clusters) {
             cfg.gridDim = dim3(CL * (sm_count() / CL), 1, 1);
             int n = 0;
             EPC_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
             EPC_CHECK_ARG(n >= 1, "tc_gemm_bres: no cluster of %d CTAs fits on this device", CL);
             max_clusters = n;
+            mc.store((size_t)n, std::memory_order_release);
         }
         const int clusters = max_clusters < m_tiles ? max_clusters : m_tiles;
         cfg.gridDim = dim3(clusters * CL, 1, 1);

@@ -213,7 +213,7 @@ int vlad_tail(const float* Y, int nslab, int B, int G, int D, const float* bn_sc
 // g[b,f] = max_n H[b,n,f]   (tf_util.max_pool2d over [N,1], models/epc-net-l.py:91).  H >= 0 is NOT assumed:
 // a float atomic max via the ordered-int trick.
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
-    if (v >= 0.f)
+    if (__float_as_int(v) >= 0)          // sign BIT, not value: -0.0f has the int pattern INT_MIN and must take the negative branch
         atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
     else
         atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));

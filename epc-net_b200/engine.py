@@ -30,6 +30,23 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def as_cuda_f32(t, what="input", dtype=None):
+    """A contiguous CUDA tensor of ``dtype`` (default fp32) for the C ABI, which takes raw device pointers and cannot check
+    them: numpy arrays and host tensors are copied to the current device, other dtypes are converted (a float64 or half
+    tensor passed by pointer would be silently reinterpreted)."""
+    _require_cuda()
+    dtype = torch.float32 if dtype is None else dtype
+    if isinstance(t, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(t))
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch tensor or a numpy array, got %s" % (what, type(t).__name__))
+    if not t.is_cuda:
+        t = t.cuda()
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
 _POISON = int(os.environ["EPC_POISON_WORKSPACE"], 0) if os.environ.get("EPC_POISON_WORKSPACE") else None
 
 
@@ -187,8 +204,9 @@ class Engine(object):
         return max(1, min(128, -(-n // self.nstreams)))
 
     # ---- device-resident API ------------------------------------------------------------------
-    def embed(self, xyz: torch.Tensor, want_feat: bool = False, out: torch.Tensor = None):
-        """xyz [B,N,3] fp32 CUDA tensor -> descriptors [B,D] (and KD features [B*N,1024])."""
+    def embed(self, xyz: torch.Tensor, want_feat: bool = False, out: torch.Tensor = None, single_call: bool = False):
+        """xyz [B,N,3] fp32 CUDA tensor -> descriptors [B,D] (and KD features [B*N,1024]).  ``single_call``: one epc_embed on
+        the current stream, no chunking and no side streams (embed_host pipelines its own chunks over its own streams)."""
         if not (xyz.is_cuda and xyz.dtype == torch.float32 and xyz.dim() == 3 and xyz.shape[-1] == 3):
             raise ValueError("embed expects a CUDA fp32 tensor [B,N,3], got %s %s %s" % (xyz.device, xyz.dtype, tuple(xyz.shape)))
         xyz = xyz.contiguous()
@@ -199,7 +217,7 @@ class Engine(object):
             raise ValueError("out must be a contiguous CUDA fp32 tensor [B,%d]" % self.output_dim)
         feat = torch.empty((B * N, 1024), dtype=torch.float32, device=xyz.device) if want_feat else None
         with torch.cuda.device(xyz.device):
-            chunk = self._chunk_for(B)
+            chunk = max(1, B) if single_call else self._chunk_for(B)
             starts = list(range(0, B, chunk))
             fan = min(self.nstreams, len(starts))
             main = torch.cuda.current_stream()
@@ -225,8 +243,8 @@ class Engine(object):
         """loupe forward on features X [B*max_samples, 1024] -> [B, D] (not L2-normalised)."""
         if not self.is_vlad:
             raise ValueError("%s has no VLAD head" % self.arch)
-        X = X.contiguous()
-        if X.shape[0] % max_samples or X.shape[1] != 1024:
+        X = as_cuda_f32(X, "reshaped_input")
+        if X.dim() != 2 or X.shape[0] % max_samples or X.shape[1] != 1024:
             raise ValueError("reshaped_input must be [B*max_samples, 1024]")
         B = X.shape[0] // max_samples
         out = torch.empty((B, self.output_dim), dtype=torch.float32, device=X.device)
@@ -291,7 +309,7 @@ class Engine(object):
                     host_free[slot] = in_ready[slot]
                 cs.wait_event(in_ready[slot])
                 with torch.cuda.stream(cs):
-                    self.embed(dev_in[slot][:e - s], out=dev_out[s:e])       # one chunk: runs on `cs`
+                    self.embed(dev_in[slot][:e - s], out=dev_out[s:e], single_call=True)       # one library call on `cs`
                 in_free[slot].record(cs)
             for cs in compute:
                 if cs is not main:

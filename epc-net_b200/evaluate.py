@@ -56,12 +56,13 @@ def get_latent_vectors(sess, ops, dict_to_process, data):
 def retrieve_topk(database_output, queries_output, k, id_offset=0):
     """Exact Euclidean k-NN on the GPU: -> (dist [Q,k] float64, idx [Q,k] int64), ascending, like
     ``KDTree(database_output).query(queries_output, k)`` (evaluate.py:463,481)."""
-    _engine._require_cuda()
     lib = _lib.load()
-    db = torch.as_tensor(np.ascontiguousarray(database_output, dtype=np.float32)).cuda() \
-        if not isinstance(database_output, torch.Tensor) else database_output.contiguous()
-    q = torch.as_tensor(np.ascontiguousarray(queries_output, dtype=np.float32)).cuda() \
-        if not isinstance(queries_output, torch.Tensor) else queries_output.contiguous()
+    db = _engine.as_cuda_f32(database_output, "database_output")
+    q = _engine.as_cuda_f32(queries_output, "queries_output")
+    if db.dim() != 2 or q.dim() != 2 or db.shape[1] != q.shape[1]:
+        raise ValueError("retrieve_topk expects (D, dim) and (Q, dim) arrays, got %s and %s" % (tuple(db.shape), tuple(q.shape)))
+    if q.device != db.device:
+        q = q.to(db.device)
     D, dim = db.shape
     Q = q.shape[0]
     idx = torch.empty((Q, k), dtype=torch.int64, device=db.device)

@@ -15,7 +15,7 @@ import torch
 
 if __package__:
     from .. import _lib, variables
-    from ..engine import _ptr, _require_cuda, _stream, workspaces
+    from ..engine import _ptr, _require_cuda, _stream, as_cuda_f32, workspaces
 else:
     # imported the reference's way -- `import tf_util` with the utils directory on sys.path (models/epc-net.py:11-14)
     import importlib as _il
@@ -28,6 +28,7 @@ else:
     variables = _il.import_module("epc-net_b200.variables")
     _eng = _il.import_module("epc-net_b200.engine")
     _ptr, _require_cuda, _stream, workspaces = _eng._ptr, _eng._require_cuda, _eng._stream, _eng.workspaces
+    as_cuda_f32 = _eng.as_cuda_f32
 
 _fp = ctypes.POINTER(ctypes.c_float)
 
@@ -67,8 +68,7 @@ def pairwise_distance(point_cloud, arith="muladd"):
 def knn(adj_matrix, k=20):
     """utils/tf_util.py:599-610: (B,N,M) pairwise distances -> (B,N,k) int32 indices of the k nearest
     (tf.nn.top_k(-adj) order: ascending distance, ties -> lower index)."""
-    _require_cuda()
-    adj = adj_matrix.contiguous()
+    adj = as_cuda_f32(adj_matrix, "adj_matrix")
     lib = _lib.load()
     R = int(np.prod(adj.shape[:-1]))
     M = adj.shape[-1]
@@ -113,7 +113,7 @@ def _dense(inputs2d, full_scope, cin, cout, bn, relu, store):
     if w.size != cin * cout:
         raise ValueError("%s/weights has %d elements, expected %d x %d" % (full_scope, w.size, cin, cout))
     layer = _lib.EpcDense(arr(w), arr(store[full_scope + "/biases"]), bnp, cin, cout)
-    x = inputs2d.contiguous()
+    x = as_cuda_f32(inputs2d, "inputs")
     y = torch.empty((x.shape[0], cout), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().epc_dense_forward(ctypes.byref(layer), _ptr(x), x.shape[0], _ptr(y), 1 if relu else 0, _stream()))
@@ -151,7 +151,7 @@ def max_pool2d(inputs, kernel_size, scope=None, stride=(2, 2), padding="VALID"):
     B, N, W, C = inputs.shape
     if W != 1 or list(kernel_size) != [N, 1] or padding != "VALID":
         raise NotImplementedError("only the global max-pool over points (kernel [num_points, 1], VALID) is implemented")
-    x = inputs.contiguous()
+    x = as_cuda_f32(inputs, "inputs")
     y = torch.empty((B, 1, 1, C), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().epc_max_pool_points(_ptr(x), B, N, C, _ptr(y), _stream()))

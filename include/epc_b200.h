@@ -14,7 +14,8 @@
  *     with respect to the host unless stated otherwise;
  *   - return value: 0 on success, negative `EPC_E*` code otherwise; `epc_last_error()` returns a
  *     thread-local message.  Nothing throws; nothing allocates device memory except
- *     `epc_model_create` (weights) -- scratch comes from the caller (`*_workspace_bytes`);
+ *     `epc_model_create` (weights) and the API-parity helper `epc_dense_forward` (see there) --
+ *     scratch comes from the caller (`*_workspace_bytes`);
  *   - there is NO CPU fallback: without a CUDA device every compute entry point returns EPC_ECUDA.
  *   - tensors are dense row-major fp32 unless noted.  N (points per cloud) must be a multiple of 32,
  *     32 <= N <= 8192 (the reference fixes N = 4096: utils/loading_pointclouds.py:32).
@@ -136,8 +137,9 @@ typedef struct EpcDense {
 } EpcDense;
 
 /* Stand-alone pointwise layer on device data: y[R,cout] = act(BN(x[R,cin] W + b)); relu != 0 applies
- * the ReLU.  Weights are uploaded on every call -- this entry point exists for API parity of
- * tf_util.conv1d / fully_connected and for tests, not for the fused path. */
+ * the ReLU.  Weights are folded, uploaded into a temporary device buffer (cudaMalloc/cudaFree) and the
+ * call SYNCHRONISES the stream before returning -- this entry point exists for API parity of
+ * tf_util.conv1d / fully_connected and for tests, not for the fused path (epc_embed never calls it). */
 int epc_dense_forward(const EpcDense* layer, const float* x, long long R, float* y, int relu, void* stream);
 
 /* tf_util.max_pool2d(x[B,N,1,C], [N,1]) (:349-372, models/epc-net-l.py:91): y[B,C] = max_n x[B,n,C] */
