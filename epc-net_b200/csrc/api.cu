@@ -223,8 +223,7 @@ int epc_knn(const float* xyz, int B, int N, int arith, int32_t* idx, float* kth,
     }
     Arena ar(workspace, workspace_bytes);
     KnnState s = knn_state_carve(ar, B, N);
-    return knn_build(xyz, B, N, arith, true, s.sorted, s.perm, s.perm16, s.aabb, s.tie, s.nbr, s.kthd, s.cnt, idx, kth, count,
-                     static_cast<cudaStream_t>(stream));
+    return knn_build(xyz, B, N, arith, true, s, idx, kth, count, static_cast<cudaStream_t>(stream));
 }
 
 // test hook: same as epc_knn with the AABB pruning switched off (results must be bit-identical)
@@ -238,8 +237,7 @@ int epc_knn_noprune(const float* xyz, int B, int N, int arith, int32_t* idx, flo
     }
     Arena ar(workspace, workspace_bytes);
     KnnState s = knn_state_carve(ar, B, N);
-    return knn_build(xyz, B, N, arith, false, s.sorted, s.perm, s.perm16, s.aabb, s.tie, s.nbr, s.kthd, s.cnt, idx, kth, count,
-                     static_cast<cudaStream_t>(stream));
+    return knn_build(xyz, B, N, arith, false, s, idx, kth, count, static_cast<cudaStream_t>(stream));
 }
 
 int epc_knn_dense(const float* xyz, int B, int N, int arith, float* mask, float* dist, void* workspace,
@@ -255,7 +253,7 @@ int epc_knn_dense(const float* xyz, int B, int N, int arith, float* mask, float*
     KnnState s = knn_state_carve(ar, B, N);
     float* kth = ar.take<float>((size_t)B * N);
     if (mask) {
-        if (int rc = knn_build(xyz, B, N, arith, true, s.sorted, s.perm, s.perm16, s.aabb, s.tie, s.nbr, s.kthd, s.cnt, nullptr, kth, nullptr, st))
+        if (int rc = knn_build(xyz, B, N, arith, true, s, nullptr, kth, nullptr, st))
             return rc;
     }
     return knn_dense(xyz, B, N, arith, kth, mask, dist, st);
@@ -571,8 +569,7 @@ int epc_embed(const EpcModel* m, const float* xyz, int B, int N, int knn_arith, 
     float* H32 = ar.take<float>((size_t)subB * N * 1024);
     float* inv = ar.take<float>((size_t)subB * N);
 
-    if (int rc = knn_build(xyz, B, N, knn_arith, true, ks.sorted, ks.perm, ks.perm16, ks.aabb, ks.tie, ks.nbr, ks.kthd, ks.cnt, nullptr, nullptr,
-                           nullptr, st))
+    if (int rc = knn_build(xyz, B, N, knn_arith, true, ks, nullptr, nullptr, nullptr, st))
         return rc;
     // ProxyConv chain: fp16 fast pass over every cloud, then the range-safe fp32 pass over the clouds it flagged
     EPC_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)B, st));

@@ -16,14 +16,16 @@ struct KnnState {          // per-cloud kNN graph in *sorted* (Morton) point ord
     float4* aabb;          // [B][2][N/32] per 32-point block: (lo.xyz, max |p|^2), then (hi.xyz, -)
     uint32_t* tie;         // [B][TIE_WORDS] per cloud: count, pad, then up to TIE_CAP entries (row << 16 | neighbour, d bits):
                            // the members of thresholded sets beyond the 20 listed ones (ties at the 20th distance)
+    float* U;              // [B,N]   pass A: upper bound of the row's 20th smallest canonical distance
+    int* slow;             // [1 + B*N] counter, then the rows whose candidate list overflowed (mass ties): exact warp-per-row path
 };
 constexpr uint32_t TIE_CAP = 510;                  // entries per cloud; more (degenerate clouds) -> the gather re-scans the cloud
 constexpr uint32_t TIE_WORDS = 2 + 2 * TIE_CAP;    // 4 KB per cloud
 int knn_check_n(int N);
 size_t knn_state_bytes(int B, int N);
 KnnState knn_state_carve(Arena& ar, int B, int N);
-int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sorted, int* perm, uint16_t* perm16, float4* aabb, uint32_t* tie, uint16_t* nbr,
-              float* kthd, int* cnt, int32_t* idx_out, float* kth_out, int32_t* count_out, cudaStream_t st);
+int knn_build(const float* xyz, int B, int N, int arith, bool prune, const KnnState& s, int32_t* idx_out, float* kth_out,
+              int32_t* count_out, cudaStream_t st);
 int knn_dense(const float* xyz, int B, int N, int arith, const float* kth, float* mask, float* dist, cudaStream_t st);
 int rows_topk_smallest(const float* adj, long long R, int M, int k, int32_t* idx, cudaStream_t st);
 

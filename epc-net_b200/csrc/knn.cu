@@ -6,6 +6,8 @@
 //       distances on the packed fp32x2 pipe in the *canonical* arithmetic (common.cuh), a
 //       warp-distributed sorted top-20 list per row, and exact AABB pruning of 32-point blocks.
 // Output (sorted space): nbr [B,N,20] u16, kthd [B,N] (20th smallest d), cnt [B,N] = |{j: d_ij <= kthd_i}|.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -196,26 +198,477 @@ __global__ void __launch_bounds__(1024) sort_kernel(const float* __restrict__ xy
 }
 
 // ------------------------------------------------------------------------------------------------
-// Per-row candidate buffer in shared memory: up to 64 (value, key) pairs; after a compaction the first 20 are the
-// current best set (unsorted) and `thr` is the 20th smallest value.  A block's hits are *appended* with one ballot,
-// one popc and a predicated store, however many there are.  A *compaction* selects the 20th smallest VALUE with a
-// value-only bitonic network (one shuffle + one min/max per step), then keeps the entries below it (plus the ties
-// needed, by lowest original index) with a ballot-rank scatter.  Only the final 20 are sorted by the full key
-// (d, original index) = tf.nn.top_k order.  `extra` counts dropped candidates equal to the 20th value (the size of
-// the thresholded set minus 20).
+// kNN graph, thread-per-row (round 2).  A CTA stages its whole cloud in shared memory once and serves 512 query rows:
+// thread = row, warp = one 32-point Morton block of rows, candidates are BROADCAST from shared memory (every lane reads the
+// same point pair), so there is not a single shuffle or ballot on the data path -- only warp votes for block-level decisions.
+//
+//   knn_bound_kernel    pass A: a valid, tight UPPER BOUND U_i of the row's 20th smallest distance.  Cheap arithmetic
+//                       (3 FFMA2 + FADD2 per candidate pair), candidates below the running threshold are parked in a per-row
+//                       shared-memory buffer and merged, two at a time, into a sorted 20-entry register list by a
+//                       branch-free min/max network (M[i] = min3(L[i], max(L[i-1],c1), max(L[i-2],c2)): FMNMX/FMNMX3 only).
+//                       Blocks are visited outwards from the row's own block (index-near = space-near) behind a two-level
+//                       box test (128-point tiles, then 32-point blocks).  Any 20 candidates give a valid bound, so neither
+//                       the pruning nor the arithmetic of this pass can affect the result -- only how tight U is.
+//   knn_collect_kernel  pass B: the CANONICAL arithmetic (common.cuh) on every block whose rigorous lower bound is <= U_i:
+//                       candidates with d <= U_i (20 + the odd extra) are listed per row; the exact 20th distance is selected
+//                       among them, then the thresholded set {j : d_ij <= kth_i} is written out: 20 listed neighbours
+//                       (out-of-tile first), the row's count, and the members beyond 20 in the cloud's tie list.
+//   knn_slow_kernel     rows whose candidate list overflowed (mass ties: quantised / duplicated / all-zero clouds):
+//                       warp-per-row exact radix select over the whole cloud.  Launched on the overflow list only.
+//   knn_public_kernel   API outputs in original point order: idx in tf.nn.top_k order (d ascending, ties -> lower original
+//                       index), kth = -d20, count.
+// Output (sorted space): nbr [B,N,20] u16, kthd [B,N] (20th smallest d), cnt [B,N] = |{j: d_ij <= kthd_i}| | n_out << 24.
 // ------------------------------------------------------------------------------------------------
-struct RowState {
-    float thr;           // 20th smallest value at the last compaction (warp-uniform)
-    int n;               // entries in the buffer (warp-uniform)
-    int extra;           // # dropped candidates with value == thr (warp-uniform)
-};
-constexpr uint32_t KEY_EMPTY = 0xffffffffu;
-constexpr int KNN_CAP = 64;      // buffer entries per row = two per lane during a compaction
-constexpr int KNN_ROWS_PER_WARP = 8;
-constexpr int KNN_WARPS = 8;
-constexpr int KNN_ROWS_PER_CTA = KNN_ROWS_PER_WARP * KNN_WARPS;
-constexpr size_t KNN_BUF_BYTES = (size_t)KNN_ROWS_PER_CTA * KNN_CAP * 8;     // candidate values + keys: the first bytes of the dynamic smem
+constexpr int KNN_THREADS = 512;      // rows per CTA
+constexpr int KNN_SUB = 8;            // candidates between two buffer checks
+constexpr int KNN_CAPB = 40;          // pass B: listed candidates per row (u16 each)
 
+struct KnnLayout {
+    int off_lo, off_hi, off_tlo, off_thi, off_buf;
+    int bytes;
+};
+__host__ __device__ inline KnnLayout knn_layout(int N, int buf_bytes_per_row) {
+    const int nblk = N >> 5, ntile = (nblk + 3) >> 2;
+    KnnLayout L;
+    int o = N * 16;                   // points, pair-SoA: (x0,x1,y0,y1) (z0,z1,s0,s1) per pair of points
+    L.off_lo = o;  o += nblk * 16;    // block boxes: (lo.xyz, max |p|^2)
+    L.off_hi = o;  o += nblk * 16;    //              (hi.xyz, -)
+    L.off_tlo = o; o += ntile * 16;   // 128-point tile boxes
+    L.off_thi = o; o += ntile * 16;
+    L.off_buf = o; o += KNN_THREADS * buf_bytes_per_row;
+    L.bytes = o;
+    return L;
+}
+
+// the whole cloud -> shared memory (pair-SoA so that a candidate pair is two LDS.128 whose halves are FFMA2 operands)
+__device__ __forceinline__ void knn_stage(const float4* __restrict__ pts, const float4* __restrict__ box, int N,
+                                          unsigned char* smem, const KnnLayout& lay) {
+    const int nblk = N >> 5, ntile = (nblk + 3) >> 2;
+    float4* sp = reinterpret_cast<float4*>(smem);
+    for (int pr = threadIdx.x; pr < (N >> 1); pr += blockDim.x) {
+        const float4 a = __ldg(pts + 2 * pr), c = __ldg(pts + 2 * pr + 1);
+        sp[2 * pr] = make_float4(a.x, c.x, a.y, c.y);
+        sp[2 * pr + 1] = make_float4(a.z, c.z, a.w, c.w);
+    }
+    float4* slo = reinterpret_cast<float4*>(smem + lay.off_lo);
+    float4* shi = reinterpret_cast<float4*>(smem + lay.off_hi);
+    for (int i = threadIdx.x; i < nblk; i += blockDim.x) {
+        slo[i] = __ldg(box + i);
+        shi[i] = __ldg(box + nblk + i);
+    }
+    __syncthreads();
+    float4* stlo = reinterpret_cast<float4*>(smem + lay.off_tlo);
+    float4* sthi = reinterpret_cast<float4*>(smem + lay.off_thi);
+    for (int t = threadIdx.x; t < ntile; t += blockDim.x) {
+        float4 lo = slo[4 * t], hi = shi[4 * t];
+        for (int k = 1; k < 4 && 4 * t + k < nblk; ++k) {
+            const float4 l2 = slo[4 * t + k], h2 = shi[4 * t + k];
+            lo = make_float4(fminf(lo.x, l2.x), fminf(lo.y, l2.y), fminf(lo.z, l2.z), fmaxf(lo.w, l2.w));
+            hi = make_float4(fmaxf(hi.x, h2.x), fmaxf(hi.y, h2.y), fmaxf(hi.z, h2.z), 0.f);
+        }
+        stlo[t] = lo;
+        sthi[t] = hi;
+    }
+    __syncthreads();
+}
+
+// squared distance from (x,y,z) to the box [lo,hi]
+__device__ __forceinline__ float box_lb(float x, float y, float z, const float4 lo, const float4 hi) {
+    const float dx = fmaxf(fmaxf(lo.x - x, x - hi.x), 0.f);
+    const float dy = fmaxf(fmaxf(lo.y - y, y - hi.y), 0.f);
+    const float dz = fmaxf(fmaxf(lo.z - z, z - hi.z), 0.f);
+    return dx * dx + dy * dy + dz * dz;
+}
+// rigorous lower bound of the *computed* canonical d over a box (DESIGN.md "pruning"): true |p-q|^2 >= lb_true >= lb(1-8u);
+// computed d >= true - 16u (s_i + s_j)
+__device__ __forceinline__ float box_bound_rigorous(float x, float y, float z, float s, const float4 lo, const float4 hi) {
+    return box_lb(x, y, z, lo, hi) * (1.0f - 1e-6f) - 1e-6f * (s + lo.w);
+}
+
+// the per-row buffers are addressed through 32-bit shared-space addresses (one register; a generic pointer costs ptxas three)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+    return v;
+}
+// d' = s_i + s_j - 2 p_i.p_j for a pair of candidates as one FFMA2 chain (q2* = -2 * query coordinate): within
+// 1e-6 (s_i + s_j) of the canonical d of either arithmetic
+__device__ __forceinline__ float2 fast_dist2(float2 q2x, float2 q2y, float2 q2z, float2 qs, const float4 A, const float4 Bv) {
+    float2 t = __ffma2_rn(q2x, make_float2(A.x, A.y), qs);
+    t = __ffma2_rn(q2y, make_float2(A.z, A.w), t);
+    t = __ffma2_rn(q2z, make_float2(Bv.x, Bv.y), t);
+    return __fadd2_rn(t, make_float2(Bv.z, Bv.w));
+}
+
+// sorted ascending list L[0..n) <- the n smallest of L u {c1, c2}: M[i] = min(L[i], max(L[i-1], lo), max(L[i-2], hi))
+template <int LEN>
+__device__ __forceinline__ void merge2(float (&L)[LEN], float c1, float c2) {
+    const float lo = fminf(c1, c2), hi = fmaxf(c1, c2);
+#pragma unroll
+    for (int i = LEN - 1; i >= 2; --i) L[i] = fminf(fminf(L[i], fmaxf(L[i - 1], lo)), fmaxf(L[i - 2], hi));
+    L[1] = fminf(fminf(L[1], fmaxf(L[0], lo)), hi);
+    L[0] = fminf(L[0], lo);
+}
+
+// ---- pass A ---------------------------------------------------------------------------------------------------
+// NL = 1: one sorted list of 20 (U = exactly the 20th smallest of the pass's values); NL = 2: two lists of 10 fed alternately
+// (U = max of the two 10th values: still >= 20 candidates below it, half the min/max work, a slightly looser bound).
+template <int NL>
+__global__ void __launch_bounds__(KNN_THREADS, 2)
+knn_bound_kernel(const float4* __restrict__ sorted, const float4* __restrict__ aabb, int N, int cap, int prune,
+                 float* __restrict__ U) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int LEN = KNN_K / NL;
+    const int nblk = N >> 5, ntile = (nblk + 3) >> 2;
+    const KnnLayout lay = knn_layout(N, cap * 4);
+    const int b = blockIdx.y, tid = threadIdx.x;
+    knn_stage(sorted + (size_t)b * N, aabb + (size_t)b * nblk * 2, N, smem_raw, lay);
+    const int r = blockIdx.x * KNN_THREADS + tid;
+    if (r >= N) return;                                   // whole warps: N % 32 == 0
+    const float4* sp = reinterpret_cast<const float4*>(smem_raw);
+    const float4* slo = reinterpret_cast<const float4*>(smem_raw + lay.off_lo);
+    const float4* shi = reinterpret_cast<const float4*>(smem_raw + lay.off_hi);
+    const float4* stlo = reinterpret_cast<const float4*>(smem_raw + lay.off_tlo);
+    const float4* sthi = reinterpret_cast<const float4*>(smem_raw + lay.off_thi);
+    const uint32_t bufp = smem_addr(smem_raw + lay.off_buf) + 4u * tid;      // slot i at bufp + i * KNN_THREADS * 4
+    constexpr uint32_t SLOT = KNN_THREADS * 4;
+
+    float x, y, z, s;
+    {
+        const float* qb = reinterpret_cast<const float*>(smem_raw) + (r >> 1) * 8 + (r & 1);
+        x = qb[0]; y = qb[2]; z = qb[4]; s = qb[6];
+    }
+    const float2 q2x = make_float2(-2.f * x, -2.f * x), q2y = make_float2(-2.f * y, -2.f * y),
+                 q2z = make_float2(-2.f * z, -2.f * z), qs2 = make_float2(s, s);
+
+    float L[NL][LEN];
+#pragma unroll
+    for (int l = 0; l < NL; ++l)
+#pragma unroll
+        for (int i = 0; i < LEN; ++i) L[l][i] = INFINITY;
+    float thr = INFINITY;
+    const int b0 = r >> 5, t0 = b0 >> 2;                  // warp-uniform
+    int tile = t0, k = -1, tl = t0 - 1, th = t0 + 1;
+    bool side = true;
+    int blk = b0, sub = 4;
+    uint32_t wp = bufp;
+    const uint32_t wlim = bufp + (uint32_t)(cap - KNN_SUB) * SLOT;
+    for (;;) {
+        bool fin = false;
+        if (sub == 4) {
+            // ---- next block: own block, rest of the own tile, then the tiles outwards; two-level box test --------
+            bool found = false;
+            if (k < 0) {
+                blk = b0;
+                k = 0;
+                found = true;
+            }
+            while (!found) {
+                while (k < 4) {
+                    const int cb = tile * 4 + k;
+                    ++k;
+                    if (cb >= nblk || cb == b0) continue;
+                    if (!prune || __any_sync(FULL, !(box_lb(x, y, z, slo[cb], shi[cb]) > thr))) {
+                        blk = cb;
+                        found = true;
+                        break;
+                    }
+                }
+                if (found) break;
+                int nt = -1;
+                while (tl >= 0 || th < ntile) {
+                    const bool take_hi = (th < ntile) && (side || tl < 0);
+                    const int cand = take_hi ? th++ : tl--;
+                    side = !take_hi;
+                    if (!prune || __any_sync(FULL, !(box_lb(x, y, z, stlo[cand], sthi[cand]) > thr))) {
+                        nt = cand;
+                        break;
+                    }
+                }
+                if (nt < 0) break;
+                tile = nt;
+                k = 0;
+            }
+            fin = !found;
+            sub = 0;
+        }
+        if (!fin) {
+            // ---- 8 candidates: d' = s_i + s_j - 2 p_i.p_j as one FFMA2 chain per pair; park those below the threshold --
+            const float4* pp = sp + blk * 32 + sub * KNN_SUB;
+#pragma unroll
+            for (int u = 0; u < KNN_SUB / 2; ++u) {
+                const float2 t = fast_dist2(q2x, q2y, q2z, qs2, pp[2 * u], pp[2 * u + 1]);
+                if (t.x < thr) {
+                    sts_f32(wp, t.x);
+                    wp += SLOT;
+                }
+                if (t.y < thr) {
+                    sts_f32(wp, t.y);
+                    wp += SLOT;
+                }
+            }
+            ++sub;
+        }
+        // ---- merge the parked values into the sorted list when a buffer may overflow, after the own block (first
+        // threshold) and at the end
+        const bool force = fin || (blk == b0 && sub == 4);
+        if (__any_sync(FULL, (wp > wlim) || (force && wp != bufp))) {
+            const int n = (int)((wp - bufp) / SLOT);
+            const int nmax = __reduce_max_sync(FULL, n);
+#pragma unroll 1
+            for (int i = 0; i < nmax; i += 2 * NL) {
+#pragma unroll
+                for (int l = 0; l < NL; ++l) {
+                    const int e = i + 2 * l;
+                    const float c1 = (e < n) ? lds_f32(bufp + e * SLOT) : INFINITY;
+                    const float c2 = (e + 1 < n) ? lds_f32(bufp + (e + 1) * SLOT) : INFINITY;
+                    merge2<LEN>(L[l], c1, c2);
+                }
+            }
+            wp = bufp;
+            thr = L[0][LEN - 1];
+#pragma unroll
+            for (int l = 1; l < NL; ++l) thr = fmaxf(thr, L[l][LEN - 1]);
+        }
+        if (fin) break;
+    }
+    // d' is within 1e-6 (s_i + s_j) of the canonical d (either arithmetic): the slack keeps U a valid upper bound of the
+    // canonical 20th distance
+    float smax = 0.f;
+    for (int t = 0; t < ntile; ++t) smax = fmaxf(smax, stlo[t].w);
+    U[(size_t)b * N + r] = thr + 2e-6f * (s + smax);
+}
+
+// ---- pass B ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tie_append(uint32_t* __restrict__ tie, uint32_t row_pos, uint32_t j, float kth) {
+    if (*reinterpret_cast<volatile uint32_t*>(tie) > TIE_CAP) return;       // overflowed already: stop counting
+    const uint32_t slot = atomicAdd(tie, 1u);
+    if (slot < TIE_CAP) reinterpret_cast<uint2*>(tie + 2)[slot] = make_uint2((row_pos << 16) | j, __float_as_uint(kth));
+}
+
+template <int ARITH>
+__device__ __forceinline__ float knn_point_dist(const float* __restrict__ spf, int j, float x, float y, float z, float s) {
+    const float* pb = spf + (j >> 1) * 8 + (j & 1);
+    return canon_dist<ARITH>(x, y, z, s, pb[0], pb[2], pb[4], pb[6]);
+}
+
+template <int ARITH>
+__global__ void __launch_bounds__(KNN_THREADS, 2)
+knn_collect_kernel(const float4* __restrict__ sorted, const float4* __restrict__ aabb, const float* __restrict__ U, int N,
+                   int prune, uint32_t* __restrict__ tie_all, uint16_t* __restrict__ nbr, float* __restrict__ kthd,
+                   int* __restrict__ cnt, int* __restrict__ slow) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nblk = N >> 5, ntile = (nblk + 3) >> 2;
+    const KnnLayout lay = knn_layout(N, KNN_CAPB * 2);
+    const int b = blockIdx.y, tid = threadIdx.x;
+    knn_stage(sorted + (size_t)b * N, aabb + (size_t)b * nblk * 2, N, smem_raw, lay);
+    const int r = blockIdx.x * KNN_THREADS + tid;
+    if (r >= N) return;
+    const float4* sp = reinterpret_cast<const float4*>(smem_raw);
+    const float* spf = reinterpret_cast<const float*>(smem_raw);
+    const float4* slo = reinterpret_cast<const float4*>(smem_raw + lay.off_lo);
+    const float4* shi = reinterpret_cast<const float4*>(smem_raw + lay.off_hi);
+    const float4* stlo = reinterpret_cast<const float4*>(smem_raw + lay.off_tlo);
+    const float4* sthi = reinterpret_cast<const float4*>(smem_raw + lay.off_thi);
+    const uint32_t bufp = smem_addr(smem_raw + lay.off_buf) + 2u * tid;      // slot i at bufp + i * KNN_THREADS * 2
+    constexpr uint32_t SLOT = KNN_THREADS * 2;
+
+    const float x = spf[(r >> 1) * 8 + (r & 1)], y = spf[(r >> 1) * 8 + (r & 1) + 2], z = spf[(r >> 1) * 8 + (r & 1) + 4],
+                s = spf[(r >> 1) * 8 + (r & 1) + 6];
+    const float2 q2x = make_float2(-2.f * x, -2.f * x), q2y = make_float2(-2.f * y, -2.f * y),
+                 q2z = make_float2(-2.f * z, -2.f * z), qs2 = make_float2(s, s);
+    const size_t row = (size_t)b * N + r;
+    const float Ui = U[row];
+    float smax = 0.f;
+    for (int t = 0; t < ntile; ++t) smax = fmaxf(smax, stlo[t].w);
+    // scan filter: a candidate whose canonical d is <= U_i has d' <= U_i + 1e-6 (s_i + s_j); the canonical arithmetic itself
+    // is spent only on the handful that pass
+    float Uf = Ui + 2e-6f * (s + smax);
+
+    // ---- every candidate that can have canonical d <= U_i, in ascending position order ---------------------------
+    uint32_t wp = bufp;
+    const uint32_t wlim = bufp + (uint32_t)(KNN_CAPB - KNN_SUB) * SLOT;
+    bool over = false;
+#pragma unroll 1
+    for (int t = 0; t < ntile; ++t) {
+        if (prune && !__any_sync(FULL, !(box_bound_rigorous(x, y, z, s, stlo[t], sthi[t]) > Ui))) continue;
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            const int blk = 4 * t + k;
+            if (blk >= nblk) break;
+            if (prune && !__any_sync(FULL, !(box_bound_rigorous(x, y, z, s, slo[blk], shi[blk]) > Ui))) continue;
+#pragma unroll 1
+            for (int sub = 0; sub < 4; ++sub) {
+                const float4* pp = sp + blk * 32 + sub * KNN_SUB;
+                uint32_t j = (uint32_t)(blk * 32 + sub * KNN_SUB);
+#pragma unroll
+                for (int u = 0; u < KNN_SUB / 2; ++u) {
+                    const float2 d = fast_dist2(q2x, q2y, q2z, qs2, pp[2 * u], pp[2 * u + 1]);
+                    if (d.x <= Uf) {
+                        sts_u16(wp, j + 2 * u);
+                        wp += SLOT;
+                    }
+                    if (d.y <= Uf) {
+                        sts_u16(wp, j + 2 * u + 1);
+                        wp += SLOT;
+                    }
+                }
+                if (wp > wlim) {            // mass ties: this row goes to the warp-per-row exact path; stop listing
+                    over = true;
+                    Uf = -INFINITY;
+                    wp = bufp;
+                }
+            }
+        }
+    }
+    const int nc = (int)((wp - bufp) / SLOT);
+    // ---- exact 20th distance among the listed candidates, then the thresholded set ----------------------------
+    const bool ok = !over && (nc >= KNN_K);
+    const int n = ok ? nc : 0;
+    const int nmax = __reduce_max_sync(FULL, n);
+    float L[KNN_K];
+#pragma unroll
+    for (int i = 0; i < KNN_K; ++i) L[i] = INFINITY;
+#pragma unroll 1
+    for (int i = 0; i < nmax; i += 2) {
+        const float c1 = (i < n) ? knn_point_dist<ARITH>(spf, lds_u16(bufp + i * SLOT), x, y, z, s) : INFINITY;
+        const float c2 = (i + 1 < n) ? knn_point_dist<ARITH>(spf, lds_u16(bufp + (i + 1) * SLOT), x, y, z, s) : INFINITY;
+        merge2<KNN_K>(L, c1, c2);
+    }
+    const float kth = L[KNN_K - 1];
+    int total = 0, n_out = 0, n_in = 0;
+    uint32_t* tie = tie_all + (size_t)b * TIE_WORDS;
+#pragma unroll 1
+    for (int i = 0; i < nmax; ++i) {
+        if (i < n) {
+            const int j = (int)lds_u16(bufp + i * SLOT);
+            const float d = knn_point_dist<ARITH>(spf, j, x, y, z, s);
+            if (d <= kth) {
+                if (total < KNN_K) {
+                    const bool outside = (j >> 7) != (r >> 7);
+                    const int pos = outside ? n_out++ : (KNN_K - 1) - n_in++;
+                    nbr[row * KNN_K + pos] = (uint16_t)j;
+                } else {
+                    tie_append(tie, (uint32_t)r, (uint32_t)j, kth);
+                }
+                ++total;
+            }
+        }
+    }
+    if (ok) {
+        kthd[row] = kth;
+        cnt[row] = total | (n_out << 24);
+    } else {
+        slow[1 + atomicAdd(slow, 1)] = (int)row;           // mass ties (or NaN input): the warp-per-row exact path
+    }
+}
+
+// ---- overflow rows: warp per row, exact, any number of ties ---------------------------------------------------------
+__device__ __forceinline__ uint32_t ordered_key(float d) {
+    const uint32_t u = __float_as_uint(d + 0.0f);           // -0.0 -> +0.0: equal as floats, equal as keys
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+constexpr int KNN_SLOW_WARPS = 4;
+template <int ARITH>
+__global__ void __launch_bounds__(KNN_SLOW_WARPS * 32)
+knn_slow_kernel(const float4* __restrict__ sorted, const float* __restrict__ U, int N, const int* __restrict__ slow,
+                uint32_t* __restrict__ tie_all, uint16_t* __restrict__ nbr, float* __restrict__ kthd, int* __restrict__ cnt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t* keys = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)wid * N;                        // [N] per warp
+    uint16_t* pos = reinterpret_cast<uint16_t*>(smem_raw + (size_t)KNN_SLOW_WARPS * N * 4) + (size_t)wid * N;
+    const int count = slow[0];
+    for (int e = blockIdx.x * KNN_SLOW_WARPS + wid; e < count; e += gridDim.x * KNN_SLOW_WARPS) {
+        const int row = slow[1 + e];
+        const int b = row / N, r = row - b * N;
+        const float4* pts = sorted + (size_t)b * N;
+        const float4 q = pts[r];
+        const float Ui = U[row];
+        // (1) the candidates with d <= U_i (at least 20 unless the input holds NaN), ascending position
+        int n = 0;
+        __syncwarp();
+        for (int j0 = 0; j0 < N; j0 += 32) {
+            const float4 p = __ldg(pts + j0 + lane);
+            const float d = canon_dist<ARITH>(q.x, q.y, q.z, q.w, p.x, p.y, p.z, p.w);
+            const unsigned m = __ballot_sync(FULL, d <= Ui);
+            if (d <= Ui) {
+                const int o = n + __popc(m & ((1u << lane) - 1u));
+                keys[o] = ordered_key(d);
+                pos[o] = (uint16_t)(j0 + lane);
+            }
+            n += __popc(m);
+        }
+        __syncwarp();
+        uint32_t* tie = tie_all + (size_t)b * TIE_WORDS;
+        if (n < KNN_K) {                                    // NaN coordinates: keep every index in range, nothing else is defined
+            if (lane < KNN_K) nbr[(size_t)row * KNN_K + lane] = (uint16_t)r;
+            if (lane == 0) {
+                kthd[row] = INFINITY;
+                cnt[row] = KNN_K;
+            }
+            continue;
+        }
+        // (2) radix select: the 20th smallest key
+        uint32_t prefix = 0;
+        int want = KNN_K;
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t hi_mask = (bit == 31) ? 0u : ~((2u << bit) - 1u);
+            int c = 0;
+            for (int i = lane; i < n; i += 32) {
+                const uint32_t kk = keys[i];
+                c += ((kk & hi_mask) == prefix && !((kk >> bit) & 1u)) ? 1 : 0;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+            if (c < want) {
+                want -= c;
+                prefix |= (1u << bit);
+            }
+        }
+        const uint32_t kkey = prefix;
+        const float kth = __uint_as_float((kkey & 0x80000000u) ? (kkey & 0x7fffffffu) : ~kkey);      // inverse of ordered_key
+        // (3) the thresholded set in ascending position: the first 20 are listed (out-of-tile ones from the front, in-tile
+        // ones from the back), the rest go to the cloud's tie list
+        int total = 0, n_out = 0, n_in = 0;
+        const unsigned lt = (1u << lane) - 1u;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            const bool mem = (i < n) && (keys[i] <= kkey);
+            const int j = (i < n) ? pos[i] : 0;
+            const bool outside = (j >> 7) != (r >> 7);
+            const unsigned mm = __ballot_sync(FULL, mem), mo = __ballot_sync(FULL, mem && outside);
+            const int lim = max(0, KNN_K - total);                        // members of this step that are still listed
+            unsigned sel = mm;
+            if (__popc(mm) > lim) sel = lim ? (mm & ((1u << __fns(mm, 0, lim + 1)) - 1u)) : 0u;
+            if (mem) {
+                if ((sel >> lane) & 1u) {
+                    const int p = outside ? n_out + __popc(sel & mo & lt) : (KNN_K - 1) - (n_in + __popc(sel & ~mo & lt));
+                    nbr[(size_t)row * KNN_K + p] = (uint16_t)j;
+                } else {
+                    tie_append(tie, (uint32_t)r, (uint32_t)j, kth);
+                }
+            }
+            n_out += __popc(sel & mo);
+            n_in += __popc(sel & ~mo);
+            total += __popc(mm);
+        }
+        if (lane == 0) {
+            kthd[row] = kth;
+            cnt[row] = total | (n_out << 24);
+        }
+    }
+}
+
+// ---- API outputs in original point order ---------------------------------------------------------------------------
 __device__ __forceinline__ bool key_lt(float av, uint32_t ak, float bv, uint32_t bk) {
     return (av < bv) || (av == bv && ak < bk);
 }
@@ -240,332 +693,70 @@ __device__ __forceinline__ void warp_sort32_keys(float& v, uint32_t& k, int lane
     }
 }
 
-// value-only bitonic sort of one float per lane (ASC or descending)
-template <bool ASC>
-__device__ __forceinline__ float warp_sort32_vals(float v, int lane) {
-#pragma unroll
-    for (int kk = 2; kk <= 32; kk <<= 1) {
-#pragma unroll
-        for (int j = kk >> 1; j > 0; j >>= 1) {
-            const float o = __shfl_xor_sync(FULL, v, j);
-            const bool keep_min = (((lane & j) == 0) == ((((lane & kk) == 0)) == ASC));
-            v = keep_min ? fminf(v, o) : fmaxf(v, o);
+constexpr int KNN_PUB_WARPS = 4;
+template <int ARITH>
+__global__ void __launch_bounds__(KNN_PUB_WARPS * 32)
+knn_public_kernel(const float4* __restrict__ sorted, const int* __restrict__ perm, const uint16_t* __restrict__ nbr,
+                  const float* __restrict__ kthd, const int* __restrict__ cnt, int N, long long rows,
+                  int32_t* __restrict__ idx_out, float* __restrict__ kth_out, int32_t* __restrict__ count_out) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long row = (long long)blockIdx.x * KNN_PUB_WARPS + wid;
+    if (row >= rows) return;
+    const long long b = row / N;
+    const int r = (int)(row - b * N);
+    const float4* pts = sorted + b * N;
+    const int* pm = perm + b * N;
+    const long long orow = b * N + pm[r];
+    const float kth = kthd[row];
+    const int count = cnt[row] & 0xffffff;
+    if (lane == 0) {
+        if (kth_out) kth_out[orow] = -kth;
+        if (count_out) count_out[orow] = count;
+    }
+    if (!idx_out) return;
+    const float4 q = pts[r];
+    if (count == KNN_K) {
+        float v = INFINITY;
+        uint32_t k = 0xffffffffu;
+        if (lane < KNN_K) {
+            const int j = nbr[row * KNN_K + lane];
+            const float4 p = pts[j];
+            v = canon_dist<ARITH>(q.x, q.y, q.z, q.w, p.x, p.y, p.z, p.w);
+            k = (uint32_t)pm[j];
         }
+        warp_sort32_keys(v, k, lane);
+        if (lane < KNN_K) idx_out[orow * KNN_K + lane] = (int32_t)k;
+        return;
     }
-    return v;
-}
-
-// buffer [0,n) -> its 20 smallest keys in [0,20) (unsorted), thr, extra.   NOT inlined, state by value: one copy of
-// the networks (inlining them per row and call site blew the instruction cache: 40 no-instruction stalls per issue).
-__device__ __noinline__ RowState compact(RowState R, float* __restrict__ bv, uint32_t* __restrict__ bk) {
-    const int lane = threadIdx.x & 31;
-    __syncwarp();
-    const float o0 = (lane < R.n) ? bv[lane] : INFINITY;
-    const float o1 = (lane + 32 < R.n) ? bv[lane + 32] : INFINITY;
-    const uint32_t k0 = (lane < R.n) ? bk[lane] : KEY_EMPTY;
-    const uint32_t k1 = (lane + 32 < R.n) ? bk[lane + 32] : KEY_EMPTY;
-    // two bitonic networks in lock step (o0 ascending, o1 descending): two independent shuffle chains in flight
-    float s = o0, s1 = o1;
-#pragma unroll
-    for (int kk = 2; kk <= 32; kk <<= 1) {
-#pragma unroll
-        for (int j = kk >> 1; j > 0; j >>= 1) {
-            const bool keep_min = (((lane & j) == 0) == ((lane & kk) == 0));
-            const float oa = __shfl_xor_sync(FULL, s, j), od = __shfl_xor_sync(FULL, s1, j);
-            s = keep_min ? fminf(s, oa) : fmaxf(s, oa);
-            s1 = keep_min ? fmaxf(s1, od) : fminf(s1, od);
-        }
-    }
-    s = fminf(s, s1);                               // bitonic sequence holding the 32 smallest values
-#pragma unroll
-    for (int j = 16; j > 0; j >>= 1) {
-        const float o = __shfl_xor_sync(FULL, s, j);
-        s = ((lane & j) == 0) ? fminf(s, o) : fmaxf(s, o);
-    }
-    const float thr_new = __shfl_sync(FULL, s, KNN_K - 1);
-    bool keep0 = o0 < thr_new, keep1 = o1 < thr_new;
-    const bool eq0 = (o0 == thr_new), eq1 = (o1 == thr_new);
-    const int c_less = __popc(__ballot_sync(FULL, keep0)) + __popc(__ballot_sync(FULL, keep1));
-    const unsigned me0 = __ballot_sync(FULL, eq0), me1 = __ballot_sync(FULL, eq1);
-    const int c_eq = __popc(me0) + __popc(me1);
-    const int need_eq = KNN_K - c_less;            // >= 1
-    if (c_eq == need_eq) {
-        keep0 |= eq0;
-        keep1 |= eq1;
-    } else {
-        // ties straddle the 20th place: keep the need_eq tied entries with the lowest original index (rare)
-        bool t0 = eq0, t1 = eq1;
-        for (int i = 0; i < need_eq; ++i) {
-            uint32_t best = min(t0 ? k0 : KEY_EMPTY, t1 ? k1 : KEY_EMPTY);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(FULL, best, o));
-            if (t0 && k0 == best) { t0 = false; keep0 = true; }
-            if (t1 && k1 == best) { t1 = false; keep1 = true; }
-        }
-        // The dropped tied candidates belong to the row's thresholded set if thr_new turns out to be its final threshold:
-        // log them (row, position, value) in the cloud's tie list so that the ProxyConv gather can add them without
-        // re-scanning the cloud.  An overflowing list (degenerate clouds) makes the gather fall back to the re-scan.
-        // (row and list are recovered from the buffer address: the candidate buffers open the dynamic shared memory and
-        // the kernel leaves the list pointer right behind them -- extra arguments would cost this call's ABI registers)
-        extern __shared__ __align__(16) unsigned char smem_raw[];
-        const uint32_t row_pos = blockIdx.x * KNN_ROWS_PER_CTA + (uint32_t)((bv - reinterpret_cast<float*>(smem_raw)) / KNN_CAP);
-        uint32_t* tie = *reinterpret_cast<uint32_t**>(smem_raw + KNN_BUF_BYTES);
-        const bool room = *reinterpret_cast<volatile uint32_t*>(tie) <= TIE_CAP;      // stop counting once the list has overflowed
-        if (t0 && room) {
-            const uint32_t slot = atomicAdd(tie, 1u);
-            if (slot < TIE_CAP) reinterpret_cast<uint2*>(tie + 2)[slot] = make_uint2((row_pos << 16) | (k0 & 0xffffu), __float_as_uint(o0));
-        }
-        if (t1 && room) {
-            const uint32_t slot = atomicAdd(tie, 1u);
-            if (slot < TIE_CAP) reinterpret_cast<uint2*>(tie + 2)[slot] = make_uint2((row_pos << 16) | (k1 & 0xffffu), __float_as_uint(o1));
-        }
-    }
-    R.extra = ((thr_new == R.thr) ? R.extra : 0) + (c_eq - need_eq);
-    R.thr = thr_new;
-    R.n = KNN_K;
-    const unsigned mk0 = __ballot_sync(FULL, keep0), mk1 = __ballot_sync(FULL, keep1);
-    const unsigned lt = (1u << lane) - 1u;
-    __syncwarp();                                   // every lane has read its entries: safe to overwrite [0,20)
-    if (keep0) {
-        const int e = __popc(mk0 & lt);
-        bv[e] = o0;
-        bk[e] = k0;
-    }
-    if (keep1) {
-        const int e = __popc(mk0) + __popc(mk1 & lt);
-        bv[e] = o1;
-        bk[e] = k1;
-    }
-    __syncwarp();
-    return R;
-}
-
-// the row's 20 survivors -> lane l gets the key of the l-th smallest (d, original index).  Not inlined (code size).
-__device__ __noinline__ uint32_t sorted_key(const float* __restrict__ rv, const uint32_t* __restrict__ rk) {
-    const int lane = threadIdx.x & 31;
-    __syncwarp();
-    float v = (lane < KNN_K) ? rv[lane] : INFINITY;
-    uint32_t k = (lane < KNN_K) ? rk[lane] : KEY_EMPTY;
-    warp_sort32_keys(v, k, lane);
-    return k;
-}
-
-// queue the candidates flagged in m (lane s holds value d for sorted position jbase + s)
-__device__ __forceinline__ void append_hits(RowState& R, unsigned m, float d, int jbase, const unsigned short* __restrict__ sperm,
-                                            float* __restrict__ bv, uint32_t* __restrict__ bk, int lane) {
-    int h = __popc(m);
-    if (R.n + h > KNN_CAP) {
-        R = compact(R, bv, bk);
-        m &= __ballot_sync(FULL, d <= R.thr);      // the bound just tightened
-        h = __popc(m);
-        if (h == 0) return;
-    }
-    if ((m >> lane) & 1u) {
-        const int e = R.n + __popc(m & ((1u << lane) - 1u));
-        bv[e] = d;
-        bk[e] = ((uint32_t)sperm[jbase + lane] << 16) | (uint32_t)(jbase + lane);
-    }
-    R.n += h;
-}
-
-// a row is re-compacted after the index-neighbour blocks only if its buffer holds more than this many candidates
-// (measured: 20 -> 9.11, 32 -> 8.79, 44 -> 8.85, 64 = never -> 8.97 us/cloud)
-constexpr int KNN_STAGE1_MIN = 32;
-
-template <int ARITH, bool PRUNE>
-__global__ void __launch_bounds__(KNN_WARPS * 32, 2)
-knn_kernel(const float4* __restrict__ sorted, const uint16_t* __restrict__ perm16, const float4* __restrict__ aabb,
-           uint32_t* __restrict__ tie_all, int N,
-           uint16_t* __restrict__ nbr, float* __restrict__ kthd, int* __restrict__ cnt, int32_t* __restrict__ idx_out,
-           float* __restrict__ kth_out, int32_t* __restrict__ count_out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int nblk = N >> 5;
-    float* sbv = reinterpret_cast<float*>(smem_raw);                          // [warps][rows][CAP] candidate values (compact() relies on offset 0)
-    uint32_t* sbk = reinterpret_cast<uint32_t*>(sbv + KNN_WARPS * KNN_ROWS_PER_WARP * KNN_CAP);   // ... and keys
-    uint32_t** stie = reinterpret_cast<uint32_t**>(smem_raw + KNN_BUF_BYTES);                     // this cloud's tie list (for compact())
-    uint64_t* ldbar = reinterpret_cast<uint64_t*>(stie + 1);
-    float4* spts = reinterpret_cast<float4*>(smem_raw + KNN_BUF_BYTES + 16);   // [N]   (x,y,z,s)
-    float4* sblo = spts + N;                              // [nblk] (lo.xyz, max s)
-    float4* sbhi = sblo + nblk;                           // [nblk] (hi.xyz, -)
-    unsigned short* sperm = reinterpret_cast<unsigned short*>(sbhi + nblk);   // [N] sorted position -> original index
-    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    // the whole cloud (points, block boxes, permutation) arrives by three TMA bulk copies issued by one thread
-    {
-        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(ldbar);
-        if (tid == 0) {
-            *stie = tie_all + (size_t)blockIdx.y * TIE_WORDS;
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (tid == 0) {
-            const uint32_t b_pts = (uint32_t)N * 16u, b_box = (uint32_t)nblk * 32u, b_perm = (uint32_t)N * 2u;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b_pts + b_box + b_perm) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"((uint32_t)__cvta_generic_to_shared(spts)), "l"(sorted + (size_t)b * N), "r"(b_pts), "r"(bar) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"((uint32_t)__cvta_generic_to_shared(sblo)), "l"(aabb + (size_t)b * nblk * 2), "r"(b_box), "r"(bar) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"((uint32_t)__cvta_generic_to_shared(sperm)), "l"(perm16 + (size_t)b * N), "r"(b_perm), "r"(bar) : "memory");
-        }
-        uint32_t ok = 0;
-        while (!ok) {
-            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                         : "=r"(ok) : "r"(bar), "r"(0u) : "memory");
-        }
-    }
-
-    const int r0 = blockIdx.x * KNN_ROWS_PER_CTA + wid * KNN_ROWS_PER_WARP;
-    if (r0 >= N) return;
-    const int b0 = r0 >> 5;
-
-    float2 qx[4], qy[4], qz[4], qs[4];
-#pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-        const float4 a = spts[r0 + 2 * rr], c = spts[r0 + 2 * rr + 1];
-        qx[rr] = make_float2(a.x, c.x);
-        qy[rr] = make_float2(a.y, c.y);
-        qz[rr] = make_float2(a.z, c.z);
-        qs[rr] = make_float2(a.w, c.w);
-    }
-    RowState L[KNN_ROWS_PER_WARP];
-    float* bv = sbv + (size_t)wid * KNN_ROWS_PER_WARP * KNN_CAP;
-    uint32_t* bk = sbk + (size_t)wid * KNN_ROWS_PER_WARP * KNN_CAP;
-
-    auto distances = [&](int blk, float (&d)[KNN_ROWS_PER_WARP]) {
-        const float4 p = spts[blk * 32 + lane];
-        const float2 px = make_float2(p.x, p.x), py = make_float2(p.y, p.y), pz = make_float2(p.z, p.z),
-                     ps = make_float2(p.w, p.w);
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-            const float2 dd = canon_dist2<ARITH>(qx[rr], qy[rr], qz[rr], qs[rr], px, py, pz, ps);
-            d[2 * rr] = dd.x;
-            d[2 * rr + 1] = dd.y;
-        }
-    };
-    auto scan_block = [&](int blk) {
-        float d[KNN_ROWS_PER_WARP];
-        distances(blk, d);
-        bool any = false;
-#pragma unroll
-        for (int r = 0; r < KNN_ROWS_PER_WARP; ++r) any |= (d[r] <= L[r].thr);
-        if (__any_sync(FULL, any)) {
-#pragma unroll
-            for (int r = 0; r < KNN_ROWS_PER_WARP; ++r) {
-                const unsigned m = __ballot_sync(FULL, d[r] <= L[r].thr);
-                if (m) append_hits(L[r], m, d[r], blk * 32, sperm, bv + r * KNN_CAP, bk + r * KNN_CAP, lane);
-            }
-        }
-    };
-
-    // ---- phase 1: the rows' own block and its index-neighbours (thr = +inf until the first compaction) --------
-    int init_blk[5];
-    int n_init = 0;
-    {
-        const int offs[5] = {0, 1, -1, 2, -2};
-#pragma unroll
-        for (int t = 0; t < 5; ++t) {
-            int blk = (b0 + offs[t] + nblk) % nblk;
-            bool dup = false;
-            for (int u = 0; u < n_init; ++u) dup |= (init_blk[u] == blk);
-            if (!dup) init_blk[n_init++] = blk;
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < KNN_ROWS_PER_WARP; ++r) {
-        L[r].thr = INFINITY;
-        L[r].n = 0;
-        L[r].extra = 0;
-    }
-    // Three stages, each closed by a compaction of all eight rows (a single call site):
-    //   0: the rows' own block and the next one (64 candidates, thr = +inf) -> first bound
-    //   1: the other index-neighbours                                       -> a tight bound before pruning
-    //   2: every remaining block whose AABB can still hold a candidate <= thr -> the final 20
-    const int nw = (nblk + 31) >> 5;
-#pragma unroll 1
-    for (int stage = 0; stage < 3; ++stage) {
-        if (stage < 2) {
-            const int t0 = stage == 0 ? 0 : 2, t1 = stage == 0 ? (n_init < 2 ? n_init : 2) : n_init;
-            for (int t = t0; t < t1; ++t) scan_block(init_blk[t]);
-        } else {
-            for (int w = 0; w < nw; ++w) {
-                const int blk = w * 32 + lane;
-                bool need = false;
-                if (blk < nblk) {
-                    bool done = false;
-                    for (int u = 0; u < n_init; ++u) done |= (init_blk[u] == blk);
-                    if (!done) {
-                        if (!PRUNE) {
-                            need = true;
-                        } else {
-                            const float4 lo = sblo[blk], hi = sbhi[blk];
-#pragma unroll
-                            for (int r = 0; r < KNN_ROWS_PER_WARP; ++r) {
-                                const float x = (r & 1) ? qx[r >> 1].y : qx[r >> 1].x;
-                                const float y = (r & 1) ? qy[r >> 1].y : qy[r >> 1].x;
-                                const float z = (r & 1) ? qz[r >> 1].y : qz[r >> 1].x;
-                                const float s = (r & 1) ? qs[r >> 1].y : qs[r >> 1].x;
-                                const float dx = fmaxf(fmaxf(lo.x - x, x - hi.x), 0.f);
-                                const float dy = fmaxf(fmaxf(lo.y - y, y - hi.y), 0.f);
-                                const float dz = fmaxf(fmaxf(lo.z - z, z - hi.z), 0.f);
-                                const float lb = dx * dx + dy * dy + dz * dz;
-                                // rigorous lower bound of the *computed* d over the block (DESIGN.md "pruning"):
-                                // true |p-q|^2 >= lb_true >= lb(1-8u); computed d >= true - 16u (s_i + s_j)
-                                const float bound = lb * (1.0f - 1e-6f) - 1e-6f * (s + lo.w);
-                                need |= !(bound > L[r].thr);
-                            }
-                        }
-                    }
-                }
-                unsigned mask = __ballot_sync(FULL, need);
-                while (mask) {
-                    const int bit = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    scan_block(w * 32 + bit);
-                }
+    // ties beyond the 20th place: the 20 smallest (d, original index) of the whole thresholded set, by repeated extraction
+    float last_v = -INFINITY;
+    uint32_t last_k = 0;
+    bool first = true;
+    for (int t = 0; t < KNN_K; ++t) {
+        float bv = INFINITY;
+        uint32_t bk = 0xffffffffu;
+        for (int j0 = 0; j0 < N; j0 += 32) {
+            const float4 p = __ldg(pts + j0 + lane);
+            const float d = canon_dist<ARITH>(q.x, q.y, q.z, q.w, p.x, p.y, p.z, p.w);
+            const uint32_t k = (uint32_t)__ldg(pm + j0 + lane);
+            if (d <= kth && (first || key_lt(last_v, last_k, d, k)) && key_lt(d, k, bv, bk)) {
+                bv = d;
+                bk = k;
             }
         }
 #pragma unroll
-        for (int r = 0; r < KNN_ROWS_PER_WARP; ++r)
-            if (L[r].n > (stage == 1 ? KNN_STAGE1_MIN : KNN_K)) L[r] = compact(L[r], bv + r * KNN_CAP, bk + r * KNN_CAP);
-    }
-
-    // ---- outputs: final compaction; the public idx output is sorted by the full key (tf.nn.top_k order), the internal
-    // list is partitioned instead: neighbours outside the row's 128-point tile first (the ProxyConv gather, backbone.cu,
-    // fetches those from global memory and the rest from its shared-memory window), their number in cnt's top byte.
-#pragma unroll
-    for (int r = 0; r < KNN_ROWS_PER_WARP; ++r) {
-        float* rv = bv + r * KNN_CAP;
-        uint32_t* rk = bk + r * KNN_CAP;
-        const size_t row = (size_t)b * N + r0 + r;
-        const bool want_pub = (idx_out || kth_out || count_out);
-        uint32_t k;
-        if (idx_out) {
-            k = sorted_key(rv, rk);
-        } else {
-            __syncwarp();
-            k = (lane < KNN_K) ? rk[lane] : KEY_EMPTY;
-        }
-        {
-            const int j = (int)(k & 0xffffu);
-            const bool valid = lane < KNN_K;
-            const bool outside = valid && ((j >> 7) != ((r0 + r) >> 7));
-            const unsigned mo = __ballot_sync(FULL, outside), mi = __ballot_sync(FULL, valid && !outside);
-            const unsigned lt = (1u << lane) - 1u;
-            const int n_out = __popc(mo);
-            const int pos = outside ? __popc(mo & lt) : n_out + __popc(mi & lt);
-            if (valid) nbr[row * KNN_K + pos] = (uint16_t)j;
-            if (lane == 0) {
-                kthd[row] = L[r].thr;
-                cnt[row] = (KNN_K + L[r].extra) | (n_out << 24);
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(FULL, bv, o);
+            const uint32_t ok = __shfl_xor_sync(FULL, bk, o);
+            if (key_lt(ov, ok, bv, bk)) {
+                bv = ov;
+                bk = ok;
             }
         }
-        if (want_pub) {
-            const size_t orow = (size_t)b * N + sperm[r0 + r];
-            if (idx_out && lane < KNN_K) idx_out[orow * KNN_K + lane] = (int32_t)(k >> 16);
-            if (kth_out && lane == 0) kth_out[orow] = -L[r].thr;
-            if (count_out && lane == 0) count_out[orow] = KNN_K + L[r].extra;
-        }
+        if (lane == 0) idx_out[orow * KNN_K + t] = (int32_t)bk;
+        last_v = bv;
+        last_k = bk;
+        first = false;
     }
 }
 
@@ -628,6 +819,13 @@ __global__ void rows_topk_smallest_kernel(const float* __restrict__ adj, long lo
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+static int sm_count_knn() {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+}
+
 static int next_pow2(int n) {
     int p = 1;
     while (p < n) p <<= 1;
@@ -642,51 +840,83 @@ int knn_check_n(int N) {
     return EPC_OK;
 }
 
-int knn_build(const float* xyz, int B, int N, int arith, bool prune, float4* sorted, int* perm, uint16_t* perm16, float4* aabb, uint32_t* tie, uint16_t* nbr,
-              float* kthd, int* cnt, int32_t* idx_out, float* kth_out, int32_t* count_out, cudaStream_t st) {
+// Tuning knobs (environment; results never depend on them): EPC_KNN_CAP = parked values per row in pass A (even, >= 16,
+// default: what lets two CTAs share an SM), EPC_KNN_LISTS = 1 | 2 sorted lists in pass A.
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+int knn_build(const float* xyz, int B, int N, int arith, bool prune, const KnnState& s, int32_t* idx_out, float* kth_out,
+              int32_t* count_out, cudaStream_t st) {
     if (int rc = knn_check_n(N)) return rc;
     EPC_CHECK_ARG(arith == EPC_KNN_ARITH_MULADD || arith == EPC_KNN_ARITH_FMA, "bad knn arith %d", arith);
     if (B == 0) return EPC_OK;
     const int NP = next_pow2(N);
     const size_t sort_smem = (size_t)NP * sizeof(unsigned long long);
-    static bool attr_done = false;
-    const size_t knn_smem = (size_t)N * 16 + (size_t)(N / 32) * 32 + (size_t)N * 2 + (size_t)KNN_WARPS * KNN_ROWS_PER_WARP * KNN_CAP * 8 + 16;
-    if (!attr_done) {
-        EPC_CUDA(cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        EPC_CUDA(cudaFuncSetAttribute(knn_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        EPC_CUDA(cudaFuncSetAttribute(knn_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        EPC_CUDA(cudaFuncSetAttribute(knn_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        EPC_CUDA(cudaFuncSetAttribute(knn_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
+    // pass A buffer: as many parked values per row as two resident CTAs per SM allow (one CTA when the cloud is large)
+    const int fixed = knn_layout(N, 0).bytes;
+    const int budget2 = (227 * 1024) / 2 - 1024, budget1 = 227 * 1024 - 1024;
+    int cap = (budget2 - fixed) / (KNN_THREADS * 4) / 2 * 2;
+    if (cap < 16) cap = (budget1 - fixed) / (KNN_THREADS * 4) / 2 * 2;
+    if (cap > 64) cap = 64;
+    {
+        const int e = env_int("EPC_KNN_CAP", 0);
+        if (e >= 16 && e % 2 == 0 && fixed + e * KNN_THREADS * 4 <= budget1) cap = e;
     }
+    EPC_CHECK_ARG(cap >= 16, "kNN: N=%d leaves no shared memory for the candidate buffers", N);
+    const int lists = env_int("EPC_KNN_LISTS", 2) == 1 ? 1 : 2;
+    const size_t smemA = (size_t)knn_layout(N, cap * 4).bytes, smemB = (size_t)knn_layout(N, KNN_CAPB * 2).bytes;
+    const size_t smemC = (size_t)KNN_SLOW_WARPS * N * 6;
+    static PerDeviceSize a_sort, a_A1, a_A2, a_B0, a_B1, a_C0, a_C1;
+    EPC_CUDA(ensure_dyn_smem(sort_kernel, 64 * 1024, a_sort));
+    EPC_CUDA(ensure_dyn_smem(knn_bound_kernel<1>, smemA, a_A1));
+    EPC_CUDA(ensure_dyn_smem(knn_bound_kernel<2>, smemA, a_A2));
+    EPC_CUDA(ensure_dyn_smem(knn_collect_kernel<0>, smemB, a_B0));
+    EPC_CUDA(ensure_dyn_smem(knn_collect_kernel<1>, smemB, a_B1));
+    EPC_CUDA(ensure_dyn_smem(knn_slow_kernel<0>, smemC, a_C0));
+    EPC_CUDA(ensure_dyn_smem(knn_slow_kernel<1>, smemC, a_C1));
     {
         ScopedStage ss(EPC_STAGE_SORT, st);
-        sort_kernel<<<B, 1024, sort_smem, st>>>(xyz, N, NP, sorted, perm, perm16, aabb);
+        sort_kernel<<<B, 1024, sort_smem, st>>>(xyz, N, NP, s.sorted, s.perm, s.perm16, s.aabb);
         EPC_LAUNCH_CHECK();
     }
-    EPC_CUDA(cudaMemsetAsync(tie, 0, (size_t)B * TIE_WORDS * sizeof(uint32_t), st));      // counters (and stale entries)
+    EPC_CUDA(cudaMemsetAsync(s.tie, 0, (size_t)B * TIE_WORDS * sizeof(uint32_t), st));      // counters (and stale entries)
+    EPC_CUDA(cudaMemsetAsync(s.slow, 0, sizeof(int), st));                                   // overflow-row counter
     ScopedStage ss(EPC_STAGE_KNN, st);
-    dim3 grid((N + KNN_ROWS_PER_CTA - 1) / KNN_ROWS_PER_CTA, B);
-    const int th = KNN_WARPS * 32;
+    dim3 grid((N + KNN_THREADS - 1) / KNN_THREADS, B);
+    if (lists == 1)
+        knn_bound_kernel<1><<<grid, KNN_THREADS, smemA, st>>>(s.sorted, s.aabb, N, cap, prune ? 1 : 0, s.U);
+    else
+        knn_bound_kernel<2><<<grid, KNN_THREADS, smemA, st>>>(s.sorted, s.aabb, N, cap, prune ? 1 : 0, s.U);
+    EPC_LAUNCH_CHECK();
+    const int slow_ctas = 2 * sm_count_knn();
     if (arith == EPC_KNN_ARITH_MULADD) {
-        if (prune)
-            knn_kernel<0, true><<<grid, th, knn_smem, st>>>(sorted, perm16, aabb, tie, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
-        else
-            knn_kernel<0, false><<<grid, th, knn_smem, st>>>(sorted, perm16, aabb, tie, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
+        knn_collect_kernel<0><<<grid, KNN_THREADS, smemB, st>>>(s.sorted, s.aabb, s.U, N, prune ? 1 : 0, s.tie, s.nbr, s.kthd, s.cnt, s.slow);
+        EPC_LAUNCH_CHECK();
+        knn_slow_kernel<0><<<slow_ctas, KNN_SLOW_WARPS * 32, smemC, st>>>(s.sorted, s.U, N, s.slow, s.tie, s.nbr, s.kthd, s.cnt);
     } else {
-        if (prune)
-            knn_kernel<1, true><<<grid, th, knn_smem, st>>>(sorted, perm16, aabb, tie, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
-        else
-            knn_kernel<1, false><<<grid, th, knn_smem, st>>>(sorted, perm16, aabb, tie, N, nbr, kthd, cnt, idx_out, kth_out, count_out);
+        knn_collect_kernel<1><<<grid, KNN_THREADS, smemB, st>>>(s.sorted, s.aabb, s.U, N, prune ? 1 : 0, s.tie, s.nbr, s.kthd, s.cnt, s.slow);
+        EPC_LAUNCH_CHECK();
+        knn_slow_kernel<1><<<slow_ctas, KNN_SLOW_WARPS * 32, smemC, st>>>(s.sorted, s.U, N, s.slow, s.tie, s.nbr, s.kthd, s.cnt);
     }
     EPC_LAUNCH_CHECK();
+    if (idx_out || kth_out || count_out) {
+        const long long rows = (long long)B * N;
+        const unsigned g = (unsigned)((rows + KNN_PUB_WARPS - 1) / KNN_PUB_WARPS);
+        if (arith == EPC_KNN_ARITH_MULADD)
+            knn_public_kernel<0><<<g, KNN_PUB_WARPS * 32, 0, st>>>(s.sorted, s.perm, s.nbr, s.kthd, s.cnt, N, rows, idx_out, kth_out, count_out);
+        else
+            knn_public_kernel<1><<<g, KNN_PUB_WARPS * 32, 0, st>>>(s.sorted, s.perm, s.nbr, s.kthd, s.cnt, N, rows, idx_out, kth_out, count_out);
+        EPC_LAUNCH_CHECK();
+    }
     return EPC_OK;
 }
 
 size_t knn_state_bytes(int B, int N) {
     const size_t R = (size_t)B * N;
     return align_up((size_t)B * TIE_WORDS * sizeof(uint32_t)) + align_up(R * sizeof(float4)) + align_up(R * sizeof(int)) + align_up(R * sizeof(uint16_t)) + align_up(R * KNN_K * sizeof(uint16_t)) +
-           align_up(R * sizeof(float)) + align_up(R * sizeof(int)) + align_up(R / 16 * sizeof(float4));
+           align_up(R * sizeof(float)) + align_up(R * sizeof(int)) + align_up(R / 16 * sizeof(float4)) + align_up(R * sizeof(float)) + align_up((R + 1) * sizeof(int));
 }
 
 KnnState knn_state_carve(Arena& ar, int B, int N) {
@@ -700,6 +930,8 @@ KnnState knn_state_carve(Arena& ar, int B, int N) {
     s.kthd = ar.take<float>(R);
     s.cnt = ar.take<int>(R);
     s.aabb = ar.take<float4>(R / 16);      // [B][2][N/32]
+    s.U = ar.take<float>(R);
+    s.slow = ar.take<int>(R + 1);
     return s;
 }
 

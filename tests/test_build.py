@@ -71,11 +71,16 @@ def test_sass_targets_sm100a_and_muladd_not_contracted(built_lib):
     archs = set(re.findall(r"sm_\d+a?", elf))
     assert archs == {"sm_100a"}, archs
     stats = sass_stats(lib_mod.LIB_PATH)
-    mul = {k: v for k, v in stats.items() if "knn_kernelILi0E" in k}
-    fma = {k: v for k, v in stats.items() if "knn_kernelILi1E" in k}
-    assert len(mul) == 2 and len(fma) == 2
-    for k, c in mul.items():
-        # per pair of query rows: 3 FMUL2 (products), 1 FFMA2 (-2*inner + s_i), 1 FADD2 (+ s_j); sums are scalar FADD
-        assert c["FMUL2"] == 3 * c["FFMA2"] and c["FADD2"] == c["FFMA2"] and c["FFMA2"] > 0, (k, dict(c))
-    for k, c in fma.items():
-        assert c["FFMA2"] == 3 * c["FMUL2"] and c["FADD2"] == c["FMUL2"], (k, dict(c))
+    # The canonical distance (common.cuh canon_dist<ARITH>) is evaluated where exactness matters: knn_collect_kernel (exact
+    # 20th distance + thresholded set) and knn_slow_kernel (mass ties).  Everything else in the two instantiations is
+    # identical, so the instruction-count DIFFERENCE isolates it: per call site MULADD = 3 FMUL + 2 FADD + FFMA + FADD,
+    # FMA = FMUL + 3 FFMA + FADD.  A contraction of the MULADD products into FFMAs would close the gap.
+    for kern in ("knn_collect_kernel", "knn_slow_kernel"):
+        mul = [v for k, v in stats.items() if kern + "ILi0E" in k]
+        fma = [v for k, v in stats.items() if kern + "ILi1E" in k]
+        assert len(mul) == 1 and len(fma) == 1, kern
+        mul, fma = mul[0], fma[0]
+        sites = (mul["FMUL"] - fma["FMUL"]) // 2
+        assert sites >= 1 and mul["FMUL"] - fma["FMUL"] == 2 * sites, (kern, dict(mul), dict(fma))
+        assert fma["FFMA"] - mul["FFMA"] == 2 * sites and mul["FADD"] - fma["FADD"] == 2 * sites, (kern, dict(mul), dict(fma))
+        assert mul["FMUL"] >= 3 * sites and mul.get("FFMA2", 0) == fma.get("FFMA2", 0)
