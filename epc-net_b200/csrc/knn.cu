@@ -198,36 +198,45 @@ __global__ void __launch_bounds__(1024) sort_kernel(const float* __restrict__ xy
 }
 
 // ------------------------------------------------------------------------------------------------
-// kNN graph, thread-per-row (round 2).  A CTA stages its whole cloud in shared memory once and serves 512 query rows:
-// thread = row, warp = one 32-point Morton block of rows, candidates are BROADCAST from shared memory (every lane reads the
-// same point pair), so there is not a single shuffle or ballot on the data path -- only warp votes for block-level decisions.
+// kNN graph (round 2).  A CTA stages its whole cloud in shared memory once and serves 128 query rows; a warp owns 8
+// consecutive rows of the Morton order, and FOUR lanes share a row, each taking every fourth candidate pair of a 32-point
+// block (lane = row + 8 * quarter).  Pruning works on 8-row groups (a third of the pairs a 32-row group would evaluate),
+// every lane still runs the same straight-line code, and there is no shuffle or ballot per candidate:
 //
 //   knn_bound_kernel    pass A: a valid, tight UPPER BOUND U_i of the row's 20th smallest distance.  Cheap arithmetic
-//                       (3 FFMA2 + FADD2 per candidate pair), candidates below the running threshold are parked in a per-row
-//                       shared-memory buffer and merged, two at a time, into a sorted 20-entry register list by a
+//                       (3 FFMA2 + FADD2 per candidate pair); candidates below the row's running threshold are parked in a
+//                       per-lane shared-memory buffer and merged, two at a time, into a short sorted register list by a
 //                       branch-free min/max network (M[i] = min3(L[i], max(L[i-1],c1), max(L[i-2],c2)): FMNMX/FMNMX3 only).
-//                       Blocks are visited outwards from the row's own block (index-near = space-near) behind a two-level
-//                       box test (128-point tiles, then 32-point blocks).  Any 20 candidates give a valid bound, so neither
-//                       the pruning nor the arithmetic of this pass can affect the result -- only how tight U is.
-//   knn_collect_kernel  pass B: the CANONICAL arithmetic (common.cuh) on every block whose rigorous lower bound is <= U_i:
-//                       candidates with d <= U_i (20 + the odd extra) are listed per row; the exact 20th distance is selected
-//                       among them, then the thresholded set {j : d_ij <= kth_i} is written out: 20 listed neighbours
-//                       (out-of-tile first), the row's count, and the members beyond 20 in the cloud's tie list.
+//                       Running threshold = max over the row's four lanes of their 5th smallest value (>= 20 candidates lie
+//                       below it); final U = the exact 20th smallest of the union of the four lists (a bitonic merge across the
+//                       four lanes).  Any 20 candidates give a valid bound, so neither the pruning nor the arithmetic of this
+//                       pass can affect the result -- only how tight U is.
+//   knn_collect_kernel  pass B: every block whose rigorous lower bound is <= U_i is scanned with the same cheap arithmetic
+//                       and the filter d' <= U_i + slack; the canonical arithmetic (common.cuh) is spent on the 20-odd listed
+//                       candidates only: thread-per-row, the exact 20th distance is selected among them, then the thresholded
+//                       set {j : d_ij <= kth_i} is written out: 20 listed neighbours (out-of-tile first), the row's count, and
+//                       the members beyond 20 in the cloud's tie list.
 //   knn_slow_kernel     rows whose candidate list overflowed (mass ties: quantised / duplicated / all-zero clouds):
 //                       warp-per-row exact radix select over the whole cloud.  Launched on the overflow list only.
 //   knn_public_kernel   API outputs in original point order: idx in tf.nn.top_k order (d ascending, ties -> lower original
 //                       index), kth = -d20, count.
 // Output (sorted space): nbr [B,N,20] u16, kthd [B,N] (20th smallest d), cnt [B,N] = |{j: d_ij <= kthd_i}| | n_out << 24.
 // ------------------------------------------------------------------------------------------------
-constexpr int KNN_THREADS = 512;      // rows per CTA
-constexpr int KNN_SUB = 8;            // candidates between two buffer checks
-constexpr int KNN_CAPB = 40;          // pass B: listed candidates per row (u16 each)
+constexpr int KNN_THREADS = 512;      // 16 warps x 8 rows
+constexpr int KNN_G = 8;              // rows per warp; 32 / KNN_G = 4 lanes per row
+constexpr int KNN_ROWS = (KNN_THREADS / 32) * KNN_G;      // 128 rows per CTA
+constexpr int KNN_BLK = 8;            // candidates a lane takes from one 32-point block (4 pairs)
+constexpr int KNN_CAPL = 24;          // pass B: listed candidates per lane (u16 each)
+constexpr int KNN_CAPB = 40;          // pass B: listed candidates per row
+constexpr int KNN_MAXMASK = 8;        // 32-block masks: N <= 8192
+constexpr int KNN_WROW = 2 * KNN_G + KNN_MAXMASK / 4;      // float4 per warp in the row/mask area
 
 struct KnnLayout {
-    int off_lo, off_hi, off_tlo, off_thi, off_buf;
+    int off_lo, off_hi, off_tlo, off_thi, off_row, off_aux, off_buf;
     int bytes;
 };
-__host__ __device__ inline KnnLayout knn_layout(int N, int buf_bytes_per_row) {
+// aux_bytes: pass B's per-row lists and per-lane counts
+__host__ __device__ inline KnnLayout knn_layout(int N, int buf_bytes_per_lane, int aux_bytes) {
     const int nblk = N >> 5, ntile = (nblk + 3) >> 2;
     KnnLayout L;
     int o = N * 16;                   // points, pair-SoA: (x0,x1,y0,y1) (z0,z1,s0,s1) per pair of points
@@ -235,7 +244,10 @@ __host__ __device__ inline KnnLayout knn_layout(int N, int buf_bytes_per_row) {
     L.off_hi = o;  o += nblk * 16;    //              (hi.xyz, -)
     L.off_tlo = o; o += ntile * 16;   // 128-point tile boxes
     L.off_thi = o; o += ntile * 16;
-    L.off_buf = o; o += KNN_THREADS * buf_bytes_per_row;
+    L.off_row = o; o += (KNN_THREADS / 32) * KNN_WROW * 16;   // per warp: 8 rows x {(x, y, z, threshold), (|p|^2,-,-,-)} for the
+                                                              // lane-parallel box tests, then the warp's block masks
+    L.off_aux = o; o += aux_bytes;
+    L.off_buf = o; o += KNN_THREADS * buf_bytes_per_lane;
     L.bytes = o;
     return L;
 }
@@ -285,7 +297,7 @@ __device__ __forceinline__ float box_bound_rigorous(float x, float y, float z, f
     return box_lb(x, y, z, lo, hi) * (1.0f - 1e-6f) - 1e-6f * (s + lo.w);
 }
 
-// the per-row buffers are addressed through 32-bit shared-space addresses (one register; a generic pointer costs ptxas three)
+// the per-lane buffers are addressed through 32-bit shared-space addresses (one register; a generic pointer costs ptxas three)
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ float lds_f32(uint32_t a) {
@@ -318,133 +330,200 @@ __device__ __forceinline__ void merge2(float (&L)[LEN], float c1, float c2) {
     L[0] = fminf(L[0], lo);
 }
 
+// Lane-parallel box tests of a warp's 8 rows: which 128-point tiles, then which 32-point blocks can hold a candidate below
+// the rows' thresholds.  RIGOROUS: the bound of pass B (canonical arithmetic); otherwise the plain box distance (pass A, where
+// pruning only affects how tight the bound gets).  srow: the warp's 8 x {(x,y,z,threshold), (|p|^2,...)}.
+template <bool RIGOROUS>
+__device__ __forceinline__ void knn_block_masks(const float4* __restrict__ srow, const float4* __restrict__ slo,
+                                                const float4* __restrict__ shi, const float4* __restrict__ stlo,
+                                                const float4* __restrict__ sthi, int nblk, int ntile, int b0, bool prune,
+                                                int lane, uint32_t* __restrict__ bmask /*shared, per warp*/) {
+    auto rows_need = [&](const float4 lo, const float4 hi) {
+        bool need = false;
+#pragma unroll
+        for (int rr = 0; rr < KNN_G; ++rr) {
+            const float4 q = srow[2 * rr];
+            if (RIGOROUS)
+                need |= !(box_bound_rigorous(q.x, q.y, q.z, srow[2 * rr + 1].x, lo, hi) > q.w);
+            else
+                need |= !(box_lb(q.x, q.y, q.z, lo, hi) > q.w);
+        }
+        return need;
+    };
+    uint32_t tmask[(KNN_MAXMASK * 32 / 4 + 31) / 32];
+#pragma unroll
+    for (int tr = 0; tr < (int)(sizeof(tmask) / 4); ++tr) {
+        const int t = tr * 32 + lane;
+        bool need = false;
+        if (tr * 32 < ntile) {
+            if (t < ntile) need = !prune || rows_need(stlo[t], sthi[t]);
+            tmask[tr] = __ballot_sync(FULL, need);
+        } else {
+            tmask[tr] = 0;
+        }
+    }
+#pragma unroll 1
+    for (int br = 0; br * 32 < nblk; ++br) {
+        const int blk = br * 32 + lane, t = blk >> 2;
+        const uint32_t tm = (t >> 5) ? tmask[1] : tmask[0];
+        const bool alive = (blk < nblk) && ((tm >> (t & 31)) & 1u) && blk != b0 && blk != b0 + 1 && blk != b0 - 1;
+        uint32_t m = 0;
+        if (__any_sync(FULL, alive)) {
+            bool need = false;
+            if (alive) need = !prune || rows_need(slo[blk], shi[blk]);
+            m = __ballot_sync(FULL, need);
+        }
+        if (lane == 0) bmask[br] = m;
+    }
+    __syncwarp();
+}
+
 // ---- pass A ---------------------------------------------------------------------------------------------------
-// NL = 1: one sorted list of 20 (U = exactly the 20th smallest of the pass's values); NL = 2: two lists of 10 fed alternately
-// (U = max of the two 10th values: still >= 20 candidates below it, half the min/max work, a slightly looser bound).
-template <int NL>
+// LEN: entries of a lane's sorted list (>= 5).  The running threshold only needs the lanes' 5th values; the longer the
+// lists, the more often the final 20th-of-the-union is the exact 20th smallest (8: always when no quarter holds more than
+// 8 of the 20 nearest).
+template <int LEN>
 __global__ void __launch_bounds__(KNN_THREADS, 2)
 knn_bound_kernel(const float4* __restrict__ sorted, const float4* __restrict__ aabb, int N, int cap, int prune,
                  float* __restrict__ U) {
+    static_assert(LEN >= 5 && LEN <= 8, "list length");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int LEN = KNN_K / NL;
     const int nblk = N >> 5, ntile = (nblk + 3) >> 2;
-    const KnnLayout lay = knn_layout(N, cap * 4);
-    const int b = blockIdx.y, tid = threadIdx.x;
+    const KnnLayout lay = knn_layout(N, cap * 4, 0);
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     knn_stage(sorted + (size_t)b * N, aabb + (size_t)b * nblk * 2, N, smem_raw, lay);
-    const int r = blockIdx.x * KNN_THREADS + tid;
-    if (r >= N) return;                                   // whole warps: N % 32 == 0
+    const int r0 = blockIdx.x * KNN_ROWS + warp * KNN_G;
+    if (r0 >= N) return;                                   // whole warps: N % 32 == 0
     const float4* sp = reinterpret_cast<const float4*>(smem_raw);
     const float4* slo = reinterpret_cast<const float4*>(smem_raw + lay.off_lo);
     const float4* shi = reinterpret_cast<const float4*>(smem_raw + lay.off_hi);
     const float4* stlo = reinterpret_cast<const float4*>(smem_raw + lay.off_tlo);
     const float4* sthi = reinterpret_cast<const float4*>(smem_raw + lay.off_thi);
+    float4* srow = reinterpret_cast<float4*>(smem_raw + lay.off_row) + warp * KNN_WROW;
+    uint32_t* bmask = reinterpret_cast<uint32_t*>(srow + 2 * KNN_G);
     const uint32_t bufp = smem_addr(smem_raw + lay.off_buf) + 4u * tid;      // slot i at bufp + i * KNN_THREADS * 4
     constexpr uint32_t SLOT = KNN_THREADS * 4;
 
+    const int rr = lane & (KNN_G - 1), qd = lane >> 3;      // row within the warp, quarter of the candidates
+    const int r = r0 + rr;
     float x, y, z, s;
     {
         const float* qb = reinterpret_cast<const float*>(smem_raw) + (r >> 1) * 8 + (r & 1);
         x = qb[0]; y = qb[2]; z = qb[4]; s = qb[6];
     }
+    if (qd == 0) {
+        srow[2 * rr] = make_float4(x, y, z, INFINITY);
+        srow[2 * rr + 1] = make_float4(s, 0.f, 0.f, 0.f);
+    }
     const float2 q2x = make_float2(-2.f * x, -2.f * x), q2y = make_float2(-2.f * y, -2.f * y),
                  q2z = make_float2(-2.f * z, -2.f * z), qs2 = make_float2(s, s);
 
-    float L[NL][LEN];
+    float L[LEN];
 #pragma unroll
-    for (int l = 0; l < NL; ++l)
-#pragma unroll
-        for (int i = 0; i < LEN; ++i) L[l][i] = INFINITY;
+    for (int i = 0; i < LEN; ++i) L[i] = INFINITY;
     float thr = INFINITY;
-    const int b0 = r >> 5, t0 = b0 >> 2;                  // warp-uniform
-    int tile = t0, k = -1, tl = t0 - 1, th = t0 + 1;
-    bool side = true;
-    int blk = b0, sub = 4;
     uint32_t wp = bufp;
-    const uint32_t wlim = bufp + (uint32_t)(cap - KNN_SUB) * SLOT;
-    for (;;) {
-        bool fin = false;
-        if (sub == 4) {
-            // ---- next block: own block, rest of the own tile, then the tiles outwards; two-level box test --------
-            bool found = false;
-            if (k < 0) {
-                blk = b0;
-                k = 0;
-                found = true;
-            }
-            while (!found) {
-                while (k < 4) {
-                    const int cb = tile * 4 + k;
-                    ++k;
-                    if (cb >= nblk || cb == b0) continue;
-                    if (!prune || __any_sync(FULL, !(box_lb(x, y, z, slo[cb], shi[cb]) > thr))) {
-                        blk = cb;
-                        found = true;
-                        break;
-                    }
-                }
-                if (found) break;
-                int nt = -1;
-                while (tl >= 0 || th < ntile) {
-                    const bool take_hi = (th < ntile) && (side || tl < 0);
-                    const int cand = take_hi ? th++ : tl--;
-                    side = !take_hi;
-                    if (!prune || __any_sync(FULL, !(box_lb(x, y, z, stlo[cand], sthi[cand]) > thr))) {
-                        nt = cand;
-                        break;
-                    }
-                }
-                if (nt < 0) break;
-                tile = nt;
-                k = 0;
-            }
-            fin = !found;
-            sub = 0;
-        }
-        if (!fin) {
-            // ---- 8 candidates: d' = s_i + s_j - 2 p_i.p_j as one FFMA2 chain per pair; park those below the threshold --
-            const float4* pp = sp + blk * 32 + sub * KNN_SUB;
-#pragma unroll
-            for (int u = 0; u < KNN_SUB / 2; ++u) {
-                const float2 t = fast_dist2(q2x, q2y, q2z, qs2, pp[2 * u], pp[2 * u + 1]);
-                if (t.x < thr) {
-                    sts_f32(wp, t.x);
-                    wp += SLOT;
-                }
-                if (t.y < thr) {
-                    sts_f32(wp, t.y);
-                    wp += SLOT;
-                }
-            }
-            ++sub;
-        }
-        // ---- merge the parked values into the sorted list when a buffer may overflow, after the own block (first
-        // threshold) and at the end
-        const bool force = fin || (blk == b0 && sub == 4);
-        if (__any_sync(FULL, (wp > wlim) || (force && wp != bufp))) {
-            const int n = (int)((wp - bufp) / SLOT);
-            const int nmax = __reduce_max_sync(FULL, n);
+    const uint32_t wlim = bufp + (uint32_t)(cap - KNN_BLK) * SLOT;
+    const int b0 = r0 >> 5;                                  // the rows' own block (warp-uniform)
+
+    // merge the parked values into the lane's list; row threshold = max of its four lanes' 5th values
+    auto compact = [&]() {
+        const int n = (int)((wp - bufp) / SLOT);
+        const int nmax = __reduce_max_sync(FULL, n);
 #pragma unroll 1
-            for (int i = 0; i < nmax; i += 2 * NL) {
-#pragma unroll
-                for (int l = 0; l < NL; ++l) {
-                    const int e = i + 2 * l;
-                    const float c1 = (e < n) ? lds_f32(bufp + e * SLOT) : INFINITY;
-                    const float c2 = (e + 1 < n) ? lds_f32(bufp + (e + 1) * SLOT) : INFINITY;
-                    merge2<LEN>(L[l], c1, c2);
-                }
-            }
-            wp = bufp;
-            thr = L[0][LEN - 1];
-#pragma unroll
-            for (int l = 1; l < NL; ++l) thr = fmaxf(thr, L[l][LEN - 1]);
+        for (int i = 0; i < nmax; i += 2) {
+            const float c1 = (i < n) ? lds_f32(bufp + i * SLOT) : INFINITY;
+            const float c2 = (i + 1 < n) ? lds_f32(bufp + (i + 1) * SLOT) : INFINITY;
+            merge2<LEN>(L, c1, c2);
         }
-        if (fin) break;
+        wp = bufp;
+        float t = L[4];
+        t = fmaxf(t, __shfl_xor_sync(FULL, t, 8));
+        t = fmaxf(t, __shfl_xor_sync(FULL, t, 16));
+        thr = t;
+        if (qd == 0) srow[2 * rr].w = t;
+    };
+    // one 32-point block: this lane's four candidate pairs (pairs qd, qd+4, qd+8, qd+12 of the block)
+    auto scan_block = [&](int blk, bool force) {
+        const float4* pp = sp + blk * 32 + 2 * qd;
+#pragma unroll
+        for (int u = 0; u < KNN_BLK / 2; ++u) {
+            const float2 t = fast_dist2(q2x, q2y, q2z, qs2, pp[8 * u], pp[8 * u + 1]);
+            if (t.x < thr) {
+                sts_f32(wp, t.x);
+                wp += SLOT;
+            }
+            if (t.y < thr) {
+                sts_f32(wp, t.y);
+                wp += SLOT;
+            }
+        }
+        if (__any_sync(FULL, (wp > wlim) || (force && wp != bufp))) compact();
+    };
+
+    // the own block (first threshold), its index neighbours (a tight threshold before the box tests), then every block the
+    // tests leave
+#pragma unroll 1
+    for (int t = 0; t < 3; ++t) {
+        const int blk = (t == 0) ? b0 : (t == 1) ? b0 + 1 : b0 - 1;
+        if (blk >= 0 && blk < nblk) scan_block(blk, t != 1);
+    }
+    __syncwarp();
+    knn_block_masks<false>(srow, slo, shi, stlo, sthi, nblk, ntile, b0, prune != 0, lane, bmask);
+#pragma unroll 1
+    for (int br = 0; br * 32 < nblk; ++br) {
+        uint32_t m = bmask[br];
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            scan_block(br * 32 + bit, false);
+        }
+    }
+    if (__any_sync(FULL, wp != bufp)) compact();
+
+    // U = the 20th smallest of the union of the row's four sorted lists (padded to 8 with +inf): a bitonic merge across the
+    // four lanes.  Round 1: lanes (q, q^1) -> sorted 16 (low half on the even quarter); round 2: the 16 largest of the 32 as a
+    // bitonic sequence H; its 4th smallest (= rank 19 of the 32) by two half-cleaners and a max.
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = (i < LEN) ? L[i] : INFINITY;
+    {
+        float c[8];
+        const bool odd = (qd & 1) != 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float o = __shfl_xor_sync(FULL, a[7 - i], 8);
+            c[i] = odd ? fmaxf(a[i], o) : fminf(a[i], o);
+        }
+#pragma unroll
+        for (int d = 4; d >= 1; d >>= 1)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if ((i & d) == 0) {
+                    const float lo = fminf(c[i], c[i + d]), hi = fmaxf(c[i], c[i + d]);
+                    c[i] = lo;
+                    c[i + d] = hi;
+                }
+        // pair (0,1) holds S[0..15], pair (2,3) holds T[0..15]; H[i] = max(S[i], T[15-i]): quarter q pairs with quarter 3-q
+        float h[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = fmaxf(c[i], __shfl_xor_sync(FULL, c[7 - i], 24));
+        // quarters 0 and 3 hold H[0..7] (3 reversed), quarters 1 and 2 hold H[8..15]: the 8 smallest of H
+        float m8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m8[i] = fminf(h[i], __shfl_xor_sync(FULL, h[i], 8));
+        // careful: quarter 0 pairs with quarter 1 (xor 8) -> H[i] with H[8+i]; quarter 3 (H reversed) pairs with quarter 2
+        // (H[8..15] reversed): the same 8 values in reverse order.  4 smallest of the 8, then their maximum.
+        float u4 = fmaxf(fmaxf(fminf(m8[0], m8[4]), fminf(m8[1], m8[5])), fmaxf(fminf(m8[2], m8[6]), fminf(m8[3], m8[7])));
+        thr = u4;
     }
     // d' is within 1e-6 (s_i + s_j) of the canonical d (either arithmetic): the slack keeps U a valid upper bound of the
     // canonical 20th distance
-    float smax = 0.f;
-    for (int t = 0; t < ntile; ++t) smax = fmaxf(smax, stlo[t].w);
-    U[(size_t)b * N + r] = thr + 2e-6f * (s + smax);
+    if (qd == 0) {
+        float smax = 0.f;
+        for (int t = 0; t < ntile; ++t) smax = fmaxf(smax, stlo[t].w);
+        U[(size_t)b * N + r] = thr + 2e-6f * (s + smax);
+    }
 }
 
 // ---- pass B ---------------------------------------------------------------------------------------------------
@@ -460,6 +539,8 @@ __device__ __forceinline__ float knn_point_dist(const float* __restrict__ spf, i
     return canon_dist<ARITH>(x, y, z, s, pb[0], pb[2], pb[4], pb[6]);
 }
 
+constexpr int KNN_AUX_B = KNN_ROWS * KNN_CAPB * 2 + KNN_THREADS * 4;      // per-row lists [slot][row] u16 + per-lane counts
+
 template <int ARITH>
 __global__ void __launch_bounds__(KNN_THREADS, 2)
 knn_collect_kernel(const float4* __restrict__ sorted, const float4* __restrict__ aabb, const float* __restrict__ U, int N,
@@ -467,71 +548,114 @@ knn_collect_kernel(const float4* __restrict__ sorted, const float4* __restrict__
                    int* __restrict__ cnt, int* __restrict__ slow) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nblk = N >> 5, ntile = (nblk + 3) >> 2;
-    const KnnLayout lay = knn_layout(N, KNN_CAPB * 2);
-    const int b = blockIdx.y, tid = threadIdx.x;
+    const KnnLayout lay = knn_layout(N, KNN_CAPL * 2, KNN_AUX_B);
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     knn_stage(sorted + (size_t)b * N, aabb + (size_t)b * nblk * 2, N, smem_raw, lay);
-    const int r = blockIdx.x * KNN_THREADS + tid;
-    if (r >= N) return;
     const float4* sp = reinterpret_cast<const float4*>(smem_raw);
     const float* spf = reinterpret_cast<const float*>(smem_raw);
     const float4* slo = reinterpret_cast<const float4*>(smem_raw + lay.off_lo);
     const float4* shi = reinterpret_cast<const float4*>(smem_raw + lay.off_hi);
     const float4* stlo = reinterpret_cast<const float4*>(smem_raw + lay.off_tlo);
     const float4* sthi = reinterpret_cast<const float4*>(smem_raw + lay.off_thi);
-    const uint32_t bufp = smem_addr(smem_raw + lay.off_buf) + 2u * tid;      // slot i at bufp + i * KNN_THREADS * 2
+    float4* srow = reinterpret_cast<float4*>(smem_raw + lay.off_row) + warp * KNN_WROW;
+    uint32_t* bmask = reinterpret_cast<uint32_t*>(srow + 2 * KNN_G);
+    const uint32_t rowlist = smem_addr(smem_raw + lay.off_aux);                       // [KNN_CAPB][KNN_ROWS] u16
+    int* scount = reinterpret_cast<int*>(smem_raw + lay.off_aux + KNN_ROWS * KNN_CAPB * 2);   // [KNN_THREADS]: listed, or -1 = overflow
+    const uint32_t bufbase = smem_addr(smem_raw + lay.off_buf);
+    const uint32_t bufp = bufbase + 2u * tid;                                          // slot i at bufp + i * KNN_THREADS * 2
     constexpr uint32_t SLOT = KNN_THREADS * 2;
 
+    const int r0 = blockIdx.x * KNN_ROWS + warp * KNN_G;
+    if (r0 < N) {
+        // ---- scan: 8 rows per warp, four lanes per row ------------------------------------------------------------
+        const int rr = lane & (KNN_G - 1), qd = lane >> 3;
+        const int r = r0 + rr;
+        const float x = spf[(r >> 1) * 8 + (r & 1)], y = spf[(r >> 1) * 8 + (r & 1) + 2], z = spf[(r >> 1) * 8 + (r & 1) + 4],
+                    s = spf[(r >> 1) * 8 + (r & 1) + 6];
+        const float2 q2x = make_float2(-2.f * x, -2.f * x), q2y = make_float2(-2.f * y, -2.f * y),
+                     q2z = make_float2(-2.f * z, -2.f * z), qs2 = make_float2(s, s);
+        const float Ui = U[(size_t)b * N + r];
+        if (qd == 0) {
+            srow[2 * rr] = make_float4(x, y, z, Ui);
+            srow[2 * rr + 1] = make_float4(s, 0.f, 0.f, 0.f);
+        }
+        float smax = 0.f;
+        for (int t = 0; t < ntile; ++t) smax = fmaxf(smax, stlo[t].w);
+        // scan filter: a candidate whose canonical d is <= U_i has d' <= U_i + 1e-6 (s_i + s_j); the canonical arithmetic
+        // itself is spent only on the handful that pass
+        float Uf = Ui + 2e-6f * (s + smax);
+        uint32_t wp = bufp;
+        const uint32_t wlim = bufp + (uint32_t)(KNN_CAPL - KNN_BLK) * SLOT;
+        bool over = false;
+        auto scan_block = [&](int blk) {
+            const float4* pp = sp + blk * 32 + 2 * qd;
+            const uint32_t j = (uint32_t)(blk * 32 + 2 * qd);
+#pragma unroll
+            for (int u = 0; u < KNN_BLK / 2; ++u) {
+                const float2 d = fast_dist2(q2x, q2y, q2z, qs2, pp[8 * u], pp[8 * u + 1]);
+                if (d.x <= Uf) {
+                    sts_u16(wp, j + 8 * u);
+                    wp += SLOT;
+                }
+                if (d.y <= Uf) {
+                    sts_u16(wp, j + 8 * u + 1);
+                    wp += SLOT;
+                }
+            }
+            if (wp > wlim) {                // mass ties: this row goes to the warp-per-row exact path; stop listing
+                over = true;
+                Uf = -INFINITY;
+                wp = bufp;
+            }
+        };
+        const int b0 = r0 >> 5;
+        __syncwarp();
+        knn_block_masks<true>(srow, slo, shi, stlo, sthi, nblk, ntile, b0, prune != 0, lane, bmask);
+        // ascending position order within a lane: b0-1, b0, b0+1 are part of the sweep
+#pragma unroll 1
+        for (int br = 0; br * 32 < nblk; ++br) {
+            uint32_t m = bmask[br];
+#pragma unroll
+            for (int t = -1; t <= 1; ++t) {
+                const int nb = b0 + t;
+                if (nb >= 0 && nb < nblk && (nb >> 5) == br) m |= 1u << (nb & 31);
+            }
+            while (m) {
+                const int bit = __ffs(m) - 1;
+                m &= m - 1;
+                scan_block(br * 32 + bit);
+            }
+        }
+        scount[tid] = over ? -1 : (int)((wp - bufp) / SLOT);
+    }
+    __syncthreads();
+    // ---- thread per row: exact 20th distance among the listed candidates, then the thresholded set --------------------
+    if (tid >= KNN_ROWS) return;
+    const int r = blockIdx.x * KNN_ROWS + tid;
+    if (r >= N) return;
+    const size_t row = (size_t)b * N + r;
     const float x = spf[(r >> 1) * 8 + (r & 1)], y = spf[(r >> 1) * 8 + (r & 1) + 2], z = spf[(r >> 1) * 8 + (r & 1) + 4],
                 s = spf[(r >> 1) * 8 + (r & 1) + 6];
-    const float2 q2x = make_float2(-2.f * x, -2.f * x), q2y = make_float2(-2.f * y, -2.f * y),
-                 q2z = make_float2(-2.f * z, -2.f * z), qs2 = make_float2(s, s);
-    const size_t row = (size_t)b * N + r;
-    const float Ui = U[row];
-    float smax = 0.f;
-    for (int t = 0; t < ntile; ++t) smax = fmaxf(smax, stlo[t].w);
-    // scan filter: a candidate whose canonical d is <= U_i has d' <= U_i + 1e-6 (s_i + s_j); the canonical arithmetic itself
-    // is spent only on the handful that pass
-    float Uf = Ui + 2e-6f * (s + smax);
-
-    // ---- every candidate that can have canonical d <= U_i, in ascending position order ---------------------------
-    uint32_t wp = bufp;
-    const uint32_t wlim = bufp + (uint32_t)(KNN_CAPB - KNN_SUB) * SLOT;
+    // gather the four lanes' lists (quarter-major, slot order: a fixed order) into the row's contiguous list
+    const uint32_t mylist = rowlist + 2u * tid;                 // slot i at mylist + i * KNN_ROWS * 2
+    constexpr uint32_t RSLOT = KNN_ROWS * 2;
+    int nc = 0;
     bool over = false;
+    {
+        const int w = tid >> 3, l0 = tid & 7;
 #pragma unroll 1
-    for (int t = 0; t < ntile; ++t) {
-        if (prune && !__any_sync(FULL, !(box_bound_rigorous(x, y, z, s, stlo[t], sthi[t]) > Ui))) continue;
-#pragma unroll 1
-        for (int k = 0; k < 4; ++k) {
-            const int blk = 4 * t + k;
-            if (blk >= nblk) break;
-            if (prune && !__any_sync(FULL, !(box_bound_rigorous(x, y, z, s, slo[blk], shi[blk]) > Ui))) continue;
-#pragma unroll 1
-            for (int sub = 0; sub < 4; ++sub) {
-                const float4* pp = sp + blk * 32 + sub * KNN_SUB;
-                uint32_t j = (uint32_t)(blk * 32 + sub * KNN_SUB);
-#pragma unroll
-                for (int u = 0; u < KNN_SUB / 2; ++u) {
-                    const float2 d = fast_dist2(q2x, q2y, q2z, qs2, pp[2 * u], pp[2 * u + 1]);
-                    if (d.x <= Uf) {
-                        sts_u16(wp, j + 2 * u);
-                        wp += SLOT;
-                    }
-                    if (d.y <= Uf) {
-                        sts_u16(wp, j + 2 * u + 1);
-                        wp += SLOT;
-                    }
-                }
-                if (wp > wlim) {            // mass ties: this row goes to the warp-per-row exact path; stop listing
-                    over = true;
-                    Uf = -INFINITY;
-                    wp = bufp;
-                }
+        for (int qd = 0; qd < 4; ++qd) {
+            const int src = w * 32 + l0 + 8 * qd;
+            const int n = scount[src];
+            if (n < 0) over = true;
+            for (int i = 0; i < n; ++i) {
+                const uint32_t j = lds_u16(bufbase + 2u * src + (uint32_t)i * SLOT);
+                if (nc < KNN_CAPB) sts_u16(mylist + (uint32_t)nc * RSLOT, j);
+                ++nc;
             }
         }
     }
-    const int nc = (int)((wp - bufp) / SLOT);
-    // ---- exact 20th distance among the listed candidates, then the thresholded set ----------------------------
-    const bool ok = !over && (nc >= KNN_K);
+    const bool ok = !over && (nc >= KNN_K) && (nc <= KNN_CAPB);
     const int n = ok ? nc : 0;
     const int nmax = __reduce_max_sync(FULL, n);
     float L[KNN_K];
@@ -539,8 +663,8 @@ knn_collect_kernel(const float4* __restrict__ sorted, const float4* __restrict__
     for (int i = 0; i < KNN_K; ++i) L[i] = INFINITY;
 #pragma unroll 1
     for (int i = 0; i < nmax; i += 2) {
-        const float c1 = (i < n) ? knn_point_dist<ARITH>(spf, lds_u16(bufp + i * SLOT), x, y, z, s) : INFINITY;
-        const float c2 = (i + 1 < n) ? knn_point_dist<ARITH>(spf, lds_u16(bufp + (i + 1) * SLOT), x, y, z, s) : INFINITY;
+        const float c1 = (i < n) ? knn_point_dist<ARITH>(spf, lds_u16(mylist + i * RSLOT), x, y, z, s) : INFINITY;
+        const float c2 = (i + 1 < n) ? knn_point_dist<ARITH>(spf, lds_u16(mylist + (i + 1) * RSLOT), x, y, z, s) : INFINITY;
         merge2<KNN_K>(L, c1, c2);
     }
     const float kth = L[KNN_K - 1];
@@ -549,7 +673,7 @@ knn_collect_kernel(const float4* __restrict__ sorted, const float4* __restrict__
 #pragma unroll 1
     for (int i = 0; i < nmax; ++i) {
         if (i < n) {
-            const int j = (int)lds_u16(bufp + i * SLOT);
+            const int j = (int)lds_u16(mylist + i * RSLOT);
             const float d = knn_point_dist<ARITH>(spf, j, x, y, z, s);
             if (d <= kth) {
                 if (total < KNN_K) {
@@ -841,7 +965,7 @@ int knn_check_n(int N) {
 }
 
 // Tuning knobs (environment; results never depend on them): EPC_KNN_CAP = parked values per row in pass A (even, >= 16,
-// default: what lets two CTAs share an SM), EPC_KNN_LISTS = 1 | 2 sorted lists in pass A.
+// default: what lets two CTAs share an SM), EPC_KNN_LEN = 5 | 6 | 8 entries of a lane's sorted list in pass A.
 static int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
@@ -855,7 +979,7 @@ int knn_build(const float* xyz, int B, int N, int arith, bool prune, const KnnSt
     const int NP = next_pow2(N);
     const size_t sort_smem = (size_t)NP * sizeof(unsigned long long);
     // pass A buffer: as many parked values per row as two resident CTAs per SM allow (one CTA when the cloud is large)
-    const int fixed = knn_layout(N, 0).bytes;
+    const int fixed = knn_layout(N, 0, 0).bytes;
     const int budget2 = (227 * 1024) / 2 - 1024, budget1 = 227 * 1024 - 1024;
     int cap = (budget2 - fixed) / (KNN_THREADS * 4) / 2 * 2;
     if (cap < 16) cap = (budget1 - fixed) / (KNN_THREADS * 4) / 2 * 2;
@@ -865,13 +989,15 @@ int knn_build(const float* xyz, int B, int N, int arith, bool prune, const KnnSt
         if (e >= 16 && e % 2 == 0 && fixed + e * KNN_THREADS * 4 <= budget1) cap = e;
     }
     EPC_CHECK_ARG(cap >= 16, "kNN: N=%d leaves no shared memory for the candidate buffers", N);
-    const int lists = env_int("EPC_KNN_LISTS", 2) == 1 ? 1 : 2;
-    const size_t smemA = (size_t)knn_layout(N, cap * 4).bytes, smemB = (size_t)knn_layout(N, KNN_CAPB * 2).bytes;
+    const int len = env_int("EPC_KNN_LEN", 8);
+    const size_t smemA = (size_t)knn_layout(N, cap * 4, 0).bytes, smemB = (size_t)knn_layout(N, KNN_CAPL * 2, KNN_AUX_B).bytes;
+    EPC_CHECK_ARG(smemB <= (size_t)budget1, "kNN: N=%d leaves no shared memory for the candidate lists", N);
     const size_t smemC = (size_t)KNN_SLOW_WARPS * N * 6;
-    static PerDeviceSize a_sort, a_A1, a_A2, a_B0, a_B1, a_C0, a_C1;
+    static PerDeviceSize a_sort, a_A5, a_A6, a_A8, a_B0, a_B1, a_C0, a_C1;
     EPC_CUDA(ensure_dyn_smem(sort_kernel, 64 * 1024, a_sort));
-    EPC_CUDA(ensure_dyn_smem(knn_bound_kernel<1>, smemA, a_A1));
-    EPC_CUDA(ensure_dyn_smem(knn_bound_kernel<2>, smemA, a_A2));
+    EPC_CUDA(ensure_dyn_smem(knn_bound_kernel<5>, smemA, a_A5));
+    EPC_CUDA(ensure_dyn_smem(knn_bound_kernel<6>, smemA, a_A6));
+    EPC_CUDA(ensure_dyn_smem(knn_bound_kernel<8>, smemA, a_A8));
     EPC_CUDA(ensure_dyn_smem(knn_collect_kernel<0>, smemB, a_B0));
     EPC_CUDA(ensure_dyn_smem(knn_collect_kernel<1>, smemB, a_B1));
     EPC_CUDA(ensure_dyn_smem(knn_slow_kernel<0>, smemC, a_C0));
@@ -884,11 +1010,13 @@ int knn_build(const float* xyz, int B, int N, int arith, bool prune, const KnnSt
     EPC_CUDA(cudaMemsetAsync(s.tie, 0, (size_t)B * TIE_WORDS * sizeof(uint32_t), st));      // counters (and stale entries)
     EPC_CUDA(cudaMemsetAsync(s.slow, 0, sizeof(int), st));                                   // overflow-row counter
     ScopedStage ss(EPC_STAGE_KNN, st);
-    dim3 grid((N + KNN_THREADS - 1) / KNN_THREADS, B);
-    if (lists == 1)
-        knn_bound_kernel<1><<<grid, KNN_THREADS, smemA, st>>>(s.sorted, s.aabb, N, cap, prune ? 1 : 0, s.U);
+    dim3 grid((N + KNN_ROWS - 1) / KNN_ROWS, B);
+    if (len == 5)
+        knn_bound_kernel<5><<<grid, KNN_THREADS, smemA, st>>>(s.sorted, s.aabb, N, cap, prune ? 1 : 0, s.U);
+    else if (len == 6)
+        knn_bound_kernel<6><<<grid, KNN_THREADS, smemA, st>>>(s.sorted, s.aabb, N, cap, prune ? 1 : 0, s.U);
     else
-        knn_bound_kernel<2><<<grid, KNN_THREADS, smemA, st>>>(s.sorted, s.aabb, N, cap, prune ? 1 : 0, s.U);
+        knn_bound_kernel<8><<<grid, KNN_THREADS, smemA, st>>>(s.sorted, s.aabb, N, cap, prune ? 1 : 0, s.U);
     EPC_LAUNCH_CHECK();
     const int slow_ctas = 2 * sm_count_knn();
     if (arith == EPC_KNN_ARITH_MULADD) {
