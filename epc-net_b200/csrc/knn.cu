@@ -26,6 +26,38 @@ __device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 10 bits -> every t
     return v;
 }
 
+// 10-bit cell coordinates -> 30-bit Hilbert index (Skilling's transpose algorithm): consecutive indices are always adjacent
+// cells, so a run of 32 sorted points is a connected, compact set (a Morton run can straddle a jump across the whole cloud,
+// which blows up its bounding box and with it the kNN block pruning).
+__device__ __forceinline__ uint32_t hilbert3(uint32_t x0, uint32_t x1, uint32_t x2) {
+    uint32_t X[3] = {x0, x1, x2};
+    constexpr uint32_t M = 1u << 9;
+#pragma unroll
+    for (uint32_t Q = M; Q > 1; Q >>= 1) {
+        const uint32_t P = Q - 1;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (X[i] & Q) {
+                X[0] ^= P;
+            } else {
+                const uint32_t t = (X[0] ^ X[i]) & P;
+                X[0] ^= t;
+                X[i] ^= t;
+            }
+        }
+    }
+    X[1] ^= X[0];
+    X[2] ^= X[1];
+    uint32_t t = 0;
+#pragma unroll
+    for (uint32_t Q = M; Q > 1; Q >>= 1)
+        if (X[2] & Q) t ^= Q - 1;
+    X[0] ^= t;
+    X[1] ^= t;
+    X[2] ^= t;
+    return (spread3(X[0]) << 2) | (spread3(X[1]) << 1) | spread3(X[2]);       // X[0] carries the most significant bit of each triple
+}
+
 // Bitonic sort of E*1024 unique 64-bit keys by 1024 threads.  Element e = slot*1024 + tid lives in register k[slot]:
 // compare-exchange distances j >= 1024 stay inside the thread, j < 32 are warp shuffles, and only 32 <= j <= 512 go
 // through shared memory (one barrier per pass, plus one to spill and one to reload) -- 32 barriers instead of 78 at N=4096.
@@ -97,7 +129,7 @@ __device__ __forceinline__ void bitonic_regs(unsigned long long* __restrict__ ke
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(1024) sort_kernel(const float* __restrict__ xyz, int N, int NP,
+__global__ void __launch_bounds__(1024) sort_kernel(const float* __restrict__ xyz, int N, int NP, int curve,
                                                      float4* __restrict__ sorted, int* __restrict__ perm,
                                                      uint16_t* __restrict__ perm16, float4* __restrict__ aabb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -148,7 +180,7 @@ __global__ void __launch_bounds__(1024) sort_kernel(const float* __restrict__ xy
                 f = fminf(fmaxf(f, 0.f), 1023.f);   // NaN -> 0
                 q[a] = (uint32_t)f;
             }
-            uint32_t code = spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2);
+            const uint32_t code = curve ? hilbert3(q[0], q[1], q[2]) : (spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2));
             k = ((unsigned long long)code << 32) | (unsigned)i;
         }
         keys[i] = k;
@@ -628,21 +660,25 @@ knn_collect_kernel(const float4* __restrict__ sorted, const float4* __restrict__
         }
         scount[tid] = over ? -1 : (int)((wp - bufp) / SLOT);
     }
-    __syncthreads();
     // ---- thread per row: exact 20th distance among the listed candidates, then the thresholded set --------------------
-    if (tid >= KNN_ROWS) return;
-    const int r = blockIdx.x * KNN_ROWS + tid;
-    if (r >= N) return;
+    // Four warps (32 rows) form a group with its own named barrier: the group's first warp finalises the 32 rows as soon as
+    // its three partners are done scanning, while the other groups and the SM's second CTA keep scanning.
+    const int group = warp >> 2;
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
+    if (warp & 3) return;
+    const int rl = group * 32 + lane;                           // row within the CTA
+    const int r = blockIdx.x * KNN_ROWS + rl;
+    if (r >= N) return;                                         // whole warps: N % 32 == 0
     const size_t row = (size_t)b * N + r;
     const float x = spf[(r >> 1) * 8 + (r & 1)], y = spf[(r >> 1) * 8 + (r & 1) + 2], z = spf[(r >> 1) * 8 + (r & 1) + 4],
                 s = spf[(r >> 1) * 8 + (r & 1) + 6];
     // gather the four lanes' lists (quarter-major, slot order: a fixed order) into the row's contiguous list
-    const uint32_t mylist = rowlist + 2u * tid;                 // slot i at mylist + i * KNN_ROWS * 2
+    const uint32_t mylist = rowlist + 2u * rl;                  // slot i at mylist + i * KNN_ROWS * 2
     constexpr uint32_t RSLOT = KNN_ROWS * 2;
     int nc = 0;
     bool over = false;
     {
-        const int w = tid >> 3, l0 = tid & 7;
+        const int w = rl >> 3, l0 = rl & 7;
 #pragma unroll 1
         for (int qd = 0; qd < 4; ++qd) {
             const int src = w * 32 + l0 + 8 * qd;
@@ -965,7 +1001,8 @@ int knn_check_n(int N) {
 }
 
 // Tuning knobs (environment; results never depend on them): EPC_KNN_CAP = parked values per row in pass A (even, >= 16,
-// default: what lets two CTAs share an SM), EPC_KNN_LEN = 5 | 6 | 8 entries of a lane's sorted list in pass A.
+// default: what lets two CTAs share an SM), EPC_KNN_LEN = 5 | 6 | 8 entries of a lane's sorted list in pass A,
+// EPC_SORT_CURVE = 0 (Morton) | 1 (Hilbert, default) order of the points.
 static int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
@@ -1004,7 +1041,7 @@ int knn_build(const float* xyz, int B, int N, int arith, bool prune, const KnnSt
     EPC_CUDA(ensure_dyn_smem(knn_slow_kernel<1>, smemC, a_C1));
     {
         ScopedStage ss(EPC_STAGE_SORT, st);
-        sort_kernel<<<B, 1024, sort_smem, st>>>(xyz, N, NP, s.sorted, s.perm, s.perm16, s.aabb);
+        sort_kernel<<<B, 1024, sort_smem, st>>>(xyz, N, NP, env_int("EPC_SORT_CURVE", 1), s.sorted, s.perm, s.perm16, s.aabb);
         EPC_LAUNCH_CHECK();
     }
     EPC_CUDA(cudaMemsetAsync(s.tie, 0, (size_t)B * TIE_WORDS * sizeof(uint32_t), st));      // counters (and stale entries)

@@ -1,5 +1,4 @@
 #!/bin/bash
-# round-2 kNN iteration: parity first, then timing of the variants
 set -u
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_knn.py -m gpu -q --tb=short -p no:cacheprovider -x 2>&1 | tail -30 | cut -c1-300 | tee gpurun_out/pytest_knn.log
@@ -13,17 +12,16 @@ for k,v in sorted(d['stages'].items(), key=lambda kv:-kv[1]['share'])[:3]: print
 "
     tail -2 gpurun_out/bench_$1.err
 }
-run_bench default
-EPC_KNN_LEN=5 run_bench len5
-EPC_KNN_LEN=6 run_bench len6
-for L in 8 5; do
-EPC_KNN_LEN=$L timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -k regex:knn -c 12 --csv --log-file gpurun_out/knn_launches_$L.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-retrieval --no-parity > /dev/null 2>&1
+run_bench hilbert
+EPC_SORT_CURVE=0 run_bench morton
+for C in 1 0; do
+EPC_SORT_CURVE=$C timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -k regex:"knn|proxy_block_kernel" -c 16 --csv --log-file gpurun_out/knn_launches_c$C.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-retrieval --no-parity > /dev/null 2>&1
 python - <<PY
 import csv
-rows=[r for r in csv.reader(open('gpurun_out/knn_launches_$L.csv')) if len(r)>10 and r[0].isdigit()]
+rows=[r for r in csv.reader(open('gpurun_out/knn_launches_c$C.csv')) if len(r)>10 and r[0].isdigit()]
 agg={}
 for r in rows:
-    name=r[4].split('(')[0]; agg.setdefault((name,r[-3]),[]).append(float(r[-1].replace(',','')))
-for k,v in agg.items(): print('LEN=$L %-40s %-28s n=%d mean=%.1f'%(k[0],k[1],len(v),sum(v)/len(v)))
+    name=r[4].split('(')[0][:44]; agg.setdefault((name,r[-3]),[]).append(float(r[-1].replace(',','')))
+for k,v in agg.items(): print('CURVE=$C %-44s %-28s n=%d mean=%.1f'%(k[0],k[1],len(v),sum(v)/len(v)))
 PY
 done
