@@ -18,6 +18,8 @@ struct KnnState {          // per-cloud kNN graph in *sorted* (Morton) point ord
                            // the members of thresholded sets beyond the 20 listed ones (ties at the 20th distance)
     float* U;              // [B,N]   pass A: upper bound of the row's 20th smallest canonical distance
     int* slow;             // [1 + B*N] counter, then the rows whose candidate list overflowed (mass ties): exact warp-per-row path
+    uint16_t* glist;       // [B,N,40] pass B: the row's listed candidates (canonical d may be <= U)
+    int* gcount;           // [B,N]    ... their number, -1 = the list overflowed
 };
 constexpr uint32_t TIE_CAP = 510;                  // entries per cloud; more (degenerate clouds) -> the gather re-scans the cloud
 constexpr uint32_t TIE_WORDS = 2 + 2 * TIE_CAP;    // 4 KB per cloud

@@ -566,23 +566,16 @@ __device__ __forceinline__ void tie_append(uint32_t* __restrict__ tie, uint32_t 
 }
 
 template <int ARITH>
-__device__ __forceinline__ float knn_point_dist(const float* __restrict__ spf, int j, float x, float y, float z, float s) {
-    const float* pb = spf + (j >> 1) * 8 + (j & 1);
-    return canon_dist<ARITH>(x, y, z, s, pb[0], pb[2], pb[4], pb[6]);
-}
-
-constexpr int KNN_AUX_B = KNN_ROWS * KNN_CAPB * 2 + KNN_THREADS * 4;      // per-row lists [slot][row] u16 + per-lane counts
-
-template <int ARITH>
 __global__ void __launch_bounds__(KNN_THREADS, 2)
 knn_collect_kernel(const float4* __restrict__ sorted, const float4* __restrict__ aabb, const float* __restrict__ U, int N,
-                   int prune, uint32_t* __restrict__ tie_all, uint16_t* __restrict__ nbr, float* __restrict__ kthd,
-                   int* __restrict__ cnt, int* __restrict__ slow) {
+                   int prune, uint16_t* __restrict__ glist, int* __restrict__ gcount) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nblk = N >> 5, ntile = (nblk + 3) >> 2;
-    const KnnLayout lay = knn_layout(N, KNN_CAPL * 2, KNN_AUX_B);
+    const KnnLayout lay = knn_layout(N, KNN_CAPL * 2, 0);
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     knn_stage(sorted + (size_t)b * N, aabb + (size_t)b * nblk * 2, N, smem_raw, lay);
+    const int r0 = blockIdx.x * KNN_ROWS + warp * KNN_G;
+    if (r0 >= N) return;
     const float4* sp = reinterpret_cast<const float4*>(smem_raw);
     const float* spf = reinterpret_cast<const float*>(smem_raw);
     const float4* slo = reinterpret_cast<const float4*>(smem_raw + lay.off_lo);
@@ -591,35 +584,46 @@ knn_collect_kernel(const float4* __restrict__ sorted, const float4* __restrict__
     const float4* sthi = reinterpret_cast<const float4*>(smem_raw + lay.off_thi);
     float4* srow = reinterpret_cast<float4*>(smem_raw + lay.off_row) + warp * KNN_WROW;
     uint32_t* bmask = reinterpret_cast<uint32_t*>(srow + 2 * KNN_G);
-    const uint32_t rowlist = smem_addr(smem_raw + lay.off_aux);                       // [KNN_CAPB][KNN_ROWS] u16
-    int* scount = reinterpret_cast<int*>(smem_raw + lay.off_aux + KNN_ROWS * KNN_CAPB * 2);   // [KNN_THREADS]: listed, or -1 = overflow
-    const uint32_t bufbase = smem_addr(smem_raw + lay.off_buf);
-    const uint32_t bufp = bufbase + 2u * tid;                                          // slot i at bufp + i * KNN_THREADS * 2
+    const uint32_t bufp = smem_addr(smem_raw + lay.off_buf) + 2u * tid;                // slot i at bufp + i * KNN_THREADS * 2
     constexpr uint32_t SLOT = KNN_THREADS * 2;
 
-    const int r0 = blockIdx.x * KNN_ROWS + warp * KNN_G;
-    if (r0 < N) {
-        // ---- scan: 8 rows per warp, four lanes per row ------------------------------------------------------------
-        const int rr = lane & (KNN_G - 1), qd = lane >> 3;
-        const int r = r0 + rr;
-        const float x = spf[(r >> 1) * 8 + (r & 1)], y = spf[(r >> 1) * 8 + (r & 1) + 2], z = spf[(r >> 1) * 8 + (r & 1) + 4],
-                    s = spf[(r >> 1) * 8 + (r & 1) + 6];
-        const float2 q2x = make_float2(-2.f * x, -2.f * x), q2y = make_float2(-2.f * y, -2.f * y),
-                     q2z = make_float2(-2.f * z, -2.f * z), qs2 = make_float2(s, s);
-        const float Ui = U[(size_t)b * N + r];
-        if (qd == 0) {
-            srow[2 * rr] = make_float4(x, y, z, Ui);
-            srow[2 * rr + 1] = make_float4(s, 0.f, 0.f, 0.f);
+    // ---- scan: 8 rows per warp, four lanes per row ----------------------------------------------------------------
+    const int rr = lane & (KNN_G - 1), qd = lane >> 3;
+    const int r = r0 + rr;
+    const float x = spf[(r >> 1) * 8 + (r & 1)], y = spf[(r >> 1) * 8 + (r & 1) + 2], z = spf[(r >> 1) * 8 + (r & 1) + 4],
+                s = spf[(r >> 1) * 8 + (r & 1) + 6];
+    const float2 q2x = make_float2(-2.f * x, -2.f * x), q2y = make_float2(-2.f * y, -2.f * y),
+                 q2z = make_float2(-2.f * z, -2.f * z), qs2 = make_float2(s, s);
+    const size_t row = (size_t)b * N + r;
+    const float Ui = U[row];
+    if (qd == 0) {
+        srow[2 * rr] = make_float4(x, y, z, Ui);
+        srow[2 * rr + 1] = make_float4(s, 0.f, 0.f, 0.f);
+    }
+    float smax = 0.f;
+    for (int t = 0; t < ntile; ++t) smax = fmaxf(smax, stlo[t].w);
+    // scan filter: a candidate whose canonical d is <= U_i has d' <= U_i + 1e-6 (s_i + s_j); the canonical arithmetic
+    // itself is spent (knn_finalize_kernel) only on the handful that pass
+    float Uf = Ui + 2e-6f * (s + smax);
+    uint32_t wp = bufp;
+    const uint32_t wlim = bufp + (uint32_t)(KNN_CAPL - KNN_BLK) * SLOT;
+    bool over = false;
+    const int b0 = r0 >> 5;
+    __syncwarp();
+    knn_block_masks<true>(srow, slo, shi, stlo, sthi, nblk, ntile, b0, prune != 0, lane, bmask);
+    // ascending position order within a lane: b0-1, b0, b0+1 are part of the sweep
+#pragma unroll 1
+    for (int br = 0; br * 32 < nblk; ++br) {
+        uint32_t m = bmask[br];
+#pragma unroll
+        for (int t = -1; t <= 1; ++t) {
+            const int nb = b0 + t;
+            if (nb >= 0 && nb < nblk && (nb >> 5) == br) m |= 1u << (nb & 31);
         }
-        float smax = 0.f;
-        for (int t = 0; t < ntile; ++t) smax = fmaxf(smax, stlo[t].w);
-        // scan filter: a candidate whose canonical d is <= U_i has d' <= U_i + 1e-6 (s_i + s_j); the canonical arithmetic
-        // itself is spent only on the handful that pass
-        float Uf = Ui + 2e-6f * (s + smax);
-        uint32_t wp = bufp;
-        const uint32_t wlim = bufp + (uint32_t)(KNN_CAPL - KNN_BLK) * SLOT;
-        bool over = false;
-        auto scan_block = [&](int blk) {
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            const int blk = br * 32 + bit;
             const float4* pp = sp + blk * 32 + 2 * qd;
             const uint32_t j = (uint32_t)(blk * 32 + 2 * qd);
 #pragma unroll
@@ -639,68 +643,59 @@ knn_collect_kernel(const float4* __restrict__ sorted, const float4* __restrict__
                 Uf = -INFINITY;
                 wp = bufp;
             }
-        };
-        const int b0 = r0 >> 5;
-        __syncwarp();
-        knn_block_masks<true>(srow, slo, shi, stlo, sthi, nblk, ntile, b0, prune != 0, lane, bmask);
-        // ascending position order within a lane: b0-1, b0, b0+1 are part of the sweep
-#pragma unroll 1
-        for (int br = 0; br * 32 < nblk; ++br) {
-            uint32_t m = bmask[br];
-#pragma unroll
-            for (int t = -1; t <= 1; ++t) {
-                const int nb = b0 + t;
-                if (nb >= 0 && nb < nblk && (nb >> 5) == br) m |= 1u << (nb & 31);
-            }
-            while (m) {
-                const int bit = __ffs(m) - 1;
-                m &= m - 1;
-                scan_block(br * 32 + bit);
-            }
         }
-        scount[tid] = over ? -1 : (int)((wp - bufp) / SLOT);
     }
-    // ---- thread per row: exact 20th distance among the listed candidates, then the thresholded set --------------------
-    // Four warps (32 rows) form a group with its own named barrier: the group's first warp finalises the 32 rows as soon as
-    // its three partners are done scanning, while the other groups and the SM's second CTA keep scanning.
-    const int group = warp >> 2;
-    asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
-    if (warp & 3) return;
-    const int rl = group * 32 + lane;                           // row within the CTA
-    const int r = blockIdx.x * KNN_ROWS + rl;
-    if (r >= N) return;                                         // whole warps: N % 32 == 0
-    const size_t row = (size_t)b * N + r;
-    const float x = spf[(r >> 1) * 8 + (r & 1)], y = spf[(r >> 1) * 8 + (r & 1) + 2], z = spf[(r >> 1) * 8 + (r & 1) + 4],
-                s = spf[(r >> 1) * 8 + (r & 1) + 6];
-    // gather the four lanes' lists (quarter-major, slot order: a fixed order) into the row's contiguous list
-    const uint32_t mylist = rowlist + 2u * rl;                  // slot i at mylist + i * KNN_ROWS * 2
-    constexpr uint32_t RSLOT = KNN_ROWS * 2;
-    int nc = 0;
-    bool over = false;
+    // ---- the row's list = its four lanes' lists, quarter-major (a fixed order) ---------------------------------------
+    const int n = (int)((wp - bufp) / SLOT);
+    int off = 0, tot = n;
+    bool any_over = over;
     {
-        const int w = rl >> 3, l0 = rl & 7;
-#pragma unroll 1
-        for (int qd = 0; qd < 4; ++qd) {
-            const int src = w * 32 + l0 + 8 * qd;
-            const int n = scount[src];
-            if (n < 0) over = true;
-            for (int i = 0; i < n; ++i) {
-                const uint32_t j = lds_u16(bufbase + 2u * src + (uint32_t)i * SLOT);
-                if (nc < KNN_CAPB) sts_u16(mylist + (uint32_t)nc * RSLOT, j);
-                ++nc;
-            }
-        }
+        const int n1 = __shfl_xor_sync(FULL, n, 8);          // quarter qd ^ 1
+        const int s01 = n + n1;                              // pair sum
+        const int n23 = __shfl_xor_sync(FULL, s01, 16);      // the other pair's sum
+        off = ((qd & 1) ? n1 : 0) + ((qd & 2) ? n23 : 0);
+        tot = s01 + n23;
+        any_over |= __shfl_xor_sync(FULL, (int)over, 8) != 0;
+        any_over |= __shfl_xor_sync(FULL, (int)any_over, 16) != 0;
     }
-    const bool ok = !over && (nc >= KNN_K) && (nc <= KNN_CAPB);
+    const bool fits = !any_over && tot <= KNN_CAPB;
+    const int nmax = __reduce_max_sync(FULL, fits ? n : 0);
+    uint16_t* gl = glist + row * KNN_CAPB + off;
+#pragma unroll 1
+    for (int i = 0; i < nmax; ++i)
+        if (fits && i < n) gl[i] = (uint16_t)lds_u16(bufp + i * SLOT);
+    if (qd == 0) gcount[row] = fits ? tot : -1;
+}
+
+// ---- pass B, second half: thread per row (a separate launch: the dependent gather / min-max chains need the latency hiding
+// of a full SM of warps, which the scan kernel's two big-shared-memory CTAs cannot give) -- the exact 20th distance among the
+// listed candidates in the CANONICAL arithmetic, then the thresholded set
+template <int ARITH>
+__global__ void __launch_bounds__(128)
+knn_finalize_kernel(const float4* __restrict__ sorted, const uint16_t* __restrict__ glist, const int* __restrict__ gcount,
+                    int N, long long rows, uint32_t* __restrict__ tie_all, uint16_t* __restrict__ nbr, float* __restrict__ kthd,
+                    int* __restrict__ cnt, int* __restrict__ slow) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;                                   // whole warps: rows % 32 == 0
+    const int b = (int)(row / N), r = (int)(row - (long long)b * N);
+    const float4* pts = sorted + (size_t)b * N;
+    const float4 q = __ldg(pts + r);
+    const uint16_t* gl = glist + row * KNN_CAPB;
+    const int nc = gcount[row];
+    const bool ok = (nc >= KNN_K) && (nc <= KNN_CAPB);
     const int n = ok ? nc : 0;
     const int nmax = __reduce_max_sync(FULL, n);
+    auto dist_of = [&](int j) {
+        const float4 p = __ldg(pts + j);
+        return canon_dist<ARITH>(q.x, q.y, q.z, q.w, p.x, p.y, p.z, p.w);
+    };
     float L[KNN_K];
 #pragma unroll
     for (int i = 0; i < KNN_K; ++i) L[i] = INFINITY;
 #pragma unroll 1
     for (int i = 0; i < nmax; i += 2) {
-        const float c1 = (i < n) ? knn_point_dist<ARITH>(spf, lds_u16(mylist + i * RSLOT), x, y, z, s) : INFINITY;
-        const float c2 = (i + 1 < n) ? knn_point_dist<ARITH>(spf, lds_u16(mylist + (i + 1) * RSLOT), x, y, z, s) : INFINITY;
+        const float c1 = (i < n) ? dist_of(gl[i]) : INFINITY;
+        const float c2 = (i + 1 < n) ? dist_of(gl[i + 1]) : INFINITY;
         merge2<KNN_K>(L, c1, c2);
     }
     const float kth = L[KNN_K - 1];
@@ -709,8 +704,8 @@ knn_collect_kernel(const float4* __restrict__ sorted, const float4* __restrict__
 #pragma unroll 1
     for (int i = 0; i < nmax; ++i) {
         if (i < n) {
-            const int j = (int)lds_u16(mylist + i * RSLOT);
-            const float d = knn_point_dist<ARITH>(spf, j, x, y, z, s);
+            const int j = gl[i];
+            const float d = dist_of(j);
             if (d <= kth) {
                 if (total < KNN_K) {
                     const bool outside = (j >> 7) != (r >> 7);
@@ -1027,7 +1022,7 @@ int knn_build(const float* xyz, int B, int N, int arith, bool prune, const KnnSt
     }
     EPC_CHECK_ARG(cap >= 16, "kNN: N=%d leaves no shared memory for the candidate buffers", N);
     const int len = env_int("EPC_KNN_LEN", 8);
-    const size_t smemA = (size_t)knn_layout(N, cap * 4, 0).bytes, smemB = (size_t)knn_layout(N, KNN_CAPL * 2, KNN_AUX_B).bytes;
+    const size_t smemA = (size_t)knn_layout(N, cap * 4, 0).bytes, smemB = (size_t)knn_layout(N, KNN_CAPL * 2, 0).bytes;
     EPC_CHECK_ARG(smemB <= (size_t)budget1, "kNN: N=%d leaves no shared memory for the candidate lists", N);
     const size_t smemC = (size_t)KNN_SLOW_WARPS * N * 6;
     static PerDeviceSize a_sort, a_A5, a_A6, a_A8, a_B0, a_B1, a_C0, a_C1;
@@ -1056,12 +1051,18 @@ int knn_build(const float* xyz, int B, int N, int arith, bool prune, const KnnSt
         knn_bound_kernel<8><<<grid, KNN_THREADS, smemA, st>>>(s.sorted, s.aabb, N, cap, prune ? 1 : 0, s.U);
     EPC_LAUNCH_CHECK();
     const int slow_ctas = 2 * sm_count_knn();
+    const long long rows_all = (long long)B * N;
+    const unsigned fin_grid = (unsigned)((rows_all + 127) / 128);
     if (arith == EPC_KNN_ARITH_MULADD) {
-        knn_collect_kernel<0><<<grid, KNN_THREADS, smemB, st>>>(s.sorted, s.aabb, s.U, N, prune ? 1 : 0, s.tie, s.nbr, s.kthd, s.cnt, s.slow);
+        knn_collect_kernel<0><<<grid, KNN_THREADS, smemB, st>>>(s.sorted, s.aabb, s.U, N, prune ? 1 : 0, s.glist, s.gcount);
+        EPC_LAUNCH_CHECK();
+        knn_finalize_kernel<0><<<fin_grid, 128, 0, st>>>(s.sorted, s.glist, s.gcount, N, rows_all, s.tie, s.nbr, s.kthd, s.cnt, s.slow);
         EPC_LAUNCH_CHECK();
         knn_slow_kernel<0><<<slow_ctas, KNN_SLOW_WARPS * 32, smemC, st>>>(s.sorted, s.U, N, s.slow, s.tie, s.nbr, s.kthd, s.cnt);
     } else {
-        knn_collect_kernel<1><<<grid, KNN_THREADS, smemB, st>>>(s.sorted, s.aabb, s.U, N, prune ? 1 : 0, s.tie, s.nbr, s.kthd, s.cnt, s.slow);
+        knn_collect_kernel<1><<<grid, KNN_THREADS, smemB, st>>>(s.sorted, s.aabb, s.U, N, prune ? 1 : 0, s.glist, s.gcount);
+        EPC_LAUNCH_CHECK();
+        knn_finalize_kernel<1><<<fin_grid, 128, 0, st>>>(s.sorted, s.glist, s.gcount, N, rows_all, s.tie, s.nbr, s.kthd, s.cnt, s.slow);
         EPC_LAUNCH_CHECK();
         knn_slow_kernel<1><<<slow_ctas, KNN_SLOW_WARPS * 32, smemC, st>>>(s.sorted, s.U, N, s.slow, s.tie, s.nbr, s.kthd, s.cnt);
     }
@@ -1081,7 +1082,8 @@ int knn_build(const float* xyz, int B, int N, int arith, bool prune, const KnnSt
 size_t knn_state_bytes(int B, int N) {
     const size_t R = (size_t)B * N;
     return align_up((size_t)B * TIE_WORDS * sizeof(uint32_t)) + align_up(R * sizeof(float4)) + align_up(R * sizeof(int)) + align_up(R * sizeof(uint16_t)) + align_up(R * KNN_K * sizeof(uint16_t)) +
-           align_up(R * sizeof(float)) + align_up(R * sizeof(int)) + align_up(R / 16 * sizeof(float4)) + align_up(R * sizeof(float)) + align_up((R + 1) * sizeof(int));
+           align_up(R * sizeof(float)) + align_up(R * sizeof(int)) + align_up(R / 16 * sizeof(float4)) + align_up(R * sizeof(float)) + align_up((R + 1) * sizeof(int)) +
+           align_up(R * KNN_CAPB * sizeof(uint16_t)) + align_up(R * sizeof(int));
 }
 
 KnnState knn_state_carve(Arena& ar, int B, int N) {
@@ -1097,6 +1099,8 @@ KnnState knn_state_carve(Arena& ar, int B, int N) {
     s.aabb = ar.take<float4>(R / 16);      // [B][2][N/32]
     s.U = ar.take<float>(R);
     s.slow = ar.take<int>(R + 1);
+    s.glist = ar.take<uint16_t>(R * KNN_CAPB);
+    s.gcount = ar.take<int>(R);
     return s;
 }
 

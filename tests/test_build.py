@@ -71,11 +71,11 @@ def test_sass_targets_sm100a_and_muladd_not_contracted(built_lib):
     archs = set(re.findall(r"sm_\d+a?", elf))
     assert archs == {"sm_100a"}, archs
     stats = sass_stats(lib_mod.LIB_PATH)
-    # The canonical distance (common.cuh canon_dist<ARITH>) is evaluated where exactness matters: knn_collect_kernel (exact
+    # The canonical distance (common.cuh canon_dist<ARITH>) is evaluated where exactness matters: knn_finalize_kernel (exact
     # 20th distance + thresholded set) and knn_slow_kernel (mass ties).  Everything else in the two instantiations is
     # identical, so the instruction-count DIFFERENCE isolates it: per call site MULADD = 3 FMUL + 2 FADD + FFMA + FADD,
     # FMA = FMUL + 3 FFMA + FADD.  A contraction of the MULADD products into FFMAs would close the gap.
-    for kern in ("knn_collect_kernel", "knn_slow_kernel"):
+    for kern in ("knn_finalize_kernel", "knn_slow_kernel", "knn_public_kernel"):
         mul = [v for k, v in stats.items() if kern + "ILi0E" in k]
         fma = [v for k, v in stats.items() if kern + "ILi1E" in k]
         assert len(mul) == 1 and len(fma) == 1, kern

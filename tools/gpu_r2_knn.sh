@@ -13,8 +13,7 @@ for k,v in sorted(d['stages'].items(), key=lambda kv:-kv[1]['share'])[:3]: print
     tail -2 gpurun_out/bench_$1.err
 }
 run_bench hilbert
-EPC_SORT_CURVE=0 run_bench morton
-for C in 1 0; do
+for C in 1; do
 EPC_SORT_CURVE=$C timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -k regex:"knn|proxy_block_kernel" -c 16 --csv --log-file gpurun_out/knn_launches_c$C.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-retrieval --no-parity > /dev/null 2>&1
 python - <<PY
 import csv
