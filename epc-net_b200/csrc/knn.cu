@@ -261,10 +261,10 @@ constexpr int KNN_BLK = 8;            // candidates a lane takes from one 32-poi
 constexpr int KNN_CAPL = 24;          // pass B: listed candidates per lane (u16 each)
 constexpr int KNN_CAPB = 40;          // pass B: listed candidates per row
 constexpr int KNN_MAXMASK = 8;        // 32-block masks: N <= 8192
-constexpr int KNN_WROW = 2 * KNN_G + KNN_MAXMASK / 4;      // float4 per warp in the row/mask area
+constexpr int KNN_WROW = 2 * KNN_G + KNN_MAXMASK / 4 + 4;  // float4 per warp: 8 rows x 2, the block masks, the live-tile list (64 B)
 
 struct KnnLayout {
-    int off_lo, off_hi, off_tlo, off_thi, off_row, off_aux, off_buf;
+    int off_lo, off_hi, off_tlo, off_thi, off_misc, off_row, off_aux, off_buf;
     int bytes;
 };
 // aux_bytes: pass B's per-row lists and per-lane counts
@@ -276,6 +276,7 @@ __host__ __device__ inline KnnLayout knn_layout(int N, int buf_bytes_per_lane, i
     L.off_hi = o;  o += nblk * 16;    //              (hi.xyz, -)
     L.off_tlo = o; o += ntile * 16;   // 128-point tile boxes
     L.off_thi = o; o += ntile * 16;
+    L.off_misc = o; o += 16;          // max |p|^2 over the cloud
     L.off_row = o; o += (KNN_THREADS / 32) * KNN_WROW * 16;   // per warp: 8 rows x {(x, y, z, threshold), (|p|^2,-,-,-)} for the
                                                               // lane-parallel box tests, then the warp's block masks
     L.off_aux = o; o += aux_bytes;
@@ -312,6 +313,12 @@ __device__ __forceinline__ void knn_stage(const float4* __restrict__ pts, const 
         }
         stlo[t] = lo;
         sthi[t] = hi;
+    }
+    if (threadIdx.x < 32) {           // max |p|^2 over the cloud (the slack of the cheap arithmetic)
+        float m = 0.f;
+        for (int i = threadIdx.x; i < nblk; i += 32) m = fmaxf(m, slo[i].w);
+        m = warp_max(m);
+        if (threadIdx.x == 0) *reinterpret_cast<float*>(smem + lay.off_misc) = m;
     }
     __syncthreads();
 }
@@ -363,13 +370,15 @@ __device__ __forceinline__ void merge2(float (&L)[LEN], float c1, float c2) {
 }
 
 // Lane-parallel box tests of a warp's 8 rows: which 128-point tiles, then which 32-point blocks can hold a candidate below
-// the rows' thresholds.  RIGOROUS: the bound of pass B (canonical arithmetic); otherwise the plain box distance (pass A, where
-// pruning only affects how tight the bound gets).  srow: the warp's 8 x {(x,y,z,threshold), (|p|^2,...)}.
+// the rows' thresholds.  Tiles are tested against the GROUP (the 8 rows' bounding box and their largest threshold: one test
+// per lane instead of eight); the blocks of the surviving tiles are enumerated densely over the lanes and tested per row.
+// RIGOROUS: the bound of pass B (canonical arithmetic); otherwise the plain box distance (pass A, where pruning only affects
+// how tight the bound gets).  srow: the warp's 8 x {(x,y,z,threshold), (|p|^2,...)}; bmask / tlist: the warp's shared scratch.
 template <bool RIGOROUS>
 __device__ __forceinline__ void knn_block_masks(const float4* __restrict__ srow, const float4* __restrict__ slo,
                                                 const float4* __restrict__ shi, const float4* __restrict__ stlo,
                                                 const float4* __restrict__ sthi, int nblk, int ntile, int b0, bool prune,
-                                                int lane, uint32_t* __restrict__ bmask /*shared, per warp*/) {
+                                                int lane, uint32_t* __restrict__ bmask, unsigned char* __restrict__ tlist) {
     auto rows_need = [&](const float4 lo, const float4 hi) {
         bool need = false;
 #pragma unroll
@@ -382,30 +391,51 @@ __device__ __forceinline__ void knn_block_masks(const float4* __restrict__ srow,
         }
         return need;
     };
-    uint32_t tmask[(KNN_MAXMASK * 32 / 4 + 31) / 32];
+    // the group: bounding box of the 8 rows, largest threshold, largest |p|^2
+    float gx0, gy0, gz0, gx1, gy1, gz1, gthr, gs;
+    {
+        const float4 q = srow[2 * (lane & (KNN_G - 1))];
+        gx0 = gx1 = q.x; gy0 = gy1 = q.y; gz0 = gz1 = q.z; gthr = q.w;
+        gs = srow[2 * (lane & (KNN_G - 1)) + 1].x;
 #pragma unroll
-    for (int tr = 0; tr < (int)(sizeof(tmask) / 4); ++tr) {
-        const int t = tr * 32 + lane;
-        bool need = false;
-        if (tr * 32 < ntile) {
-            if (t < ntile) need = !prune || rows_need(stlo[t], sthi[t]);
-            tmask[tr] = __ballot_sync(FULL, need);
-        } else {
-            tmask[tr] = 0;
+        for (int o = 1; o < KNN_G; o <<= 1) {
+            gx0 = fminf(gx0, __shfl_xor_sync(FULL, gx0, o)); gx1 = fmaxf(gx1, __shfl_xor_sync(FULL, gx1, o));
+            gy0 = fminf(gy0, __shfl_xor_sync(FULL, gy0, o)); gy1 = fmaxf(gy1, __shfl_xor_sync(FULL, gy1, o));
+            gz0 = fminf(gz0, __shfl_xor_sync(FULL, gz0, o)); gz1 = fmaxf(gz1, __shfl_xor_sync(FULL, gz1, o));
+            gthr = fmaxf(gthr, __shfl_xor_sync(FULL, gthr, o));
+            gs = fmaxf(gs, __shfl_xor_sync(FULL, gs, o));
         }
     }
+    if (lane < KNN_MAXMASK) bmask[lane] = 0;
+    int nalive = 0;
 #pragma unroll 1
-    for (int br = 0; br * 32 < nblk; ++br) {
-        const int blk = br * 32 + lane, t = blk >> 2;
-        const uint32_t tm = (t >> 5) ? tmask[1] : tmask[0];
-        const bool alive = (blk < nblk) && ((tm >> (t & 31)) & 1u) && blk != b0 && blk != b0 + 1 && blk != b0 - 1;
-        uint32_t m = 0;
-        if (__any_sync(FULL, alive)) {
-            bool need = false;
-            if (alive) need = !prune || rows_need(slo[blk], shi[blk]);
-            m = __ballot_sync(FULL, need);
+    for (int t0 = 0; t0 < ntile; t0 += 32) {
+        const int t = t0 + lane;
+        bool alive = false;
+        if (t < ntile) {
+            const float4 lo = stlo[t], hi = sthi[t];
+            // box-to-box distance: every row's point lies in the group box and no row's threshold exceeds gthr
+            const float dx = fmaxf(fmaxf(lo.x - gx1, gx0 - hi.x), 0.f);
+            const float dy = fmaxf(fmaxf(lo.y - gy1, gy0 - hi.y), 0.f);
+            const float dz = fmaxf(fmaxf(lo.z - gz1, gz0 - hi.z), 0.f);
+            const float lb = dx * dx + dy * dy + dz * dz;
+            const float bound = RIGOROUS ? lb * (1.0f - 1e-6f) - 1e-6f * (gs + lo.w) : lb;
+            alive = !prune || !(bound > gthr);
         }
-        if (lane == 0) bmask[br] = m;
+        const unsigned m = __ballot_sync(FULL, alive);
+        if (alive) tlist[nalive + __popc(m & ((1u << lane) - 1u))] = (unsigned char)t;
+        nalive += __popc(m);
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int e0 = 0; e0 < 4 * nalive; e0 += 32) {
+        const int e = e0 + lane;
+        if (e < 4 * nalive) {
+            const int blk = 4 * (int)tlist[e >> 2] + (e & 3);
+            if (blk < nblk && blk != b0 && blk != b0 + 1 && blk != b0 - 1) {
+                if (!prune || rows_need(slo[blk], shi[blk])) atomicOr(&bmask[blk >> 5], 1u << (blk & 31));
+            }
+        }
     }
     __syncwarp();
 }
@@ -433,6 +463,7 @@ knn_bound_kernel(const float4* __restrict__ sorted, const float4* __restrict__ a
     const float4* sthi = reinterpret_cast<const float4*>(smem_raw + lay.off_thi);
     float4* srow = reinterpret_cast<float4*>(smem_raw + lay.off_row) + warp * KNN_WROW;
     uint32_t* bmask = reinterpret_cast<uint32_t*>(srow + 2 * KNN_G);
+    unsigned char* tlist = reinterpret_cast<unsigned char*>(srow + 2 * KNN_G + KNN_MAXMASK / 4);
     const uint32_t bufp = smem_addr(smem_raw + lay.off_buf) + 4u * tid;      // slot i at bufp + i * KNN_THREADS * 4
     constexpr uint32_t SLOT = KNN_THREADS * 4;
 
@@ -501,7 +532,7 @@ knn_bound_kernel(const float4* __restrict__ sorted, const float4* __restrict__ a
         if (blk >= 0 && blk < nblk) scan_block(blk, t != 1);
     }
     __syncwarp();
-    knn_block_masks<false>(srow, slo, shi, stlo, sthi, nblk, ntile, b0, prune != 0, lane, bmask);
+    knn_block_masks<false>(srow, slo, shi, stlo, sthi, nblk, ntile, b0, prune != 0, lane, bmask, tlist);
 #pragma unroll 1
     for (int br = 0; br * 32 < nblk; ++br) {
         uint32_t m = bmask[br];
@@ -551,11 +582,7 @@ knn_bound_kernel(const float4* __restrict__ sorted, const float4* __restrict__ a
     }
     // d' is within 1e-6 (s_i + s_j) of the canonical d (either arithmetic): the slack keeps U a valid upper bound of the
     // canonical 20th distance
-    if (qd == 0) {
-        float smax = 0.f;
-        for (int t = 0; t < ntile; ++t) smax = fmaxf(smax, stlo[t].w);
-        U[(size_t)b * N + r] = thr + 2e-6f * (s + smax);
-    }
+    if (qd == 0) U[(size_t)b * N + r] = thr + 2e-6f * (s + *reinterpret_cast<const float*>(smem_raw + lay.off_misc));
 }
 
 // ---- pass B ---------------------------------------------------------------------------------------------------
@@ -584,6 +611,7 @@ knn_collect_kernel(const float4* __restrict__ sorted, const float4* __restrict__
     const float4* sthi = reinterpret_cast<const float4*>(smem_raw + lay.off_thi);
     float4* srow = reinterpret_cast<float4*>(smem_raw + lay.off_row) + warp * KNN_WROW;
     uint32_t* bmask = reinterpret_cast<uint32_t*>(srow + 2 * KNN_G);
+    unsigned char* tlist = reinterpret_cast<unsigned char*>(srow + 2 * KNN_G + KNN_MAXMASK / 4);
     const uint32_t bufp = smem_addr(smem_raw + lay.off_buf) + 2u * tid;                // slot i at bufp + i * KNN_THREADS * 2
     constexpr uint32_t SLOT = KNN_THREADS * 2;
 
@@ -600,8 +628,7 @@ knn_collect_kernel(const float4* __restrict__ sorted, const float4* __restrict__
         srow[2 * rr] = make_float4(x, y, z, Ui);
         srow[2 * rr + 1] = make_float4(s, 0.f, 0.f, 0.f);
     }
-    float smax = 0.f;
-    for (int t = 0; t < ntile; ++t) smax = fmaxf(smax, stlo[t].w);
+    const float smax = *reinterpret_cast<const float*>(smem_raw + lay.off_misc);
     // scan filter: a candidate whose canonical d is <= U_i has d' <= U_i + 1e-6 (s_i + s_j); the canonical arithmetic
     // itself is spent (knn_finalize_kernel) only on the handful that pass
     float Uf = Ui + 2e-6f * (s + smax);
@@ -610,7 +637,7 @@ knn_collect_kernel(const float4* __restrict__ sorted, const float4* __restrict__
     bool over = false;
     const int b0 = r0 >> 5;
     __syncwarp();
-    knn_block_masks<true>(srow, slo, shi, stlo, sthi, nblk, ntile, b0, prune != 0, lane, bmask);
+    knn_block_masks<true>(srow, slo, shi, stlo, sthi, nblk, ntile, b0, prune != 0, lane, bmask, tlist);
     // ascending position order within a lane: b0-1, b0, b0+1 are part of the sweep
 #pragma unroll 1
     for (int br = 0; br * 32 < nblk; ++br) {
@@ -670,52 +697,93 @@ knn_collect_kernel(const float4* __restrict__ sorted, const float4* __restrict__
 // ---- pass B, second half: thread per row (a separate launch: the dependent gather / min-max chains need the latency hiding
 // of a full SM of warps, which the scan kernel's two big-shared-memory CTAs cannot give) -- the exact 20th distance among the
 // listed candidates in the CANONICAL arithmetic, then the thresholded set
+constexpr int KNN_FIN_THREADS = 128;
 template <int ARITH>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(KNN_FIN_THREADS)
 knn_finalize_kernel(const float4* __restrict__ sorted, const uint16_t* __restrict__ glist, const int* __restrict__ gcount,
                     int N, long long rows, uint32_t* __restrict__ tie_all, uint16_t* __restrict__ nbr, float* __restrict__ kthd,
                     int* __restrict__ cnt, int* __restrict__ slow) {
-    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint16_t sj[KNN_CAPB][KNN_FIN_THREADS];         // the row's candidates, [slot][thread]: conflict-free columns
+    __shared__ float sd[KNN_CAPB][KNN_FIN_THREADS];            // ... and their canonical distances
+    const int tid = threadIdx.x;
+    const long long row = (long long)blockIdx.x * KNN_FIN_THREADS + tid;
     if (row >= rows) return;                                   // whole warps: rows % 32 == 0
     const int b = (int)(row / N), r = (int)(row - (long long)b * N);
     const float4* pts = sorted + (size_t)b * N;
     const float4 q = __ldg(pts + r);
-    const uint16_t* gl = glist + row * KNN_CAPB;
     const int nc = gcount[row];
     const bool ok = (nc >= KNN_K) && (nc <= KNN_CAPB);
     const int n = ok ? nc : 0;
     const int nmax = __reduce_max_sync(FULL, n);
-    auto dist_of = [&](int j) {
-        const float4 p = __ldg(pts + j);
-        return canon_dist<ARITH>(q.x, q.y, q.z, q.w, p.x, p.y, p.z, p.w);
-    };
-    float L[KNN_K];
+    // the list (80 B per row, 16-byte aligned) -> shared memory; then every distance, independent gathers in flight together
+    {
+        const uint4* g4 = reinterpret_cast<const uint4*>(glist + row * KNN_CAPB);
 #pragma unroll
-    for (int i = 0; i < KNN_K; ++i) L[i] = INFINITY;
-#pragma unroll 1
-    for (int i = 0; i < nmax; i += 2) {
-        const float c1 = (i < n) ? dist_of(gl[i]) : INFINITY;
-        const float c2 = (i + 1 < n) ? dist_of(gl[i + 1]) : INFINITY;
-        merge2<KNN_K>(L, c1, c2);
+        for (int k = 0; k < KNN_CAPB / 8; ++k) {
+            if (8 * k < nmax) {
+                const uint4 v = __ldg(g4 + k);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    sj[8 * k + 2 * e][tid] = (uint16_t)(w[e] & 0xffffu);
+                    sj[8 * k + 2 * e + 1][tid] = (uint16_t)(w[e] >> 16);
+                }
+            }
+        }
     }
-    const float kth = L[KNN_K - 1];
+#pragma unroll 4
+    for (int i = 0; i < nmax; ++i) {
+        if (i < n) {
+            const float4 p = __ldg(pts + sj[i][tid]);
+            sd[i][tid] = canon_dist<ARITH>(q.x, q.y, q.z, q.w, p.x, p.y, p.z, p.w);
+        }
+    }
+    // the 20th smallest of n values is the (n-19)-th largest: with nmax - 19 <= 8 (no mass ties in this warp) an 8-entry
+    // descending list does it at 40 % of the min/max work of the 20-entry ascending one
+    float kth;
+    if (nmax - (KNN_K - 1) <= 8) {
+        float D[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) D[i] = -INFINITY;
+#pragma unroll 1
+        for (int i = 0; i < nmax; i += 2) {
+            const float c1 = (i < n) ? sd[i][tid] : -INFINITY;
+            const float c2 = (i + 1 < n) ? sd[i + 1][tid] : -INFINITY;
+            const float hi = fmaxf(c1, c2), lo = fminf(c1, c2);
+#pragma unroll
+            for (int k = 7; k >= 2; --k) D[k] = fmaxf(fmaxf(D[k], fminf(D[k - 1], hi)), fminf(D[k - 2], lo));
+            D[1] = fmaxf(fmaxf(D[1], fminf(D[0], hi)), lo);
+            D[0] = fmaxf(D[0], hi);
+        }
+        kth = D[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) kth = (n - KNN_K == k) ? D[k] : kth;
+    } else {
+        float L[KNN_K];
+#pragma unroll
+        for (int i = 0; i < KNN_K; ++i) L[i] = INFINITY;
+#pragma unroll 1
+        for (int i = 0; i < nmax; i += 2) {
+            const float c1 = (i < n) ? sd[i][tid] : INFINITY;
+            const float c2 = (i + 1 < n) ? sd[i + 1][tid] : INFINITY;
+            merge2<KNN_K>(L, c1, c2);
+        }
+        kth = L[KNN_K - 1];
+    }
     int total = 0, n_out = 0, n_in = 0;
     uint32_t* tie = tie_all + (size_t)b * TIE_WORDS;
 #pragma unroll 1
     for (int i = 0; i < nmax; ++i) {
-        if (i < n) {
-            const int j = gl[i];
-            const float d = dist_of(j);
-            if (d <= kth) {
-                if (total < KNN_K) {
-                    const bool outside = (j >> 7) != (r >> 7);
-                    const int pos = outside ? n_out++ : (KNN_K - 1) - n_in++;
-                    nbr[row * KNN_K + pos] = (uint16_t)j;
-                } else {
-                    tie_append(tie, (uint32_t)r, (uint32_t)j, kth);
-                }
-                ++total;
+        if (i < n && sd[i][tid] <= kth) {
+            const int j = sj[i][tid];
+            if (total < KNN_K) {
+                const bool outside = (j >> 7) != (r >> 7);
+                const int pos = outside ? n_out++ : (KNN_K - 1) - n_in++;
+                nbr[row * KNN_K + pos] = (uint16_t)j;
+            } else {
+                tie_append(tie, (uint32_t)r, (uint32_t)j, kth);
             }
+            ++total;
         }
     }
     if (ok) {
@@ -1052,17 +1120,17 @@ int knn_build(const float* xyz, int B, int N, int arith, bool prune, const KnnSt
     EPC_LAUNCH_CHECK();
     const int slow_ctas = 2 * sm_count_knn();
     const long long rows_all = (long long)B * N;
-    const unsigned fin_grid = (unsigned)((rows_all + 127) / 128);
+    const unsigned fin_grid = (unsigned)((rows_all + KNN_FIN_THREADS - 1) / KNN_FIN_THREADS);
     if (arith == EPC_KNN_ARITH_MULADD) {
         knn_collect_kernel<0><<<grid, KNN_THREADS, smemB, st>>>(s.sorted, s.aabb, s.U, N, prune ? 1 : 0, s.glist, s.gcount);
         EPC_LAUNCH_CHECK();
-        knn_finalize_kernel<0><<<fin_grid, 128, 0, st>>>(s.sorted, s.glist, s.gcount, N, rows_all, s.tie, s.nbr, s.kthd, s.cnt, s.slow);
+        knn_finalize_kernel<0><<<fin_grid, KNN_FIN_THREADS, 0, st>>>(s.sorted, s.glist, s.gcount, N, rows_all, s.tie, s.nbr, s.kthd, s.cnt, s.slow);
         EPC_LAUNCH_CHECK();
         knn_slow_kernel<0><<<slow_ctas, KNN_SLOW_WARPS * 32, smemC, st>>>(s.sorted, s.U, N, s.slow, s.tie, s.nbr, s.kthd, s.cnt);
     } else {
         knn_collect_kernel<1><<<grid, KNN_THREADS, smemB, st>>>(s.sorted, s.aabb, s.U, N, prune ? 1 : 0, s.glist, s.gcount);
         EPC_LAUNCH_CHECK();
-        knn_finalize_kernel<1><<<fin_grid, 128, 0, st>>>(s.sorted, s.glist, s.gcount, N, rows_all, s.tie, s.nbr, s.kthd, s.cnt, s.slow);
+        knn_finalize_kernel<1><<<fin_grid, KNN_FIN_THREADS, 0, st>>>(s.sorted, s.glist, s.gcount, N, rows_all, s.tie, s.nbr, s.kthd, s.cnt, s.slow);
         EPC_LAUNCH_CHECK();
         knn_slow_kernel<1><<<slow_ctas, KNN_SLOW_WARPS * 32, smemC, st>>>(s.sorted, s.U, N, s.slow, s.tie, s.nbr, s.kthd, s.cnt);
     }
