@@ -592,13 +592,15 @@ __device__ __forceinline__ void tie_append(uint32_t* __restrict__ tie, uint32_t 
     if (slot < TIE_CAP) reinterpret_cast<uint2*>(tie + 2)[slot] = make_uint2((row_pos << 16) | j, __float_as_uint(kth));
 }
 
+constexpr int KNN_AUX_B = KNN_ROWS * KNN_CAPB * 2;      // pass B: the CTA's row lists, assembled for coalesced stores
+
 template <int ARITH>
 __global__ void __launch_bounds__(KNN_THREADS, 2)
 knn_collect_kernel(const float4* __restrict__ sorted, const float4* __restrict__ aabb, const float* __restrict__ U, int N,
                    int prune, uint16_t* __restrict__ glist, int* __restrict__ gcount) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nblk = N >> 5, ntile = (nblk + 3) >> 2;
-    const KnnLayout lay = knn_layout(N, KNN_CAPL * 2, 0);
+    const KnnLayout lay = knn_layout(N, KNN_CAPL * 2, KNN_AUX_B);
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     knn_stage(sorted + (size_t)b * N, aabb + (size_t)b * nblk * 2, N, smem_raw, lay);
     const int r0 = blockIdx.x * KNN_ROWS + warp * KNN_G;
@@ -687,10 +689,23 @@ knn_collect_kernel(const float4* __restrict__ sorted, const float4* __restrict__
     }
     const bool fits = !any_over && tot <= KNN_CAPB;
     const int nmax = __reduce_max_sync(FULL, fits ? n : 0);
-    uint16_t* gl = glist + row * KNN_CAPB + off;
+    // the warp's 8 rows x 80 B are contiguous in glist: assemble them in shared memory, then 16-byte coalesced stores
+    // (lane-scattered 2-byte global stores cost a 32-byte sector write each)
+    const uint32_t stg = smem_addr(smem_raw + lay.off_aux) + (uint32_t)warp * (KNN_G * KNN_CAPB * 2);
+    const uint32_t mine = stg + (uint32_t)(rr * KNN_CAPB + off) * 2u;
 #pragma unroll 1
     for (int i = 0; i < nmax; ++i)
-        if (fits && i < n) gl[i] = (uint16_t)lds_u16(bufp + i * SLOT);
+        if (fits && i < n) sts_u16(mine + 2u * i, lds_u16(bufp + i * SLOT));
+    __syncwarp();
+    {
+        uint4* dst = reinterpret_cast<uint4*>(glist + ((size_t)b * N + r0) * KNN_CAPB);
+        constexpr int CH = KNN_G * KNN_CAPB * 2 / 16;           // 40 chunks of 16 B
+        for (int c = lane; c < CH; c += 32) {
+            uint4 v;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(stg + 16u * c) : "memory");
+            dst[c] = v;
+        }
+    }
     if (qd == 0) gcount[row] = fits ? tot : -1;
 }
 
@@ -705,9 +720,12 @@ knn_finalize_kernel(const float4* __restrict__ sorted, const uint16_t* __restric
                     int* __restrict__ cnt, int* __restrict__ slow) {
     __shared__ uint16_t sj[KNN_CAPB][KNN_FIN_THREADS];         // the row's candidates, [slot][thread]: conflict-free columns
     __shared__ float sd[KNN_CAPB][KNN_FIN_THREADS];            // ... and their canonical distances
+    __shared__ __align__(16) uint16_t snbr[KNN_FIN_THREADS * KNN_K];   // the CTA's neighbour rows, written out coalesced
     const int tid = threadIdx.x;
-    const long long row = (long long)blockIdx.x * KNN_FIN_THREADS + tid;
-    if (row >= rows) return;                                   // whole warps: rows % 32 == 0
+    const long long row0 = (long long)blockIdx.x * KNN_FIN_THREADS;
+    const long long row = row0 + tid;
+    const bool live = row < rows;                              // whole warps: rows % 32 == 0
+    if (live) {
     const int b = (int)(row / N), r = (int)(row - (long long)b * N);
     const float4* pts = sorted + (size_t)b * N;
     const float4 q = __ldg(pts + r);
@@ -779,7 +797,7 @@ knn_finalize_kernel(const float4* __restrict__ sorted, const uint16_t* __restric
             if (total < KNN_K) {
                 const bool outside = (j >> 7) != (r >> 7);
                 const int pos = outside ? n_out++ : (KNN_K - 1) - n_in++;
-                nbr[row * KNN_K + pos] = (uint16_t)j;
+                snbr[tid * KNN_K + pos] = (uint16_t)j;
             } else {
                 tie_append(tie, (uint32_t)r, (uint32_t)j, kth);
             }
@@ -790,7 +808,18 @@ knn_finalize_kernel(const float4* __restrict__ sorted, const uint16_t* __restric
         kthd[row] = kth;
         cnt[row] = total | (n_out << 24);
     } else {
-        slow[1 + atomicAdd(slow, 1)] = (int)row;           // mass ties (or NaN input): the warp-per-row exact path
+        slow[1 + atomicAdd(slow, 1)] = (int)row;           // mass ties (or NaN input): the warp-per-row exact path; it
+#pragma unroll                                             // rewrites the row, which here only needs in-range indices
+        for (int i = 0; i < KNN_K; ++i) snbr[tid * KNN_K + i] = (uint16_t)r;
+    }
+    }
+    __syncthreads();
+    {
+        const long long nrows = (rows - row0 < KNN_FIN_THREADS) ? (rows - row0) : KNN_FIN_THREADS;
+        const int chunks = (int)(nrows * KNN_K * 2 / 16);       // rows % 32 == 0 -> a whole number of 16-byte chunks
+        uint4* dst = reinterpret_cast<uint4*>(nbr + row0 * KNN_K);
+        const uint4* src = reinterpret_cast<const uint4*>(snbr);
+        for (int c = tid; c < chunks; c += KNN_FIN_THREADS) dst[c] = src[c];
     }
 }
 
@@ -1090,7 +1119,7 @@ int knn_build(const float* xyz, int B, int N, int arith, bool prune, const KnnSt
     }
     EPC_CHECK_ARG(cap >= 16, "kNN: N=%d leaves no shared memory for the candidate buffers", N);
     const int len = env_int("EPC_KNN_LEN", 8);
-    const size_t smemA = (size_t)knn_layout(N, cap * 4, 0).bytes, smemB = (size_t)knn_layout(N, KNN_CAPL * 2, 0).bytes;
+    const size_t smemA = (size_t)knn_layout(N, cap * 4, 0).bytes, smemB = (size_t)knn_layout(N, KNN_CAPL * 2, KNN_AUX_B).bytes;
     EPC_CHECK_ARG(smemB <= (size_t)budget1, "kNN: N=%d leaves no shared memory for the candidate lists", N);
     const size_t smemC = (size_t)KNN_SLOW_WARPS * N * 6;
     static PerDeviceSize a_sort, a_A5, a_A6, a_A8, a_B0, a_B1, a_C0, a_C1;
