@@ -73,6 +73,10 @@ PROTOTYPES = {
     "epc_retrieve_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "epc_retrieve_topk": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_longlong, c_void_p, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),
+    "epc_retrieve_index_bytes": (c_size_t, [c_int, c_int]),
+    "epc_retrieve_index_build": (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "epc_retrieve_topk_indexed": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_void_p,
+                                          c_void_p, c_void_p, c_size_t, c_void_p]),
     "epc_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "epc_radius_count": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p]),
     "epc_radius_fill": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p]),

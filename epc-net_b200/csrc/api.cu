@@ -700,9 +700,27 @@ size_t epc_retrieve_workspace_bytes(int D, int Q, int dim, int k) { return retri
 
 int epc_retrieve_topk(const float* db, int D, const float* q, int Q, int dim, int k, long long id_offset, int64_t* idx,
                       double* dist, void* workspace, size_t workspace_bytes, void* stream) {
-    EPC_CHECK_ARG(db && (q || Q == 0) && idx && dist && workspace, "epc_retrieve_topk: NULL argument");
-    if (int rc = ensure_device(db)) return rc;
-    return retrieve_topk(db, D, q, Q, dim, k, id_offset, idx, dist, workspace, workspace_bytes,
+    EPC_CHECK_ARG((db || D == 0) && (q || Q == 0) && idx && dist && (workspace || D == 0), "epc_retrieve_topk: NULL argument");
+    if (int rc = ensure_device(idx)) return rc;
+    return retrieve_topk(db, D, q, Q, dim, k, id_offset, nullptr, idx, dist, workspace, workspace_bytes,
+                         static_cast<cudaStream_t>(stream));
+}
+
+size_t epc_retrieve_index_bytes(int D, int dim) { return retrieve_index_bytes(D, dim); }
+
+int epc_retrieve_index_build(const float* db, int D, int dim, void* index, size_t index_bytes, void* stream) {
+    EPC_CHECK_ARG((db || D == 0) && index, "epc_retrieve_index_build: NULL argument");
+    if (int rc = ensure_device(index)) return rc;
+    return retrieve_index_build(db, D, dim, index, index_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int epc_retrieve_topk_indexed(const float* db, int D, const void* index, const float* q, int Q, int dim, int k,
+                              long long id_offset, int64_t* idx, double* dist, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+    EPC_CHECK_ARG((db || D == 0) && (index || D == 0) && (q || Q == 0) && idx && dist && (workspace || D == 0),
+                  "epc_retrieve_topk_indexed: NULL argument");
+    if (int rc = ensure_device(idx)) return rc;
+    return retrieve_topk(db, D, q, Q, dim, k, id_offset, index, idx, dist, workspace, workspace_bytes,
                          static_cast<cudaStream_t>(stream));
 }
 

@@ -106,8 +106,18 @@ int kd_feat(const float* H, const float* inv, const int* perm, int B, int N, int
 
 // ---- retrieval.cu ------------------------------------------------------------------------------
 size_t retrieve_workspace_bytes(int D, int Q, int dim, int k);
-int retrieve_topk(const float* db, int D, const float* q, int Q, int dim, int k, long long id_offset, int64_t* idx,
-                  double* dist, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t retrieve_index_bytes(int D, int dim);
+int retrieve_index_build(const float* db, int D, int dim, void* index_mem, size_t index_bytes, cudaStream_t st);
+// index: memory prepared by retrieve_index_build for this (db, D, dim), or nullptr (built in the workspace)
+int retrieve_topk(const float* db, int D, const float* q, int Q, int dim, int k, long long id_offset, const void* index,
+                  int64_t* idx, double* dist, void* ws, size_t ws_bytes, cudaStream_t st);
+// ---- retrieval_tc.cu ---------------------------------------------------------------------------
+bool retr_tc_supported(int dim);
+int retr_ranges(int Q, int n_tiles);
+int retr_split2(const float* X, int R, int Rpad, int dim, __nv_bfloat16* out, float* norms, cudaStream_t st);
+int retr_scores(const __nv_bfloat16* q2, int Q, const __nv_bfloat16* db2, int D, int dim, int n_tiles, int tile_stride, int n_ranges,
+                const float* qn, const float* dn, float* scores, int ld, const float* thr, uint2* cand, int* cand_count, int cap,
+                cudaStream_t st);
 int radius_search(const double* db, int D, const double* q, int Q, int dim, double r, int32_t* counts, const int64_t* offsets,
                   int32_t* indices, cudaStream_t st);
 int merge_topk(const double* dist, const int64_t* idx, int R, int Q, int k, double* out_dist, int64_t* out_idx,

@@ -2,9 +2,10 @@
 // Replaces `KDTree(database_output).query(q, k=25)` of evaluate.get_recall (evaluate.py:463,481), which
 // evaluates float64 Euclidean distances on the fp32 descriptors one query at a time on the CPU.
 //
-//   1. fp32-accurate scoring  s_ij = (|q_i|^2 + |d_j|^2) - 2 q_i.d_j: the GEMM runs on TF32 tensor cores with the 3xTF32
-//      operand split (q = qh + ql, d = dh + dl; qh.dh + qh.dl + ql.dh as ONE GEMM with K = 3 dim), FFMA when dim % 32 != 0
-//   2. per query: the 32 smallest scores (warp-distributed list)            -> candidates
+//   1. fp32-accurate scoring  s_ij = (|q_i|^2 + |d_j|^2) - 2 q_i.d_j on tcgen05 with bf16 operand pairs (retrieval_tc.cu:
+//      q = qh + ql, d = dh + dl; qh.dh + ql.dh + qh.dl), the candidate filter fused into the TMEM-drain epilogue so that the
+//      Q x D score matrix is never written (FFMA GEMM + dense scan when dim is not a multiple of 64 or > 256)
+//   2. per query: the 32 smallest scores among the emitted candidates       -> candidates
 //   3. float64 re-rank of the candidates, sequential sum_k (q_k - d_k)^2    -> top-k, ascending (dist, index)
 //   4. proof of exactness per query: every non-candidate has score >= a32 (the 32nd candidate's score),
 //      hence exact d^2 >= a32 - err;  if the exact k-th distance^2 is < a32 - err the answer equals a
@@ -55,6 +56,8 @@ __device__ __forceinline__ bool key_less(double av, long long ai, double bv, lon
 
 // One warp per query: 32 smallest of score_j = (qn + dn[j]) - 2 dot[j], ascending; columns ascend so ties keep
 // the lower index.
+// RAW: `dots` already holds the scores (the tensor-core epilogue applied the norms)
+template <bool RAW>
 __global__ void candidates_kernel(const float* __restrict__ dots, int ld, const float* __restrict__ qn,
                                   const float* __restrict__ dn, int Qt, int D, int* __restrict__ cand,
                                   float* __restrict__ a32) {
@@ -62,7 +65,7 @@ __global__ void candidates_kernel(const float* __restrict__ dots, int ld, const 
     const int lane = threadIdx.x & 31;
     if (qi >= Qt) return;
     const float* row = dots + (size_t)qi * ld;
-    const float qq = qn[qi];
+    const float qq = RAW ? 0.f : qn[qi];
     float val = INFINITY;
     int vi = -1;
     int filled = 0;
@@ -73,7 +76,7 @@ __global__ void candidates_kernel(const float* __restrict__ dots, int ld, const 
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int j = jb + 32 * u + lane;
-            sv[u] = (j < D) ? fmaf(-2.0f, __ldg(row + j), qq + __ldg(dn + j)) : INFINITY;
+            sv[u] = (j < D) ? (RAW ? __ldg(row + j) : fmaf(-2.0f, __ldg(row + j), qq + __ldg(dn + j))) : INFINITY;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -242,92 +245,266 @@ __global__ void max_reduce_kernel(const float* __restrict__ x, int n, float* __r
     }
 }
 
-static int query_tile(int D, int Q) {
-    const long long budget = 256ll << 20;   // bytes of fp32 scores per tile
-    long long qt = budget / ((long long)(D > 0 ? D : 1) * 4);
-    if (qt < 32) qt = 32;
-    if (qt > Q) qt = Q;
-    return (int)(qt > 0 ? qt : 1);
+// One warp per query: the 32 smallest (score, row) among the candidates the scoring epilogue emitted into the query's
+// regions (retrieval_tc.cu).  The emission order is arbitrary, the (score, row) order makes the result deterministic.
+__global__ void select_kernel(const uint2* __restrict__ cand_in, const int* __restrict__ counts, int n_ranges, int cap, int Qt,
+                              int* __restrict__ cand, float* __restrict__ a32) {
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (qi >= Qt) return;
+    float val = INFINITY;
+    int vi = 0x7fffffff;
+    int filled = 0;
+    float thr = INFINITY;
+    int thr_i = 0x7fffffff;
+    bool overflow = false;
+    for (int r = 0; r < n_ranges; ++r) {
+        const int c = counts[(size_t)qi * n_ranges + r];
+        if (c < 0) {
+            overflow = true;
+            continue;
+        }
+        const uint2* reg = cand_in + ((size_t)qi * n_ranges + r) * cap;
+        for (int e0 = 0; e0 < c; e0 += 32) {
+            const bool have = e0 + lane < c;
+            const uint2 ent = have ? __ldg(reg + e0 + lane) : make_uint2(0x7f800000u, 0x7fffffffu);
+            const float s = __uint_as_float(ent.x);
+            const int si = (int)ent.y;
+            unsigned m = __ballot_sync(FULL, have && (filled < RC || s < thr || (s == thr && si < thr_i)));
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const float cv = __shfl_sync(FULL, s, src);
+                const int ci = __shfl_sync(FULL, si, src);
+                const bool before = (lane < filled) && (val < cv || (val == cv && vi < ci));
+                const int pos = __popc(__ballot_sync(FULL, before));
+                if (pos < RC) {
+                    const float upv = __shfl_up_sync(FULL, val, 1);
+                    const int upi = __shfl_up_sync(FULL, vi, 1);
+                    if (lane == pos) {
+                        val = cv;
+                        vi = ci;
+                    } else if (lane > pos) {
+                        val = upv;
+                        vi = upi;
+                    }
+                    filled = min(filled + 1, RC);
+                    if (filled == RC) {
+                        thr = __shfl_sync(FULL, val, RC - 1);
+                        thr_i = __shfl_sync(FULL, vi, RC - 1);
+                    }
+                }
+            }
+        }
+    }
+    cand[(size_t)qi * RC + lane] = (lane < filled) ? vi : -1;
+    // an overflowed region may hide a better candidate, and fewer than 32 emitted entries (cannot happen while the sample's
+    // own rows score the same in both passes) leave no bound on the others: a32 = -inf sends the query to the exact fallback
+    if (lane == 0) a32[qi] = (overflow || filled < RC) ? -INFINITY : thr;
 }
 
+__global__ void fill_empty_kernel(int64_t* __restrict__ idx, double* __restrict__ dist, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        idx[i] = -1;
+        dist[i] = INFINITY;
+    }
+}
+
+static int pad128(int D) { return (D + 127) / 128 * 128; }
 static int pad256(int D) { return (D + 255) / 256 * 256; }
+
+constexpr int RETR_DENSE_MAX = 4096;      // databases up to this many rows: dense scores + scan (the matrix is small)
+constexpr int RETR_QTILE = 8192;          // queries per pass (bounds the workspace)
+
+// size of the threshold sample (rows, a multiple of 128) and of a candidate region for the emit path
+static int sample_rows(int D) {
+    int t = pad128(D) / 128 / 8;
+    if (t < 8) t = 8;
+    if (t > 32) t = 32;
+    return t * 128;
+}
+static int region_cap(int D, int tiles_per_range) {
+    // expected entries per region = 32 * rows_in_range / sample_rows; 2.5x + 64 headroom
+    const long long e = 32ll * tiles_per_range * 128 / sample_rows(D);
+    return (int)((e * 5 / 2 + 64 + 7) / 8 * 8);
+}
+
+// ---- the prepared database ("index"): what KDTree(database_output) (evaluate.py:463) is to the reference --------------------
+struct RetrIndex {             // laid out at the start of the caller's index memory
+    int D, dim, tensor;
+    float dn_max;              // (device copy lives in dn_max_dev)
+};
+size_t retrieve_index_bytes(int D, int dim) {
+    const int Dp = pad128(D);
+    return 256 + align_up((size_t)Dp * 4) + align_up(16) + (retr_tc_supported(dim) ? align_up((size_t)(D > 0 ? D : 1) * 2 * dim * 2) : 0) + 256;
+}
+struct IndexView {
+    float* dn;                 // [pad128(D)] |d|^2, +inf padding
+    float* dn_max;             // [1]
+    __nv_bfloat16* db2;        // [D, 2 dim] (tensor path)
+};
+static IndexView index_view(void* mem, int D, int dim) {
+    Arena ar(mem, (size_t)1 << 60);
+    IndexView v;
+    v.dn = ar.take<float>(pad128(D));
+    v.dn_max = ar.take<float>(4);
+    v.db2 = retr_tc_supported(dim) ? ar.take<__nv_bfloat16>((size_t)(D > 0 ? D : 1) * 2 * dim) : nullptr;
+    return v;
+}
+int retrieve_index_build(const float* db, int D, int dim, void* index_mem, size_t index_bytes, cudaStream_t st) {
+    EPC_CHECK_ARG(D >= 0 && dim >= 1, "retrieve_index_build: bad sizes D=%d dim=%d", D, dim);
+    EPC_CHECK_ARG(index_mem && index_bytes >= retrieve_index_bytes(D, dim), "retrieve_index_build: index memory %zu < required %zu",
+                  index_bytes, retrieve_index_bytes(D, dim));
+    if (D == 0) return EPC_OK;
+    IndexView v = index_view(index_mem, D, dim);
+    const int Dp = pad128(D);
+    if (v.db2) {
+        if (int rc = retr_split2(db, D, Dp, dim, v.db2, v.dn, st)) return rc;
+    } else {
+        sq_norm_kernel<<<(D + 7) / 8, 256, 0, st>>>(db, D, dim, v.dn);
+        EPC_LAUNCH_CHECK();
+    }
+    max_reduce_kernel<<<1, 1024, 0, st>>>(v.dn, D, v.dn_max);
+    EPC_LAUNCH_CHECK();
+    return EPC_OK;
+}
 
 size_t retrieve_workspace_bytes(int D, int Q, int dim, int k) {
     (void)k;
-    const int Dp = pad256(D);
-    const int qt = query_tile(Dp, Q);
-    return align_up((size_t)D * 4) + align_up((size_t)Q * 4) + align_up((size_t)qt * Dp * 4) +
-           align_up((size_t)qt * RC * 4) + align_up((size_t)qt * 4) + align_up((size_t)qt * 4) +
-           align_up((size_t)Dp * 3 * dim * 4) + align_up((size_t)qt * 3 * dim * 4) + 512;
+    const int qt = Q < RETR_QTILE ? (Q > 0 ? Q : 1) : RETR_QTILE;
+    size_t s = retrieve_index_bytes(D, dim) + align_up((size_t)qt * 4) * 3 + align_up((size_t)qt * RC * 4) + 1024;
+    if (retr_tc_supported(dim)) {
+        s += align_up((size_t)qt * 2 * dim * 2);
+        const int Dp = pad128(D);
+        if (D <= RETR_DENSE_MAX) {
+            s += align_up((size_t)qt * Dp * 4);
+        } else {
+            const int n_tiles = Dp / 128;
+            const int nr = retr_ranges(qt, n_tiles);
+            const int tpr = (n_tiles + nr - 1) / nr;
+            s += align_up((size_t)qt * sample_rows(D) * 4) + align_up((size_t)qt * nr * region_cap(D, tpr) * 8) + align_up((size_t)qt * nr * 4);
+        }
+    } else {
+        s += align_up((size_t)qt * pad256(D) * 4);
+    }
+    return s;
 }
 
-int retrieve_topk(const float* db, int D, const float* q, int Q, int dim, int k, long long id_offset, int64_t* idx,
-                  double* dist, void* ws, size_t ws_bytes, cudaStream_t st) {
+int retrieve_topk(const float* db, int D, const float* q, int Q, int dim, int k, long long id_offset, const void* index,
+                  int64_t* idx, double* dist, void* ws, size_t ws_bytes, cudaStream_t st) {
     EPC_CHECK_ARG(k >= 1 && k <= 32, "retrieve_topk: k=%d unsupported (1..32)", k);
-    EPC_CHECK_ARG(D >= 1 && dim >= 1 && Q >= 0, "retrieve_topk: bad sizes D=%d Q=%d dim=%d", D, Q, dim);
+    EPC_CHECK_ARG(D >= 0 && dim >= 1 && Q >= 0, "retrieve_topk: bad sizes D=%d Q=%d dim=%d", D, Q, dim);
     if (Q == 0) return EPC_OK;
+    if (D == 0) {               // an empty shard (more ranks than rows): all padding
+        const long long n = (long long)Q * k;
+        fill_empty_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(idx, dist, n);
+        EPC_LAUNCH_CHECK();
+        return EPC_OK;
+    }
     if (ws_bytes < retrieve_workspace_bytes(D, Q, dim, k)) {
         set_error("retrieve_topk: workspace %zu < required %zu", ws_bytes, retrieve_workspace_bytes(D, Q, dim, k));
         return EPC_EWORKSPACE;
     }
-    const int Dp = pad256(D);
-    const int qt = query_tile(Dp, Q);
-    const bool tensor = (dim % 32 == 0);            // 3 dim must be a multiple of the TF32 k-block (32)
-    const int ld = tensor ? Dp : D;
+    const bool tensor = retr_tc_supported(dim);
+    const int Dp = pad128(D);
+    const int qt = Q < RETR_QTILE ? Q : RETR_QTILE;
     Arena ar(ws, ws_bytes);
-    float* dn = ar.take<float>(D);
-    float* qn = ar.take<float>(Q);
-    float* dots = ar.take<float>((size_t)qt * Dp);
-    int* cand = ar.take<int>((size_t)qt * RC);
+    void* own_index = ar.take<unsigned char>(retrieve_index_bytes(D, dim));
+    float* qn = ar.take<float>(qt);
     float* a32 = ar.take<float>(qt);
     int* flags = ar.take<int>(qt);
-    float* dn_max_dev = ar.take<float>(1);
-    float* db3 = ar.take<float>((size_t)Dp * 3 * dim);
-    float* q3 = ar.take<float>((size_t)qt * 3 * dim);
-    const float err_unit = tensor ? 2.4e-7f * (float)(3 * dim + 8) : 1.2e-7f * (float)(dim + 8);
-    if (tensor) {
+    int* cand = ar.take<int>((size_t)qt * RC);
+    if (!index) {
         ScopedStage ss(EPC_STAGE_RETRIEVE_SCORE, st);
-        const long long n = (long long)Dp * dim;
-        split3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(db, D, Dp, dim, 1, db3);
-        EPC_LAUNCH_CHECK();
+        if (int rc = retrieve_index_build(db, D, dim, own_index, retrieve_index_bytes(D, dim), st)) return rc;
+        index = own_index;
     }
-
-    sq_norm_kernel<<<(D + 7) / 8, 256, 0, st>>>(db, D, dim, dn);
-    EPC_LAUNCH_CHECK();
-    sq_norm_kernel<<<(Q + 7) / 8, 256, 0, st>>>(q, Q, dim, qn);
-    EPC_LAUNCH_CHECK();
-    max_reduce_kernel<<<1, 1024, 0, st>>>(dn, D, dn_max_dev);
-    EPC_LAUNCH_CHECK();
+    const IndexView iv = index_view(const_cast<void*>(index), D, dim);
+    // scoring error bound: |score - exact d^2| <= err_unit (|q|^2 + max |d|^2).  bf16-pair path: dropped ql.dl and split
+    // residues 2^-16, accumulation of 3 dim products at <= 2^-22 each (the tensor core may truncate); FFMA path: dim-term FMA
+    // chain + norm sums, 1.2e-7 (dim + 8) -- both generous.
+    const float err_unit = tensor ? 2.4e-7f * (float)(3 * dim + 8) + 4e-5f : 1.2e-7f * (float)(dim + 8);
 
     for (int q0 = 0; q0 < Q; q0 += qt) {
         const int nq = (Q - q0 < qt) ? (Q - q0) : qt;
-        GemmArgs g = {};
-        g.A = q + (size_t)q0 * dim;  g.sAm = dim; g.sAk = 1;
-        g.B = db;                    g.sBk = 1;   g.sBn = dim;
-        g.C = dots; g.ldc = D; g.M = nq; g.N = D; g.K = dim; g.batch = 1; g.splitk = 1;
-        {
-            ScopedStage ss(EPC_STAGE_RETRIEVE_SCORE, st);
-            if (tensor) {
-                const long long n = (long long)nq * dim;
-                split3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q + (size_t)q0 * dim, nq, nq, dim, 0, q3);
+        const float* qp = q + (size_t)q0 * dim;
+        if (tensor) {
+            __nv_bfloat16* q2 = ar.take<__nv_bfloat16>((size_t)qt * 2 * dim);
+            const int n_tiles = Dp / 128;
+            {
+                ScopedStage ss(EPC_STAGE_RETRIEVE_SCORE, st);
+                if (int rc = retr_split2(qp, nq, nq, dim, q2, qn, st)) return rc;
+            }
+            if (D <= RETR_DENSE_MAX) {
+                float* scores = ar.take<float>((size_t)qt * Dp);
+                {
+                    ScopedStage ss(EPC_STAGE_RETRIEVE_SCORE, st);
+                    if (int rc = retr_scores(q2, nq, iv.db2, D, dim, n_tiles, 1, retr_ranges(nq, n_tiles), qn, iv.dn, scores, Dp, nullptr,
+                                             nullptr, nullptr, 0, st))
+                        return rc;
+                }
+                ScopedStage ss(EPC_STAGE_RETRIEVE_SELECT, st);
+                candidates_kernel<true><<<(nq + 7) / 8, 256, 0, st>>>(scores, Dp, qn, iv.dn, nq, D, cand, a32);
                 EPC_LAUNCH_CHECK();
-                if (int rc = tc_scores(q3, nq, db3, Dp, 3 * dim, dots, st)) return rc;
             } else {
+                const int S = sample_rows(D);
+                int nr = retr_ranges(nq, n_tiles);
+                const int tpr = (n_tiles + nr - 1) / nr;
+                nr = (n_tiles + tpr - 1) / tpr;
+                const int cap = region_cap(D, tpr);
+                float* sample = ar.take<float>((size_t)qt * S);
+                uint2* regions = ar.take<uint2>((size_t)qt * nr * cap);
+                int* counts = ar.take<int>((size_t)qt * nr);
+                {   // the 32nd smallest score over S rows (every stride-th tile): an upper bound of the 32nd smallest over all rows
+                    ScopedStage ss(EPC_STAGE_RETRIEVE_SCORE, st);
+                    if (int rc = retr_scores(q2, nq, iv.db2, D, dim, S / 128, n_tiles / (S / 128), retr_ranges(nq, S / 128), qn, iv.dn, sample, S, nullptr,
+                                             nullptr, nullptr, 0, st))
+                        return rc;
+                }
+                {
+                    ScopedStage ss(EPC_STAGE_RETRIEVE_SELECT, st);
+                    candidates_kernel<true><<<(nq + 7) / 8, 256, 0, st>>>(sample, S, qn, iv.dn, nq, S, cand, a32);
+                    EPC_LAUNCH_CHECK();
+                }
+                {   // every row scoring below it, straight from the accumulators
+                    ScopedStage ss(EPC_STAGE_RETRIEVE_SCORE, st);
+                    if (int rc = retr_scores(q2, nq, iv.db2, D, dim, n_tiles, 1, nr, qn, iv.dn, nullptr, 0, a32, regions, counts, cap, st))
+                        return rc;
+                }
+                ScopedStage ss(EPC_STAGE_RETRIEVE_SELECT, st);
+                select_kernel<<<(nq + 7) / 8, 256, 0, st>>>(regions, counts, nr, cap, nq, cand, a32);
+                EPC_LAUNCH_CHECK();
+            }
+        } else {
+            const int ld = pad256(D);
+            float* dots = ar.take<float>((size_t)qt * ld);
+            {
+                ScopedStage ss(EPC_STAGE_RETRIEVE_SCORE, st);
+                sq_norm_kernel<<<(nq + 7) / 8, 256, 0, st>>>(qp, nq, dim, qn);
+                EPC_LAUNCH_CHECK();
+                GemmArgs g = {};
+                g.A = qp;  g.sAm = dim; g.sAk = 1;
+                g.B = db;  g.sBk = 1;   g.sBn = dim;
+                g.C = dots; g.ldc = ld; g.M = nq; g.N = D; g.K = dim; g.batch = 1; g.splitk = 1;
                 if (int rc = sgemm(g, st)) return rc;
             }
-        }
-        {
             ScopedStage ss(EPC_STAGE_RETRIEVE_SELECT, st);
-            candidates_kernel<<<(nq + 7) / 8, 256, 0, st>>>(dots, ld, qn + q0, dn, nq, D, cand, a32);
+            candidates_kernel<false><<<(nq + 7) / 8, 256, 0, st>>>(dots, ld, qn, iv.dn, nq, D, cand, a32);
             EPC_LAUNCH_CHECK();
         }
         ScopedStage ss(EPC_STAGE_RETRIEVE_RERANK, st);
-        rerank_kernel<<<(nq + 7) / 8, 256, 0, st>>>(db, q + (size_t)q0 * dim, cand, a32, qn + q0, dn_max_dev, nq, dim, k,
-                                                    id_offset, idx + (size_t)q0 * k, dist + (size_t)q0 * k, flags, err_unit);
+        rerank_kernel<<<(nq + 7) / 8, 256, 0, st>>>(db, qp, cand, a32, qn, iv.dn_max, nq, dim, k, id_offset, idx + (size_t)q0 * k,
+                                                    dist + (size_t)q0 * k, flags, err_unit);
         EPC_LAUNCH_CHECK();
-        exact_fallback_kernel<<<(nq + 7) / 8, 256, 0, st>>>(db, q + (size_t)q0 * dim, flags, nq, D, dim, k, id_offset,
-                                                            idx + (size_t)q0 * k, dist + (size_t)q0 * k);
+        exact_fallback_kernel<<<(nq + 7) / 8, 256, 0, st>>>(db, qp, flags, nq, D, dim, k, id_offset, idx + (size_t)q0 * k,
+                                                            dist + (size_t)q0 * k);
         EPC_LAUNCH_CHECK();
+        ar.off = (size_t)((char*)cand - ar.base) + align_up((size_t)qt * RC * 4);      // the per-pass buffers are reused by the next pass
+    }
+    if (!ar.ok()) {
+        set_error("retrieve_topk: internal workspace accounting error");
+        return EPC_EWORKSPACE;
     }
     return EPC_OK;
 }

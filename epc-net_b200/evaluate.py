@@ -53,9 +53,48 @@ def get_latent_vectors(sess, ops, dict_to_process, data):
     return eng.embed_host(data)
 
 
+class RetrievalIndex:
+    """The prepared database: stands where ``database_nbrs = KDTree(database_output)`` (evaluate.py:463) stands in the
+    reference -- built once per database set, queried by every query set.  ``query(q, k)`` returns
+    (dist [Q,k] float64, idx [Q,k] int64) like ``KDTree.query``, as CUDA tensors.  ``id_offset`` is added to every
+    returned row id (a database shard reports global ids)."""
+
+    def __init__(self, database_output, id_offset=0):
+        lib = _lib.load()
+        db = _engine.as_cuda_f32(database_output, "database_output")
+        if db.dim() != 2:
+            raise ValueError("RetrievalIndex expects a (D, dim) array, got %s" % (tuple(db.shape),))
+        self.db = db
+        self.id_offset = int(id_offset)
+        D, dim = db.shape
+        with torch.cuda.device(db.device):
+            self.mem = torch.empty((int(lib.epc_retrieve_index_bytes(D, dim)),), dtype=torch.uint8, device=db.device)
+            _lib.check(lib.epc_retrieve_index_build(_ptr(db), D, dim, _ptr(self.mem), self.mem.numel(), _stream()))
+
+    def query(self, queries_output, k):
+        lib = _lib.load()
+        db = self.db
+        q = _engine.as_cuda_f32(queries_output, "queries_output")
+        if q.dim() != 2 or db.shape[1] != q.shape[1]:
+            raise ValueError("query expects a (Q, %d) array, got %s" % (db.shape[1], tuple(q.shape)))
+        if q.device != db.device:
+            q = q.to(db.device)
+        D, dim = db.shape
+        Q = q.shape[0]
+        k = int(k)
+        idx = torch.empty((Q, k), dtype=torch.int64, device=db.device)
+        dist = torch.empty((Q, k), dtype=torch.float64, device=db.device)
+        with torch.cuda.device(db.device):
+            ws = workspaces.get(lib.epc_retrieve_workspace_bytes(D, Q, dim, k))
+            _lib.check(lib.epc_retrieve_topk_indexed(_ptr(db), D, _ptr(self.mem), _ptr(q), Q, dim, k, self.id_offset,
+                                                     _ptr(idx), _ptr(dist), _ptr(ws), ws.numel(), _stream()))
+        return dist, idx
+
+
 def retrieve_topk(database_output, queries_output, k, id_offset=0):
     """Exact Euclidean k-NN on the GPU: -> (dist [Q,k] float64, idx [Q,k] int64), ascending, like
-    ``KDTree(database_output).query(queries_output, k)`` (evaluate.py:463,481)."""
+    ``KDTree(database_output).query(queries_output, k)`` (evaluate.py:463,481).  One-shot form: the database is
+    prepared inside the call (see RetrievalIndex for the build-once form)."""
     lib = _lib.load()
     db = _engine.as_cuda_f32(database_output, "database_output")
     q = _engine.as_cuda_f32(queries_output, "queries_output")
@@ -65,6 +104,7 @@ def retrieve_topk(database_output, queries_output, k, id_offset=0):
         q = q.to(db.device)
     D, dim = db.shape
     Q = q.shape[0]
+    k = int(k)
     idx = torch.empty((Q, k), dtype=torch.int64, device=db.device)
     dist = torch.empty((Q, k), dtype=torch.float64, device=db.device)
     with torch.cuda.device(db.device):
@@ -137,6 +177,20 @@ def recall_from_neighbors(indices, valid, true_neighbors_list, queries_output, d
     return recall, top1_similarity_score, one_percent_recall
 
 
+_INDEX_CACHE = {}       # m -> (DATABASE_VECTORS[m] object, RetrievalIndex): one "KDTree" per database set, not per (m, n) pair
+
+
+def _database_index(m):
+    vec = DATABASE_VECTORS[m]
+    hit = _INDEX_CACHE.get(m)
+    if hit is None or hit[0] is not vec:
+        for key in [key for key, v in _INDEX_CACHE.items() if not any(v[0] is d for d in DATABASE_VECTORS)]:
+            del _INDEX_CACHE[key]                                               # sets of an earlier evaluation
+        hit = (vec, RetrievalIndex(np.asarray(vec)))
+        _INDEX_CACHE[m] = hit
+    return hit[1]
+
+
 def get_recall(sess, ops, m, n, fout=None):
     """evaluate.py:455-537 on the module globals DATABASE_VECTORS / QUERY_VECTORS / QUERY_SETS.
     Returns (recall, top1_similarity_score, one_percent_recall, for_plot)."""
@@ -152,7 +206,7 @@ def get_recall(sess, ops, m, n, fout=None):
     if not valid:
         raise ZeroDivisionError("no query of set %d has a true neighbour in set %d" % (n, m))   # :529 divides by 0
     k = min(NUM_NEIGHBORS, len(database_output))
-    _, idx = retrieve_topk(database_output, queries_output[valid], k)
+    _, idx = _database_index(m).query(queries_output[valid], k)
     idx = idx.cpu().numpy()
     recall, sim, opr = recall_from_neighbors(idx, valid, truth, queries_output, database_output, len(database_output))
     for_plot = []

@@ -205,6 +205,17 @@ size_t epc_retrieve_workspace_bytes(int D, int Q, int dim, int k);
 int epc_retrieve_topk(const float* db /*[D,dim]*/, int D, const float* q /*[Q,dim]*/, int Q, int dim, int k,
                       long long id_offset, int64_t* idx, double* dist,
                       void* workspace, size_t workspace_bytes, void* stream);
+/* The prepared database -- what the `database_nbrs = KDTree(database_output)` object of evaluate.py:463 is to the
+ * reference: built once per database set, queried by every query set of the m != n pair loop (evaluate.py:291-300).
+ * It holds |d|^2 per row and the bf16 (hi | lo) operand pairs of the scoring GEMM in caller-owned device memory of
+ * epc_retrieve_index_bytes(D, dim) bytes; `db` itself must stay alive (the float64 re-rank reads it).
+ * epc_retrieve_topk_indexed == epc_retrieve_topk minus the per-call database preparation.  D == 0 is legal
+ * (an empty shard): every idx is -1 and every dist +inf. */
+size_t epc_retrieve_index_bytes(int D, int dim);
+int epc_retrieve_index_build(const float* db /*[D,dim]*/, int D, int dim, void* index, size_t index_bytes, void* stream);
+int epc_retrieve_topk_indexed(const float* db /*[D,dim]*/, int D, const void* index, const float* q /*[Q,dim]*/, int Q,
+                              int dim, int k, long long id_offset, int64_t* idx, double* dist,
+                              void* workspace, size_t workspace_bytes, void* stream);
 /* Merge R per-shard candidate lists (e.g. after an NCCL all-gather): dist/idx [R,Q,k] -> [Q,k],
  * ordered by (distance, index) so the result does not depend on the shard count. */
 int epc_merge_topk(const double* dist /*[R,Q,k]*/, const int64_t* idx /*[R,Q,k]*/, int R, int Q, int k,

@@ -38,6 +38,87 @@ def test_matches_float64_oracle(ev, D, Q, k):
         assert (i.cpu().numpy()[:, D:] == -1).all()
 
 
+@pytest.mark.parametrize("dim,D,Q", [(64, 6000, 200), (128, 9000, 130), (192, 5000, 77), (256, 4096, 129), (256, 4097, 128),
+                                     (100, 3000, 50), (320, 5000, 40), (256, 127, 300)])
+def test_dims_and_paths(ev, dim, D, Q):
+    """Every scoring path: tcgen05 bf16-pair scoring with the fused candidate filter (dim % 64 == 0, D > 4096), its dense
+    form (D <= 4096), and the FFMA path (other dims) -- indices equal the float64 brute force."""
+    db, q, _ = _data.retrieval_problem(D=D, Q=Q, dim=dim, seed=dim + D)
+    d, i = ev.retrieve_topk(db, q, 25)
+    rd, ri = R.knn_f64(db, q, 25)
+    assert np.array_equal(i.cpu().numpy(), ri)
+    assert np.abs(d.cpu().numpy() - rd).max() <= 1e-12
+
+
+def test_index_object_equals_one_shot_calls(ev):
+    """RetrievalIndex (the KDTree(database_output) object of evaluate.py:463): built once, queried repeatedly."""
+    db, q, _ = _data.retrieval_problem(D=7000, Q=300, seed=2)
+    index = ev.RetrievalIndex(db, id_offset=1000)
+    for lo, hi, k in ((0, 300, 25), (0, 1, 1), (10, 140, 32), (299, 300, 25)):
+        d, i = index.query(q[lo:hi], k)
+        d0, i0 = ev.retrieve_topk(db, q[lo:hi], k, id_offset=1000)
+        assert torch.equal(i, i0) and torch.equal(d, d0)
+    rd, ri = R.knn_f64(db, q, 25)
+    assert np.array_equal(index.query(q, 25)[1].cpu().numpy() - 1000, ri)
+
+
+def test_empty_shard_is_all_padding(ev):
+    """More ranks than database rows: a rank's shard has no rows (dist.shard_range) -> idx -1, dist +inf."""
+    q = _data.retrieval_problem(D=64, Q=5, seed=1)[1]
+    d, i = ev.retrieve_topk(np.zeros((0, 256), np.float32), q, 25, id_offset=7)
+    assert (i.cpu().numpy() == -1).all() and np.isinf(d.cpu().numpy()).all()
+    d, i = ev.RetrievalIndex(np.zeros((0, 256), np.float32)).query(q, 3)
+    assert (i.cpu().numpy() == -1).all() and np.isinf(d.cpu().numpy()).all()
+
+
+def test_more_queries_than_one_pass(ev):
+    """Q above the per-pass query tile (8192): passes reuse the workspace; same rows as separate calls."""
+    db, q, _ = _data.retrieval_problem(D=5000, Q=9000, seed=4)
+    d, i = ev.retrieve_topk(db, q, 25)
+    d1, i1 = ev.retrieve_topk(db, q[8000:], 25)
+    d2, i2 = ev.retrieve_topk(db, q[:700], 25)
+    assert torch.equal(i[8000:], i1) and torch.equal(d[8000:], d1)
+    assert torch.equal(i[:700], i2) and torch.equal(d[:700], d2)
+    rd, ri = R.knn_f64(db, q[8100:8300], 25)
+    assert np.array_equal(i[8100:8300].cpu().numpy(), ri)
+
+
+def test_trajectory_ordered_database(ev):
+    """Oxford databases are ordered along the vehicle's route: neighbouring rows are similar, so a contiguous sample would
+    be biased.  Place descriptors drift along the row index here; the result must still equal the float64 brute force."""
+    rng = np.random.default_rng(8)
+    D, dim = 12000, 256
+    steps = rng.standard_normal((D, dim)).astype(np.float32) * 0.08
+    db = np.cumsum(steps, 0) + rng.standard_normal((1, dim)).astype(np.float32)
+    db = (db / np.linalg.norm(db, axis=1, keepdims=True)).astype(np.float32)
+    src = rng.permutation(D)[:400]
+    q = db[src] + 0.02 * rng.standard_normal((400, dim)).astype(np.float32)
+    q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    d, i = ev.retrieve_topk(db, q, 25)
+    rd, ri = R.knn_f64(db, q, 25)
+    assert np.array_equal(i.cpu().numpy(), ri)
+
+
+def test_candidate_region_overflow_falls_back_exactly(ev):
+    """A database whose sampled rows (every stride-th 128-row tile) are all far from the queries while every other row is
+    near: the sample threshold admits nearly every row, the candidate regions overflow, and the query must take the exact
+    float64 scan -- never a truncated candidate list."""
+    rng = np.random.default_rng(5)
+    D, dim = 6000, 64
+    centre = rng.standard_normal((1, dim)).astype(np.float32)
+    db = centre + 0.01 * rng.standard_normal((D, dim)).astype(np.float32)
+    n_tiles = (D + 127) // 128
+    s_tiles = min(32, max(8, n_tiles // 8))
+    stride = n_tiles // s_tiles
+    for t in range(s_tiles):
+        lo = t * stride * 128
+        db[lo:lo + 128] = 5.0 * rng.standard_normal((len(db[lo:lo + 128]), dim)).astype(np.float32)
+    q = centre + 0.01 * rng.standard_normal((6, dim)).astype(np.float32)
+    d, i = ev.retrieve_topk(db, q, 25)
+    rd, ri = R.knn_f64(db, q, 25)
+    assert np.array_equal(i.cpu().numpy(), ri)
+
+
 def test_near_ties_take_the_exact_fallback(ev):
     """Database rows that differ below fp32 scoring resolution: the float64 re-rank / exact fallback must still
     return the float64 order, ties -> lower index."""
