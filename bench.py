@@ -63,7 +63,7 @@ def stage_roofline(stage, ms, clouds, peaks):
     out = {"hbm_gbs": hbm, "hbm_frac": hbm / peaks["hbm_gbs"]}
     if flop:
         tf = flop * clouds / sec / 1e12
-        peak = peaks["bf16_tflops_sustained"] if pipe == "tensor" else FP32_ALU_TFLOPS
+        peak = peaks["bf16_tflops_sustained"] if pipe == "tensor" else peaks.get("fp32_tflops", FP32_ALU_TFLOPS)
         out.update({"tflops": tf, "flop_peak": peak, "flop_frac": tf / peak, "pipe": pipe})
     return out
 
@@ -74,8 +74,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--clouds", type=int, default=256, help="clouds per GPU per step")
+    ap.add_argument("--clouds", type=int, default=8192, help="clouds per GPU per step (a multiple of --batch)")
+    ap.add_argument("--batch", type=int, default=256, help="clouds per embed() call (split over --streams library calls)")
     ap.add_argument("--chunk", type=int, default=128, help="clouds per library call")
+    ap.add_argument("--e2e-clouds", type=int, default=4096, help="clouds per step of the end-to-end (host buffer) measurement")
+    ap.add_argument("--no-epc-net-l", action="store_true", help="skip the EPC-Net-L extra key")
     ap.add_argument("--streams", type=int, default=2, help="CUDA streams the calls of one step alternate over")
     ap.add_argument("--cpu-sample", type=int, default=24, help="clouds in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -229,6 +232,143 @@ def run_reference(args):
     }))
 
 
+def measure_arch(arch, args, mods, rank, world, local, dist, full):
+    """Device-resident throughput, end-to-end throughput, per-stage table and parity of one architecture.
+    full=False (the EPC-Net-L extra key): fewer steps, no clock sampling."""
+    import torch
+    lib_mod, variables, engine_mod, evaluate, models = mods
+    V = variables.synthetic_variables(arch, 1)
+    store = variables.VariableStore(V)
+    params = dict(_data.default_params(arch), EMBED_CHUNK=args.chunk, EMBED_STREAMS=args.streams, VARIABLES=store)
+    eng = engine_mod.get_engine(arch, params, store=store)
+    eng_serial = engine_mod.get_engine(arch, dict(params, EMBED_STREAMS=1), store=store)      # per-stage timing pass only
+    K, W = (args.steps, args.warmup) if full else (min(args.steps, 6), 3)
+    CB = args.batch                                                # clouds per embed() call (args.chunk per library call)
+    calls = max(1, (args.clouds + CB - 1) // CB)
+    B = calls * CB                                                 # clouds per GPU per step
+    nbatch = 4                                                     # distinct batches the calls rotate over
+    host_batches = [make_clouds(CB, 1000 + 97 * rank + i) for i in range(nbatch)]
+    dev_batches = [torch.from_numpy(b).cuda() for b in host_batches]
+    outs = [torch.empty((CB, 256), dtype=torch.float32, device="cuda") for _ in range(2)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i, e):
+        for j in range(calls):
+            c = i * calls + j
+            e.embed(dev_batches[c % nbatch], out=outs[c & 1])
+        return (i * calls + calls - 1)                             # index of the step's last call
+
+    # ---- device-resident throughput -------------------------------------------------------------------
+    for i in range(W):
+        step(i, eng)
+    barrier()
+    sampler = ClockSampler(local) if (full and rank == 0) else None
+    if sampler:
+        sampler.start()
+    lib_mod.launch_count_reset()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(K):
+        last_call = step(W + i, eng)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib_mod.launch_count()
+    last_outs = {c: outs[c & 1].cpu().numpy() for c in (last_call - 1, last_call)} if calls > 1 else {last_call: outs[last_call & 1].cpu().numpy()}
+    # a few steps once more with the per-stage event brackets on, on ONE stream (brackets of concurrent streams would time
+    # each other's kernels); they stay out of `value`
+    Kp = min(K, 3)
+    lib_mod.profile_reset()
+    lib_mod.profile_enable(True)
+    for i in range(Kp):
+        step(W + i, eng_serial)
+    torch.cuda.synchronize()
+    stages = lib_mod.profile_read()
+    lib_mod.profile_enable(False)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * K / (ms * 1e-3)
+
+    # ---- end to end: host arrays in, host arrays out, through the reference-facing call ---------------------
+    # One get_latent_vectors call over the K steps' clouds, the way evaluate.py:283-293 calls it on a whole database set:
+    # every 128-cloud call is staged through pinned memory, copied H2D, embedded, and the descriptors copied back -- all
+    # inside the timed region; the engine overlaps call i+1's copy with call i's compute.
+    ops = {"MODEL": models.load(arch), "params": params}
+    Be = min(B, args.e2e_clouds)                                   # clouds per e2e step (bounds the host array: K x Be x 48 KB)
+    reps = (K * Be + nbatch * CB - 1) // (nbatch * CB)
+    big = np.concatenate(host_batches * reps, 0)[:K * Be]
+    names = {i: {} for i in range(len(big))}
+    warm = np.concatenate(host_batches[:2], 0)
+    evaluate.get_latent_vectors(None, ops, {i: {} for i in range(len(warm))}, warm)
+    evaluate.get_latent_vectors(None, ops, names, big)                  # sizes the staging buffers for the timed call
+    barrier()
+    t0 = time.perf_counter()
+    desc = evaluate.get_latent_vectors(None, ops, names, big)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = world * Be * K / e2e_s
+    clocks = sampler.stop() if sampler else None          # sampled across both timed regions
+    assert desc.shape == (Be * K, 256) and np.isfinite(desc).all()
+    # parity of what was just timed: first/last descriptor of each library call of the last device-resident calls and of the
+    # end-to-end result against the CPU oracle (the checker, never the thing measured)
+    parity = None
+    if rank == 0 and not args.no_parity:
+        worst_abs, worst_cos, n_rows = 0.0, 1.0, 0
+        for c, got in last_outs.items():
+            rows = sorted({0, min(args.chunk, CB) - 1, min(args.chunk, CB - 1), CB - 1}) if full else [0, CB - 1]
+            a, b = parity_check(got, host_batches[c % nbatch], rows, V, arch)
+            worst_abs, worst_cos, n_rows = max(worst_abs, a), min(worst_cos, b), n_rows + len(rows)
+        rows2 = sorted({0, CB - 1, len(big) - CB, len(big) - 1}) if full else [0, len(big) - 1]
+        a, b = parity_check(desc, big, rows2, V, arch)
+        worst_abs, worst_cos, n_rows = max(worst_abs, a), min(worst_cos, b), n_rows + len(rows2)
+        parity = {"parity_checked": True, "max_abs": worst_abs, "min_cos": worst_cos, "rows_checked": n_rows,
+                  "tolerance": {"max_abs": 1e-3, "min_cos": 0.9999},
+                  "against": "oracle/epc_oracle.forward (dense-as-written restatement of models/%s.py)" % arch}
+        assert worst_abs <= 1e-3 and worst_cos >= 0.9999, parity
+    return {"arch": arch, "V": V, "value": value, "ms": ms, "K": K, "W": W, "B": B, "CB": CB, "calls": calls, "nbatch": nbatch,
+            "launches": launches, "stages": stages, "stage_clouds": B * Kp, "e2e": e2e, "e2e_s": e2e_s, "Be": Be,
+            "clocks": clocks, "parity": parity}
+
+
+def ffma_peak(lib_mod, torch):
+    """The FP32 pipe's peak measured now, on this GPU, at the clocks of the moment (epc_microbench_ffma)."""
+    import ctypes
+    lib = lib_mod.load()
+    fl = ctypes.c_double(0.0)
+    st = torch.cuda.current_stream().cuda_stream
+    lib_mod.check(lib.epc_microbench_ffma(4096, ctypes.byref(fl), st))
+    best = 0.0
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lib_mod.check(lib.epc_microbench_ffma(65536, ctypes.byref(fl), st))
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, fl.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
+def stage_table_of(stages, clouds, peaks):
+    total = sum(v[0] for v in stages.values()) or 1.0
+    table = {}
+    for k, v in stages.items():
+        e = {"us_per_cloud": v[0] / clouds * 1e3, "share": v[0] / total, "launches": v[1]}
+        if k in STAGE_MODEL and v[0] > 0:
+            e.update(stage_roofline(k, v[0], clouds, peaks))
+        table[k] = e
+    return table, total
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -250,94 +390,18 @@ def main():
     engine_mod = importlib.import_module("epc-net_b200.engine")
     evaluate = importlib.import_module("epc-net_b200.evaluate")
     models = importlib.import_module("epc-net_b200.models")
+    mods = (lib_mod, variables, engine_mod, evaluate, models)
 
     arch = args.arch
-    V = variables.synthetic_variables(arch, 1)
-    store = variables.VariableStore(V)
-    params = dict(_data.default_params(arch), EMBED_CHUNK=args.chunk, EMBED_STREAMS=args.streams, VARIABLES=store)
-    eng = engine_mod.get_engine(arch, params, store=store)
-    eng_serial = engine_mod.get_engine(arch, dict(params, EMBED_STREAMS=1), store=store)      # per-stage timing pass only
-    B, K, W = args.clouds, args.steps, args.warmup
-    nbatch = min(K + W, 4)                                         # rotate distinct inputs; intermediates >> L2 anyway
-    host_batches = [make_clouds(B, 1000 + 97 * rank + i) for i in range(nbatch)]
-    dev_batches = [torch.from_numpy(b).cuda() for b in host_batches]
-    out = torch.empty((B, 256), dtype=torch.float32, device="cuda")
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident throughput -------------------------------------------------------------------
-    for i in range(W):
-        eng.embed(dev_batches[i % nbatch], out=out)
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    lib_mod.launch_count_reset()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for i in range(K):
-        eng.embed(dev_batches[(W + i) % nbatch], out=out)
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = lib_mod.launch_count()
-    # the same K steps once more with the per-stage event brackets on, on ONE stream (brackets of concurrent streams would
-    # time each other's kernels); they stay out of `value`
-    lib_mod.profile_reset()
-    lib_mod.profile_enable(True)
-    for i in range(K):
-        eng_serial.embed(dev_batches[(W + i) % nbatch], out=out)
-    torch.cuda.synchronize()
-    stages = lib_mod.profile_read()
-    lib_mod.profile_enable(False)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    value = world * B * K / (ms * 1e-3)
-
-    # ---- end to end: host arrays in, host arrays out, through the reference-facing call ---------------------
-    # One get_latent_vectors call over the K steps' clouds, the way evaluate.py:283-293 calls it on a whole database set
-    # (hundreds of clouds): every step's 128 clouds are staged through pinned memory, copied H2D, embedded, and the
-    # descriptors copied back -- all inside the timed region; the engine overlaps step i+1's copy with step i's compute.
-    ops = {"MODEL": models.load(arch), "params": params}
-    big = np.concatenate([host_batches[(W + i) % nbatch] for i in range(K)], 0)
-    names = {i: {} for i in range(len(big))}
-    warm = np.concatenate([host_batches[i % nbatch] for i in range(max(2, min(W, 3)))], 0)
-    evaluate.get_latent_vectors(None, ops, {i: {} for i in range(len(warm))}, warm)
-    evaluate.get_latent_vectors(None, ops, names, big)                  # sizes the staging buffers for the timed call
-    barrier()
-    t0 = time.perf_counter()
-    desc = evaluate.get_latent_vectors(None, ops, names, big)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e = world * B * K / e2e_s
-    clocks = sampler.stop() if rank == 0 else None          # sampled across both timed regions
-    assert desc.shape == (B * K, 256) and np.isfinite(desc).all()
-    # parity of what was just timed: first/last descriptor of each library call of the last device-resident step and of the
-    # end-to-end result against the CPU oracle (the checker, never the thing measured)
-    parity = None
-    if rank == 0 and not args.no_parity:
-        last = host_batches[(W + K - 1) % nbatch]
-        rows = sorted({0, min(args.chunk, B) - 1, min(args.chunk, B - 1), B - 1})
-        p1 = parity_check(out.cpu().numpy(), last, rows, V, arch)
-        rows2 = sorted({0, B - 1, (K - 1) * B, K * B - 1})
-        p2 = parity_check(desc, big, rows2, V, arch)
-        parity = {"parity_checked": True, "max_abs": max(p1[0], p2[0]), "min_cos": min(p1[1], p2[1]),
-                  "rows_checked": len(rows) + len(rows2), "tolerance": {"max_abs": 1e-3, "min_cos": 0.9999},
-                  "against": "oracle/epc_oracle.forward (dense-as-written restatement of models/epc-net.py:29-157)"}
-        assert parity["max_abs"] <= 1e-3 and parity["min_cos"] >= 0.9999, parity
-
+    r = measure_arch(arch, args, mods, rank, world, local, dist, full=True)
+    other = None
+    if arch == "epc-net" and not args.no_epc_net_l:
+        # BASELINE.json configs[2]: the lightweight variant at its own batch shape (256 clouds per library call)
+        largs = argparse.Namespace(**dict(vars(args), chunk=256, batch=512))
+        other = measure_arch("epc-net-l", largs, mods, rank, world, local, dist, full=False)
     retr = None
     if not args.no_retrieval:
-        retr = bench_retrieval(evaluate, torch, dist if world > 1 else None, rank, world)      # collective when world > 1
+        retr = bench_retrieval(evaluate, lib_mod, torch, dist if world > 1 else None, rank, world)      # collective when world > 1
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -345,65 +409,78 @@ def main():
 
     # ---- roofline of the dominant kernel (stage with the largest share of device time) ----------------
     peaks = measured_peaks()
-    total_stage_ms = sum(v[0] for v in stages.values()) or 1.0
+    fp32_peak = ffma_peak(lib_mod, torch)
+    peaks["fp32_tflops"] = fp32_peak
+    stages, B, K, W = r["stages"], r["B"], r["K"], r["W"]
+    stage_table, total_stage_ms = stage_table_of(stages, r["stage_clouds"], peaks)
     top = max(stages.items(), key=lambda kv: kv[1][0])[0]
     top_ms, top_n = stages[top]
-    clouds_per_launch = B * K / float(top_n)
+    clouds_per_launch = r["stage_clouds"] / float(top_n)
     traffic = ncu_traffic(top)
     roof = {"kernel": top, "share_of_step": top_ms / total_stage_ms, "launches": top_n,
-            "avg_launch_ms": top_ms / top_n, "peak_source": peaks["source"],
-            "traffic": traffic * 1.0 if traffic is not None else None}
-    r = stage_roofline(top, top_ms, B * K, peaks) if top in STAGE_MODEL else None
-    if r is not None and r.get("pipe") == "tensor" and r["flop_frac"] >= r["hbm_frac"]:
-        roof.update({"bound": "tensor", "achieved": r["tflops"], "peak": r["flop_peak"], "unit": "TFLOP/s", "frac": r["flop_frac"],
+            "avg_launch_ms": top_ms / top_n, "clouds_per_launch": clouds_per_launch, "peak_source": peaks["source"],
+            "traffic": traffic * 1.0 if traffic is not None else None,
+            "timing": "CUDA events bracketing the stage's kernels on their stream, in a separate single-stream pass of %d steps "
+                      "right after the timed region (stage sum there: %.2f us/cloud; timed two-stream pass: %.2f us/cloud)"
+                      % (min(K, 3), total_stage_ms / r["stage_clouds"] * 1e3, r["ms"] / (B * K) * 1e3)}
+    sr = stage_roofline(top, top_ms, r["stage_clouds"], peaks) if top in STAGE_MODEL else None
+    if sr is not None and sr.get("pipe") == "tensor" and sr["flop_frac"] >= sr["hbm_frac"]:
+        roof.update({"bound": "tensor", "achieved": sr["tflops"], "peak": sr["flop_peak"], "unit": "TFLOP/s", "frac": sr["flop_frac"],
                      "note": "algorithmic FLOP of the stage / event-timed duration; peak = measured sustained bf16 cuBLAS"})
-    elif r is not None:
-        roof.update({"bound": "hbm", "achieved": r["hbm_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": r["hbm_frac"],
+    elif sr is not None and sr.get("pipe") == "alu" and sr.get("flop_frac", 0.0) >= sr["hbm_frac"]:
+        roof.update({"bound": "fp32", "achieved": sr["tflops"], "peak": fp32_peak, "unit": "TFLOP/s", "frac": sr["flop_frac"],
+                     "peak_source": "measured in this run: epc_microbench_ffma (register-only FFMA chains on every SM), %.1f TFLOP/s; "
+                                    "theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = %.1f" % (fp32_peak, FP32_ALU_TFLOPS),
+                     "hbm_frac": sr["hbm_frac"],
+                     "note": "ALU-bound: the whole cloud sits in shared memory, HBM traffic is negligible (hbm_frac).  achieved = "
+                             "dense-equivalent 8 N^2 FLOP per cloud (SURVEY 8d) / event-timed duration; exact AABB pruning skips most "
+                             "pairs, the selection networks are the remaining work"})
+        inst = ncu_warp_instructions(top)
+        if inst and r["clocks"] and r["clocks"].get("sm_mhz"):
+            ach = inst / 128.0 * clouds_per_launch / (top_ms / top_n * 1e-3) / 1e9
+            peak = torch.cuda.get_device_properties(local).multi_processor_count * 4 * r["clocks"]["sm_mhz"] * 1e6 / 1e9
+            roof.update({"issue_achieved": ach, "issue_peak": peak, "issue_unit": "G warp-instr/s", "issue_frac": ach / peak,
+                         "issue_note": "warp instructions of the stage's kernels per 128 clouds from the committed ncu capture "
+                                       "(profiles/traffic.json), duration event-timed here"})
+    elif sr is not None:
+        roof.update({"bound": "hbm", "achieved": sr["hbm_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": sr["hbm_frac"],
                      "algorithmic_bytes_per_launch": STAGE_MODEL[top][1] * clouds_per_launch})
-        if top == "knn":
-            roof["note"] = ("the kNN kernel keeps the whole cloud in shared memory and is bound by FP32-ALU/issue work (distance "
-                            "evaluation + top-20 selection networks), not by HBM: see alt_*; dense-equivalent 8*N^2 FLOP per cloud "
-                            "(exact AABB pruning skips ~84 % of the pairs)")
-            roof.update({"alt_bound": "fp32-alu (dense-equivalent)", "alt_achieved": r["tflops"], "alt_peak": FP32_ALU_TFLOPS,
-                         "alt_unit": "TFLOP/s", "alt_frac": r["flop_frac"]})
-            inst = ncu_warp_instructions(top)
-            if inst and clocks and clocks.get("sm_mhz") and abs(clouds_per_launch - 128) < 1e-6:
-                # what actually bounds it: warp-instruction issue (4 schedulers per SM, one instruction per clock each)
-                ach = inst / (top_ms / top_n * 1e-3) / 1e9
-                peak = torch.cuda.get_device_properties(local).multi_processor_count * 4 * clocks["sm_mhz"] * 1e6 / 1e9
-                roof.update({"issue_bound": "warp-instruction issue slots", "issue_achieved": ach, "issue_peak": peak,
-                             "issue_unit": "G warp-instr/s", "issue_frac": ach / peak,
-                             "issue_note": "instructions per 128-cloud launch from the committed ncu capture (profiles/traffic.json), "
-                                           "launch duration event-timed here"})
-    stage_table = {}
-    for k, v in stages.items():
-        e = {"ms_per_cloud": v[0] / (B * K), "share": v[0] / total_stage_ms}
-        if k in STAGE_MODEL and v[0] > 0:
-            e.update(stage_roofline(k, v[0], B * K, peaks))
-        stage_table[k] = e
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": r["ms"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "tensor_operands": "fp16 (ProxyConv 64x64 layers), bf16 (conv5/assignment/VLAD), tf32 (hidden FC; EPC-Net-L conv5); fp32 accumulation",
         "data": "synthetic",
         "config": {"workload": ("EPC-Net (configs/epc-net.yaml: 4 ProxyConv blocks + G_VLAD, 256-d)" if arch == "epc-net" else
                                 "EPC-Net-L (configs/epc-net-l.yaml: 2 ProxyConv blocks + max-pool + FC, 256-d)") +
                                " batch embedding of synthetic uniform(-1,1) 4096-point clouds, seeded random-init weights, "
                                "batch-sharded",
-                   "clouds_per_gpu_per_step": B, "clouds_per_call": args.chunk, "streams": args.streams, "knn_arith": "muladd",
-                   "l2": "inputs rotate over %d distinct batches; every call streams >0.5 GB of intermediates "
-                         "(>> 126 MB L2)" % nbatch},
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * N_POINTS * 3 * 4, "d2h_bytes_per_step": B * 256 * 4,
-                "api": "one evaluate.get_latent_vectors(host ndarray of steps x clouds) -> host ndarray call; per-step pinned staging, H2D and D2H inside"},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "stages": stage_table,
+                   "clouds_per_gpu_per_step": B, "clouds_per_call": args.chunk, "calls_per_step": r["calls"] * max(1, r["CB"] // args.chunk),
+                   "streams": args.streams, "knn_arith": "muladd", "timed_region_s": r["ms"] * 1e-3,
+                   "l2": "the calls of a step rotate over %d distinct %d-cloud batches; every call streams >0.5 GB of intermediates "
+                         "(>> 126 MB L2)" % (r["nbatch"], r["CB"])},
+        "e2e": {"value": r["e2e"], "unit": UNIT, "h2d_bytes_per_step": r["Be"] * N_POINTS * 3 * 4, "d2h_bytes_per_step": r["Be"] * 256 * 4,
+                "clouds_per_step": r["Be"], "timed_region_s": r["e2e_s"],
+                "api": "one evaluate.get_latent_vectors(host ndarray of steps x clouds) -> host ndarray call; per-call pinned staging, H2D and D2H inside"},
+        "gpu_launches": int(r["launches"]), "clocks": r["clocks"], "roofline": roof, "stages": stage_table,
     }
-    if parity is not None:
-        line.update(parity)
+    if r["parity"] is not None:
+        line.update(r["parity"])
+    if other is not None:
+        ltable, ltotal = stage_table_of(other["stages"], other["stage_clouds"], peaks)
+        ltop = max(other["stages"].items(), key=lambda kv: kv[1][0])[0]
+        line["epc_net_l"] = {
+            "workload": "EPC-Net-L (configs/epc-net-l.yaml; BASELINE configs[2]) large-batch embedding, %d clouds per step, %d per library call"
+                        % (other["B"], 256),
+            "value": other["value"], "unit": UNIT, "steps": other["K"], "warmup": other["W"], "timed_region_s": other["ms"] * 1e-3,
+            "e2e": {"value": other["e2e"], "unit": UNIT, "clouds_per_step": other["Be"]},
+            "gpu_launches": int(other["launches"]), "dominant_kernel": ltop, "dominant_share": other["stages"][ltop][0] / ltotal,
+            "stages": {k: {"us_per_cloud": v["us_per_cloud"], "share": v["share"]} for k, v in ltable.items() if v["share"] >= 0.02},
+            "parity": other["parity"]}
     if not args.no_retrieval:
         line["retrieval"] = retr
     if not args.no_cpu_baseline:
-        cps, med = cpu_baseline(args.cpu_sample, V, _data.default_params(arch), arch)
+        cps, med = cpu_baseline(args.cpu_sample, r["V"], _data.default_params(arch), arch)
         line["cpu_baseline"] = {"value": cps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                 "sample": "%d clouds, 1 cloud per call (evaluate.py:355), median %.3f s/cloud; numpy/BLAS "
                                           "dense-as-written restatement of the TF-1.12 graph" % (args.cpu_sample, med)}
@@ -412,42 +489,56 @@ def main():
         dist.destroy_process_group()
 
 
-def bench_retrieval(evaluate, torch, dist, rank, world):
+def bench_retrieval(evaluate, lib_mod, torch, dist, rank, world):
     """Secondary metrics of BASELINE.json: retrieval queries/s and recall@1 on SURVEY 8d C5 (D=20k, Q=3k, k=25).
-    With N ranks the database rows are sharded N ways (queries replicated); every rank finds its local top-25 with global
-    row ids, one NCCL all-gather of (distance, index)[Q,25] per rank, then the (distance, index) merge (epc_merge_topk)."""
-    from oracle import retrieval_oracle
-    D, Q, k = 20000, 3000, 25
+    The database is prepared once (RetrievalIndex = the reference's KDTree(database_output) object, evaluate.py:463) and
+    every timed call is one query() of all Q queries.  With N ranks the database rows are sharded N ways (queries
+    replicated); every rank finds its local top-25 with global row ids, ONE NCCL all-gather of the packed (distance | index)
+    [2,Q,25] buffer per rank, then the (distance, index) merge (epc_merge_topk_strided)."""
+    D, Q, k, dim = 20000, 3000, 25, 256
     db, q, src = _data.retrieval_problem(D=D, Q=Q, seed=7)
     qt = torch.from_numpy(q).cuda()
     if dist is None:
-        dbt = torch.from_numpy(db).cuda()
-        run = lambda: evaluate.retrieve_topk(dbt, qt, k)
+        index = evaluate.RetrievalIndex(torch.from_numpy(db).cuda())
     else:
         dmod = importlib.import_module("epc-net_b200.dist")
-        s, e = dmod.shard_range(D, rank, world)
-        dbt = torch.from_numpy(db[s:e]).cuda()
-        run = lambda: dmod.retrieve_sharded(dmod.cuda_local_topk, dmod.cuda_merge, dbt, s, qt, k)
-    for _ in range(2):
-        d, i = run()
+        index = dmod.ShardedRetrieval(db)
+
+    def timed(qq, reps):
+        for _ in range(3):
+            d, i = index.query(qq, k)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            d, i = index.query(qq, k)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / reps, i
+
+    ms, i = timed(qt, 50)
+    # per-stage device time of the local (per-shard) work, single stream
+    lib_mod.profile_reset()
+    lib_mod.profile_enable(True)
+    for _ in range(5):
+        index.query(qt, k)
     torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    reps = 5
-    for _ in range(reps):
-        d, i = run()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    st = {n: v[0] / 5 for n, v in lib_mod.profile_read().items() if n.startswith("retrieve")}
+    lib_mod.profile_enable(False)
+    # a large query batch (16 x Q): the per-call latencies (launches, the all-gather) amortise, the sharded work dominates
+    QL = 16 * Q
+    ql = torch.from_numpy(np.tile(q, (16, 1)) + np.random.default_rng(5).normal(0, 0.01, (QL, dim)).astype(np.float32)).cuda()
+    ms_l, _ = timed(ql, 5)
     if rank != 0:
         return None
-    qps = reps * Q / (ms * 1e-3)
+    peaks = measured_peaks()
     idx = i.cpu().numpy()
     n_cpu = 200
     from sklearn.neighbors import KDTree
@@ -456,9 +547,30 @@ def bench_retrieval(evaluate, torch, dist, rank, world):
     t0 = time.perf_counter()
     ref = np.stack([tree.query(q[j:j + 1], k=k)[1][0] for j in range(n_cpu)], 0)     # evaluate.py:481, one query per call
     cpu_qps = n_cpu / (time.perf_counter() - t0)
-    return {"queries_per_s": qps, "recall_at_1": float((idx[:, 0] == src).mean()), "D": D, "Q": Q, "k": k,
-            "db_shards": world, "collective": "nccl all_gather of (fp64 dist, int64 idx)[Q,25] per rank + merge" if world > 1 else None,
+    d_local = (D + world - 1) // world
+    sample_rows = 2048 if d_local > 4096 else 0
+    score_flop = 3 * 2.0 * Q * (d_local + sample_rows) * dim          # three bf16 products per fp32-accurate dot product
+    roof = {}
+    if st.get("retrieve_score"):
+        tf = score_flop / (st["retrieve_score"] * 1e-3) / 1e12
+        roof["score"] = {"ms": st["retrieve_score"], "bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"],
+                         "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops_sustained"],
+                         "note": "bf16-pair split + threshold sample + tcgen05 scoring with the candidate filter in the epilogue; "
+                                 "FLOP = 3 products x 2 Q (D_local + sample rows) dim; no Q x D matrix is written"}
+    if st.get("retrieve_select"):
+        roof["select"] = {"ms": st["retrieve_select"], "bound": "latency/issue",
+                          "note": "one warp per query over the emitted (score, row) lists (~2 % of the rows)"}
+    if st.get("retrieve_rerank"):
+        gb = Q * 32.0 * dim * 4 / (st["retrieve_rerank"] * 1e-3) / 1e9
+        roof["rerank"] = {"ms": st["retrieve_rerank"], "bound": "fp64 pipe / gather", "achieved": gb, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                          "frac": gb / peaks["hbm_gbs"],
+                          "note": "float64 re-rank of 32 candidates per query (sequential sums, sklearn order) + the exact-fallback launch"}
+    return {"queries_per_s": Q / (ms * 1e-3), "ms_per_call": ms, "recall_at_1": float((idx[:, 0] == src).mean()), "D": D, "Q": Q, "k": k,
+            "db_shards": world,
+            "collective": "one nccl all_gather of the packed (fp64 dist | int64 idx)[2,Q,25] buffer per rank + merge" if world > 1 else None,
             "top25_identical_to_kdtree": bool(np.array_equal(idx[:n_cpu], ref)),
+            "stages_ms": st, "roofline": roof,
+            "large_batch": {"Q": QL, "queries_per_s": QL / (ms_l * 1e-3), "ms_per_call": ms_l},
             "cpu_kdtree_queries_per_s": cpu_qps, "cpu_sample": "%d queries, sklearn KDTree, 1 query per call" % n_cpu}
 
 

@@ -55,6 +55,7 @@ PROTOTYPES = {
     "epc_profile_reset": (None, []),
     "epc_profile_read": (c_int, [c_int, POINTER(c_double), POINTER(c_longlong)]),
     "epc_stage_name": (c_char_p, [c_int]),
+    "epc_microbench_ffma": (c_int, [c_int, POINTER(c_double), c_void_p]),
     "epc_set_device": (c_int, [c_int]),
     "epc_device_count": (c_int, []),
     "epc_knn_workspace_bytes": (c_size_t, [c_int, c_int]),
@@ -78,6 +79,7 @@ PROTOTYPES = {
     "epc_retrieve_topk_indexed": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_void_p,
                                           c_void_p, c_void_p, c_size_t, c_void_p]),
     "epc_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "epc_merge_topk_strided": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "epc_radius_count": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p]),
     "epc_radius_fill": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p]),
 }

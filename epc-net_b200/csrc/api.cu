@@ -694,6 +694,39 @@ int epc_vlad_forward(const EpcModel* m, const float* X, int B, int N, float* out
 }
 
 // -------------------------------------------------------------------------------------------------
+// measurement aid
+// -------------------------------------------------------------------------------------------------
+}  // extern "C"
+namespace epc {
+__global__ void __launch_bounds__(256) ffma_peak_kernel(int iters, float seed, float* sink) {
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = seed + (float)(threadIdx.x + i);
+    const float m = 1.0f + seed * 1e-9f, c = seed * 1e-7f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], m, c);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == 123.456f) sink[0] = s;          // never true: keeps the chains alive
+}
+}  // namespace epc
+extern "C" {
+int epc_microbench_ffma(int iters, double* flops, void* stream) {
+    EPC_CHECK_ARG(iters >= 1 && flops, "epc_microbench_ffma: bad arguments");
+    int dev = 0, sms = 148;
+    EPC_CUDA(cudaGetDevice(&dev));
+    EPC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 8;
+    epc::ffma_peak_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(iters, 1.0f, nullptr);
+    EPC_LAUNCH_CHECK();
+    *flops = 2.0 * 16.0 * (double)iters * 256.0 * (double)blocks;
+    return EPC_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
 // retrieval
 // -------------------------------------------------------------------------------------------------
 size_t epc_retrieve_workspace_bytes(int D, int Q, int dim, int k) { return retrieve_workspace_bytes(D, Q, dim, k); }
@@ -741,7 +774,14 @@ int epc_merge_topk(const double* dist, const int64_t* idx, int R, int Q, int k, 
                    void* stream) {
     EPC_CHECK_ARG(dist && idx && out_dist && out_idx, "epc_merge_topk: NULL argument");
     if (int rc = ensure_device(dist)) return rc;
-    return merge_topk(dist, idx, R, Q, k, out_dist, out_idx, static_cast<cudaStream_t>(stream));
+    return merge_topk(dist, idx, (long long)Q * k, R, Q, k, out_dist, out_idx, static_cast<cudaStream_t>(stream));
+}
+
+int epc_merge_topk_strided(const double* dist, const int64_t* idx, long long rank_stride, int R, int Q, int k, double* out_dist,
+                           int64_t* out_idx, void* stream) {
+    EPC_CHECK_ARG(dist && idx && out_dist && out_idx, "epc_merge_topk_strided: NULL argument");
+    if (int rc = ensure_device(dist)) return rc;
+    return merge_topk(dist, idx, rank_stride, R, Q, k, out_dist, out_idx, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

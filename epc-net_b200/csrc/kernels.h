@@ -116,11 +116,10 @@ bool retr_tc_supported(int dim);
 int retr_ranges(int Q, int n_tiles);
 int retr_split2(const float* X, int R, int Rpad, int dim, __nv_bfloat16* out, float* norms, cudaStream_t st);
 int retr_scores(const __nv_bfloat16* q2, int Q, const __nv_bfloat16* db2, int D, int dim, int n_tiles, int tile_stride, int n_ranges,
-                const float* qn, const float* dn, float* scores, int ld, const float* thr, uint2* cand, int* cand_count, int cap,
-                cudaStream_t st);
+                const float* dn, float* scores, int ld, const float* thr, uint2* cand, int* cand_count, int cap, cudaStream_t st);
 int radius_search(const double* db, int D, const double* q, int Q, int dim, double r, int32_t* counts, const int64_t* offsets,
                   int32_t* indices, cudaStream_t st);
-int merge_topk(const double* dist, const int64_t* idx, int R, int Q, int k, double* out_dist, int64_t* out_idx,
+int merge_topk(const double* dist, const int64_t* idx, long long rank_stride, int R, int Q, int k, double* out_dist, int64_t* out_idx,
                cudaStream_t st);
 
 }  // namespace epc

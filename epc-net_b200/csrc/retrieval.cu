@@ -54,8 +54,8 @@ __device__ __forceinline__ bool key_less(double av, long long ai, double bv, lon
     return (av < bv) || (av == bv && ai < bi);
 }
 
-// One warp per query: 32 smallest of score_j = (qn + dn[j]) - 2 dot[j], ascending; columns ascend so ties keep
-// the lower index.
+// One warp per query: 32 smallest of score_j = dn[j] - 2 dot[j] (= |q - d_j|^2 - |q|^2), ascending; columns ascend so ties
+// keep the lower index.
 // RAW: `dots` already holds the scores (the tensor-core epilogue applied the norms)
 template <bool RAW>
 __global__ void candidates_kernel(const float* __restrict__ dots, int ld, const float* __restrict__ qn,
@@ -65,7 +65,6 @@ __global__ void candidates_kernel(const float* __restrict__ dots, int ld, const 
     const int lane = threadIdx.x & 31;
     if (qi >= Qt) return;
     const float* row = dots + (size_t)qi * ld;
-    const float qq = RAW ? 0.f : qn[qi];
     float val = INFINITY;
     int vi = -1;
     int filled = 0;
@@ -76,7 +75,7 @@ __global__ void candidates_kernel(const float* __restrict__ dots, int ld, const 
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int j = jb + 32 * u + lane;
-            sv[u] = (j < D) ? (RAW ? __ldg(row + j) : fmaf(-2.0f, __ldg(row + j), qq + __ldg(dn + j))) : INFINITY;
+            sv[u] = (j < D) ? (RAW ? __ldg(row + j) : fmaf(-2.0f, __ldg(row + j), __ldg(dn + j))) : INFINITY;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -141,6 +140,34 @@ __device__ __forceinline__ double exact_d2(const float* __restrict__ q, const fl
     return acc;
 }
 
+// the same sum with the query already converted to float64 (shared memory, one copy per warp): half the F2F conversions
+__device__ __forceinline__ double exact_d2_staged(const double* __restrict__ qd, const float* __restrict__ d, int dim) {
+    double acc = 0.0;
+    int k = 0;
+    if ((dim & 3) == 0 && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+        const float4* d4 = reinterpret_cast<const float4*>(d);
+        for (; k + 16 <= dim; k += 16) {
+            float4 b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) b[u] = __ldg(d4 + (k >> 2) + u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double t0 = qd[k + 4 * u] - (double)b[u].x, t1 = qd[k + 4 * u + 1] - (double)b[u].y;
+                const double t2 = qd[k + 4 * u + 2] - (double)b[u].z, t3 = qd[k + 4 * u + 3] - (double)b[u].w;
+                acc = __dadd_rn(acc, __dmul_rn(t0, t0));
+                acc = __dadd_rn(acc, __dmul_rn(t1, t1));
+                acc = __dadd_rn(acc, __dmul_rn(t2, t2));
+                acc = __dadd_rn(acc, __dmul_rn(t3, t3));
+            }
+        }
+    }
+    for (; k < dim; ++k) {
+        const double t = qd[k] - (double)d[k];
+        acc = __dadd_rn(acc, __dmul_rn(t, t));
+    }
+    return acc;
+}
+
 // bitonic sort of one (value,index) pair per lane, ascending
 __device__ __forceinline__ void warp_sort_pairs(double& v, long long& i, int lane) {
 #pragma unroll
@@ -160,6 +187,7 @@ __device__ __forceinline__ void warp_sort_pairs(double& v, long long& i, int lan
     }
 }
 
+template <bool STAGED>       // STAGED: dynamic shared memory = warps per block x dim doubles
 __global__ void rerank_kernel(const float* __restrict__ db, const float* __restrict__ q, const int* __restrict__ cand,
                               const float* __restrict__ a32, const float* __restrict__ qn, const float* __restrict__ dn_max_p, int Qt, int dim,
                               int k, long long id_offset, int64_t* __restrict__ idx, double* __restrict__ dist,
@@ -170,8 +198,14 @@ __global__ void rerank_kernel(const float* __restrict__ db, const float* __restr
     const int c = cand[(size_t)qi * RC + lane];
     double v = INFINITY;
     long long gi = 0x7fffffffffffffffLL;
+    extern __shared__ double s_q[];
+    double* qd = s_q + (size_t)(threadIdx.x >> 5) * dim;
+    if (STAGED) {
+        for (int i = lane; i < dim; i += 32) qd[i] = (double)q[(size_t)qi * dim + i];
+        __syncwarp();
+    }
     if (c >= 0) {
-        v = exact_d2(q + (size_t)qi * dim, db + (size_t)c * dim, dim);
+        v = STAGED ? exact_d2_staged(qd, db + (size_t)c * dim, dim) : exact_d2(q + (size_t)qi * dim, db + (size_t)c * dim, dim);
         gi = (long long)c + id_offset;
     }
     warp_sort_pairs(v, gi, lane);
@@ -185,7 +219,7 @@ __global__ void rerank_kernel(const float* __restrict__ db, const float* __restr
         // sums, 1.2e-7 (dim + 8).  3xTF32 path: products exact in fp32, dropped ql.dl and split residues 3 x 2^-22, accumulation
         // of 3 dim terms at <= 2^-22 each (the tensor core may truncate): 2.4e-7 (3 dim + 8) -- both generous.
         const float err = err_unit * (qn[qi] + *dn_max_p);
-        const float a = a32[qi];
+        const float a = a32[qi] + qn[qi];              // scores omit the query's own |q|^2
         flags[qi] = (a == INFINITY) ? 0 : !((float)kth * (1.0f + 2e-7f) < a - err);
     }
 }
@@ -245,54 +279,101 @@ __global__ void max_reduce_kernel(const float* __restrict__ x, int n, float* __r
     }
 }
 
-// One warp per query: the 32 smallest (score, row) among the candidates the scoring epilogue emitted into the query's
-// regions (retrieval_tc.cu).  The emission order is arbitrary, the (score, row) order makes the result deterministic.
-__global__ void select_kernel(const uint2* __restrict__ cand_in, const int* __restrict__ counts, int n_ranges, int cap, int Qt,
-                              int* __restrict__ cand, float* __restrict__ a32) {
+// One warp per query: an upper bound of the 32nd smallest of the query's S sample scores that at most ~40 of them reach
+// (bisection on the value between the smallest lane minimum and the largest lane minimum -- each lane's minimum is a
+// distinct sample element, so 32 of them lie at or below the largest).  S <= 32 * PER_LANE.
+template <int PER_LANE>
+__global__ void sample_threshold_kernel(const float* __restrict__ scores, int ld, int S, int Qt, float* __restrict__ thr) {
     const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (qi >= Qt) return;
+    const float* row = scores + (size_t)qi * ld;
+    float v[PER_LANE];
+    float mn = INFINITY;
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) {
+        v[i] = (32 * i + lane < S) ? __ldg(row + 32 * i + lane) : INFINITY;
+        mn = fminf(mn, v[i]);
+    }
+    float lo = warp_min(mn), hi = warp_max(mn);
+    for (int it = 0; it < 16; ++it) {
+        const float t = 0.5f * lo + 0.5f * hi;
+        if (!(t > lo && t < hi)) break;
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) c += (v[i] <= t) ? 1 : 0;
+        c = __reduce_add_sync(FULL, c);
+        if (c >= RC) {
+            hi = t;
+            if (c <= RC + 8) break;
+        } else {
+            lo = t;
+        }
+    }
+    if (lane == 0) thr[qi] = hi;
+}
+
+// One warp per query: the 32 smallest (score, row) among the candidates the scoring epilogue emitted into the query's
+// regions (retrieval_tc.cu).  The emission order is arbitrary, the (score, row) order makes the result deterministic.
+__global__ void select_kernel(const uint2* __restrict__ cand_in, const int* __restrict__ counts, int n_regions, int cap, int Qt,
+                              int* __restrict__ cand, float* __restrict__ a32) {
+    extern __shared__ int s_counts[];                     // [warps per block][n_regions]
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * (blockDim.x >> 5) + w;
+    if (qi >= Qt) return;
+    int* cnt = s_counts + w * n_regions;
+    bool overflow = false;
+    for (int r = lane; r < n_regions; r += 32) {
+        const int c = __ldg(counts + (size_t)qi * n_regions + r);
+        overflow |= c < 0;
+        cnt[r] = c < 0 ? 0 : c;
+    }
+    overflow = __any_sync(FULL, overflow);
+    __syncwarp();
+    const uint2* base = cand_in + (size_t)qi * n_regions * cap;
+    const uint2 none = make_uint2(0x7f800000u, 0x7fffffffu);
+    // chunks of 32 entries, walked region by region; the next chunk's load is in flight while this one is merged
+    int r = 0, e0 = 0;
+    while (r < n_regions && cnt[r] == 0) ++r;
+    uint2 nxt = (r < n_regions && e0 + lane < cnt[r]) ? __ldg(base + (size_t)r * cap + e0 + lane) : none;
     float val = INFINITY;
     int vi = 0x7fffffff;
     int filled = 0;
     float thr = INFINITY;
     int thr_i = 0x7fffffff;
-    bool overflow = false;
-    for (int r = 0; r < n_ranges; ++r) {
-        const int c = counts[(size_t)qi * n_ranges + r];
-        if (c < 0) {
-            overflow = true;
-            continue;
+    while (r < n_regions) {
+        const uint2 ent = nxt;
+        e0 += 32;
+        if (e0 >= cnt[r]) {
+            e0 = 0;
+            ++r;
+            while (r < n_regions && cnt[r] == 0) ++r;
         }
-        const uint2* reg = cand_in + ((size_t)qi * n_ranges + r) * cap;
-        for (int e0 = 0; e0 < c; e0 += 32) {
-            const bool have = e0 + lane < c;
-            const uint2 ent = have ? __ldg(reg + e0 + lane) : make_uint2(0x7f800000u, 0x7fffffffu);
-            const float s = __uint_as_float(ent.x);
-            const int si = (int)ent.y;
-            unsigned m = __ballot_sync(FULL, have && (filled < RC || s < thr || (s == thr && si < thr_i)));
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const float cv = __shfl_sync(FULL, s, src);
-                const int ci = __shfl_sync(FULL, si, src);
-                const bool before = (lane < filled) && (val < cv || (val == cv && vi < ci));
-                const int pos = __popc(__ballot_sync(FULL, before));
-                if (pos < RC) {
-                    const float upv = __shfl_up_sync(FULL, val, 1);
-                    const int upi = __shfl_up_sync(FULL, vi, 1);
-                    if (lane == pos) {
-                        val = cv;
-                        vi = ci;
-                    } else if (lane > pos) {
-                        val = upv;
-                        vi = upi;
-                    }
-                    filled = min(filled + 1, RC);
-                    if (filled == RC) {
-                        thr = __shfl_sync(FULL, val, RC - 1);
-                        thr_i = __shfl_sync(FULL, vi, RC - 1);
-                    }
+        nxt = (r < n_regions && e0 + lane < cnt[r]) ? __ldg(base + (size_t)r * cap + e0 + lane) : none;
+        const float s = __uint_as_float(ent.x);
+        const int si = (int)ent.y;
+        unsigned m = __ballot_sync(FULL, si != 0x7fffffff && (filled < RC || s < thr || (s == thr && si < thr_i)));
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const float cv = __shfl_sync(FULL, s, src);
+            const int ci = __shfl_sync(FULL, si, src);
+            const bool before = (lane < filled) && (val < cv || (val == cv && vi < ci));
+            const int pos = __popc(__ballot_sync(FULL, before));
+            if (pos < RC) {
+                const float upv = __shfl_up_sync(FULL, val, 1);
+                const int upi = __shfl_up_sync(FULL, vi, 1);
+                if (lane == pos) {
+                    val = cv;
+                    vi = ci;
+                } else if (lane > pos) {
+                    val = upv;
+                    vi = upi;
+                }
+                filled = min(filled + 1, RC);
+                if (filled == RC) {
+                    thr = __shfl_sync(FULL, val, RC - 1);
+                    thr_i = __shfl_sync(FULL, vi, RC - 1);
                 }
             }
         }
@@ -311,23 +392,17 @@ __global__ void fill_empty_kernel(int64_t* __restrict__ idx, double* __restrict_
     }
 }
 
-static int pad128(int D) { return (D + 127) / 128 * 128; }
 static int pad256(int D) { return (D + 255) / 256 * 256; }
 
 constexpr int RETR_DENSE_MAX = 4096;      // databases up to this many rows: dense scores + scan (the matrix is small)
 constexpr int RETR_QTILE = 8192;          // queries per pass (bounds the workspace)
+constexpr int RETR_SAMPLE_TILES = 16;     // threshold sample: 16 tiles of 128 rows spread over the database
 
-// size of the threshold sample (rows, a multiple of 128) and of a candidate region for the emit path
-static int sample_rows(int D) {
-    int t = pad128(D) / 128 / 8;
-    if (t < 8) t = 8;
-    if (t > 32) t = 32;
-    return t * 128;
-}
-static int region_cap(int D, int tiles_per_range) {
-    // expected entries per region = 32 * rows_in_range / sample_rows; 2.5x + 64 headroom
-    const long long e = 32ll * tiles_per_range * 128 / sample_rows(D);
-    return (int)((e * 5 / 2 + 64 + 7) / 8 * 8);
+// entries of one candidate region (one query x one range x one column half).  The threshold lets 32..40 of the 2048 sample
+// scores through, i.e. ~2 % of exchangeable rows; 3x headroom + 32.
+static int region_cap(int tiles_per_range) {
+    const long long rows = 64ll * tiles_per_range;
+    return (int)((rows * 6 / 100 + 32 + 7) / 8 * 8);
 }
 
 // ---- the prepared database ("index"): what KDTree(database_output) (evaluate.py:463) is to the reference --------------------
@@ -336,18 +411,18 @@ struct RetrIndex {             // laid out at the start of the caller's index me
     float dn_max;              // (device copy lives in dn_max_dev)
 };
 size_t retrieve_index_bytes(int D, int dim) {
-    const int Dp = pad128(D);
+    const int Dp = pad256(D);
     return 256 + align_up((size_t)Dp * 4) + align_up(16) + (retr_tc_supported(dim) ? align_up((size_t)(D > 0 ? D : 1) * 2 * dim * 2) : 0) + 256;
 }
 struct IndexView {
-    float* dn;                 // [pad128(D)] |d|^2, +inf padding
+    float* dn;                 // [pad256(D)] |d|^2, +inf padding
     float* dn_max;             // [1]
     __nv_bfloat16* db2;        // [D, 2 dim] (tensor path)
 };
 static IndexView index_view(void* mem, int D, int dim) {
     Arena ar(mem, (size_t)1 << 60);
     IndexView v;
-    v.dn = ar.take<float>(pad128(D));
+    v.dn = ar.take<float>(pad256(D));
     v.dn_max = ar.take<float>(4);
     v.db2 = retr_tc_supported(dim) ? ar.take<__nv_bfloat16>((size_t)(D > 0 ? D : 1) * 2 * dim) : nullptr;
     return v;
@@ -358,7 +433,7 @@ int retrieve_index_build(const float* db, int D, int dim, void* index_mem, size_
                   index_bytes, retrieve_index_bytes(D, dim));
     if (D == 0) return EPC_OK;
     IndexView v = index_view(index_mem, D, dim);
-    const int Dp = pad128(D);
+    const int Dp = pad256(D);
     if (v.db2) {
         if (int rc = retr_split2(db, D, Dp, dim, v.db2, v.dn, st)) return rc;
     } else {
@@ -374,19 +449,19 @@ size_t retrieve_workspace_bytes(int D, int Q, int dim, int k) {
     (void)k;
     const int qt = Q < RETR_QTILE ? (Q > 0 ? Q : 1) : RETR_QTILE;
     size_t s = retrieve_index_bytes(D, dim) + align_up((size_t)qt * 4) * 3 + align_up((size_t)qt * RC * 4) + 1024;
+    const int Dp = pad256(D);
     if (retr_tc_supported(dim)) {
         s += align_up((size_t)qt * 2 * dim * 2);
-        const int Dp = pad128(D);
         if (D <= RETR_DENSE_MAX) {
             s += align_up((size_t)qt * Dp * 4);
         } else {
             const int n_tiles = Dp / 128;
             const int nr = retr_ranges(qt, n_tiles);
             const int tpr = (n_tiles + nr - 1) / nr;
-            s += align_up((size_t)qt * sample_rows(D) * 4) + align_up((size_t)qt * nr * region_cap(D, tpr) * 8) + align_up((size_t)qt * nr * 4);
+            s += align_up((size_t)qt * RETR_SAMPLE_TILES * 128 * 4) + align_up((size_t)qt * 2 * nr * region_cap(tpr) * 8) + align_up((size_t)qt * 2 * nr * 4);
         }
     } else {
-        s += align_up((size_t)qt * pad256(D) * 4);
+        s += align_up((size_t)qt * Dp * 4);
     }
     return s;
 }
@@ -407,7 +482,7 @@ int retrieve_topk(const float* db, int D, const float* q, int Q, int dim, int k,
         return EPC_EWORKSPACE;
     }
     const bool tensor = retr_tc_supported(dim);
-    const int Dp = pad128(D);
+    const int Dp = pad256(D);
     const int qt = Q < RETR_QTILE ? Q : RETR_QTILE;
     Arena ar(ws, ws_bytes);
     void* own_index = ar.take<unsigned char>(retrieve_index_bytes(D, dim));
@@ -421,7 +496,7 @@ int retrieve_topk(const float* db, int D, const float* q, int Q, int dim, int k,
         index = own_index;
     }
     const IndexView iv = index_view(const_cast<void*>(index), D, dim);
-    // scoring error bound: |score - exact d^2| <= err_unit (|q|^2 + max |d|^2).  bf16-pair path: dropped ql.dl and split
+    // scoring error bound: |score + |q|^2 - exact d^2| <= err_unit (|q|^2 + max |d|^2).  bf16-pair path: dropped ql.dl and split
     // residues 2^-16, accumulation of 3 dim products at <= 2^-22 each (the tensor core may truncate); FFMA path: dim-term FMA
     // chain + norm sums, 1.2e-7 (dim + 8) -- both generous.
     const float err_unit = tensor ? 2.4e-7f * (float)(3 * dim + 8) + 4e-5f : 1.2e-7f * (float)(dim + 8);
@@ -440,40 +515,35 @@ int retrieve_topk(const float* db, int D, const float* q, int Q, int dim, int k,
                 float* scores = ar.take<float>((size_t)qt * Dp);
                 {
                     ScopedStage ss(EPC_STAGE_RETRIEVE_SCORE, st);
-                    if (int rc = retr_scores(q2, nq, iv.db2, D, dim, n_tiles, 1, retr_ranges(nq, n_tiles), qn, iv.dn, scores, Dp, nullptr,
-                                             nullptr, nullptr, 0, st))
+                    if (int rc = retr_scores(q2, nq, iv.db2, D, dim, n_tiles, 1, retr_ranges(nq, n_tiles), iv.dn, scores, Dp, nullptr, nullptr,
+                                             nullptr, 0, st))
                         return rc;
                 }
                 ScopedStage ss(EPC_STAGE_RETRIEVE_SELECT, st);
                 candidates_kernel<true><<<(nq + 7) / 8, 256, 0, st>>>(scores, Dp, qn, iv.dn, nq, D, cand, a32);
                 EPC_LAUNCH_CHECK();
             } else {
-                const int S = sample_rows(D);
-                int nr = retr_ranges(nq, n_tiles);
+                const int nr = retr_ranges(nq, n_tiles);
                 const int tpr = (n_tiles + nr - 1) / nr;
-                nr = (n_tiles + tpr - 1) / tpr;
-                const int cap = region_cap(D, tpr);
+                const int cap = region_cap(tpr);
+                constexpr int S = RETR_SAMPLE_TILES * 128;
                 float* sample = ar.take<float>((size_t)qt * S);
-                uint2* regions = ar.take<uint2>((size_t)qt * nr * cap);
-                int* counts = ar.take<int>((size_t)qt * nr);
-                {   // the 32nd smallest score over S rows (every stride-th tile): an upper bound of the 32nd smallest over all rows
-                    ScopedStage ss(EPC_STAGE_RETRIEVE_SCORE, st);
-                    if (int rc = retr_scores(q2, nq, iv.db2, D, dim, S / 128, n_tiles / (S / 128), retr_ranges(nq, S / 128), qn, iv.dn, sample, S, nullptr,
-                                             nullptr, nullptr, 0, st))
-                        return rc;
-                }
+                uint2* regions = ar.take<uint2>((size_t)qt * 2 * nr * cap);
+                int* counts = ar.take<int>((size_t)qt * 2 * nr);
                 {
-                    ScopedStage ss(EPC_STAGE_RETRIEVE_SELECT, st);
-                    candidates_kernel<true><<<(nq + 7) / 8, 256, 0, st>>>(sample, S, qn, iv.dn, nq, S, cand, a32);
-                    EPC_LAUNCH_CHECK();
-                }
-                {   // every row scoring below it, straight from the accumulators
                     ScopedStage ss(EPC_STAGE_RETRIEVE_SCORE, st);
-                    if (int rc = retr_scores(q2, nq, iv.db2, D, dim, n_tiles, 1, nr, qn, iv.dn, nullptr, 0, a32, regions, counts, cap, st))
+                    // scores of 16 tiles spread over the database -> an upper bound of every query's 32nd smallest score ...
+                    if (int rc = retr_scores(q2, nq, iv.db2, D, dim, RETR_SAMPLE_TILES, n_tiles / RETR_SAMPLE_TILES,
+                                             retr_ranges(nq, RETR_SAMPLE_TILES), iv.dn, sample, S, nullptr, nullptr, nullptr, 0, st))
+                        return rc;
+                    sample_threshold_kernel<S / 32><<<(nq + 7) / 8, 256, 0, st>>>(sample, S, S, nq, a32);
+                    EPC_LAUNCH_CHECK();
+                    // ... then every row scoring at or below it, straight from the accumulators
+                    if (int rc = retr_scores(q2, nq, iv.db2, D, dim, n_tiles, 1, nr, iv.dn, nullptr, 0, a32, regions, counts, cap, st))
                         return rc;
                 }
                 ScopedStage ss(EPC_STAGE_RETRIEVE_SELECT, st);
-                select_kernel<<<(nq + 7) / 8, 256, 0, st>>>(regions, counts, nr, cap, nq, cand, a32);
+                select_kernel<<<(nq + 7) / 8, 256, (size_t)8 * 2 * nr * sizeof(int), st>>>(regions, counts, 2 * nr, cap, nq, cand, a32);
                 EPC_LAUNCH_CHECK();
             }
         } else {
@@ -494,8 +564,12 @@ int retrieve_topk(const float* db, int D, const float* q, int Q, int dim, int k,
             EPC_LAUNCH_CHECK();
         }
         ScopedStage ss(EPC_STAGE_RETRIEVE_RERANK, st);
-        rerank_kernel<<<(nq + 7) / 8, 256, 0, st>>>(db, qp, cand, a32, qn, iv.dn_max, nq, dim, k, id_offset, idx + (size_t)q0 * k,
-                                                    dist + (size_t)q0 * k, flags, err_unit);
+        if (dim <= 512)
+            rerank_kernel<true><<<(nq + 7) / 8, 256, (size_t)8 * dim * sizeof(double), st>>>(
+                db, qp, cand, a32, qn, iv.dn_max, nq, dim, k, id_offset, idx + (size_t)q0 * k, dist + (size_t)q0 * k, flags, err_unit);
+        else
+            rerank_kernel<false><<<(nq + 7) / 8, 256, 0, st>>>(db, qp, cand, a32, qn, iv.dn_max, nq, dim, k, id_offset,
+                                                               idx + (size_t)q0 * k, dist + (size_t)q0 * k, flags, err_unit);
         EPC_LAUNCH_CHECK();
         exact_fallback_kernel<<<(nq + 7) / 8, 256, 0, st>>>(db, qp, flags, nq, D, dim, k, id_offset, idx + (size_t)q0 * k,
                                                             dist + (size_t)q0 * k);
@@ -553,8 +627,8 @@ int radius_search(const double* db, int D, const double* q, int Q, int dim, doub
 }
 
 // Merge R shard lists per query by (distance, index): one warp per query, lists staged in shared memory.
-__global__ void merge_topk_kernel(const double* __restrict__ dist, const int64_t* __restrict__ idx, int R, int Q, int k,
-                                  double* __restrict__ out_dist, int64_t* __restrict__ out_idx) {
+__global__ void merge_topk_kernel(const double* __restrict__ dist, const int64_t* __restrict__ idx, long long rank_stride, int R,
+                                  int Q, int k, double* __restrict__ out_dist, int64_t* __restrict__ out_idx) {
     extern __shared__ __align__(16) unsigned char sm[];
     const int qi = blockIdx.x, lane = threadIdx.x;
     const int n = R * k;
@@ -562,7 +636,7 @@ __global__ void merge_topk_kernel(const double* __restrict__ dist, const int64_t
     long long* si = reinterpret_cast<long long*>(sd + n);
     for (int t = lane; t < n; t += 32) {
         const int r = t / k, j = t % k;
-        const size_t src = ((size_t)r * Q + qi) * k + j;
+        const size_t src = (size_t)r * rank_stride + (size_t)qi * k + j;
         long long id = idx[src];
         sd[t] = (id < 0) ? (double)INFINITY : dist[src];
         si[t] = (id < 0) ? 0x7fffffffffffffffLL : id;
@@ -602,11 +676,12 @@ __global__ void merge_topk_kernel(const double* __restrict__ dist, const int64_t
     }
 }
 
-int merge_topk(const double* dist, const int64_t* idx, int R, int Q, int k, double* out_dist, int64_t* out_idx,
-               cudaStream_t st) {
+int merge_topk(const double* dist, const int64_t* idx, long long rank_stride, int R, int Q, int k, double* out_dist,
+               int64_t* out_idx, cudaStream_t st) {
     EPC_CHECK_ARG(R >= 1 && k >= 1 && (size_t)R * k * 16 <= 48 * 1024, "merge_topk: R=%d k=%d unsupported", R, k);
+    EPC_CHECK_ARG(rank_stride >= (long long)Q * k, "merge_topk: rank_stride %lld < Q k", rank_stride);
     if (Q == 0) return EPC_OK;
-    merge_topk_kernel<<<Q, 32, (size_t)R * k * 16, st>>>(dist, idx, R, Q, k, out_dist, out_idx);
+    merge_topk_kernel<<<Q, 32, (size_t)R * k * 16, st>>>(dist, idx, rank_stride, R, Q, k, out_dist, out_idx);
     EPC_LAUNCH_CHECK();
     return EPC_OK;
 }

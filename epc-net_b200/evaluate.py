@@ -71,7 +71,8 @@ class RetrievalIndex:
             self.mem = torch.empty((int(lib.epc_retrieve_index_bytes(D, dim)),), dtype=torch.uint8, device=db.device)
             _lib.check(lib.epc_retrieve_index_build(_ptr(db), D, dim, _ptr(self.mem), self.mem.numel(), _stream()))
 
-    def query(self, queries_output, k):
+    def query(self, queries_output, k, out=None):
+        """``out``: optional preallocated (dist [Q,k] float64, idx [Q,k] int64) contiguous CUDA tensors."""
         lib = _lib.load()
         db = self.db
         q = _engine.as_cuda_f32(queries_output, "queries_output")
@@ -82,8 +83,14 @@ class RetrievalIndex:
         D, dim = db.shape
         Q = q.shape[0]
         k = int(k)
-        idx = torch.empty((Q, k), dtype=torch.int64, device=db.device)
-        dist = torch.empty((Q, k), dtype=torch.float64, device=db.device)
+        if out is not None:
+            dist, idx = out
+            if (dist.dtype != torch.float64 or idx.dtype != torch.int64 or tuple(dist.shape) != (Q, k) or tuple(idx.shape) != (Q, k)
+                    or not dist.is_contiguous() or not idx.is_contiguous() or dist.device != db.device or idx.device != db.device):
+                raise ValueError("out must be contiguous (float64 [Q,k], int64 [Q,k]) tensors on the database's device")
+        else:
+            idx = torch.empty((Q, k), dtype=torch.int64, device=db.device)
+            dist = torch.empty((Q, k), dtype=torch.float64, device=db.device)
         with torch.cuda.device(db.device):
             ws = workspaces.get(lib.epc_retrieve_workspace_bytes(D, Q, dim, k))
             _lib.check(lib.epc_retrieve_topk_indexed(_ptr(db), D, _ptr(self.mem), _ptr(q), Q, dim, k, self.id_offset,

@@ -80,6 +80,11 @@ void epc_profile_enable(int on);
 void epc_profile_reset(void);
 int epc_profile_read(int stage, double* ms, long long* launches);
 const char* epc_stage_name(int stage);
+/* Measurement aid for bench.py's roofline (not on the data path): launches a register-only FFMA loop on every SM,
+ * `iters` x 16 independent fused multiply-adds per thread, and returns the FLOP count of the launch (2 per FMA) in
+ * *flops.  The caller times it with events on `stream`: FLOP / time = the FP32 pipe's achievable peak at the clocks
+ * of the moment, which is the roofline of the ALU-bound kNN kernels. */
+int epc_microbench_ffma(int iters, double* flops, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * kNN graph  (replaces tf_util.pairwise_distance_mask, utils/tf_util.py:647-666; and
@@ -220,6 +225,10 @@ int epc_retrieve_topk_indexed(const float* db /*[D,dim]*/, int D, const void* in
  * ordered by (distance, index) so the result does not depend on the shard count. */
 int epc_merge_topk(const double* dist /*[R,Q,k]*/, const int64_t* idx /*[R,Q,k]*/, int R, int Q, int k,
                    double* out_dist /*[Q,k]*/, int64_t* out_idx /*[Q,k]*/, void* stream);
+/* The same merge on lists whose rank-r slab starts rank_stride elements after rank r-1's (>= Q*k): lets every rank send
+ * ONE packed (dist | idx) buffer through a single all-gather (dist = buf, idx = buf + Q*k, rank_stride = 2*Q*k). */
+int epc_merge_topk_strided(const double* dist, const int64_t* idx, long long rank_stride, int R, int Q, int k,
+                           double* out_dist /*[Q,k]*/, int64_t* out_idx /*[Q,k]*/, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Radius search  (replaces KDTree(db[['northing','easting']]).query_radius(coor, r) of

@@ -107,10 +107,9 @@ def test_candidate_region_overflow_falls_back_exactly(ev):
     D, dim = 6000, 64
     centre = rng.standard_normal((1, dim)).astype(np.float32)
     db = centre + 0.01 * rng.standard_normal((D, dim)).astype(np.float32)
-    n_tiles = (D + 127) // 128
-    s_tiles = min(32, max(8, n_tiles // 8))
-    stride = n_tiles // s_tiles
-    for t in range(s_tiles):
+    n_tiles = (D + 255) // 256 * 2                                # retrieval.cu: 16 sample tiles of 128 rows, every stride-th
+    stride = n_tiles // 16
+    for t in range(16):
         lo = t * stride * 128
         db[lo:lo + 128] = 5.0 * rng.standard_normal((len(db[lo:lo + 128]), dim)).astype(np.float32)
     q = centre + 0.01 * rng.standard_normal((6, dim)).astype(np.float32)
@@ -146,6 +145,12 @@ def test_sharded_merge_is_shard_count_invariant(ev):
             ds.append(d)
             is_.append(i)
         md, mi = dist_mod.cuda_merge(torch.stack(ds), torch.stack(is_))
+        assert torch.equal(mi, i0) and torch.equal(md, d0), world
+        # the packed layout one all-gather delivers: [world, 2, Q, k], ids as float64 bit patterns
+        g = torch.stack([torch.stack([d, i.view(torch.float64)]) for d, i in zip(ds, is_)])
+        md, mi = dist_mod.cuda_merge(g[:, 0], g[:, 1].view(torch.int64))
+        assert torch.equal(mi, i0) and torch.equal(md, d0), world
+        md, mi = dist_mod._merge_strided(g, world, 64, 25)
         assert torch.equal(mi, i0) and torch.equal(md, d0), world
 
 
