@@ -77,9 +77,9 @@ def _merge_strided(g, R, Q, k):
     from .engine import _ptr, _stream
     od = torch.empty((Q, k), dtype=torch.float64, device=g.device)
     oi = torch.empty((Q, k), dtype=torch.int64, device=g.device)
-    base = _ptr(g)
+    assert g.is_contiguous() and g.dtype == torch.float64 and tuple(g.shape) == (R, 2, Q, k)
     with torch.cuda.device(g.device):
-        _lib.check(_lib.load().epc_merge_topk_strided(base, base + Q * k * 8, 2 * Q * k, R, Q, k, _ptr(od), _ptr(oi), _stream()))
+        _lib.check(_lib.load().epc_merge_topk_strided(_ptr(g[0, 0]), _ptr(g[0, 1]), 2 * Q * k, R, Q, k, _ptr(od), _ptr(oi), _stream()))
     return od, oi
 
 
