@@ -49,6 +49,8 @@ STAGE_MODEL = {
     "conv5": (2.0 * N_POINTS * 256 * 1024, 2 * MiB + 8 * MiB, "tensor"),           # concat16 in, H (bf16) out
     "assign_gemm": (2.0 * N_POINTS * 1024 * 64, 8 * MiB + 0.5 * MiB, "tensor"),    # H in, S' out
     "vlad_gemm": (2.0 * 64 * N_POINTS * 1024, 8 * MiB + 0.5 * MiB + 0.5 * MiB, "tensor"),
+    # assignment + VLAD in one launch: H read once from HBM (VLAD's pass is served by the L2), S' written, V slabs written
+    "assign_vlad": (2 * 2.0 * N_POINTS * 1024 * 64, 8 * MiB + 0.5 * MiB + 0.5 * MiB, "tensor"),
     "vlad_finalize": (0.0, 3 * 0.25 * MiB + 2 * 0.25 * MiB, "alu"),
     "hidden_gemm": (2.0 * 4 * 16384 * 256, 0.25 * MiB + 16.8e6 / 128.0, "tensor"),   # 16.8 MB of weights per 128-cloud call
 }

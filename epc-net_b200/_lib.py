@@ -109,7 +109,7 @@ def check(rc):
         raise EpcError(rc, load().epc_last_error().decode("utf-8", "replace"))
 
 
-STAGE_COUNT = 19
+STAGE_COUNT = 20
 
 
 def profile_enable(on: bool):

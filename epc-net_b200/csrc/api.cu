@@ -187,7 +187,7 @@ const char* epc_stage_name(int stage) {
     static const char* names[EPC_STAGE_COUNT] = {"sort", "knn", "conv_in", "proxy_block", "conv5", "rownorm",
                                                  "assign_gemm", "assign_softmax", "vlad_gemm", "vlad_finalize",
                                                  "hidden_gemm", "tail", "colmax", "fc", "kd_feat", "retrieve_score",
-                                                 "retrieve_select", "retrieve_rerank", "proxy_block_safe"};
+                                                 "retrieve_select", "retrieve_rerank", "proxy_block_safe", "assign_vlad"};
     return (stage >= 0 && stage < EPC_STAGE_COUNT) ? names[stage] : "?";
 }
 
@@ -456,6 +456,7 @@ struct HeadWs {                 // buffers of the G_VLAD / NetVLAD head
     float* v;                   // [B, 65536]
     float* Y;                   // [HIDDEN_SPLITK][B*G, D]
     float* colss;               // [B, 8, 64] partial column sums of squares of the VLAD residuals
+    int* ready;                 // [sub] per-cloud tile counters of the fused assignment + VLAD launch
 };
 
 size_t head_bytes(const EpcModel* m, int B, int N) {
@@ -463,7 +464,7 @@ size_t head_bytes(const EpcModel* m, int B, int N) {
     return align_up(sub * 1024 * 2) + align_up(sub * CONV5_ROWSS_PARTS * 4) + align_up(sub * 64 * 2) +
            align_up((size_t)B * (N / 128) * 64 * 4) + align_up((size_t)VLAD_SPLITK * B * 1024 * 64 * 4) +
            align_up((size_t)B * 1024 * 64 * 4) + align_up((size_t)HIDDEN_SPLITK * B * m->G * m->D * 4) +
-           align_up((size_t)B * 8 * 64 * 4);
+           align_up((size_t)B * 8 * 64 * 4) + align_up((size_t)(B < HEAD_SUB ? B : HEAD_SUB) * 4);
 }
 
 HeadWs head_carve(Arena& ar, const EpcModel* m, int B, int N) {
@@ -477,12 +478,22 @@ HeadWs head_carve(Arena& ar, const EpcModel* m, int B, int N) {
     h.v = ar.take<float>((size_t)B * 1024 * 64);
     h.Y = ar.take<float>((size_t)HIDDEN_SPLITK * B * m->G * m->D);
     h.colss = ar.take<float>((size_t)B * 8 * 64);
+    h.ready = ar.take<int>((size_t)(B < HEAD_SUB ? B : HEAD_SUB));
     return h;
 }
 
 // assignment + VLAD accumulate for clouds [b0, b0+nb) whose bf16 features and rowss are in h.H16 / h.rowss
 int head_assign_vlad(const EpcModel* m, int B, int N, int b0, int nb, const HeadWs& h, int rowss_parts, cudaStream_t st) {
     const long long Rs = (long long)nb * N;
+    // one launch for both GEMMs: VLAD's read of H comes from the L2 the assignment CTAs filled (head_fused.cu);
+    // EPC_HEAD_FUSED=0 selects the two separate kernels (same results bit for bit: identical tiles and summation order)
+    static const bool fused = !(getenv("EPC_HEAD_FUSED") && atoi(getenv("EPC_HEAD_FUSED")) == 0);
+    if (fused) {
+        ScopedStage ss(EPC_STAGE_ASSIGN_VLAD, st);
+        return tc_assign_vlad(h.H16, nb, N, m->Wct16, h.rowss, rowss_parts, m->cbn_scale, m->cbn_shift, h.S16,
+                              h.a_part + (size_t)b0 * (N / 128) * 64, h.V + (size_t)b0 * 1024 * 64, VLAD_SPLITK,
+                              (long long)B * 1024 * 64, h.ready, st);
+    }
     {
         ScopedStage ss(EPC_STAGE_ASSIGN_GEMM, st);
         if (int rc = tc_assign(h.H16, Rs, m->Wct16, h.rowss, rowss_parts, m->cbn_scale, m->cbn_shift, h.S16,

@@ -89,6 +89,10 @@ constexpr int CONV5_ROWSS_PARTS = 8;   // 1024 / BN(256) N tiles x 2 epilogue wa
 int conv5_rowss_parts();
 int tc_assign(const __nv_bfloat16* H, long long R, const __nv_bfloat16* Wct, const float* rowss, int parts,
               const float* bn_scale, const float* bn_shift, __nv_bfloat16* S, float* a_part, cudaStream_t st);
+// head_fused.cu: both of the above in one launch (VLAD's read of H is served by the L2)
+int tc_assign_vlad(const __nv_bfloat16* H, int clouds, int N, const __nv_bfloat16* Wct, const float* rowss, int parts,
+                   const float* bn_scale, const float* bn_shift, __nv_bfloat16* S, float* a_part, float* V, int splitk, long long slab,
+                   int* ready, cudaStream_t st);
 int tc_vlad(const __nv_bfloat16* H, const __nv_bfloat16* S, int B, int N, float* V, int splitk, long long slab,
             cudaStream_t st);
 int tc_conv5_colmax(const float* Xc, long long R, int cin, int rows_per_cloud, const float* W5t, const float* b5,

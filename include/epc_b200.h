@@ -74,7 +74,8 @@ enum {
     EPC_STAGE_SORT = 0, EPC_STAGE_KNN, EPC_STAGE_CONV_IN, EPC_STAGE_BLOCK, EPC_STAGE_CONV5, EPC_STAGE_ROWNORM,
     EPC_STAGE_ASSIGN_GEMM, EPC_STAGE_ASSIGN_SOFTMAX, EPC_STAGE_VLAD_GEMM, EPC_STAGE_VLAD_FINALIZE,
     EPC_STAGE_HIDDEN_GEMM, EPC_STAGE_TAIL, EPC_STAGE_COLMAX, EPC_STAGE_FC, EPC_STAGE_KD_FEAT,
-    EPC_STAGE_RETRIEVE_SCORE, EPC_STAGE_RETRIEVE_SELECT, EPC_STAGE_RETRIEVE_RERANK, EPC_STAGE_BLOCK_SAFE, EPC_STAGE_COUNT
+    EPC_STAGE_RETRIEVE_SCORE, EPC_STAGE_RETRIEVE_SELECT, EPC_STAGE_RETRIEVE_RERANK, EPC_STAGE_BLOCK_SAFE, EPC_STAGE_ASSIGN_VLAD,
+    EPC_STAGE_COUNT
 };
 void epc_profile_enable(int on);
 void epc_profile_reset(void);
