@@ -77,8 +77,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--clouds", type=int, default=8192, help="clouds per GPU per step (a multiple of --batch)")
-    ap.add_argument("--batch", type=int, default=256, help="clouds per embed() call (split over --streams library calls)")
-    ap.add_argument("--chunk", type=int, default=128, help="clouds per library call")
+    ap.add_argument("--batch", type=int, default=512, help="clouds per embed() call (split over --streams library calls)")
+    ap.add_argument("--chunk", type=int, default=256, help="clouds per library call")
     ap.add_argument("--e2e-clouds", type=int, default=4096, help="clouds per step of the end-to-end (host buffer) measurement")
     ap.add_argument("--no-epc-net-l", action="store_true", help="skip the EPC-Net-L extra key")
     ap.add_argument("--streams", type=int, default=2, help="CUDA streams the calls of one step alternate over")

@@ -438,12 +438,13 @@ void epc_model_destroy(EpcModel* m) {
 namespace {
 
 // clouds per head sub-batch: the bf16 conv5 output H (8 MiB per cloud) of one sub-batch is produced and consumed by
-// three GEMM launches back to back.  Measured on B200 (us/cloud for conv5+assign+VLAD): 8 -> 10.2, 32 -> 8.2, 64 -> 7.5,
-// 128 -> 7.1: launch/prologue/wave-quantisation costs outweigh keeping H inside the L2.  EPC_HEAD_SUB overrides (tuning aid).
+// the GEMM launches back to back.  Measured on B200 (us/cloud for conv5+assign+VLAD): 8 -> 10.2, 32 -> 8.2, 64 -> 7.5,
+// 128 -> 7.1 (round 1, three kernels); conv5 + fused assignment/VLAD, round 2: 64 -> 5.72, 128 -> 5.45, 256 -> 5.49:
+// launch/prologue/wave-quantisation costs outweigh keeping H inside the L2.  EPC_HEAD_SUB overrides (tuning aid).
 static int head_sub_init() {
     const char* e = getenv("EPC_HEAD_SUB");
     int v = e ? atoi(e) : 0;
-    return (v >= 1 && v <= 256) ? v : 64;
+    return (v >= 1 && v <= 256) ? v : 128;
 }
 static const int HEAD_SUB = head_sub_init();
 

@@ -201,7 +201,7 @@ class Engine(object):
     def _chunk_for(self, n: int) -> int:
         if self.chunk:
             return self.chunk
-        return max(1, min(128, -(-n // self.nstreams)))
+        return max(1, min(256, -(-n // self.nstreams)))
 
     # ---- device-resident API ------------------------------------------------------------------
     def embed(self, xyz: torch.Tensor, want_feat: bool = False, out: torch.Tensor = None, single_call: bool = False):

@@ -1,8 +1,8 @@
 """-m gpu: parity AT THE BENCHMARKED BATCH SHAPE (BASELINE configs[1]/[2]; evaluate.py:351-452 is the 1-cloud contract
 being widened).  One epc_embed call with B > 64 walks the head sub-batch loop (csrc/api.cu: `b0 += HEAD_SUB`) more than
-once; bench.py times 2 x 128-cloud calls on two streams.  Every shape timed there is compared here with
+once; bench.py times 2 x 256-cloud calls on two streams.  Every shape timed there is compared here with
 
-  (a) the same clouds embedded in <= 64-cloud calls (bit for bit: inference BN has no cross-sample coupling), and
+  (a) the same clouds embedded in small calls (bit for bit: inference BN has no cross-sample coupling), and
   (b) the CPU oracle (oracle/epc_oracle.py, the dense-as-written restatement of models/epc-net.py:29-157) on the first and
       last cloud of every sub-batch, within the north_star tolerance (max-abs <= 1e-3 after L2, cosine >= 0.9999).
 """
@@ -57,7 +57,7 @@ def _engine(pkg, arch, V, **kw):
 
 
 def test_epc_net_single_call_130_clouds(pkg):
-    """130 clouds in ONE epc_embed call: head sub-batches of 64, 64 and 2 clouds."""
+    """130 clouds in ONE epc_embed call: head sub-batches of 128 and 2 clouds."""
     arch = "epc-net"
     V = pkg.variables.synthetic_variables(arch, 1)
     clouds = _clouds(130, 1000)
@@ -74,18 +74,21 @@ def test_epc_net_single_call_130_clouds(pkg):
 
 
 def test_epc_net_bench_step_two_streams(pkg):
-    """bench.py's step: 256 clouds as two 128-cloud calls alternating over two streams."""
+    """bench.py's embed() call: 512 clouds as two 256-cloud library calls alternating over two streams (each walks the head
+    sub-batch loop twice: 128 + 128 clouds)."""
     arch = "epc-net"
     V = pkg.variables.synthetic_variables(arch, 1)
-    clouds = _clouds(256, 1097)
+    clouds = _clouds(512, 1097)
     x = torch.from_numpy(clouds).cuda()
-    eng = _engine(pkg, arch, V, EMBED_CHUNK=128, EMBED_STREAMS=2)
-    out = torch.empty((256, 256), dtype=torch.float32, device="cuda")
+    eng = _engine(pkg, arch, V, EMBED_CHUNK=256, EMBED_STREAMS=2)
+    out = torch.empty((512, 256), dtype=torch.float32, device="cuda")
     for _ in range(3):                                   # repeated steps reuse the per-stream workspaces
         eng.embed(x, out=out)
     ref = _engine(pkg, arch, V, EMBED_CHUNK=32, EMBED_STREAMS=1).embed(x)
     assert torch.equal(out, ref)
-    _check_rows(out.cpu().numpy(), clouds, [0, 127, 128, 255], arch, V, "epc-net 2x128 on two streams")
+    _check_rows(out.cpu().numpy(), clouds, [0, 127, 128, 255, 256, 383, 384, 511], arch, V, "epc-net 2x256 on two streams")
+    ref128 = _engine(pkg, arch, V, EMBED_CHUNK=128, EMBED_STREAMS=2).embed(x)        # the round-1 bench shape
+    assert torch.equal(out, ref128)
 
 
 def test_epc_net_l_single_call_300_clouds(pkg):
@@ -120,7 +123,7 @@ print("SHA", hashlib.sha256(out.tobytes()).hexdigest())
 
 def test_head_sub_batch_loop_small_sub(pkg):
     """EPC_HEAD_SUB=4 (read once at library load, hence the subprocess): 10 clouds walk the conv5 -> assignment -> VLAD
-    sub-batch loop three times (4, 4, 2).  Same bits as the default sub-batch of 64, and within tolerance of the oracle."""
+    sub-batch loop three times (4, 4, 2).  Same bits as the default sub-batch of 128, and within tolerance of the oracle."""
     arch = "epc-net"
     V = pkg.variables.synthetic_variables(arch, 6)
     rng = np.random.default_rng(77)

@@ -1,6 +1,13 @@
 mkdir -p gpurun_out
-for h in 1 2 3; do
-echo "== EPC_HEAD_L2_HINTS=$h"
-EPC_HEAD_L2_HINTS=$h timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct --clock-control none -k regex:assign_vlad -c 2 --csv --log-file gpurun_out/hf_$h.csv python bench.py --steps 1 --warmup 1 --clouds 64 --batch 64 --chunk 64 --no-cpu-baseline --no-retrieval --no-epc-net-l --no-parity > /dev/null 2>&1
-grep -E "dram__bytes|gpu__time|hit_rate" gpurun_out/hf_$h.csv | awk -F'","' '{print $(NF-2), $(NF)}' | tr -d '"' | head -4
-done
+run() { echo "== $*"; env "$@" timeout 600 python bench.py --steps 4 --warmup 2 --no-cpu-baseline --no-retrieval --no-epc-net-l --no-parity $EXTRA 2>gpurun_out/bench.err | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+s=d['stages']
+print('value',round(d['value'],1),'e2e',round(d['e2e']['value'],1),' '.join('%s %.2f'%(k,s[k]['us_per_cloud']) for k in ('knn','proxy_block','conv5','assign_vlad','sort') if k in s))
+"; tail -2 gpurun_out/bench.err; }
+EXTRA="" run EPC_HEAD_SUB=64
+EXTRA="" run EPC_HEAD_SUB=128
+EXTRA="--chunk 256 --batch 512" run EPC_HEAD_SUB=64
+EXTRA="--chunk 256 --batch 512" run EPC_HEAD_SUB=128
+EXTRA="--chunk 256 --batch 512" run EPC_HEAD_SUB=256
+EXTRA="--chunk 128 --batch 384 --streams 3" run EPC_HEAD_SUB=128
