@@ -538,6 +538,17 @@ def bench_retrieval(evaluate, lib_mod, torch, dist, rank, world):
     QL = 16 * Q
     ql = torch.from_numpy(np.tile(q, (16, 1)) + np.random.default_rng(5).normal(0, 0.01, (QL, dim)).astype(np.float32)).cuda()
     ms_l, _ = timed(ql, 5)
+    # world >= 4: also the (2 database shards x world/2 query groups) layout -- the per-query work (selection, re-rank, merge)
+    # that pure database sharding repeats on every rank is split as well; same results
+    grid2 = None
+    if dist is not None and world >= 4 and world % 2 == 0:
+        index = dmod.ShardedRetrieval(db, db_shards=2)
+        g_ms, g_i = timed(qt, 50)
+        g_ms_l, _ = timed(ql, 5)
+        grid2 = {"db_shards": 2, "query_groups": world // 2, "queries_per_s": Q / (g_ms * 1e-3), "ms_per_call": g_ms,
+                 "large_batch_queries_per_s": QL / (g_ms_l * 1e-3), "same_indices": bool(torch.equal(g_i, i)),
+                 "collective": "all_gather of the packed lists inside each 2-rank shard group + all_gather of the merged query "
+                               "slices across the groups"}
     if rank != 0:
         return None
     peaks = measured_peaks()
@@ -572,7 +583,7 @@ def bench_retrieval(evaluate, lib_mod, torch, dist, rank, world):
             "collective": "one nccl all_gather of the packed (fp64 dist | int64 idx)[2,Q,25] buffer per rank + merge" if world > 1 else None,
             "top25_identical_to_kdtree": bool(np.array_equal(idx[:n_cpu], ref)),
             "stages_ms": st, "roofline": roof,
-            "large_batch": {"Q": QL, "queries_per_s": QL / (ms_l * 1e-3), "ms_per_call": ms_l},
+            "large_batch": {"Q": QL, "queries_per_s": QL / (ms_l * 1e-3), "ms_per_call": ms_l}, "grid_2d": grid2,
             "cpu_kdtree_queries_per_s": cpu_qps, "cpu_sample": "%d queries, sklearn KDTree, 1 query per call" % n_cpu}
 
 

@@ -448,12 +448,13 @@ static int head_sub_init() {
 }
 static const int HEAD_SUB = head_sub_init();
 
+
 struct HeadWs {                 // buffers of the G_VLAD / NetVLAD head
     __nv_bfloat16* H16;         // [sub*N, 1024]   conv5 output (operand of the assignment and VLAD GEMMs)
     float* rowss;               // [sub*N, 4]      partial |H_n|^2
     __nv_bfloat16* S16;         // [sub*N, 64]     S' = softmax/|H|
     float* a_part;              // [B*N/128, 64]   partial column sums of the soft assignment
-    float* V;                   // [VLAD_SPLITK][B,1024,64]
+    float* V;                   // [vlad_splitk()][B,1024,64]
     float* v;                   // [B, 65536]
     float* Y;                   // [HIDDEN_SPLITK][B*G, D]
     float* colss;               // [B, 8, 64] partial column sums of squares of the VLAD residuals
@@ -463,7 +464,7 @@ struct HeadWs {                 // buffers of the G_VLAD / NetVLAD head
 size_t head_bytes(const EpcModel* m, int B, int N) {
     const size_t sub = (size_t)(B < HEAD_SUB ? B : HEAD_SUB) * N;
     return align_up(sub * 1024 * 2) + align_up(sub * CONV5_ROWSS_PARTS * 4) + align_up(sub * 64 * 2) +
-           align_up((size_t)B * (N / 128) * 64 * 4) + align_up((size_t)VLAD_SPLITK * B * 1024 * 64 * 4) +
+           align_up((size_t)B * (N / 128) * 64 * 4) + align_up((size_t)vlad_splitk() * B * 1024 * 64 * 4) +
            align_up((size_t)B * 1024 * 64 * 4) + align_up((size_t)HIDDEN_SPLITK * B * m->G * m->D * 4) +
            align_up((size_t)B * 8 * 64 * 4) + align_up((size_t)(B < HEAD_SUB ? B : HEAD_SUB) * 4);
 }
@@ -475,7 +476,7 @@ HeadWs head_carve(Arena& ar, const EpcModel* m, int B, int N) {
     h.rowss = ar.take<float>(sub * CONV5_ROWSS_PARTS);
     h.S16 = ar.take<__nv_bfloat16>(sub * 64);
     h.a_part = ar.take<float>((size_t)B * (N / 128) * 64);
-    h.V = ar.take<float>((size_t)VLAD_SPLITK * B * 1024 * 64);
+    h.V = ar.take<float>((size_t)vlad_splitk() * B * 1024 * 64);
     h.v = ar.take<float>((size_t)B * 1024 * 64);
     h.Y = ar.take<float>((size_t)HIDDEN_SPLITK * B * m->G * m->D);
     h.colss = ar.take<float>((size_t)B * 8 * 64);
@@ -492,7 +493,7 @@ int head_assign_vlad(const EpcModel* m, int B, int N, int b0, int nb, const Head
     if (fused) {
         ScopedStage ss(EPC_STAGE_ASSIGN_VLAD, st);
         return tc_assign_vlad(h.H16, nb, N, m->Wct16, h.rowss, rowss_parts, m->cbn_scale, m->cbn_shift, h.S16,
-                              h.a_part + (size_t)b0 * (N / 128) * 64, h.V + (size_t)b0 * 1024 * 64, VLAD_SPLITK,
+                              h.a_part + (size_t)b0 * (N / 128) * 64, h.V + (size_t)b0 * 1024 * 64, vlad_splitk(),
                               (long long)B * 1024 * 64, h.ready, st);
     }
     {
@@ -502,7 +503,7 @@ int head_assign_vlad(const EpcModel* m, int B, int N, int b0, int nb, const Head
             return rc;
     }
     ScopedStage ss(EPC_STAGE_VLAD_GEMM, st);
-    return tc_vlad(h.H16, h.S16, nb, N, h.V + (size_t)b0 * 1024 * 64, VLAD_SPLITK, (long long)B * 1024 * 64, st);
+    return tc_vlad(h.H16, h.S16, nb, N, h.V + (size_t)b0 * 1024 * 64, vlad_splitk(), (long long)B * 1024 * 64, st);
 }
 
 // finalise + hidden FC + gating (+ L2) for all B clouds
@@ -510,7 +511,7 @@ int head_tail(const EpcModel* m, int B, int N, const HeadWs& h, int l2, float* o
     const int D = m->D;
     {
         ScopedStage ss(EPC_STAGE_VLAD_FINALIZE, st);
-        if (int rc = vlad_finalize(h.V, VLAD_SPLITK, (long long)B * 1024 * 64, h.a_part, N / 128, m->Wc2, B, 1024, 64, h.v, h.colss, st))
+        if (int rc = vlad_finalize(h.V, vlad_splitk(), (long long)B * 1024 * 64, h.a_part, N / 128, m->Wc2, B, 1024, 64, h.v, h.colss, st))
             return rc;
     }
     {   // hidden FC (loupe.py:302-320): rows of length hidden_in, G per cloud; TF32 tensor cores, split-K slabs

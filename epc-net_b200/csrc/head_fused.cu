@@ -1,15 +1,19 @@
-// Cluster assignment + VLAD accumulate (loupe.py:255-291) in ONE launch, so that the bf16 per-point features H
-// (8 MiB per cloud, written by conv5) cross the HBM bus once instead of twice.
+// Cluster assignment + VLAD accumulate (loupe.py:255-291) in ONE launch with two CTA roles.
 //
-// The two contractions need different traversals of H -- the assignment reduces over the 1024 features of a point
-// (S' = softmax(BN(Hn Wc))/|H|), VLAD over the 4096 points of a cloud (V = H^T S') and only after the cloud's S' is complete
-// -- and a single CTA cannot hold both accumulators, so they stay two GEMMs.  What they can share is
-// the 126 MB L2: the grid is one CTA per SM, all co-resident; the first `n_assign` CTAs run the assignment GEMM over the row
-// tiles in cloud order (today's persistent kernel: Wc^T resident in shared memory, H tiles through a TMA ring, softmax in the
-// TMEM-drain epilogue) and publish a per-cloud tile counter; the remaining CTAs run the VLAD GEMM over work items
-// (cloud, 128-feature tile, split-K slab) in the same cloud order, each waiting (acquire) for its cloud's counter.  VLAD trails
-// the assignment by a few clouds = a few tens of MB, so its re-read of H is served by the L2 the assignment CTAs just
-// filled.  CTAs are dispatched in block-id order, so an assignment CTA (low id) is never queued behind a waiting VLAD CTA.
+// The two contractions need different traversals of the bf16 per-point features H (8 MiB per cloud, written by conv5) -- the
+// assignment reduces over the 1024 features of a point (S' = softmax(BN(Hn Wc))/|H|), VLAD over the 4096 points of a cloud
+// (V = H^T S') and only after the cloud's S' is complete -- and a single CTA cannot hold both accumulators (DESIGN.md
+// section 7), so they stay two GEMMs.  Both are bound by how many bytes one SM can keep in flight (shared memory is the
+// ring: 96 KB next to the resident Wc^T, 192 KB for VLAD) against a ~2.5 us loaded memory latency, not by the tensor pipe,
+// so running them side by side -- the first `n_assign` CTAs the assignment over the row tiles in cloud order, the others
+// the VLAD work items (cloud, 128-feature tile, split-K slab) in the same order, each waiting (acquire) for its cloud's tile
+// counter -- overlaps two latency-bound streams and removes a launch boundary: 3.52 -> 3.06 us/cloud on B200.  The grid is
+// one CTA per SM, all co-resident; CTAs are dispatched in block-id order, so an assignment CTA (low id) is never queued
+// behind a waiting VLAD CTA.
+// What it does NOT achieve (measured): serving VLAD's re-read of H from the L2.  A tile takes ~7 us to
+// stream through an assignment CTA's ring, so a cloud's lines are first touched up to ~20 us before VLAD needs them again;
+// at 3 us/cloud that is > 50 MB of fills, and tools/l2_probe.cu shows the L2 keeps a re-read line for ~30 MB of intervening
+// fills (73 % hits at 32 MB, 11 % at 64 MB; 59 % at 64 MB with evict_last/evict_first hints, which the loads here carry).
 #include <cuda_bf16.h>
 #include <stdio.h>
 #include <vector>
@@ -340,7 +344,7 @@ int tc_assign_vlad(const __nv_bfloat16* H, int clouds, int N, const __nv_bfloat1
     }
     const int sms = sm_count();
     static const int env_assign = getenv("EPC_HEAD_ASSIGN_CTAS") ? atoi(getenv("EPC_HEAD_ASSIGN_CTAS")) : 0;
-    int n_assign = env_assign > 0 ? env_assign : (sms * 82 + 74) / 148;
+    int n_assign = env_assign > 0 ? env_assign : (sms * 90 + 74) / 148;       // measured best split on B200 (148 SMs): 90 / 58
     if (n_assign < 1) n_assign = 1;
     if (n_assign > sms - 1) n_assign = sms - 1;
     P.n_assign = n_assign;

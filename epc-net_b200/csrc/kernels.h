@@ -80,7 +80,7 @@ int row_inv_norm(const float* X, long long R, int F, float* inv, cudaStream_t st
 int vlad_finalize(const float* V, int nslab, long long slab, const float* a_sum, int a_parts, const float* Wc2, int B,
                   int F, int K, float* v, float* colss /*[B, F/128, K] scratch*/, cudaStream_t st);
 constexpr int HIDDEN_SPLITK = 32;  // hidden FC split-K slabs [HIDDEN_SPLITK, B*G, D]
-constexpr int VLAD_SPLITK = 2;     // VLAD accumulate split-K slabs
+int vlad_splitk();                 // VLAD accumulate split-K slabs (api.cu; EPC_VLAD_SPLITK = 1 | 2 | 4 | 8)
 
 // ---- tc_gemm.cu (tcgen05 tensor-core contractions) ---------------------------------------------------
 int tc_conv5_bf16(const __nv_bfloat16* Xc, long long R, int cin, const __nv_bfloat16* W5t, const float* b5,

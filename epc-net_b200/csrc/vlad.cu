@@ -1,6 +1,8 @@
 // K4 -- G_VLAD / NetVLAD aggregation tail and the EPC-Net-L head (loupe.py:233-333, 61-101;
 // models/epc-net.py:147-155; models/epc-net-l.py:88-100).  Small, bandwidth-bound pieces that sit
 // around the three dense contractions (cluster assignment, VLAD accumulate, hidden FC).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -126,6 +128,18 @@ vlad_scale_kernel(float* __restrict__ v, const float* __restrict__ colss, int F,
     }
 }
 
+// Split-K slabs of the VLAD accumulate.  More slabs = smaller work items for the VLAD CTAs of the fused assignment + VLAD
+// launch, which therefore stay within ~1 cloud of the assignment front (head_fused.cu) at the price of 256 KB of fp32
+// partial sums per slab and cloud.
+int vlad_splitk() {
+    static const int v = [] {
+        const char* e = getenv("EPC_VLAD_SPLITK");
+        const int x = e ? atoi(e) : 0;
+        return (x == 1 || x == 2 || x == 4 || x == 8) ? x : 2;
+    }();
+    return v;
+}
+
 int vlad_finalize(const float* V, int nslab, long long slab, const float* a_sum, int a_parts, const float* Wc2, int B,
                   int F, int K, float* v, float* colss, cudaStream_t st) {
     EPC_CHECK_ARG(K >= 1 && K <= 64, "vlad_finalize: cluster_size=%d unsupported (1..64)", K);
@@ -137,8 +151,10 @@ int vlad_finalize(const float* V, int nslab, long long slab, const float* a_sum,
         vlad_residual_kernel<2><<<grid, 256, 0, st>>>(V, slab, a_sum, a_parts, Wc2, F, K, v, colss);
     else if (nslab == 4)
         vlad_residual_kernel<4><<<grid, 256, 0, st>>>(V, slab, a_sum, a_parts, Wc2, F, K, v, colss);
+    else if (nslab == 8)
+        vlad_residual_kernel<8><<<grid, 256, 0, st>>>(V, slab, a_sum, a_parts, Wc2, F, K, v, colss);
     else {
-        set_error("vlad_finalize: %d split-K slabs unsupported (1, 2 or 4)", nslab);
+        set_error("vlad_finalize: %d split-K slabs unsupported (1, 2, 4 or 8)", nslab);
         return EPC_EUNSUPPORTED;
     }
     EPC_LAUNCH_CHECK();

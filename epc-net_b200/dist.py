@@ -102,22 +102,97 @@ def cuda_merge(gd, gi):
     return od, oi
 
 
+def make_grid_groups(db_shards: int):
+    """Process groups of a (query groups x database shards) layout of the default world: rank = qg * db_shards + ds.
+    Returns (ds, qg, q_groups, shard_group, peer_group): shard_group = the db_shards ranks that hold the shards of one query
+    group's database copy (their candidate lists are merged); peer_group = the ranks with the same shard index across the
+    query groups (they exchange the merged results of their query slices).  Collective: every rank must call it."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if db_shards < 1 or world % db_shards != 0:
+        raise ValueError("db_shards=%d must divide the world size %d" % (db_shards, world))
+    q_groups = world // db_shards
+    ds, qg = rank % db_shards, rank // db_shards
+    shard_group = peer_group = None
+    if q_groups > 1:
+        for g in range(q_groups):
+            h = dist.new_group([g * db_shards + d for d in range(db_shards)])
+            if g == qg:
+                shard_group = h
+        for d in range(db_shards):
+            h = dist.new_group([g * db_shards + d for g in range(q_groups)])
+            if d == ds:
+                peer_group = h
+    return ds, qg, q_groups, shard_group, peer_group
+
+
+def _all_gather_packed(packed, n, group):
+    g = torch.empty((n,) + tuple(packed.shape), dtype=packed.dtype, device=packed.device)
+    if packed.is_cuda:
+        dist.all_gather_into_tensor(g, packed, group=group)
+    else:
+        dist.all_gather(list(g.unbind(0)), packed, group=group)
+    return g
+
+
+def retrieve_sharded_2d(local_topk_fn, merge_fn, db_local, id_offset: int, queries, k: int, grid):
+    """Database sharded ``db_shards`` ways AND queries split over ``q_groups`` groups (grid = make_grid_groups(db_shards)):
+    a rank scores its query slice against its database shard, the db_shards lists of a slice are all-gathered and merged
+    inside the shard group, and the merged slices are all-gathered across the query groups.  Every rank returns the full
+    (dist [Q,k], idx [Q,k]).  With q_groups == 1 this is retrieve_sharded.  Per-rank work is 1/world of the scoring AND
+    1/q_groups of the per-query work (re-rank, selection, merge) that pure database sharding repeats on every rank."""
+    ds, qg, q_groups, shard_group, peer_group = grid
+    db_shards = dist.get_world_size() // q_groups
+    Q = queries.shape[0]
+    s, e = shard_range(Q, qg, q_groups)
+    d, i = local_topk_fn(db_local, queries[s:e], k, id_offset)
+    nq = e - s
+    packed = torch.empty((2, nq, k), dtype=torch.float64, device=d.device)
+    packed[0].copy_(d)
+    packed[1].copy_(i.view(torch.float64))
+    g = _all_gather_packed(packed, db_shards, shard_group)
+    md, mi = merge_fn(g[:, 0], g[:, 1].view(torch.int64))
+    if q_groups == 1:
+        return md, mi
+    nmax = -(-Q // q_groups)
+    mine = torch.zeros((2, nmax, k), dtype=torch.float64, device=md.device)
+    mine[0, :nq].copy_(md)
+    mine[1, :nq].copy_(mi.view(torch.float64))
+    allq = _all_gather_packed(mine, q_groups, peer_group)
+    od = torch.empty((Q, k), dtype=torch.float64, device=md.device)
+    oi = torch.empty((Q, k), dtype=torch.int64, device=md.device)
+    for gq in range(q_groups):
+        a, b = shard_range(Q, gq, q_groups)
+        od[a:b].copy_(allq[gq, 0, :b - a])
+        oi[a:b].copy_(allq[gq, 1, :b - a].view(torch.int64))
+    return od, oi
+
+
 class ShardedRetrieval:
     """evaluate.get_recall's ``KDTree(database_output)`` (evaluate.py:463) over a database whose rows are sharded across the
-    ranks of ``group``: the rank's shard is prepared once (evaluate.RetrievalIndex, global row ids), every ``query`` finds the
-    local top-k straight into one packed (dist | idx) buffer, all-gathers it in a single NCCL call and merges by
-    (distance, index) -- the result does not depend on the shard count.  ``database_output``: the FULL [D, dim] host array
-    (each rank keeps only its slice on the device) or, with ``local=True``, this rank's rows."""
+    ranks: the rank's shard is prepared once (evaluate.RetrievalIndex, global row ids), every ``query`` finds the local
+    top-k straight into one packed (dist | idx) buffer, all-gathers it in a single NCCL call and merges by (distance, index)
+    -- the result does not depend on the shard count.  ``database_output``: the FULL [D, dim] host array (each rank keeps
+    only its slice on the device) or, with ``local=True``, this rank's rows.
+    ``db_shards`` < world size: the ranks form (world / db_shards) query groups, each holding one sharded copy of the database
+    and answering 1/groups of the queries (retrieve_sharded_2d); the default is one group = the database sharded over every
+    rank (BASELINE.json configs[4])."""
 
-    def __init__(self, database_output, group=None, local=False, id_offset=0):
+    def __init__(self, database_output, group=None, local=False, id_offset=0, db_shards=None):
         from . import evaluate
         self.group = group
         self.world = dist.get_world_size(group)
         rank = dist.get_rank(group)
+        self.db_shards = int(db_shards) if db_shards else self.world
+        self.grid = None
+        if self.db_shards != self.world:
+            if group is not None or local:
+                raise ValueError("db_shards < world size needs the default process group and the full database array")
+            self.grid = make_grid_groups(self.db_shards)
+            rank = self.grid[0]
         if local:
             rows, off = database_output, int(id_offset)
         else:
-            s, e = shard_range(len(database_output), rank, self.world)
+            s, e = shard_range(len(database_output), rank, self.db_shards)
             rows, off = database_output[s:e], s
         self.index = evaluate.RetrievalIndex(rows, id_offset=off)
 
@@ -125,6 +200,8 @@ class ShardedRetrieval:
         from .engine import as_cuda_f32
         q = as_cuda_f32(queries_output, "queries_output")
         Q, k = q.shape[0], int(k)
+        if self.grid is not None:
+            return retrieve_sharded_2d(lambda _db, qq, kk, _off: self.index.query(qq, kk), cuda_merge, None, 0, q, k, self.grid)
         packed = torch.empty((2, Q, k), dtype=torch.float64, device=q.device)
         self.index.query(q, k, out=(packed[0], packed[1].view(torch.int64)))
         g = torch.empty((self.world, 2, Q, k), dtype=torch.float64, device=q.device)

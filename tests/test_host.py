@@ -165,6 +165,54 @@ def test_sharded_retrieval_and_embedding_world2_gloo():
     assert all(r[1] and r[2] for r in res), res
 
 
+def _worker_2d(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from oracle import retrieval_oracle as R
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        db, qs, _ = _data.retrieval_problem(D=601, Q=43, dim=64, seed=13)
+        grid = dist_mod.make_grid_groups(2)                      # 2 database shards x 2 query groups
+        ds, qg, q_groups = grid[0], grid[1], grid[2]
+        s, e = dist_mod.shard_range(len(db), ds, 2)
+
+        def local_topk(dbl, queries, k, off):
+            d, i = R.knn_f64(dbl, queries.numpy(), k)
+            return torch.from_numpy(d), torch.from_numpy(i + off)
+
+        def merge(gd, gi):
+            Rr, Q, k = gd.shape
+            d = gd.permute(1, 0, 2).reshape(Q, Rr * k).numpy()
+            i = gi.permute(1, 0, 2).reshape(Q, Rr * k).numpy()
+            order = np.lexsort((i, d), axis=1)[:, :k]
+            return torch.from_numpy(np.take_along_axis(d, order, 1)), torch.from_numpy(np.take_along_axis(i, order, 1))
+
+        md, mi = dist_mod.retrieve_sharded_2d(local_topk, merge, db[s:e], s, torch.from_numpy(qs), 25, grid)
+        rd, ri = R.knn_f64(db, qs, 25)
+        q.put((rank, bool(np.array_equal(mi.numpy(), ri)) and bool(np.abs(md.numpy() - rd).max() <= 1e-12), (ds, qg, q_groups)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_retrieval_2d_world4_gloo():
+    """2 database shards x 2 query groups: every rank ends with the full, shard-layout-independent result."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_2d, args=(r, 4, port, q)) for r in range(4)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(4)]
+    for p in procs:
+        p.join(60)
+    assert sorted(r[0] for r in res) == [0, 1, 2, 3]
+    assert all(r[1] for r in res), res
+    assert sorted(r[2] for r in res) == [(0, 0, 2), (0, 1, 2), (1, 0, 2), (1, 1, 2)]
+
+
 def test_loading_pointclouds_wire_formats(tmp_path):
     """.bin float64 clouds (utils/loading_pointclouds.py:26-65) and the evaluation pickles."""
     import pickle
