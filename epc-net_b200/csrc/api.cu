@@ -516,10 +516,10 @@ int head_tail(const EpcModel* m, int B, int N, const HeadWs& h, int l2, float* o
     }
     {   // hidden FC (loupe.py:302-320): rows of length hidden_in, G per cloud; TF32 tensor cores, split-K slabs
         ScopedStage ss(EPC_STAGE_HIDDEN_GEMM, st);
-        if (D == 256 && m->hidden_in % (HIDDEN_SPLITK * 32) == 0) {
+        if (D % 64 == 0 && m->hidden_in % (HIDDEN_SPLITK * 32) == 0) {
             if (int rc = tc_hidden(h.v, B * m->G, m->hidden_in, m->Wh, D, h.Y, HIDDEN_SPLITK, st)) return rc;
         } else {
-            set_error("hidden FC: output_dim=%d / hidden_in=%d unsupported by the tensor-core path", D, m->hidden_in);
+            set_error("hidden FC: output_dim=%d (must be a multiple of 64) / hidden_in=%d unsupported by the tensor-core path", D, m->hidden_in);
             return EPC_EUNSUPPORTED;
         }
     }
@@ -656,7 +656,7 @@ int epc_embed(const EpcModel* m, const float* xyz, int B, int N, int knn_arith, 
         }
         {
             ScopedStage ss(EPC_STAGE_FC, st);
-            if (m->D == 256) {
+            if (m->D % 64 == 0) {
                 if (int rc = tc_fc_relu(gmax, B, 1024, m->fc1_Wt, m->fc1.b, m->D, o, st)) return rc;
             } else {
                 GemmArgs g = {};

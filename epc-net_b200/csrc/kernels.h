@@ -99,7 +99,6 @@ int tc_conv5_colmax(const float* Xc, long long R, int cin, int rows_per_cloud, c
                     float* g, int clouds, cudaStream_t st);
 int tc_hidden(const float* v, int rows, int hidden_in, const float* Wht, int D, float* Y, int splitk, cudaStream_t st);
 int tc_fc_relu(const float* g, int rows, int K, const float* Wt, const float* bias, int D, float* out, cudaStream_t st);
-int tc_scores(const float* q3, int nq, const float* db3, int Dpad, int K3, float* dots, cudaStream_t st);
 int tc_conv5_f32(const float* Xc, long long R, int cin, const float* W5t, const float* b5, float* H, cudaStream_t st);
 int vlad_tail(const float* Y, int nslab, int B, int G, int D, const float* bn_scale, const float* bn_shift, const float* Wg,
               const float* g_scale, const float* g_shift, int gating, int l2, float* out, cudaStream_t st);

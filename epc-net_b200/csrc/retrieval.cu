@@ -31,24 +31,6 @@ __global__ void sq_norm_kernel(const float* __restrict__ X, int R, int dim, floa
     if (lane == 0) out[r] = ss;
 }
 
-// 3xTF32 operand split of X [R, dim] -> out [Rpad, 3 dim]: (hi | hi | lo) for the queries, (hi | lo | hi) for the database,
-// hi = tf32(x), lo = tf32(x - hi); rows >= R are zero (N padding of the GEMM)
-__global__ void split3_kernel(const float* __restrict__ X, int R, int Rpad, int dim, int db_side, float* __restrict__ out) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)Rpad * dim) return;
-    const int r = (int)(t / dim), c = (int)(t - (long long)r * dim);
-    float hi = 0.f, lo = 0.f;
-    if (r < R) {
-        const float x = X[t];
-        hi = round_tf32(x);
-        lo = round_tf32(x - hi);
-    }
-    float* o = out + (size_t)r * 3 * dim + c;
-    o[0] = hi;
-    o[dim] = db_side ? lo : hi;
-    o[2 * dim] = db_side ? hi : lo;
-}
-
 // lexicographic (value, index) "a before b"
 __device__ __forceinline__ bool key_less(double av, long long ai, double bv, long long bi) {
     return (av < bv) || (av == bv && ai < bi);

@@ -67,7 +67,11 @@ int tc_hidden(const float* v, int rows, int hidden_in, const float* Wht /*[D, hi
     tc::GemmParams p = {};
     p.M = rows; p.N = D; p.K = hidden_in / splitk; p.splitk = splitk; p.C = Y; p.ldc = D; p.c_slab = (long long)rows * D;
     Operand<float> a{v, rows, hidden_in, hidden_in}, b{Wht, D, hidden_in, hidden_in};
-    return tc_gemm_launch<float, 256, false, false, tc::EPI_STORE_F32>(a, b, p, 1, st, 1);
+    // N tile = the widest of 256 / 128 / 64 that divides FEATURE_OUTPUT_DIM (256 in every shipped config)
+    if (D % 256 == 0) return tc_gemm_launch<float, 256, false, false, tc::EPI_STORE_F32>(a, b, p, 1, st, 1);
+    if (D % 128 == 0) return tc_gemm_launch<float, 128, false, false, tc::EPI_STORE_F32>(a, b, p, 1, st, 1);
+    EPC_CHECK_ARG(D % 64 == 0, "tc_hidden: output_dim=%d must be a multiple of 64", D);
+    return tc_gemm_launch<float, 64, false, false, tc::EPI_STORE_F32>(a, b, p, 1, st, 1);
 }
 
 // EPC-Net-L head FC (models/epc-net-l.py:95): o[B, D] = relu(g[B,1024] . Wfc + b) on TF32 tensor cores (BN folded into W, b)
@@ -75,16 +79,10 @@ int tc_fc_relu(const float* g, int rows, int K, const float* Wt /*[D, K]*/, cons
     tc::GemmParams p = {};
     p.M = rows; p.N = D; p.K = K; p.splitk = 1; p.C = out; p.ldc = D; p.bias = bias; p.relu = 1;
     Operand<float> a{g, rows, K, K}, b{Wt, D, K, K};
-    return tc_gemm_launch<float, 256, false, false, tc::EPI_STORE_F32>(a, b, p, 1, st, 1);
-}
-
-// retrieval scores (retrieval.cu): dots[nq, Dpad] = Q3[nq, K3] . DB3[Dpad, K3]^T on TF32 tensor cores; Q3/DB3 hold the
-// 3xTF32 split of the fp32 operands (hi|hi|lo vs hi|lo|hi), so the sum is q.d to ~2^-21 relative
-int tc_scores(const float* q3, int nq, const float* db3, int Dpad, int K3, float* dots, cudaStream_t st) {
-    tc::GemmParams p = {};
-    p.M = nq; p.N = Dpad; p.K = K3; p.splitk = 1; p.C = dots; p.ldc = Dpad;
-    Operand<float> a{q3, nq, K3, K3}, b{db3, Dpad, K3, K3};
-    return tc_gemm_launch<float, 256, false, false, tc::EPI_STORE_F32>(a, b, p, 1, st, 1);
+    if (D % 256 == 0) return tc_gemm_launch<float, 256, false, false, tc::EPI_STORE_F32>(a, b, p, 1, st, 1);
+    if (D % 128 == 0) return tc_gemm_launch<float, 128, false, false, tc::EPI_STORE_F32>(a, b, p, 1, st, 1);
+    EPC_CHECK_ARG(D % 64 == 0, "tc_fc_relu: output_dim=%d must be a multiple of 64", D);
+    return tc_gemm_launch<float, 64, false, false, tc::EPI_STORE_F32>(a, b, p, 1, st, 1);
 }
 
 }  // namespace epc

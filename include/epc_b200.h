@@ -158,8 +158,10 @@ int epc_max_pool_points(const float* x /*[B,N,C]*/, int B, int N, int C, float* 
 typedef struct EpcWeights {
     int arch;                 /* EPC_ARCH_*                                                     */
     int knn_k;                /* params["KNN"]: ONLY the divisor of the neighbour mean (20)     */
-    int cluster_size;         /* params["CLUSTER_SIZE"] (64)                                    */
-    int output_dim;           /* params["FEATURE_OUTPUT_DIM"] (256)                             */
+    int cluster_size;         /* params["CLUSTER_SIZE"]: 64 only (EPC_EUNSUPPORTED otherwise) -- */
+                              /* deliberate: every shipped config uses 64 and the assignment      */
+                              /* epilogue keeps a point's 64 logits in one thread's registers     */
+    int output_dim;           /* params["FEATURE_OUTPUT_DIM"] (256): any multiple of 64 <= 1024  */
     int groups;               /* params["GROUPS"] (4); ignored for NETVLAD / -L                 */
     int pooling;              /* EPC_POOL_*                                                     */
     int gating;               /* loupe gating flag (1)                                          */

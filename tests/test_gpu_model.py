@@ -95,6 +95,20 @@ def test_forward_matches_oracle_small(pkg, arch, arith):
     _check_desc(out.cpu().numpy(), ref64.astype(np.float32), "%s/%s vs fp64 shadow" % (arch, arith))
 
 
+@pytest.mark.parametrize("arch,dim", [("epc-net", 128), ("epc-net", 512), ("epc-net", 64), ("epc-net-l", 128), ("epc-net-l", 512)])
+def test_feature_output_dim_other_than_256(pkg, arch, dim):
+    """FEATURE_OUTPUT_DIM (configs/*.yaml: 256) is a free parameter of the reference (loupe.py:233-247 output_dim,
+    models/epc-net-l.py:95): multiples of 64 run on the tensor-core FC paths."""
+    N = 512
+    clouds = np.stack([_data.cloud(k, 820 + i, N) for i, k in enumerate(["uniform", "clustered", "coarse"])], 0)[None]
+    V = pkg.variables.synthetic_variables(arch, 33, output_dim=dim)
+    params = dict(_data.default_params(arch), NUM_POINTS=N, FEATURE_OUTPUT_DIM=dim, VARIABLES=pkg.variables.VariableStore(V))
+    out = pkg.models.load(arch).forward(torch.from_numpy(clouds).cuda(), False, params=params)
+    ref = epc_oracle.forward(arch, clouds, V, params)
+    assert tuple(out.shape) == (1, 3, dim)
+    _check_desc(out.cpu().numpy(), ref, "%s output_dim=%d" % (arch, dim))
+
+
 def test_batch_independence_and_determinism(pkg):
     """Inference BN has no cross-sample coupling: a cloud's descriptor is bit-identical alone, in a batch, at any
     chunking, and run to run (this is what lets get_latent_vectors batch where the reference runs 1 cloud/sess.run)."""
