@@ -293,6 +293,57 @@ __global__ void exact_fallback_kernel(const float* __restrict__ db, const float*
     }
 }
 
+// k > 32 (KDTree.query accepts any k; train.py:857-869 passes num_to_take): exact float64 scans in passes of 32 -- pass p
+// collects the 32 smallest (d^2, row) keys that are lexicographically greater than the last key of pass p - 1.  One warp per
+// query and D x dim float64 operations per pass: the rare path, exact by construction.
+__global__ void exact_scan_pass_kernel(const float* __restrict__ db, const float* __restrict__ q, int Qt, int D, int dim, int kk,
+                                       int col0, int ld, long long id_offset, int has_lb, double* __restrict__ lb_d2,
+                                       long long* __restrict__ lb_row, int64_t* __restrict__ idx, double* __restrict__ dist) {
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (qi >= Qt) return;
+    const double bd = has_lb ? lb_d2[qi] : -1.0;
+    const long long br = has_lb ? lb_row[qi] : -1;
+    double val = INFINITY;
+    long long vi = 0x7fffffffffffffffLL;
+    int filled = 0;
+    double thr = INFINITY;
+    for (int j0 = 0; j0 < D; j0 += 32) {
+        const int j = j0 + lane;
+        const double s = (j < D) ? exact_d2(q + (size_t)qi * dim, db + (size_t)j * dim, dim) : (double)INFINITY;
+        const bool after_lb = (s > bd) || (s == bd && (long long)j > br);
+        unsigned m = __ballot_sync(FULL, (j < D) && after_lb && (filled < kk || s < thr));
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const double c = __shfl_sync(FULL, s, src);
+            const bool before = (lane < filled) && (val <= c);
+            const int pos = __popc(__ballot_sync(FULL, before));
+            if (pos < kk) {
+                const double upv = __shfl_up_sync(FULL, val, 1);
+                const long long upi = __shfl_up_sync(FULL, vi, 1);
+                if (lane == pos) {
+                    val = c;
+                    vi = (long long)(j0 + src);
+                } else if (lane > pos && lane < kk) {
+                    val = upv;
+                    vi = upi;
+                }
+                filled = min(filled + 1, kk);
+                thr = (filled == kk) ? __shfl_sync(FULL, val, kk - 1) : (double)INFINITY;
+            }
+        }
+    }
+    if (lane < kk) {
+        idx[(size_t)qi * ld + col0 + lane] = (lane < filled) ? vi + id_offset : -1;
+        dist[(size_t)qi * ld + col0 + lane] = sqrt(val);
+    }
+    if (lane == kk - 1) {               // the next pass continues after this key (inf / max row when the database is exhausted)
+        lb_d2[qi] = val;
+        lb_row[qi] = vi;
+    }
+}
+
 __global__ void max_reduce_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
     __shared__ float s[32];
     float m = 0.f;
@@ -473,7 +524,7 @@ int retrieve_index_build(const float* db, int D, int dim, void* index_mem, size_
 }
 
 size_t retrieve_workspace_bytes(int D, int Q, int dim, int k) {
-    (void)k;
+    if (k > 32) return align_up((size_t)(Q > 0 ? Q : 1) * 8) * 2 + 512;
     const int qt = Q < RETR_QTILE ? (Q > 0 ? Q : 1) : RETR_QTILE;
     size_t s = retrieve_index_bytes(D, dim) + align_up((size_t)qt * 4) * 3 + align_up((size_t)qt * RC * 4) + 1024;
     const int Dp = pad256(D);
@@ -495,9 +546,24 @@ size_t retrieve_workspace_bytes(int D, int Q, int dim, int k) {
 
 int retrieve_topk(const float* db, int D, const float* q, int Q, int dim, int k, long long id_offset, const void* index,
                   int64_t* idx, double* dist, void* ws, size_t ws_bytes, cudaStream_t st) {
-    EPC_CHECK_ARG(k >= 1 && k <= 32, "retrieve_topk: k=%d unsupported (1..32)", k);
+    EPC_CHECK_ARG(k >= 1, "retrieve_topk: k=%d", k);
     EPC_CHECK_ARG(D >= 0 && dim >= 1 && Q >= 0, "retrieve_topk: bad sizes D=%d Q=%d dim=%d", D, Q, dim);
     if (Q == 0) return EPC_OK;
+    if (k > 32 && D > 0) {      // more neighbours than the candidate lists hold: exact float64 scans, 32 per pass
+        if (ws_bytes < retrieve_workspace_bytes(D, Q, dim, k)) {
+            set_error("retrieve_topk: workspace %zu < required %zu", ws_bytes, retrieve_workspace_bytes(D, Q, dim, k));
+            return EPC_EWORKSPACE;
+        }
+        Arena ar(ws, ws_bytes);
+        double* lb_d2 = ar.take<double>(Q);
+        long long* lb_row = ar.take<long long>(Q);
+        for (int col0 = 0; col0 < k; col0 += 32) {
+            const int kk = (k - col0 < 32) ? (k - col0) : 32;
+            exact_scan_pass_kernel<<<(Q + 7) / 8, 256, 0, st>>>(db, q, Q, D, dim, kk, col0, k, id_offset, col0 > 0, lb_d2, lb_row, idx, dist);
+            EPC_LAUNCH_CHECK();
+        }
+        return EPC_OK;
+    }
     if (D == 0) {               // an empty shard (more ranks than rows): all padding
         const long long n = (long long)Q * k;
         fill_empty_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(idx, dist, n);

@@ -207,7 +207,8 @@ int epc_vlad_forward(const EpcModel* m, const float* X, int B, int N, float* out
  * returns) -- ascending distance, ties -> lower index first.
  *   idx  [Q,k] int64 (database row + id_offset: lets a shard report global row ids)
  *   dist [Q,k] float64 Euclidean distances
- * k <= 32.
+ * k <= 32 takes the tensor-core path; k > 32 (any k, as KDTree.query allows) runs exact float64 scans of the whole
+ * database in passes of 32 neighbours -- correct, but meant for the occasional small call (train.py:857-869).
  * ------------------------------------------------------------------------------------------- */
 size_t epc_retrieve_workspace_bytes(int D, int Q, int dim, int k);
 int epc_retrieve_topk(const float* db /*[D,dim]*/, int D, const float* q /*[Q,dim]*/, int Q, int dim, int k,

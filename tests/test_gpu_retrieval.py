@@ -50,6 +50,20 @@ def test_dims_and_paths(ev, dim, D, Q):
     assert np.abs(d.cpu().numpy() - rd).max() <= 1e-12
 
 
+@pytest.mark.parametrize("D,Q,k", [(500, 20, 40), (300, 7, 100), (50, 5, 64), (2000, 3, 33)])
+def test_more_than_32_neighbours(ev, D, Q, k):
+    """KDTree.query takes any k (train.py:857-869 passes num_to_take): k > 32 runs exact float64 scans, 32 per pass."""
+    db, q, _ = _data.retrieval_problem(D=D, Q=Q, seed=k)
+    db[7] = db[3]                                                   # an exact duplicate: ties -> lower index first, across passes
+    d, i = ev.retrieve_topk(db, q, k)
+    rd, ri = R.knn_f64(db, q, k)
+    kk = min(k, D)
+    assert np.array_equal(i.cpu().numpy()[:, :kk], ri)
+    assert np.abs(d.cpu().numpy()[:, :kk] - rd).max() <= 1e-12
+    if k > D:
+        assert (i.cpu().numpy()[:, D:] == -1).all()
+
+
 def test_index_object_equals_one_shot_calls(ev):
     """RetrievalIndex (the KDTree(database_output) object of evaluate.py:463): built once, queried repeatedly."""
     db, q, _ = _data.retrieval_problem(D=7000, Q=300, seed=2)
