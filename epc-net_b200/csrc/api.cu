@@ -8,6 +8,7 @@
 #include <vector>
 
 #include <cuda_bf16.h>
+#include <cuda_fp8.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -81,6 +82,10 @@ struct EpcModel {
     const __nv_bfloat16 *W5t16 = nullptr, *Wct16 = nullptr;   // [1024, cin], [64, 1024]
     const float *cbn_scale = nullptr, *cbn_shift = nullptr, *Wc2 = nullptr, *Wh = nullptr,
                 *hbn_scale = nullptr, *hbn_shift = nullptr, *Wg = nullptr, *gbn_scale = nullptr, *gbn_shift = nullptr;
+    uint8_t* blob8 = nullptr;                           // fp8 (e4m3) operands of the fp8 head (head_fp8.cu)
+    const uint8_t* Wct8 = nullptr;                      // 2^w Wc^T [64, 1024]
+    const float* cbn_scale8 = nullptr;                  // cluster-BN scale x 2^-w
+    float l1max = 0.f, bmax = 0.f;                      // max_f sum_c |W5[c,f]| (bf16 operand values), max_f |b5[f]|
     int hidden_in = 0;                // rows of hidden1_weights
     DenseDev fc1;
     const float* fc1_Wt = nullptr;      // fc1 weights transposed [D, 1024], TF32-rounded: K-major B operand of the tensor-core FC
@@ -352,6 +357,8 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
     offW[12] = pk.add(W5t); offb[12] = pk.add(b);
     std::vector<__nv_bfloat16> h16;                              // bf16 operands (EPC-Net head)
     size_t o16_W5 = 0, o16_Wc = 0;
+    std::vector<uint8_t> h8;                                     // fp8 operands (fp8 head)
+    size_t oCs8 = 0;
     size_t oCs = 0, oCh = 0, oWc2 = 0, oWh = 0, oHs = 0, oHh = 0, oWg = 0, oGs = 0, oGh = 0, oFW = 0, oFb = 0, oFWt = 0;
     if (vlad) {
         const int K = w->cluster_size, D = w->output_dim;
@@ -371,6 +378,26 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
         for (int f = 0; f < 1024; ++f)                          // Wc^T [K, 1024]: K-major B operand of the assignment GEMM
             for (int c = 0; c < K; ++c) h16[o16_Wc + (size_t)c * 1024 + f] = __float2bfloat16(w->cluster_weights_host[(size_t)f * K + c]);
         bn_affine(w->cluster_bn, K, sc, sh); oCs = pk.add(sc); oCh = pk.add(sh);
+        {   // fp8 head: Wc' = 2^wexp Wc as e4m3 (|Wc'| <= 256), 2^-wexp folded into the cluster-BN scale; conv5 output bound
+            float wmax = 0.f;
+            for (size_t i = 0; i < (size_t)1024 * K; ++i) wmax = std::max(wmax, std::fabs(w->cluster_weights_host[i]));
+            int ex = 0;
+            std::frexp(wmax + 1e-30f, &ex);
+            const float ws = std::ldexp(1.0f, 8 - ex);
+            h8.resize((size_t)64 * 1024);
+            for (int f = 0; f < 1024; ++f)
+                for (int c = 0; c < K; ++c)
+                    h8[(size_t)c * 1024 + f] = (uint8_t)__nv_cvt_float_to_fp8(w->cluster_weights_host[(size_t)f * K + c] * ws, __NV_SATFINITE, __NV_E4M3);
+            std::vector<float> sc8(K);
+            for (int c = 0; c < K; ++c) sc8[c] = sc[c] / ws;
+            oCs8 = pk.add(sc8);
+            for (int n = 0; n < 1024; ++n) {
+                float l1 = 0.f;
+                for (int k = 0; k < c5; ++k) l1 += std::fabs(__bfloat162float(h16[(size_t)n * c5 + k]));
+                m->l1max = std::max(m->l1max, l1);
+                m->bmax = std::max(m->bmax, std::fabs(b[n]));
+            }
+        }
         oWc2 = pk.add(w->cluster_weights2_host, (size_t)1024 * K);
         {   // hidden1_weights [hidden_in, D] -> transposed [D, hidden_in], TF32-rounded: K-major B operand of the tensor-core FC
             std::vector<float> Wht((size_t)D * m->hidden_in);
@@ -403,10 +430,15 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
         e = cudaMalloc(&m->blob16, h16.size() * sizeof(__nv_bfloat16));
         if (e == cudaSuccess) e = cudaMemcpy(m->blob16, h16.data(), h16.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
     }
+    if (e == cudaSuccess && !h8.empty()) {
+        e = cudaMalloc(&m->blob8, h8.size());
+        if (e == cudaSuccess) e = cudaMemcpy(m->blob8, h8.data(), h8.size(), cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) {
         set_error("epc_model_create: %s", cudaGetErrorString(e));
         if (m->blob) cudaFree(m->blob);
         if (m->blob16) cudaFree(m->blob16);
+        if (m->blob8) cudaFree(m->blob8);
         delete m;
         return EPC_ECUDA;
     }
@@ -418,6 +450,7 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
     if (vlad) {
         m->W5t16 = m->blob16 + o16_W5; m->Wct16 = m->blob16 + o16_Wc;
         m->cbn_scale = m->blob + oCs; m->cbn_shift = m->blob + oCh; m->Wc2 = m->blob + oWc2;
+        m->Wct8 = m->blob8; m->cbn_scale8 = m->blob + oCs8;
         m->Wh = m->blob + oWh; m->hbn_scale = m->blob + oHs; m->hbn_shift = m->blob + oHh;
         if (w->gating) { m->Wg = m->blob + oWg; m->gbn_scale = m->blob + oGs; m->gbn_shift = m->blob + oGh; }
     } else {
@@ -432,6 +465,7 @@ void epc_model_destroy(EpcModel* m) {
     if (!m) return;
     if (m->blob) cudaFree(m->blob);
     if (m->blob16) cudaFree(m->blob16);
+    if (m->blob8) cudaFree(m->blob8);
     delete m;
 }
 
@@ -447,6 +481,14 @@ static int head_sub_init() {
     return (v >= 1 && v <= 256) ? v : 128;
 }
 static const int HEAD_SUB = head_sub_init();
+// the head's storage format of the per-point features: e4m3 with exact power-of-two scales (head_fp8.cu) unless EPC_HEAD_FP8=0
+// -- for clouds of at least 2048 points: the quantisation errors average out over the points of a cloud (measured descriptor
+// error at N = 4096: 6e-5, the bf16 head's own level), so the precision budget is spent where the sums are long; smaller clouds
+// (unit tests, the stand-alone loupe API at small max_samples) keep the bf16 head
+static bool head_fp8(int N) {
+    static const bool v = !(getenv("EPC_HEAD_FP8") && atoi(getenv("EPC_HEAD_FP8")) == 0);
+    return v && N >= 2048;
+}
 
 
 struct HeadWs {                 // buffers of the G_VLAD / NetVLAD head
@@ -459,6 +501,9 @@ struct HeadWs {                 // buffers of the G_VLAD / NetVLAD head
     float* Y;                   // [HIDDEN_SPLITK][B*G, D]
     float* colss;               // [B, 8, 64] partial column sums of squares of the VLAD residuals
     int* ready;                 // [sub] per-cloud tile counters of the fused assignment + VLAD launch
+    float* absmax;              // [sub] fp8 head: max |conv5 input| per cloud
+    float* tscale;              // [sub] fp8 head: power-of-two scale of the cloud's S''
+    float* tinv;                // [B]   its inverse, applied when V is finalised
 };
 
 size_t head_bytes(const EpcModel* m, int B, int N) {
@@ -466,7 +511,7 @@ size_t head_bytes(const EpcModel* m, int B, int N) {
     return align_up(sub * 1024 * 2) + align_up(sub * CONV5_ROWSS_PARTS * 4) + align_up(sub * 64 * 2) +
            align_up((size_t)B * (N / 128) * 64 * 4) + align_up((size_t)vlad_splitk() * B * 1024 * 64 * 4) +
            align_up((size_t)B * 1024 * 64 * 4) + align_up((size_t)HIDDEN_SPLITK * B * m->G * m->D * 4) +
-           align_up((size_t)B * 8 * 64 * 4) + align_up((size_t)(B < HEAD_SUB ? B : HEAD_SUB) * 4);
+           align_up((size_t)B * 8 * 64 * 4) + 3 * align_up((size_t)(B < HEAD_SUB ? B : HEAD_SUB) * 4) + align_up((size_t)B * 4);
 }
 
 HeadWs head_carve(Arena& ar, const EpcModel* m, int B, int N) {
@@ -481,6 +526,9 @@ HeadWs head_carve(Arena& ar, const EpcModel* m, int B, int N) {
     h.Y = ar.take<float>((size_t)HIDDEN_SPLITK * B * m->G * m->D);
     h.colss = ar.take<float>((size_t)B * 8 * 64);
     h.ready = ar.take<int>((size_t)(B < HEAD_SUB ? B : HEAD_SUB));
+    h.absmax = ar.take<float>((size_t)(B < HEAD_SUB ? B : HEAD_SUB));
+    h.tscale = ar.take<float>((size_t)(B < HEAD_SUB ? B : HEAD_SUB));
+    h.tinv = ar.take<float>((size_t)B);
     return h;
 }
 
@@ -490,6 +538,13 @@ int head_assign_vlad(const EpcModel* m, int B, int N, int b0, int nb, const Head
     // one launch for both GEMMs: VLAD's read of H comes from the L2 the assignment CTAs filled (head_fused.cu);
     // EPC_HEAD_FUSED=0 selects the two separate kernels (same results bit for bit: identical tiles and summation order)
     static const bool fused = !(getenv("EPC_HEAD_FUSED") && atoi(getenv("EPC_HEAD_FUSED")) == 0);
+    if (head_fp8(N)) {      // H16 / S16 hold the e4m3 tensors (head_fp8.cu): rowss are those of the scaled H'
+        ScopedStage ss(EPC_STAGE_ASSIGN_VLAD, st);
+        if (int rc = sprime_scale(h.rowss, rowss_parts, nb, N, h.tscale, h.tinv + b0, st)) return rc;
+        return tc_assign_vlad_fp8(reinterpret_cast<const uint8_t*>(h.H16), nb, N, m->Wct8, h.rowss, rowss_parts, m->cbn_scale8, m->cbn_shift,
+                                  h.tscale, reinterpret_cast<uint8_t*>(h.S16), h.a_part + (size_t)b0 * (N / 128) * 64,
+                                  h.V + (size_t)b0 * 1024 * 64, vlad_splitk(), (long long)B * 1024 * 64, h.ready, st);
+    }
     if (fused) {
         ScopedStage ss(EPC_STAGE_ASSIGN_VLAD, st);
         return tc_assign_vlad(h.H16, nb, N, m->Wct16, h.rowss, rowss_parts, m->cbn_scale, m->cbn_shift, h.S16,
@@ -511,7 +566,7 @@ int head_tail(const EpcModel* m, int B, int N, const HeadWs& h, int l2, float* o
     const int D = m->D;
     {
         ScopedStage ss(EPC_STAGE_VLAD_FINALIZE, st);
-        if (int rc = vlad_finalize(h.V, vlad_splitk(), (long long)B * 1024 * 64, h.a_part, N / 128, m->Wc2, B, 1024, 64, h.v, h.colss, st))
+        if (int rc = vlad_finalize(h.V, vlad_splitk(), (long long)B * 1024 * 64, head_fp8(N) ? h.tinv : nullptr, h.a_part, N / 128, m->Wc2, B, 1024, 64, h.v, h.colss, st))
             return rc;
     }
     {   // hidden FC (loupe.py:302-320): rows of length hidden_in, G per cloud; TF32 tensor cores, split-K slabs
@@ -544,7 +599,7 @@ size_t epc_embed_workspace_bytes(const EpcModel* m, int B, int N) {
     const size_t R = (size_t)B * N;
     const size_t sub = (size_t)(B < HEAD_SUB ? B : HEAD_SUB) * N;
     const int ctot = 64 * m->n_blocks;
-    size_t s = knn_state_bytes(B, N) + 2 * align_up(R * 64 * 2) + 2 * align_up(R * 64 * 4) + align_up((size_t)B * 4) + align_up(R * ctot * 4) /*concat32 (L, or KD export)*/ +
+    size_t s = knn_state_bytes(B, N) + 2 * align_up(R * 64 * 2) + 2 * align_up(R * 64 * 4) + 2 * align_up((size_t)B * 4) + align_up(R * ctot * 4) /*concat32 (L, or KD export)*/ +
                align_up(R * ctot * 2) /*concat16*/ + align_up(sub * 1024 * 4) /*H32 (KD export)*/ + align_up(sub * 4);
     if (m->vlad_head)
         s += head_bytes(m, B, N);
@@ -577,6 +632,7 @@ int epc_embed(const EpcModel* m, const float* xyz, int B, int N, int knn_arith, 
     float* xa32 = ar.take<float>(R * 64);                      // fp32 activations of the range-safe pass (flagged clouds only)
     float* xb32 = ar.take<float>(R * 64);
     int* flags = ar.take<int>(B);                              // clouds whose activations left the fp16 range
+    float* cabs_buf = ar.take<float>(B);                       // fp8 head: per-cloud max of the conv5 input
     float* concat32 = ar.take<float>(R * ctot);
     __nv_bfloat16* concat16 = ar.take<__nv_bfloat16>(R * ctot);
     float* H32 = ar.take<float>((size_t)subB * N * 1024);
@@ -586,6 +642,8 @@ int epc_embed(const EpcModel* m, const float* xyz, int B, int N, int knn_arith, 
         return rc;
     // ProxyConv chain: fp16 fast pass over every cloud, then the range-safe fp32 pass over the clouds it flagged
     EPC_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)B, st));
+    float* cabsmax = (m->vlad_head && head_fp8(N)) ? cabs_buf : nullptr;     // per-cloud max of the conv5 input, tracked by the blocks
+    if (cabsmax) EPC_CUDA(cudaMemsetAsync(cabsmax, 0, sizeof(float) * (size_t)B, st));
     {
         {
             ScopedStage ss(EPC_STAGE_CONV_IN, st);
@@ -598,7 +656,7 @@ int epc_embed(const EpcModel* m, const float* xyz, int B, int N, int knn_arith, 
                 ScopedStage ss(EPC_STAGE_BLOCK, st);
                 if (int rc = proxy_block(cur, ks, B, N, knn_arith, m->divisor, m->conv[3 * blk + 1], m->conv[3 * blk + 2],
                                          next, want32 ? concat32 : nullptr, m->vlad_head ? concat16 : nullptr, ctot,
-                                         64 * blk, nxt, flags, st))
+                                         64 * blk, nxt, flags, cabsmax, st))
                     return rc;
             }
             uint16_t* t = cur; cur = nxt; nxt = t;
@@ -612,7 +670,7 @@ int epc_embed(const EpcModel* m, const float* xyz, int B, int N, int knn_arith, 
             const DenseDev* next = (blk + 1 < nb) ? &m->conv[3 * (blk + 1)] : nullptr;
             if (int rc = proxy_block_f32(flags, cur, ks, B, N, knn_arith, m->divisor, m->conv[3 * blk + 1], m->conv[3 * blk + 2],
                                          next, want32 ? concat32 : nullptr, m->vlad_head ? concat16 : nullptr, ctot,
-                                         64 * blk, nxt, st))
+                                         64 * blk, nxt, cabsmax, st))
                 return rc;
             float* t = cur; cur = nxt; nxt = t;
         }
@@ -638,8 +696,12 @@ int epc_embed(const EpcModel* m, const float* xyz, int B, int N, int knn_arith, 
             const int nbs = (B - b0 < HEAD_SUB) ? (B - b0) : HEAD_SUB;
             {   // conv5 (models/epc-net.py:136-139) on bf16 tensor cores; H stays in L2 for the next two GEMMs
                 ScopedStage ss(EPC_STAGE_CONV5, st);
-                if (int rc = tc_conv5_bf16(concat16 + (size_t)b0 * N * ctot, (long long)nbs * N, ctot, m->W5t16, m->b5, h.H16,
-                                           h.rowss, st))
+                if (head_fp8(N)) {
+                    if (int rc = tc_conv5_fp8(concat16 + (size_t)b0 * N * ctot, (long long)nbs * N, ctot, N, m->W5t16, m->b5, cabsmax + b0,
+                                              m->l1max, m->bmax, reinterpret_cast<uint8_t*>(h.H16), h.rowss, st))
+                        return rc;
+                } else if (int rc = tc_conv5_bf16(concat16 + (size_t)b0 * N * ctot, (long long)nbs * N, ctot, m->W5t16, m->b5, h.H16,
+                                                  h.rowss, st))
                     return rc;
             }
             if (int rc = head_assign_vlad(m, B, N, b0, nbs, h, conv5_rowss_parts(), st)) return rc;
@@ -700,7 +762,9 @@ int epc_vlad_forward(const EpcModel* m, const float* X, int B, int N, float* out
     for (int b0 = 0; b0 < B; b0 += HEAD_SUB) {
         const int nbs = (B - b0 < HEAD_SUB) ? (B - b0) : HEAD_SUB;
         // the caller's rows are used as given (loupe.py does not normalise): bf16 operands, |row| := 1
-        if (int rc = f32_to_bf16_rows(X + (size_t)b0 * N * 1024, (long long)nbs * N, 1024, h.H16, h.rowss, st)) return rc;
+        if (head_fp8(N)) {
+            if (int rc = f32_to_fp8_rows(X + (size_t)b0 * N * 1024, (long long)nbs * N, 1024, N, reinterpret_cast<uint8_t*>(h.H16), h.rowss, st)) return rc;
+        } else if (int rc = f32_to_bf16_rows(X + (size_t)b0 * N * 1024, (long long)nbs * N, 1024, h.H16, h.rowss, st)) return rc;
         if (int rc = head_assign_vlad(m, B, N, b0, nbs, h, 1, st)) return rc;
     }
     return head_tail(m, B, N, h, /*l2=*/0, out, st);

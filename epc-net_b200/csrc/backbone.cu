@@ -226,6 +226,8 @@ struct PbArgs {
     const float *ba, *bb, *bn;
     float* concat32;          // [B,N,ctot] fp32 (TF32-rounded) or nullptr
     __nv_bfloat16* concat16;  // [B,N,ctot] bf16 or nullptr
+    float* cloud_absmax;      // [B] or nullptr: running max of the bf16 concat values of each cloud (>= 0; atomicMax on the bits) --
+                              // the fp8 head derives the cloud's conv5 output bound from it (head_fp8.cu)
     int ctot, coff;
     uint16_t* xnext;          // [B,N,64] 16-bit (HAS_NEXT)
 };
@@ -546,11 +548,23 @@ __global__ void __launch_bounds__(PB_THREADS, 1) proxy_block_kernel(const PbArgs
                 pb_issue_gemm<FMT>(tmem_d, a_st, w2, my_mma);     // first conv of the next block
             }
             if (p.concat16) {                              // coalesced copy-out: 8 lanes write one 128 B row slice
+                __nv_bfloat162 cm = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int q = gtid + 128 * i, r = q >> 3, ch = q & 7;
                     const uint4 val = lds128(m_st + sw128_off(r, ch));
                     *reinterpret_cast<uint4*>(p.concat16 + (grow0 + r) * p.ctot + p.coff + 8 * ch) = val;
+                    if (p.cloud_absmax) {                  // block outputs are >= 0 (relu + a mean of non-negative rows)
+                        cm = __hmax2(cm, *reinterpret_cast<const __nv_bfloat162*>(&val.x));
+                        cm = __hmax2(cm, *reinterpret_cast<const __nv_bfloat162*>(&val.y));
+                        cm = __hmax2(cm, *reinterpret_cast<const __nv_bfloat162*>(&val.z));
+                        cm = __hmax2(cm, *reinterpret_cast<const __nv_bfloat162*>(&val.w));
+                    }
+                }
+                if (p.cloud_absmax) {
+                    const float2 f = __bfloat1622float2(cm);
+                    const unsigned mx = __reduce_max_sync(FULL, __float_as_uint(fmaxf(fmaxf(f.x, f.y), 0.f)));
+                    if ((gtid & 31) == 0 && mx) atomicMax(reinterpret_cast<unsigned*>(p.cloud_absmax) + b, mx);
                 }
             }
             if (HAS_NEXT) {
@@ -592,7 +606,7 @@ __global__ void __launch_bounds__(PB_THREADS, 1) proxy_block_kernel(const PbArgs
 
 int proxy_block(const uint16_t* x, const KnnState& g, int B, int N, int arith, float divisor, const DenseDev& conv_a,
                 const DenseDev& conv_b, const DenseDev* conv_next, float* concat, __nv_bfloat16* concat16, int ctot,
-                int coff, uint16_t* xnext, int* flags, cudaStream_t st) {
+                int coff, uint16_t* xnext, int* flags, float* cloud_absmax, cudaStream_t st) {
     EPC_CHECK_ARG(conv_a.cin == 64 && conv_a.cout == 64 && conv_b.cin == 64 && conv_b.cout == 64,
                   "ProxyConv block layers must be 64->64");
     EPC_CHECK_ARG(N % PB_TILE == 0, "proxy_block: N=%d must be a multiple of %d", N, PB_TILE);
@@ -611,7 +625,7 @@ int proxy_block(const uint16_t* x, const KnnState& g, int B, int N, int arith, f
     a.Wb_img = img(conv_b); a.bb = conv_b.b;
     a.Wn_img = conv_next ? img(*conv_next) : nullptr;
     a.bn = conv_next ? conv_next->b : nullptr;
-    a.concat32 = concat; a.concat16 = concat16; a.ctot = ctot; a.coff = coff; a.xnext = xnext;
+    a.concat32 = concat; a.concat16 = concat16; a.ctot = ctot; a.coff = coff; a.xnext = xnext; a.cloud_absmax = cloud_absmax;
     const int ctas = persistent_ctas("EPC_BLOCK_CTAS");
     const int grid = a.num_tiles < ctas ? a.num_tiles : ctas;
     if (conv_next)

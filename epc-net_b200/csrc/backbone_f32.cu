@@ -97,7 +97,7 @@ proxy_block_f32_kernel(const int* __restrict__ flags, int B, const float* __rest
                    const float* __restrict__ Wa_img, const float* __restrict__ ba, const float* __restrict__ Wb_img,
                    const float* __restrict__ bb, const float* __restrict__ Wn_img, const float* __restrict__ bn,
                    float* __restrict__ concat, __nv_bfloat16* __restrict__ concat16, int ctot, int coff,
-                   float* __restrict__ xnext) {
+                   float* __restrict__ xnext, float* __restrict__ cloud_absmax) {
     {                                                    // only the clouds the fp16 pass flagged: usually none
         bool any = false;
         for (int bb2 = blockIdx.y; bb2 < B; bb2 += gridDim.y) any |= (flags[bb2] != 0);
@@ -288,6 +288,13 @@ proxy_block_f32_kernel(const int* __restrict__ flags, int B, const float* __rest
                     dst[i] = make_float4(round_tf32(o[4 * i]), round_tf32(o[4 * i + 1]), round_tf32(o[4 * i + 2]), round_tf32(o[4 * i + 3]));
             }
             if (concat16) {
+                if (cloud_absmax) {                       // the fp8 head's range bound must cover the re-computed rows too
+                    float mx = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fabsf(o[i]));
+                    mx = fminf(mx * 1.01f, 3.0e38f);      // bf16 rounding may round up
+                    if (mx > 0.f) atomicMax(reinterpret_cast<unsigned*>(cloud_absmax) + (int)(grow / N), __float_as_uint(mx));
+                }
                 uint4* dst = reinterpret_cast<uint4*>(concat16 + grow * ctot + coff + 32 * h);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -340,7 +347,7 @@ proxy_block_f32_kernel(const int* __restrict__ flags, int B, const float* __rest
 
 int proxy_block_f32(const int* flags, const float* x, const KnnState& g, int B, int N, int arith, float divisor, const DenseDev& conv_a,
                 const DenseDev& conv_b, const DenseDev* conv_next, float* concat, __nv_bfloat16* concat16, int ctot,
-                int coff, float* xnext, cudaStream_t st) {
+                int coff, float* xnext, float* cloud_absmax, cudaStream_t st) {
     EPC_CHECK_ARG(conv_a.cin == 64 && conv_a.cout == 64 && conv_b.cin == 64 && conv_b.cout == 64,
                   "ProxyConv block layers must be 64->64");
     EPC_CHECK_ARG(N % PB_TILE == 0, "proxy_block: N=%d must be a multiple of %d", N, PB_TILE);
@@ -354,11 +361,11 @@ int proxy_block_f32(const int* flags, const float* x, const KnnState& g, int B, 
         proxy_block_f32_kernel<true><<<grid, PB_THREADS, PB_SMEM, st>>>(flags, B, x, g.nbr, g.kthd, g.cnt, g.sorted, N, arith, divisor,
                                                                     conv_a.Wimg32, conv_a.b, conv_b.Wimg32, conv_b.b,
                                                                     conv_next->Wimg32, conv_next->b, concat, concat16, ctot,
-                                                                    coff, xnext);
+                                                                    coff, xnext, cloud_absmax);
     } else {
         proxy_block_f32_kernel<false><<<grid, PB_THREADS, PB_SMEM, st>>>(flags, B, x, g.nbr, g.kthd, g.cnt, g.sorted, N, arith, divisor,
                                                                      conv_a.Wimg32, conv_a.b, conv_b.Wimg32, conv_b.b, nullptr,
-                                                                     nullptr, concat, concat16, ctot, coff, nullptr);
+                                                                     nullptr, concat, concat16, ctot, coff, nullptr, cloud_absmax);
     }
     EPC_LAUNCH_CHECK();
     return EPC_OK;

@@ -50,12 +50,12 @@ int conv_in(const float4* sorted, int B, int N, const DenseDev& L, uint16_t* x, 
 // and/or bf16 concat buffer (either may be nullptr)
 int proxy_block(const uint16_t* x, const KnnState& g, int B, int N, int arith, float divisor, const DenseDev& conv_a,
                 const DenseDev& conv_b, const DenseDev* conv_next, float* concat32, __nv_bfloat16* concat16, int ctot,
-                int coff, uint16_t* xnext, int* flags, cudaStream_t st);
+                int coff, uint16_t* xnext, int* flags, float* cloud_absmax, cudaStream_t st);
 // range-safe fp32/TF32 pass over the flagged clouds only (backbone_f32.cu)
 int conv_in_f32(const float4* sorted, int B, int N, const DenseDev& L, float* x, const int* flags, cudaStream_t st);
 int proxy_block_f32(const int* flags, const float* x, const KnnState& g, int B, int N, int arith, float divisor, const DenseDev& conv_a,
                     const DenseDev& conv_b, const DenseDev* conv_next, float* concat32, __nv_bfloat16* concat16, int ctot,
-                    int coff, float* xnext, cudaStream_t st);
+                    int coff, float* xnext, float* cloud_absmax, cudaStream_t st);
 
 // ---- gemm.cu -----------------------------------------------------------------------------------
 struct GemmArgs {
@@ -77,8 +77,8 @@ int sgemm(const GemmArgs& g, cudaStream_t st);
 // ---- vlad.cu -----------------------------------------------------------------------------------
 int row_inv_norm(const float* X, long long R, int F, float* inv, cudaStream_t st);
 // V: nslab split-K slabs of [B,F,K] (slab elements apart); a_sum: [B, a_parts, K] partial column sums
-int vlad_finalize(const float* V, int nslab, long long slab, const float* a_sum, int a_parts, const float* Wc2, int B,
-                  int F, int K, float* v, float* colss /*[B, F/128, K] scratch*/, cudaStream_t st);
+int vlad_finalize(const float* V, int nslab, long long slab, const float* vscale, const float* a_sum, int a_parts, const float* Wc2,
+                  int B, int F, int K, float* v, float* colss, cudaStream_t st);
 constexpr int HIDDEN_SPLITK = 32;  // hidden FC split-K slabs [HIDDEN_SPLITK, B*G, D]
 int vlad_splitk();                 // VLAD accumulate split-K slabs (api.cu; EPC_VLAD_SPLITK = 1 | 2 | 4 | 8)
 
@@ -93,6 +93,15 @@ int tc_assign(const __nv_bfloat16* H, long long R, const __nv_bfloat16* Wct, con
 int tc_assign_vlad(const __nv_bfloat16* H, int clouds, int N, const __nv_bfloat16* Wct, const float* rowss, int parts,
                    const float* bn_scale, const float* bn_shift, __nv_bfloat16* S, float* a_part, float* V, int splitk, long long slab,
                    int* ready, cudaStream_t st);
+// head_fp8.cu: the same head on an fp8 (e4m3) copy of H with exact power-of-two scales
+int cloud_absmax(const __nv_bfloat16* X, int clouds, int N, int C, float* absmax, cudaStream_t st);
+int tc_conv5_fp8(const __nv_bfloat16* Xc, long long R, int cin, int rows_per_cloud, const __nv_bfloat16* W5t, const float* b5,
+                 const float* cloud_absmax_dev, float l1max, float bmax, uint8_t* H8, float* rowss, cudaStream_t st);
+int sprime_scale(const float* rowss, int parts, int clouds, int N, float* t, float* t_inv, cudaStream_t st);
+int f32_to_fp8_rows(const float* X, long long R, int F, int rows_per_cloud, uint8_t* Y, float* rowss, cudaStream_t st);
+int tc_assign_vlad_fp8(const uint8_t* H8, int clouds, int N, const uint8_t* Wct8, const float* rowss, int parts, const float* bn_scale,
+                       const float* bn_shift, const float* sscale, uint8_t* S8, float* a_part, float* V, int splitk, long long slab,
+                       int* ready, cudaStream_t st);
 int tc_vlad(const __nv_bfloat16* H, const __nv_bfloat16* S, int B, int N, float* V, int splitk, long long slab,
             cudaStream_t st);
 int tc_conv5_colmax(const float* Xc, long long R, int cin, int rows_per_cloud, const float* W5t, const float* b5,

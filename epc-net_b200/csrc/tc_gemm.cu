@@ -10,6 +10,7 @@ int tc_conv5_bf16(const __nv_bfloat16* Xc, long long R, int cin, const __nv_bflo
                   __nv_bfloat16* H, float* rowss, cudaStream_t st) {
     tc::GemmParams p = {};
     p.M = (int)R; p.N = 1024; p.K = cin; p.splitk = 1; p.C = H; p.ldc = 1024; p.bias = b5; p.relu = 1; p.aux = rowss;
+    { static const int pf = getenv("EPC_CONV5_PREFETCH") ? atoi(getenv("EPC_CONV5_PREFETCH")) : 0; p.l2_prefetch_tiles = pf; }
     Operand<__nv_bfloat16> a{Xc, R, cin, cin}, b{W5t, 1024, cin, cin};
     // Variant with the A tiles TMA-multicast to a cluster of the 4 N-tile CTAs (L2->SM operand traffic / 4): correct, but
     // measured slower on B200 (2.72 vs 2.47 us/cloud) -- the kernel is bound by the 8 MiB/cloud H write, not by operand

@@ -11,6 +11,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp8.h>
 #include "common.cuh"
 
 namespace epc {
@@ -74,6 +75,11 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 __device__ __forceinline__ void cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// pull a 2-D tile into the L2 only (no shared-memory destination, no barrier): hides the DRAM latency of a tile that a
+// shallow shared-memory ring will ask for a few tiles later
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
@@ -168,7 +174,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N, int a_m
 // ---------------------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------------------
-enum { EPI_STORE_F32 = 0, EPI_CONV5_BF16 = 1, EPI_COLMAX = 2, EPI_ASSIGN = 3 };
+enum { EPI_STORE_F32 = 0, EPI_CONV5_BF16 = 1, EPI_COLMAX = 2, EPI_ASSIGN = 3, EPI_CONV5_FP8 = 4, EPI_ASSIGN_FP8 = 5 };
 
 struct GemmParams {
     int M, N, K;              // per batch; K = contraction length handled by one split
@@ -186,7 +192,11 @@ struct GemmParams {
     int rowss_parts;
     const float* bn_scale;    // ASSIGN: cluster_bn affine [64]
     const float* bn_shift;
-    int rows_per_cloud;       // COLMAX: N points per cloud
+    const float* cloud_absmax;  // CONV5_FP8: [clouds] max |x| over the cloud's conv5 input rows (bounds the output range)
+    float l1max, bmax;          // CONV5_FP8: max_f sum_c |W5[c,f]|, max_f |b5[f]|   (|H[r,f]| <= absmax * l1max + bmax)
+    const float* sscale;        // ASSIGN_FP8: [clouds] power-of-two scale of the cloud's S' (fp8 range), see head_fp8.cu
+    int rows_per_cloud;       // COLMAX / CONV5_FP8 / ASSIGN_FP8: N points per cloud
+    int l2_prefetch_tiles;    // persistent kernels: ask the L2 for the A tile this many of the CTA's tiles ahead (0 = off)
     int reverse_m;            // persistent kernels: walk the row tiles from the last to the first (the producer kernel wrote
                               // the last tiles most recently: they are the ones still in L2)
 };
@@ -212,6 +222,26 @@ struct TileCfg {
     static constexpr int STAGES = STAGES_MAX > 8 ? 8 : STAGES_MAX;
     static constexpr size_t smem(int stages) { return (size_t)stages * (A_BYTES + B_BYTES) + 1024 + 256; }
 };
+
+// Four floats -> four e4m3 bytes (x0 in the lowest byte) with STOCHASTIC rounding (cvt.rs, sm_100a): unbiased, so the
+// quantisation errors of different points average out in the sums over points / features even when the points are identical
+// (an all-zero or duplicated cloud quantised round-to-nearest repeats the SAME error 4096 times: measured 1.2e-3 on the
+// descriptor, over the tolerance).  The random bits are a hash of (row within the cloud, column): deterministic, and independent
+// of where in a batch the cloud sits.
+__device__ __forceinline__ uint32_t hash_bits(uint32_t row, uint32_t col) {
+    uint32_t h = row * 0x9E3779B1u + col * 0x85EBCA77u + 0x165667B1u;
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 12;
+    h *= 0x297A2D39u;
+    h ^= h >> 15;
+    return h;
+}
+__device__ __forceinline__ uint32_t f32x4_to_e4m3_sr(float x0, float x1, float x2, float x3, uint32_t rbits) {
+    uint32_t d;
+    asm volatile("cvt.rs.satfinite.e4m3x4.f32 %0, {%1, %2, %3, %4}, %5;" : "=r"(d) : "f"(x3), "f"(x2), "f"(x1), "f"(x0), "r"(rbits));
+    return d;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // epilogues (shared by the one-tile-per-CTA kernel and the persistent B-resident kernel)
@@ -303,6 +333,55 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const EpiCtx&
                 __syncwarp();
             }
             if (m < p.M) p.aux[(size_t)m * c.nparts + c.npart] = ss;
+        } else if (EPI == EPI_CONV5_FP8) {
+            // H' = 2^e relu(acc + b) stored as fp8 e4m3, e per CLOUD from a bound of the cloud's |H| (absmax(x) * l1max + bmax
+            // <= 2^E  =>  e = 8 - E, so |H'| <= 256 < 448 always: no overflow, no fallback); the per-row sum of squares is taken
+            // from the SCALED fp32 values, so every consumer sees H'/|H'| = H/|H| -- the power of two cancels exactly in the row
+            // normalisation of models/epc-net.py:147-148.  A thread owns 128 columns = one full 128-byte line of its row; the
+            // warp still stages its 32 lines in shared memory so that each store instruction writes whole lines.
+            uint8_t* H = reinterpret_cast<uint8_t*>(p.C);
+            const uint32_t stage = smem_u32(c.scratch) + (uint32_t)c.warp_slot * 4096u;
+            const int r_in = lane;
+            const int m_warp = m - lane;
+            int ex;
+            frexpf(fmaf(__ldg(p.cloud_absmax + c.m0 / p.rows_per_cloud), p.l1max, p.bmax) + 1e-30f, &ex);
+            const float scale = ldexpf(1.0f, 8 - ex);
+            const uint32_t row_in_cloud = (uint32_t)(m % p.rows_per_cloud);
+            float ss = 0.f;
+    #pragma unroll 1
+            for (int h = 0; h < 4; ++h) {
+                float v[32];
+                tmem_ld32(trow + (uint32_t)(c.col_begin + 32 * h), v);
+    #pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    uint32_t pk[4];
+                    uint32_t rb = hash_bits(row_in_cloud, (uint32_t)(n0 + c.col_begin + 32 * h + 16 * q));     // one hash per 16 columns,
+    #pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int i = 16 * q + 4 * e;
+                        rb = (rb ^ (rb >> 13)) * 0x9E3779B1u;                                              // stepped per group of four
+                        const float4 bb = *reinterpret_cast<const float4*>(c.bias + c.col_begin + 32 * h + i);
+                        const float x0 = fmaxf(v[i] + bb.x, 0.f) * scale, x1 = fmaxf(v[i + 1] + bb.y, 0.f) * scale;
+                        const float x2 = fmaxf(v[i + 2] + bb.z, 0.f) * scale, x3 = fmaxf(v[i + 3] + bb.w, 0.f) * scale;
+                        ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
+                        pk[e] = f32x4_to_e4m3_sr(x0, x1, x2, x3, rb);
+                    }
+                    const int ch = 2 * h + q;                    // 16-byte chunk (16 columns) of the 128-byte line
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (uint32_t)r_in * 128u + (uint32_t)((ch ^ (r_in & 7)) << 4)),
+                                 "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+                }
+            }
+            __syncwarp();
+    #pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int idx = lane + 32 * i, r = idx >> 3, ch = idx & 7;
+                uint4 val;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                             : "r"(stage + (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4)) : "memory");
+                if (m_warp + r < p.M) *reinterpret_cast<uint4*>(H + (size_t)(m_warp + r) * p.ldc + n0 + c.col_begin + 16 * ch) = val;
+            }
+            __syncwarp();
+            if (m < p.M) p.aux[(size_t)m * c.nparts + c.npart] = ss;
         } else if (EPI == EPI_COLMAX) {
             // max over the tile's rows of relu(acc + b): values >= 0, so unsigned-int order == float order
             const int cloud = c.m0 / p.rows_per_cloud;
@@ -320,7 +399,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const EpiCtx&
                 }
                 atomicMax(g + n0 + c0 + lane, (int)mine);
             }
-        } else if (EPI == EPI_ASSIGN) {
+        } else if (EPI == EPI_ASSIGN || EPI == EPI_ASSIGN_FP8) {
             // BN == 64: this thread owns all 64 cluster logits of its point (loupe.py:255-276)
             float v[64];
             {
@@ -358,7 +437,30 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const EpiCtx&
             const float rden = 1.0f / den;
     #pragma unroll
             for (int i = 0; i < 64; ++i) v[i] *= rden;
-            if (m < p.M) {
+            if (EPI == EPI_ASSIGN_FP8) {
+                // S'' = t softmax / |H'| as fp8 e4m3 in a 128-byte row (64 values + 64 bytes of padding that the VLAD MMA reads as
+                // unused accumulator columns); t = the cloud's power-of-two scale (undone exactly when V is finalised)
+                if (m < p.M) {
+                    const float ts = inv * __ldg(p.sscale + c.m0 / p.rows_per_cloud);
+                    const uint32_t row_in_cloud = (uint32_t)(m % p.rows_per_cloud);
+                    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.C) + (size_t)m * 128);
+    #pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint32_t pk[4];
+                        uint32_t rb = hash_bits(row_in_cloud, 4096u + (uint32_t)(16 * i));
+    #pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            rb = (rb ^ (rb >> 13)) * 0x9E3779B1u;
+                            pk[j] = f32x4_to_e4m3_sr(v[16 * i + 4 * j] * ts, v[16 * i + 4 * j + 1] * ts, v[16 * i + 4 * j + 2] * ts,
+                                                     v[16 * i + 4 * j + 3] * ts, rb);
+                        }
+                        dst[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                } else {
+    #pragma unroll
+                    for (int i = 0; i < 64; ++i) v[i] = 0.f;
+                }
+            } else if (m < p.M) {
                 uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)m * 64);
     #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -531,7 +633,7 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     using Tr = ElemTraits<T>;
     constexpr int BK = Tr::PER128;
     constexpr uint32_t A_BYTES = TC_BM * 128, B_BYTES = BN * 128;
-    constexpr size_t SCRATCH = (EPI == EPI_ASSIGN) ? (size_t)4 * 64 * 4 : (EPI == EPI_CONV5_BF16) ? (size_t)EW * 4096 : 0;
+    constexpr size_t SCRATCH = (EPI == EPI_ASSIGN) ? (size_t)4 * 64 * 4 : (EPI == EPI_CONV5_BF16 || EPI == EPI_CONV5_FP8) ? (size_t)EW * 4096 : 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int nkb = p.K / BK;
@@ -589,6 +691,11 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int kb = 0; kb < nkb; ++kb) tma_load_2d(sB + (size_t)kb * B_BYTES, &tmB, b_full, kb * BK, n0);
             int it = 0;
             for (int mt = cta_m; mt < num_m_tiles; mt += m_stride) {
+                if (p.l2_prefetch_tiles > 0 && n_tile == (mt / m_stride) % NT) {     // one of the NT CTAs that share the A tile asks the L2 for it early
+                    const int ahead = mt + p.l2_prefetch_tiles * m_stride;
+                    if (ahead < num_m_tiles)
+                        for (int kb = 0; kb < nkb; ++kb) tma_prefetch_l2_2d(&tmA, kb * BK, tile_of(ahead) * TC_BM);
+                }
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % a_stages;
                     const uint32_t ph = (it / a_stages) & 1;
@@ -695,7 +802,7 @@ inline int make_tmap_2d(CUtensorMap* tm, const T* ptr, uint64_t rows, uint64_t c
     cuuint64_t strides[1] = {ld * sizeof(T)};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : sizeof(T) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
     CUresult r = enc(tm, dt, 2, const_cast<T*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -777,7 +884,7 @@ template <typename T, int BN, int EPI, int EW = 4, int CL = 1>
 inline int tc_gemm_bres_launch(const Operand<T>& A, const Operand<T>& B, const tc::GemmParams& p, cudaStream_t st) {
     constexpr int BK = tc::ElemTraits<T>::PER128;
     constexpr size_t A_BYTES = tc::TC_BM * 128, B_BYTES = BN * 128;
-    constexpr size_t SCRATCH = (EPI == tc::EPI_ASSIGN) ? (size_t)4 * 64 * 4 : (EPI == tc::EPI_CONV5_BF16) ? (size_t)EW * 4096 : 0;
+    constexpr size_t SCRATCH = (EPI == tc::EPI_ASSIGN) ? (size_t)4 * 64 * 4 : (EPI == tc::EPI_CONV5_BF16 || EPI == tc::EPI_CONV5_FP8) ? (size_t)EW * 4096 : 0;
     EPC_CHECK_ARG(p.K % BK == 0 && p.K >= BK && p.N % BN == 0 && p.splitk == 1, "tc_gemm_bres: bad shape K=%d N=%d", p.K, p.N);
     EPC_CHECK_ARG((reinterpret_cast<uintptr_t>(A.ptr) & 15) == 0 && (reinterpret_cast<uintptr_t>(B.ptr) & 15) == 0 &&
                       (A.ld * sizeof(T)) % 16 == 0 && (B.ld * sizeof(T)) % 16 == 0,

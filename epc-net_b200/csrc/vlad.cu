@@ -39,10 +39,11 @@ constexpr int VF_ROWS = 128;
 
 template <int NSLAB>
 __global__ void __launch_bounds__(256)
-vlad_residual_kernel(const float* __restrict__ V, long long slab, const float* __restrict__ a_sum, int a_parts,
-                     const float* __restrict__ Wc2, int F, int K, float* __restrict__ v, float* __restrict__ colss) {
+vlad_residual_kernel(const float* __restrict__ V, long long slab, const float* __restrict__ vscale, const float* __restrict__ a_sum,
+                     int a_parts, const float* __restrict__ Wc2, int F, int K, float* __restrict__ v, float* __restrict__ colss) {
     __shared__ float s_part[4][64];
     const int b = blockIdx.y, sl = blockIdx.x, tid = threadIdx.x;
+    const float vs = vscale ? __ldg(vscale + b) : 1.0f;      // fp8 head: V carries the cloud's power-of-two S'' scale (head_fp8.cu)
     const int c = tid & 63, grp = tid >> 6;
     float as = 0.f;                                  // fixed summation order; the loads are issued eight at a time
     if (c < K) {
@@ -81,7 +82,7 @@ vlad_residual_kernel(const float* __restrict__ V, long long slab, const float* _
                     float acc = 0.f;                 // split-K slabs summed in a fixed order
 #pragma unroll
                     for (int s = 0; s < NSLAB; ++s) acc += part[u][s];
-                    const float r = acc - as * w2[u];
+                    const float r = acc * vs - as * w2[u];
                     vb[(size_t)f * K + c] = r;
                     ss += r * r;
                 }
@@ -140,19 +141,19 @@ int vlad_splitk() {
     return v;
 }
 
-int vlad_finalize(const float* V, int nslab, long long slab, const float* a_sum, int a_parts, const float* Wc2, int B,
-                  int F, int K, float* v, float* colss, cudaStream_t st) {
+int vlad_finalize(const float* V, int nslab, long long slab, const float* vscale, const float* a_sum, int a_parts, const float* Wc2,
+                  int B, int F, int K, float* v, float* colss, cudaStream_t st) {
     EPC_CHECK_ARG(K >= 1 && K <= 64, "vlad_finalize: cluster_size=%d unsupported (1..64)", K);
     if (B == 0) return EPC_OK;
     dim3 grid((F + VF_ROWS - 1) / VF_ROWS, B);
     if (nslab == 1)
-        vlad_residual_kernel<1><<<grid, 256, 0, st>>>(V, slab, a_sum, a_parts, Wc2, F, K, v, colss);
+        vlad_residual_kernel<1><<<grid, 256, 0, st>>>(V, slab, vscale, a_sum, a_parts, Wc2, F, K, v, colss);
     else if (nslab == 2)
-        vlad_residual_kernel<2><<<grid, 256, 0, st>>>(V, slab, a_sum, a_parts, Wc2, F, K, v, colss);
+        vlad_residual_kernel<2><<<grid, 256, 0, st>>>(V, slab, vscale, a_sum, a_parts, Wc2, F, K, v, colss);
     else if (nslab == 4)
-        vlad_residual_kernel<4><<<grid, 256, 0, st>>>(V, slab, a_sum, a_parts, Wc2, F, K, v, colss);
+        vlad_residual_kernel<4><<<grid, 256, 0, st>>>(V, slab, vscale, a_sum, a_parts, Wc2, F, K, v, colss);
     else if (nslab == 8)
-        vlad_residual_kernel<8><<<grid, 256, 0, st>>>(V, slab, a_sum, a_parts, Wc2, F, K, v, colss);
+        vlad_residual_kernel<8><<<grid, 256, 0, st>>>(V, slab, vscale, a_sum, a_parts, Wc2, F, K, v, colss);
     else {
         set_error("vlad_finalize: %d split-K slabs unsupported (1, 2, 4 or 8)", nslab);
         return EPC_EUNSUPPORTED;

@@ -1,12 +1,12 @@
 mkdir -p gpurun_out
-for sk in 2 4 8; do for a in 74 90; do
-echo "== EPC_VLAD_SPLITK=$sk n_assign=$a"
-EPC_VLAD_SPLITK=$sk EPC_HEAD_ASSIGN_CTAS=$a timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:assign_vlad -s 1 -c 1 --csv --log-file gpurun_out/hf.csv python bench.py --steps 1 --warmup 1 --clouds 128 --batch 128 --chunk 128 --streams 1 --no-cpu-baseline --no-retrieval --no-epc-net-l --no-parity > /dev/null 2>&1
-grep -E "dram__bytes|gpu__time" gpurun_out/hf.csv | awk -F'","' '{print $(NF-2), $(NF)}' | tr -d '"' | tr '\n' ' '; echo
-EPC_VLAD_SPLITK=$sk EPC_HEAD_ASSIGN_CTAS=$a timeout 600 python bench.py --steps 4 --warmup 2 --no-cpu-baseline --no-retrieval --no-epc-net-l 2>gpurun_out/bench.err | python -c "
+run() { echo "== $*"; env "$@" timeout 600 python bench.py --steps 4 --warmup 2 --no-cpu-baseline --no-retrieval --no-epc-net-l --no-parity 2>gpurun_out/bench.err | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
 s=d['stages']
-print('value',round(d['value'],1),' '.join('%s %.2f'%(k,s[k]['us_per_cloud']) for k in ('conv5','assign_vlad','vlad_finalize') if k in s), 'parity', d.get('max_abs'))
-"; tail -2 gpurun_out/bench.err
-done; done
+print('value',round(d['value'],1),' '.join('%s %.2f'%(k,s[k]['us_per_cloud']) for k in ('conv5','assign_vlad','vlad_finalize') if k in s))
+"; tail -2 gpurun_out/bench.err; }
+run EPC_HEAD_FP8=1 EPC_HEAD_ASSIGN_CTAS=115
+run EPC_HEAD_FP8=1 EPC_HEAD_ASSIGN_CTAS=125
+run EPC_HEAD_FP8=1 EPC_HEAD_ASSIGN_CTAS=105 EPC_CONV5_PREFETCH=2
+run EPC_HEAD_FP8=1 EPC_HEAD_ASSIGN_CTAS=105 EPC_CONV5_PREFETCH=6
+run EPC_HEAD_FP8=0 EPC_CONV5_PREFETCH=4
