@@ -139,3 +139,20 @@ def test_head_sub_batch_loop_small_sub(pkg):
     params = dict(_data.default_params(arch), NUM_POINTS=1024)
     ref = epc_oracle.forward(arch, clouds[None], V, params).reshape(10, 256)
     assert np.abs(out - ref).max() <= TOL_ABS and (out * ref).sum(-1).min() >= TOL_COS
+
+
+@pytest.mark.parametrize("gain", [1000.0, 1.0e-3])
+def test_fp8_head_is_range_safe(pkg, gain):
+    """The head stores the per-point features as fp8 e4m3 (csrc/head_fp8.cu) with a per-cloud power-of-two scale derived
+    from a bound of |H|.  conv5's BN gamma/beta times `gain` multiplies H = relu(BN(conv5)) by `gain` exactly
+    (models/epc-net.py:136-139): 1000 would saturate e4m3 (max 448) and 1e-3 would flush to zero without the scale; with
+    it the descriptors (invariant to the gain: per-point L2 norm, models/epc-net.py:147-148) stay within tolerance."""
+    arch = "epc-net"
+    V = dict(pkg.variables.synthetic_variables(arch, 12))
+    for leaf in ("gamma", "beta"):
+        k = "query_triplets/fastdgcnn/conv5/bn/" + leaf
+        V[k] = (V[k] * gain).astype(np.float32)
+    clouds = np.stack([_data.cloud(kind, 300 + i, 4096) for i, kind in enumerate(["uniform", "clustered", "duplicated", "zeros"])], 0)
+    out = _engine(pkg, arch, V, EMBED_CHUNK=4, EMBED_STREAMS=1).embed(torch.from_numpy(clouds).cuda()).cpu().numpy()
+    assert np.isfinite(out).all()
+    _check_rows(out, clouds, [0, 1, 2, 3], arch, V, "epc-net, conv5 gain %g" % gain)
