@@ -17,7 +17,7 @@ B="python bench.py --steps 1 --warmup 1 --clouds 128 --batch 128 --chunk 128 --s
 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:knn_|proxy_block_kernel|sort_kernel|conv_in_kernel" -s 10 -c 10 \
     -o gpurun_out/${tag}_front -f $B > gpurun_out/ncu_${tag}_front.log 2>&1
 tail -1 gpurun_out/ncu_${tag}_front.log | cut -c1-200
-timeout 900 ncu --set full --clock-control none --import-source on -k "regex:tc_gemm|vlad_|assign_vlad" -s 6 -c 6 \
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:tc_gemm|vlad_|assign_vlad|sprime" -s 7 -c 7 \
     -o gpurun_out/${tag}_head -f $B > gpurun_out/ncu_${tag}_head.log 2>&1
 tail -1 gpurun_out/ncu_${tag}_head.log | cut -c1-200
 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:tc_gemm_bres" -s 1 -c 1 \
