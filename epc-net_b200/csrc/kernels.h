@@ -104,6 +104,8 @@ int tc_assign_vlad_fp8(const uint8_t* H8, int clouds, int N, const uint8_t* Wct8
                        int* ready, cudaStream_t st);
 int tc_vlad(const __nv_bfloat16* H, const __nv_bfloat16* S, int B, int N, float* V, int splitk, long long slab,
             cudaStream_t st);
+int tc_conv5_colmax_bf16(const __nv_bfloat16* Xc, long long R, int cin, int rows_per_cloud, const __nv_bfloat16* W5t, const float* b5,
+                         float* g, int clouds, cudaStream_t st);
 int tc_conv5_colmax(const float* Xc, long long R, int cin, int rows_per_cloud, const float* W5t, const float* b5,
                     float* g, int clouds, cudaStream_t st);
 int tc_hidden(const float* v, int rows, int hidden_in, const float* Wht, int D, float* Y, int splitk, cudaStream_t st);

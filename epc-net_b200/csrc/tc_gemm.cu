@@ -52,6 +52,16 @@ int tc_conv5_colmax(const float* Xc, long long R, int cin, int rows_per_cloud, c
     return tc_gemm_bres_launch<float, 256, tc::EPI_COLMAX, 8>(a, b, p, st);
 }
 
+// the same with bf16 operands (fp32 accumulation): half the operand bytes through shared memory, twice the tensor rate
+int tc_conv5_colmax_bf16(const __nv_bfloat16* Xc, long long R, int cin, int rows_per_cloud, const __nv_bfloat16* W5t, const float* b5,
+                         float* g, int clouds, cudaStream_t st) {
+    EPC_CUDA(cudaMemsetAsync(g, 0, sizeof(float) * (size_t)clouds * 1024, st));
+    tc::GemmParams p = {};
+    p.M = (int)R; p.N = 1024; p.K = cin; p.splitk = 1; p.bias = b5; p.aux = g; p.rows_per_cloud = rows_per_cloud;
+    Operand<__nv_bfloat16> a{Xc, R, cin, cin}, b{W5t, 1024, cin, cin};
+    return tc_gemm_bres_launch<__nv_bfloat16, 256, tc::EPI_COLMAX, 8>(a, b, p, st);
+}
+
 // fp32-output conv5 on TF32 tensor cores (KD feature export, models/kd_epc-net.py:158)
 int tc_conv5_f32(const float* Xc, long long R, int cin, const float* W5t, const float* b5, float* H, cudaStream_t st) {
     tc::GemmParams p = {};

@@ -1,12 +1,11 @@
 mkdir -p gpurun_out
-run() { echo "== $*"; env "$@" timeout 600 python bench.py --steps 4 --warmup 2 --no-cpu-baseline --no-retrieval --no-epc-net-l --no-parity 2>gpurun_out/bench.err | python -c "
+for f in 0 1; do
+echo "== EPC_L_BF16=$f"
+EPC_L_BF16=$f timeout 900 python -m pytest tests/test_gpu_model.py tests/test_gpu_batch_shape.py -m gpu -q --tb=line -p no:cacheprovider -k "epc-net-l or epc_net_l or golden or oracle_small or permutation or output_dim" 2>&1 | tail -4 | cut -c1-300
+EPC_L_BF16=$f timeout 600 python bench.py --arch epc-net-l --steps 5 --warmup 2 --batch 512 --chunk 256 --no-cpu-baseline --no-retrieval 2>gpurun_out/bench.err | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
 s=d['stages']
-print('value',round(d['value'],1),' '.join('%s %.2f'%(k,s[k]['us_per_cloud']) for k in ('conv5','assign_vlad','vlad_finalize') if k in s))
-"; tail -2 gpurun_out/bench.err; }
-run EPC_HEAD_FP8=1 EPC_HEAD_ASSIGN_CTAS=115
-run EPC_HEAD_FP8=1 EPC_HEAD_ASSIGN_CTAS=125
-run EPC_HEAD_FP8=1 EPC_HEAD_ASSIGN_CTAS=105 EPC_CONV5_PREFETCH=2
-run EPC_HEAD_FP8=1 EPC_HEAD_ASSIGN_CTAS=105 EPC_CONV5_PREFETCH=6
-run EPC_HEAD_FP8=0 EPC_CONV5_PREFETCH=4
+print('L value',round(d['value'],1),'e2e',round(d['e2e']['value'],1),'parity',d.get('max_abs'),' '.join('%s %.2f'%(k,s[k]['us_per_cloud']) for k in ('knn','proxy_block','conv5','fc') if k in s))
+"; tail -2 gpurun_out/bench.err
+done
