@@ -7,11 +7,11 @@ import numpy as np, torch, _data
 from oracle import epc_oracle, knn_c
 variables = importlib.import_module("epc-net_b200.variables"); models = importlib.import_module("epc-net_b200.models")
 tfu = importlib.import_module("epc-net_b200.utils.tf_util")
-kinds = ["uniform", "clustered", "coarse", "duplicated", "planar", "zeros"]
-rng = np.random.default_rng(123)
+kinds = ["uniform", "clustered", "coarse", "duplicated", "planar", "zeros", "quantised"]
+rng = np.random.default_rng(int(os.environ.get("STRESS_SEED", 123)))
 worst = 0.0
 for trial in range(int(sys.argv[1]) if len(sys.argv) > 1 else 10):
-    N = int(rng.choice([128, 256, 512, 1024, 2048]))
+    N = int(rng.choice([int(x) for x in os.environ.get("STRESS_N", "128,256,512,1024,2048,4096,4096").split(",")]))
     B = int(rng.integers(1, 9))
     arch = ["epc-net", "epc-net-l", "kd_epc-net"][trial % 3]
     ks = [kinds[int(rng.integers(0, len(kinds)))] for _ in range(B)]
