@@ -452,7 +452,7 @@ def main():
         "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": r["ms"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "tensor_operands": "fp16 (ProxyConv 64x64 layers), bf16 (conv5), fp8 e4m3 with exact power-of-two scales and stochastic rounding "
-                           "(per-point features H for assignment/VLAD), tf32 (hidden FC; EPC-Net-L conv5); fp32 accumulation",
+                           "(per-point features H for assignment/VLAD), tf32 (hidden FC), fp16 (EPC-Net-L conv5); fp32 accumulation",
         "data": "synthetic",
         "config": {"workload": ("EPC-Net (configs/epc-net.yaml: 4 ProxyConv blocks + G_VLAD, 256-d)" if arch == "epc-net" else
                                 "EPC-Net-L (configs/epc-net-l.yaml: 2 ProxyConv blocks + max-pool + FC, 256-d)") +

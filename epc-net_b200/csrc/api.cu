@@ -9,6 +9,7 @@
 
 #include <cuda_bf16.h>
 #include <cuda_fp8.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -82,6 +83,7 @@ struct EpcModel {
     const __nv_bfloat16 *W5t16 = nullptr, *Wct16 = nullptr;   // [1024, cin], [64, 1024]
     const float *cbn_scale = nullptr, *cbn_shift = nullptr, *Wc2 = nullptr, *Wh = nullptr,
                 *hbn_scale = nullptr, *hbn_shift = nullptr, *Wg = nullptr, *gbn_scale = nullptr, *gbn_shift = nullptr;
+    __half* blobf16 = nullptr;                          // conv5 as an fp16 operand [1024, cin] (EPC-Net-L)
     uint8_t* blob8 = nullptr;                           // fp8 (e4m3) operands of the fp8 head (head_fp8.cu)
     const uint8_t* Wct8 = nullptr;                      // 2^w Wc^T [64, 1024]
     const float* cbn_scale8 = nullptr;                  // cluster-BN scale x 2^-w
@@ -429,6 +431,12 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
         e = cudaMalloc(&m->blob16, h16.size() * sizeof(__nv_bfloat16));
         if (e == cudaSuccess) e = cudaMemcpy(m->blob16, h16.data(), h16.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice);
     }
+    if (e == cudaSuccess && !vlad) {       // EPC-Net-L: conv5 weights as fp16 (10-bit mantissa like TF32; |W| is far inside the range)
+        std::vector<__half> hf(W5t.size());
+        for (size_t i = 0; i < W5t.size(); ++i) hf[i] = __float2half_rn(W5t[i]);
+        e = cudaMalloc(&m->blobf16, hf.size() * sizeof(__half));
+        if (e == cudaSuccess) e = cudaMemcpy(m->blobf16, hf.data(), hf.size() * sizeof(__half), cudaMemcpyHostToDevice);
+    }
     if (e == cudaSuccess && !h8.empty()) {
         e = cudaMalloc(&m->blob8, h8.size());
         if (e == cudaSuccess) e = cudaMemcpy(m->blob8, h8.data(), h8.size(), cudaMemcpyHostToDevice);
@@ -438,6 +446,7 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
         if (m->blob) cudaFree(m->blob);
         if (m->blob16) cudaFree(m->blob16);
         if (m->blob8) cudaFree(m->blob8);
+        if (m->blobf16) cudaFree(m->blobf16);
         delete m;
         return EPC_ECUDA;
     }
@@ -466,6 +475,7 @@ void epc_model_destroy(EpcModel* m) {
     if (m->blob) cudaFree(m->blob);
     if (m->blob16) cudaFree(m->blob16);
     if (m->blob8) cudaFree(m->blob8);
+    if (m->blobf16) cudaFree(m->blobf16);
     delete m;
 }
 
@@ -624,12 +634,17 @@ int epc_embed(const EpcModel* m, const float* xyz, int B, int N, int knn_arith, 
     EPC_CHECK_ARG(R < (1ull << 31), "too many points in one call (B*N = %zu)", R);
     const int nb = m->n_blocks, ctot = 64 * nb;
     const int subB = B < HEAD_SUB ? B : HEAD_SUB;
-    // EPC-Net-L conv5 operands: TF32 (default).  EPC_L_BF16=1 selects bf16 operands: +9.6 % clouds/s (no fp32 concat, twice the
-    // tensor rate) but the descriptor error grows 1.6e-4 -> 5e-4 and one configuration leaves the tolerance (1.04e-3): the
-    // max-pool picks extremes, nothing averages the operand rounding out.  Rejected; kept for experiments.
+    // EPC-Net-L conv5 operands: fp16 (default; EPC_L_F16=0 -> TF32 on an fp32 concat).  fp16 keeps TF32's 10-bit mantissa, so the
+    // precision is unchanged, but the blocks write a 16-bit concat instead of an fp32 one and the tensor rate doubles; clouds that
+    // leave the fp16 range (flags) are re-done below by the TF32 kernel on the fp32 rows of the range-safe pass.
+    // EPC_L_BF16=1 selects bf16 operands: a little faster still, but the descriptor error grows 1.6e-4 -> 5e-4 and one
+    // configuration leaves the tolerance (1.04e-3): the max-pool picks extremes, nothing averages the rounding out.  Rejected.
     static const bool l_bf16 = getenv("EPC_L_BF16") && atoi(getenv("EPC_L_BF16")) != 0;
-    const bool want32 = (!m->vlad_head && !l_bf16) || feat != nullptr;     // fp32 concat: TF32 conv5 (EPC_L_BF16=0) and the KD feature export
-    const bool want16 = m->vlad_head || l_bf16;
+    static const bool l_f16 = !l_bf16 && !(getenv("EPC_L_F16") && atoi(getenv("EPC_L_F16")) == 0);
+    const bool lite16 = !m->vlad_head && (l_bf16 || l_f16);
+    const bool want32 = (!m->vlad_head && !lite16) || feat != nullptr;     // fp32 concat of the fast pass: TF32 conv5 and the KD feature export
+    const bool want16 = m->vlad_head || lite16;
+    const int concat_f16 = (!m->vlad_head && l_f16) ? 1 : 0;
     Arena ar(workspace, workspace_bytes);
     KnnState ks = knn_state_carve(ar, B, N);
     uint16_t* xa = ar.take<uint16_t>(R * 64);
@@ -661,7 +676,7 @@ int epc_embed(const EpcModel* m, const float* xyz, int B, int N, int knn_arith, 
                 ScopedStage ss(EPC_STAGE_BLOCK, st);
                 if (int rc = proxy_block(cur, ks, B, N, knn_arith, m->divisor, m->conv[3 * blk + 1], m->conv[3 * blk + 2],
                                          next, want32 ? concat32 : nullptr, want16 ? concat16 : nullptr, ctot,
-                                         64 * blk, nxt, flags, cabsmax, st))
+                                         64 * blk, nxt, flags, cabsmax, concat_f16, st))
                     return rc;
             }
             uint16_t* t = cur; cur = nxt; nxt = t;
@@ -674,7 +689,7 @@ int epc_embed(const EpcModel* m, const float* xyz, int B, int N, int knn_arith, 
         for (int blk = 0; blk < nb; ++blk) {
             const DenseDev* next = (blk + 1 < nb) ? &m->conv[3 * (blk + 1)] : nullptr;
             if (int rc = proxy_block_f32(flags, cur, ks, B, N, knn_arith, m->divisor, m->conv[3 * blk + 1], m->conv[3 * blk + 2],
-                                         next, want32 ? concat32 : nullptr, want16 ? concat16 : nullptr, ctot,
+                                         next, (want32 || concat_f16) ? concat32 : nullptr, (want16 && !concat_f16) ? concat16 : nullptr, ctot,
                                          64 * blk, nxt, cabsmax, st))
                 return rc;
             float* t = cur; cur = nxt; nxt = t;
@@ -721,7 +736,13 @@ int epc_embed(const EpcModel* m, const float* xyz, int B, int N, int knn_arith, 
             ScopedStage ss(EPC_STAGE_CONV5, st);
             if (l_bf16) {
                 if (int rc = tc_conv5_colmax_bf16(concat16, (long long)R, ctot, N, m->W5t16, m->b5, gmax, B, st)) return rc;
-            } else if (int rc = tc_conv5_colmax(concat32, (long long)R, ctot, N, m->W5t, m->b5, gmax, B, st)) return rc;
+            } else if (l_f16) {
+                if (int rc = tc_conv5_colmax_f16(reinterpret_cast<const __half*>(concat16), (long long)R, ctot, N, m->blobf16, m->b5, gmax, B, st))
+                    return rc;
+                // clouds outside the fp16 range: their fp16 rows are garbage -> TF32 on the fp32 rows of the safe pass (usually none)
+                if (int rc = reset_rows_flagged(gmax, flags, B, 1024, st)) return rc;
+                if (int rc = tc_conv5_colmax(concat32, (long long)R, ctot, N, m->W5t, m->b5, gmax, B, flags, st)) return rc;
+            } else if (int rc = tc_conv5_colmax(concat32, (long long)R, ctot, N, m->W5t, m->b5, gmax, B, nullptr, st)) return rc;
         }
         {
             ScopedStage ss(EPC_STAGE_FC, st);

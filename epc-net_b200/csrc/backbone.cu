@@ -225,7 +225,8 @@ struct PbArgs {
     const uint4 *Wa_img, *Wb_img, *Wn_img;     // swizzled weight images in the kernel's format
     const float *ba, *bb, *bn;
     float* concat32;          // [B,N,ctot] fp32 (TF32-rounded) or nullptr
-    __nv_bfloat16* concat16;  // [B,N,ctot] bf16 or nullptr
+    __nv_bfloat16* concat16;  // [B,N,ctot] 16-bit or nullptr: bf16, or fp16 when concat_f16 (EPC-Net-L: the fp16 conv5 operand)
+    int concat_f16;
     float* cloud_absmax;      // [B] or nullptr: running max of the bf16 concat values of each cloud (>= 0; atomicMax on the bits) --
                               // the fp8 head derives the cloud's conv5 output bound from it (head_fp8.cu)
     int ctot, coff;
@@ -531,8 +532,11 @@ __global__ void __launch_bounds__(PB_THREADS, 1) proxy_block_kernel(const PbArgs
                     if (HAS_NEXT) {
                         if (FMT == FMT_F16) vmax = fmaxf(vmax, max8(o));
                         sts128(a_st + off, pack8<FMT>(o));
+                    } else if (p.concat_f16) {
+                        vmax = fmaxf(vmax, max8(o));           // the fp16 concat slice must stay in range too
                     }
-                    if (p.concat16) sts128(m_st + off, pack8<FMT_BF16>(o));   // bf16 concat slice, staged over the consumed m chunk
+                    if (p.concat16)                            // 16-bit concat slice, staged over the consumed m chunk
+                        sts128(m_st + off, p.concat_f16 ? pack8<FMT_F16>(o) : pack8<FMT_BF16>(o));
                     if (p.concat32) {                      // operand of the TF32 conv5 (EPC-Net-L, KD export): store it rounded
                         float4* dst = reinterpret_cast<float4*>(p.concat32 + (grow0 + gtid) * p.ctot + p.coff + 32 * h + 8 * q);
                         dst[0] = make_float4(round_tf32(o[0]), round_tf32(o[1]), round_tf32(o[2]), round_tf32(o[3]));
@@ -606,7 +610,7 @@ __global__ void __launch_bounds__(PB_THREADS, 1) proxy_block_kernel(const PbArgs
 
 int proxy_block(const uint16_t* x, const KnnState& g, int B, int N, int arith, float divisor, const DenseDev& conv_a,
                 const DenseDev& conv_b, const DenseDev* conv_next, float* concat, __nv_bfloat16* concat16, int ctot,
-                int coff, uint16_t* xnext, int* flags, float* cloud_absmax, cudaStream_t st) {
+                int coff, uint16_t* xnext, int* flags, float* cloud_absmax, int concat_f16, cudaStream_t st) {
     EPC_CHECK_ARG(conv_a.cin == 64 && conv_a.cout == 64 && conv_b.cin == 64 && conv_b.cout == 64,
                   "ProxyConv block layers must be 64->64");
     EPC_CHECK_ARG(N % PB_TILE == 0, "proxy_block: N=%d must be a multiple of %d", N, PB_TILE);
@@ -625,7 +629,7 @@ int proxy_block(const uint16_t* x, const KnnState& g, int B, int N, int arith, f
     a.Wb_img = img(conv_b); a.bb = conv_b.b;
     a.Wn_img = conv_next ? img(*conv_next) : nullptr;
     a.bn = conv_next ? conv_next->b : nullptr;
-    a.concat32 = concat; a.concat16 = concat16; a.ctot = ctot; a.coff = coff; a.xnext = xnext; a.cloud_absmax = cloud_absmax;
+    a.concat32 = concat; a.concat16 = concat16; a.ctot = ctot; a.coff = coff; a.xnext = xnext; a.cloud_absmax = cloud_absmax; a.concat_f16 = concat_f16;
     const int ctas = persistent_ctas("EPC_BLOCK_CTAS");
     const int grid = a.num_tiles < ctas ? a.num_tiles : ctas;
     if (conv_next)

@@ -1,6 +1,7 @@
 // Internal (C++) interface between the translation units of libepc_b200.so.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace epc {
@@ -50,7 +51,7 @@ int conv_in(const float4* sorted, int B, int N, const DenseDev& L, uint16_t* x, 
 // and/or bf16 concat buffer (either may be nullptr)
 int proxy_block(const uint16_t* x, const KnnState& g, int B, int N, int arith, float divisor, const DenseDev& conv_a,
                 const DenseDev& conv_b, const DenseDev* conv_next, float* concat32, __nv_bfloat16* concat16, int ctot,
-                int coff, uint16_t* xnext, int* flags, float* cloud_absmax, cudaStream_t st);
+                int coff, uint16_t* xnext, int* flags, float* cloud_absmax, int concat_f16, cudaStream_t st);
 // range-safe fp32/TF32 pass over the flagged clouds only (backbone_f32.cu)
 int conv_in_f32(const float4* sorted, int B, int N, const DenseDev& L, float* x, const int* flags, cudaStream_t st);
 int proxy_block_f32(const int* flags, const float* x, const KnnState& g, int B, int N, int arith, float divisor, const DenseDev& conv_a,
@@ -106,8 +107,13 @@ int tc_vlad(const __nv_bfloat16* H, const __nv_bfloat16* S, int B, int N, float*
             cudaStream_t st);
 int tc_conv5_colmax_bf16(const __nv_bfloat16* Xc, long long R, int cin, int rows_per_cloud, const __nv_bfloat16* W5t, const float* b5,
                          float* g, int clouds, cudaStream_t st);
+// fp16 operands (10-bit mantissa = TF32 precision, twice the tensor rate); cloud_mask: only clouds with a non-zero entry
+int tc_conv5_colmax_f16(const __half* Xc, long long R, int cin, int rows_per_cloud, const __half* W5t, const float* b5, float* g, int clouds,
+                        cudaStream_t st);
+int reset_rows_flagged(float* g, const int* flags, int clouds, int cols, cudaStream_t st);
+// cloud_mask != NULL: only the clouds with a non-zero entry are processed, and g is NOT cleared (reset_rows_flagged does that)
 int tc_conv5_colmax(const float* Xc, long long R, int cin, int rows_per_cloud, const float* W5t, const float* b5,
-                    float* g, int clouds, cudaStream_t st);
+                    float* g, int clouds, const int* cloud_mask, cudaStream_t st);
 int tc_hidden(const float* v, int rows, int hidden_in, const float* Wht, int D, float* Y, int splitk, cudaStream_t st);
 int tc_fc_relu(const float* g, int rows, int K, const float* Wt, const float* bias, int D, float* out, cudaStream_t st);
 int tc_conv5_f32(const float* Xc, long long R, int cin, const float* W5t, const float* b5, float* H, cudaStream_t st);

@@ -44,10 +44,10 @@ int tc_vlad(const __nv_bfloat16* H, const __nv_bfloat16* S, int B, int N, float*
 
 // EPC-Net-L (models/epc-net-l.py:84-91): g[b,:] = max_n relu(Xc W5 + b5) -- H is never written.  TF32.
 int tc_conv5_colmax(const float* Xc, long long R, int cin, int rows_per_cloud, const float* W5t, const float* b5,
-                    float* g, int clouds, cudaStream_t st) {
-    EPC_CUDA(cudaMemsetAsync(g, 0, sizeof(float) * (size_t)clouds * 1024, st));
+                    float* g, int clouds, const int* cloud_mask, cudaStream_t st) {
+    if (!cloud_mask) EPC_CUDA(cudaMemsetAsync(g, 0, sizeof(float) * (size_t)clouds * 1024, st));
     tc::GemmParams p = {};
-    p.M = (int)R; p.N = 1024; p.K = cin; p.splitk = 1; p.bias = b5; p.aux = g; p.rows_per_cloud = rows_per_cloud;
+    p.M = (int)R; p.N = 1024; p.K = cin; p.splitk = 1; p.bias = b5; p.aux = g; p.rows_per_cloud = rows_per_cloud; p.cloud_mask = cloud_mask;
     Operand<float> a{Xc, R, cin, cin}, b{W5t, 1024, cin, cin};
     return tc_gemm_bres_launch<float, 256, tc::EPI_COLMAX, 8>(a, b, p, st);
 }
@@ -60,6 +60,28 @@ int tc_conv5_colmax_bf16(const __nv_bfloat16* Xc, long long R, int cin, int rows
     p.M = (int)R; p.N = 1024; p.K = cin; p.splitk = 1; p.bias = b5; p.aux = g; p.rows_per_cloud = rows_per_cloud;
     Operand<__nv_bfloat16> a{Xc, R, cin, cin}, b{W5t, 1024, cin, cin};
     return tc_gemm_bres_launch<__nv_bfloat16, 256, tc::EPI_COLMAX, 8>(a, b, p, st);
+}
+
+// fp16 operands: the same 10-bit mantissa as TF32 at twice the tensor rate and half the operand bytes.  Clouds whose values left
+// the fp16 range (flags) hold garbage here; the caller re-does them with the masked TF32 kernel on the fp32 safe-pass rows.
+int tc_conv5_colmax_f16(const __half* Xc, long long R, int cin, int rows_per_cloud, const __half* W5t, const float* b5, float* g, int clouds,
+                        cudaStream_t st) {
+    EPC_CUDA(cudaMemsetAsync(g, 0, sizeof(float) * (size_t)clouds * 1024, st));
+    tc::GemmParams p = {};
+    p.M = (int)R; p.N = 1024; p.K = cin; p.splitk = 1; p.bias = b5; p.aux = g; p.rows_per_cloud = rows_per_cloud;
+    Operand<__half> a{Xc, R, cin, cin}, b{W5t, 1024, cin, cin};
+    return tc_gemm_bres_launch<__half, 256, tc::EPI_COLMAX, 8>(a, b, p, st);
+}
+
+__global__ void reset_rows_flagged_kernel(float* __restrict__ g, const int* __restrict__ flags, int cols) {
+    if (!flags[blockIdx.x]) return;
+    for (int i = threadIdx.x; i < cols; i += blockDim.x) g[(size_t)blockIdx.x * cols + i] = 0.f;
+}
+int reset_rows_flagged(float* g, const int* flags, int clouds, int cols, cudaStream_t st) {
+    if (clouds == 0) return EPC_OK;
+    reset_rows_flagged_kernel<<<clouds, 256, 0, st>>>(g, flags, cols);
+    EPC_LAUNCH_CHECK();
+    return EPC_OK;
 }
 
 // fp32-output conv5 on TF32 tensor cores (KD feature export, models/kd_epc-net.py:158)

@@ -12,6 +12,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp8.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace epc {
@@ -196,6 +197,7 @@ struct GemmParams {
     float l1max, bmax;          // CONV5_FP8: max_f sum_c |W5[c,f]|, max_f |b5[f]|   (|H[r,f]| <= absmax * l1max + bmax)
     const float* sscale;        // ASSIGN_FP8: [clouds] power-of-two scale of the cloud's S' (fp8 range), see head_fp8.cu
     int rows_per_cloud;       // COLMAX / CONV5_FP8 / ASSIGN_FP8: N points per cloud
+    const int* cloud_mask;    // persistent kernels: if set, only row tiles of clouds (rows_per_cloud rows each) with a non-zero entry
     int l2_prefetch_tiles;    // persistent kernels: ask the L2 for the A tile this many of the CTA's tiles ahead (0 = off)
     int reverse_m;            // persistent kernels: walk the row tiles from the last to the first (the producer kernel wrote
                               // the last tiles most recently: they are the ones still in L2)
@@ -205,6 +207,10 @@ template <typename T> struct ElemTraits;
 template <> struct ElemTraits<float> {
     static constexpr int PER128 = 32, UMMA_K = 8, FMT = 2;
     static constexpr bool F16 = false;
+};
+template <> struct ElemTraits<__half> {
+    static constexpr int PER128 = 64, UMMA_K = 16, FMT = 0;
+    static constexpr bool F16 = true;
 };
 template <> struct ElemTraits<__nv_bfloat16> {
     static constexpr int PER128 = 64, UMMA_K = 16, FMT = 1;
@@ -657,6 +663,7 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1u);
     const int num_m_tiles = (p.M + TC_BM - 1) / TC_BM;
     auto tile_of = [&](int mt) { return p.reverse_m ? num_m_tiles - 1 - mt : mt; };
+    auto tile_on = [&](int mt) { return !p.cloud_mask || p.cloud_mask[(tile_of(mt) * TC_BM) / p.rows_per_cloud] != 0; };
     constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
 
     if (warp == 0 && lane == 0) {
@@ -691,6 +698,7 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int kb = 0; kb < nkb; ++kb) tma_load_2d(sB + (size_t)kb * B_BYTES, &tmB, b_full, kb * BK, n0);
             int it = 0;
             for (int mt = cta_m; mt < num_m_tiles; mt += m_stride) {
+                if (!tile_on(mt)) continue;
                 if (p.l2_prefetch_tiles > 0 && n_tile == (mt / m_stride) % NT) {     // one of the NT CTAs that share the A tile asks the L2 for it early
                     const int ahead = mt + p.l2_prefetch_tiles * m_stride;
                     if (ahead < num_m_tiles)
@@ -713,7 +721,8 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             constexpr uint32_t idesc = make_idesc(Tr::FMT, TC_BM, BN, 0, 0);
             mbar_wait(b_full, 0);
             int it = 0, tile = 0;
-            for (int mt = cta_m; mt < num_m_tiles; mt += m_stride, ++tile) {
+            for (int mt = cta_m; mt < num_m_tiles; mt += m_stride) {
+                if (!tile_on(mt)) continue;
                 const int buf = tile & 1;
                 mbar_wait(&tempty[buf], ((tile >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
                 tc_fence_after();
@@ -737,13 +746,15 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         mma_commit_mc(&empty[s], CL_MASK);
                 }
                 mma_commit(&tfull[buf]);
+                ++tile;
             }
         }
     } else {
         const int q = warp & 3;
         const int row = q * 32 + lane;
         int tile = 0;
-        for (int mt = cta_m; mt < num_m_tiles; mt += m_stride, ++tile) {
+        for (int mt = cta_m; mt < num_m_tiles; mt += m_stride) {
+            if (!tile_on(mt)) continue;
             const int buf = tile & 1;
             mbar_wait(&tfull[buf], (tile >> 1) & 1);
             tc_fence_after();
@@ -760,6 +771,7 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[buf]);
+            ++tile;
         }
     }
     tc_fence_before();
