@@ -396,12 +396,21 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const EpiCtx&
             for (int c0 = c.col_begin; c0 < c.col_end; c0 += 32) {
                 float v[32];
                 tmem_ld32(trow + (uint32_t)c0, v);
+                if (m >= p.M) {                                  // rows past the end (never with N % 128 == 0): relu(-inf + b) = 0
+    #pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = -INFINITY;
+                }
                 unsigned mine = 0;
     #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float x = (m < p.M) ? fmaxf(v[i] + c.bias[c0 + i], 0.f) : 0.f;
-                    const unsigned r = __reduce_max_sync(FULL, __float_as_uint(x));
-                    if (lane == i) mine = r;
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(c.bias + c0 + 4 * i4);       // same address in every lane
+                    const float bs[4] = {bb.x, bb.y, bb.z, bb.w};
+    #pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int i = 4 * i4 + e;
+                        const unsigned r = __reduce_max_sync(FULL, __float_as_uint(fmaxf(v[i] + bs[e], 0.f)));
+                        if (lane == i) mine = r;
+                    }
                 }
                 atomicMax(g + n0 + c0 + lane, (int)mine);
             }
