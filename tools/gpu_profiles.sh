@@ -8,6 +8,8 @@ timeout 1500 python -m pytest tests -m gpu -q --tb=line -p no:cacheprovider 2>&1
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4 | tee gpurun_out/smoke_${tag}.log
 timeout 900 python bench.py --steps 20 --warmup 5 2> gpurun_out/bench.err | tee gpurun_out/bench_${tag}.json | cut -c1-300
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>> gpurun_out/bench.err | tee gpurun_out/bench_ref_${tag}.json | cut -c1-200
+echo "== randomized parity sweep (oracle-checked; N = 2048 / 4096 so that the fp8 head and the fp16 EPC-Net-L path are the ones exercised)"
+STRESS_N=2048,4096,4096 STRESS_SEED=11 timeout 1200 python tools/gpu_stress.py 36 > gpurun_out/stress_${tag}.log 2>&1; tail -1 gpurun_out/stress_${tag}.log
 echo "== ncu launch list (same command, short)"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${tag}.csv \
     python bench.py --steps 1 --warmup 1 --clouds 512 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
