@@ -286,25 +286,6 @@ assign_vlad_fp8_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_con
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// max |x| over each cloud's rows of the bf16 conv5 input [clouds * N, C] (values >= 0 or not: |.| is taken)
-__global__ void __launch_bounds__(256) cloud_absmax_kernel(const __nv_bfloat16* __restrict__ X, long long per_cloud_vec8,
-                                                          float* __restrict__ out) {
-    const int b = blockIdx.y;
-    const uint4* x = reinterpret_cast<const uint4*>(X) + (size_t)b * per_cloud_vec8;
-    float m = 0.f;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_cloud_vec8; i += (long long)gridDim.x * blockDim.x) {
-        const uint4 v = __ldg(x + i);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            m = fmaxf(m, fabsf(__uint_as_float(w[j] << 16)));
-            m = fmaxf(m, fabsf(__uint_as_float(w[j] & 0xffff0000u)));
-        }
-    }
-    m = warp_max(m);
-    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(out) + b, __float_as_int(m));       // m >= 0: int order == float order
-}
-
 // per cloud: t = 2^(8 - E) with 1 / min_r |H'_r| <= 2^E  (rows with a vanishing norm are skipped: their H' is ~0 and their
 // S'' saturates harmlessly), and 1 / t for the finalise.  rowss [R, parts] partial sums of squares.
 __global__ void __launch_bounds__(256) sprime_scale_kernel(const float* __restrict__ rowss, int parts, int N, float* __restrict__ t,
@@ -361,16 +342,6 @@ __global__ void __launch_bounds__(256) f32_to_fp8_rows_kernel(const float* __res
 }
 
 }  // namespace h8
-
-// max |x| per cloud of the bf16 conv5 input (C columns, N rows per cloud) -> absmax [clouds]
-int cloud_absmax(const __nv_bfloat16* X, int clouds, int N, int C, float* absmax, cudaStream_t st) {
-    EPC_CHECK_ARG(((long long)N * C) % 8 == 0, "cloud_absmax: N * C must be a multiple of 8");
-    if (clouds == 0) return EPC_OK;
-    EPC_CUDA(cudaMemsetAsync(absmax, 0, sizeof(float) * (size_t)clouds, st));
-    h8::cloud_absmax_kernel<<<dim3(32, clouds), 256, 0, st>>>(X, (long long)N * C / 8, absmax);
-    EPC_LAUNCH_CHECK();
-    return EPC_OK;
-}
 
 // conv5 (models/epc-net.py:136-139) with the fp8 output format described at the head of this file: H8 [R, 1024] e4m3 bytes,
 // rowss [R, 8] partial sums of squares of the scaled fp32 values

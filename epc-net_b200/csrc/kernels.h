@@ -95,7 +95,6 @@ int tc_assign_vlad(const __nv_bfloat16* H, int clouds, int N, const __nv_bfloat1
                    const float* bn_scale, const float* bn_shift, __nv_bfloat16* S, float* a_part, float* V, int splitk, long long slab,
                    int* ready, cudaStream_t st);
 // head_fp8.cu: the same head on an fp8 (e4m3) copy of H with exact power-of-two scales
-int cloud_absmax(const __nv_bfloat16* X, int clouds, int N, int C, float* absmax, cudaStream_t st);
 int tc_conv5_fp8(const __nv_bfloat16* Xc, long long R, int cin, int rows_per_cloud, const __nv_bfloat16* W5t, const float* b5,
                  const float* cloud_absmax_dev, float l1max, float bmax, uint8_t* H8, float* rowss, cudaStream_t st);
 int sprime_scale(const float* rowss, int parts, int clouds, int N, float* t, float* t_inv, cudaStream_t st);

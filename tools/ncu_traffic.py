@@ -5,7 +5,7 @@ import csv, io, json, os, subprocess, sys
 
 STAGE_OF = [("knn_bound_kernel", "knn"), ("knn_collect_kernel", "knn"), ("knn_finalize_kernel", "knn"), ("knn_slow_kernel", "knn"),
             ("sort_kernel", "sort"), ("conv_in_kernel", "conv_in"), ("proxy_block_kernel", "proxy_block"),
-            ("tc_gemm_bres_kernel<__nv_bfloat16, 256", "conv5"), ("tc_gemm_bres_kernel<float, 256, 2", "colmax"),
+            ("tc_gemm_bres_kernel<__nv_bfloat16, 256", "conv5"), ("tc_gemm_bres_kernel<float, 256, 2", "colmax"), ("tc_gemm_bres_kernel<__half, 256, 2", "colmax"),
             ("tc_gemm_bres_kernel<__nv_bfloat16, 64", "assign_gemm"),
             ("assign_vlad_kernel", "assign_vlad"), ("assign_vlad_fp8_kernel", "assign_vlad"), ("tc_gemm_kernel<__nv_bfloat16, 64", "vlad_gemm"), ("tc_gemm_kernel<float, 256", "hidden_gemm"),
             ("vlad_residual_kernel", "vlad_finalize"), ("retr_score_kernel<1>", "retrieve_emit"), ("retr_score_kernel<0>", "retrieve_sample"),
