@@ -12,8 +12,8 @@ variables = importlib.import_module("epc-net_b200.variables")
 models = importlib.import_module("epc-net_b200.models")
 evaluate = importlib.import_module("epc-net_b200.evaluate")
 tf_util = importlib.import_module("epc-net_b200.utils.tf_util")
-N = int(os.environ.get("SAN_N", 512))
-clouds = np.stack([_data.cloud(k, 50 + i, N) for i, k in enumerate(["uniform", "clustered", "coarse"])], 0)
+N = int(os.environ.get("SAN_N", 2048))
+clouds = np.stack([_data.cloud(k, 50 + i, N) for i, k in enumerate(["uniform", "clustered", "zeros"])], 0)
 idx, kth, cnt = tf_util.knn_graph(torch.from_numpy(clouds).cuda())
 for arch in ("epc-net", "epc-net-l"):
     V = variables.synthetic_variables(arch, 5)
