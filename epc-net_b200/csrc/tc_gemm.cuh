@@ -343,24 +343,21 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const EpiCtx&
             // H' = 2^e relu(acc + b) stored as fp8 e4m3, e per CLOUD from a bound of the cloud's |H| (absmax(x) * l1max + bmax
             // <= 2^E  =>  e = 8 - E, so |H'| <= 256 < 448 always: no overflow, no fallback); the per-row sum of squares is taken
             // from the SCALED fp32 values, so every consumer sees H'/|H'| = H/|H| -- the power of two cancels exactly in the row
-            // normalisation of models/epc-net.py:147-148.  A thread owns 128 columns = one full 128-byte line of its row; the
-            // warp still stages its 32 lines in shared memory so that each store instruction writes whole lines.
+            // normalisation of models/epc-net.py:147-148.  A thread owns 128 columns = one full 128-byte line of its row.
             uint8_t* H = reinterpret_cast<uint8_t*>(p.C);
-            const uint32_t stage = smem_u32(c.scratch) + (uint32_t)c.warp_slot * 4096u;
-            const int r_in = lane;
-            const int m_warp = m - lane;
             int ex;
             frexpf(fmaf(__ldg(p.cloud_absmax + c.m0 / p.rows_per_cloud), p.l1max, p.bmax) + 1e-30f, &ex);
             const float scale = ldexpf(1.0f, 8 - ex);
             const uint32_t row_in_cloud = (uint32_t)(m % p.rows_per_cloud);
+            uint8_t* dst = H + (size_t)m * p.ldc + n0 + c.col_begin;
             float ss = 0.f;
     #pragma unroll 1
             for (int h = 0; h < 4; ++h) {
                 float v[32];
                 tmem_ld32(trow + (uint32_t)(c.col_begin + 32 * h), v);
+                uint32_t pk[8];
     #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    uint32_t pk[4];
                     uint32_t rb = hash_bits(row_in_cloud, (uint32_t)(n0 + c.col_begin + 32 * h + 16 * q));     // one hash per 16 columns,
     #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -370,23 +367,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const EpiCtx&
                         const float x0 = fmaxf(v[i] + bb.x, 0.f) * scale, x1 = fmaxf(v[i + 1] + bb.y, 0.f) * scale;
                         const float x2 = fmaxf(v[i + 2] + bb.z, 0.f) * scale, x3 = fmaxf(v[i + 3] + bb.w, 0.f) * scale;
                         ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
-                        pk[e] = f32x4_to_e4m3_sr(x0, x1, x2, x3, rb);
+                        pk[4 * q + e] = f32x4_to_e4m3_sr(x0, x1, x2, x3, rb);
                     }
-                    const int ch = 2 * h + q;                    // 16-byte chunk (16 columns) of the 128-byte line
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (uint32_t)r_in * 128u + (uint32_t)((ch ^ (r_in & 7)) << 4)),
-                                 "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
                 }
+                // 32 columns = 32 bytes = one full sector of this thread's own 128-byte line: a single 256-bit store, no
+                // shared-memory staging (the bf16 epilogue needs it because 16-byte pieces of 32 different rows half-fill sectors)
+                if (m < p.M)
+                    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 32 * h), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                                 "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
             }
-            __syncwarp();
-    #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int idx = lane + 32 * i, r = idx >> 3, ch = idx & 7;
-                uint4 val;
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
-                             : "r"(stage + (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4)) : "memory");
-                if (m_warp + r < p.M) *reinterpret_cast<uint4*>(H + (size_t)(m_warp + r) * p.ldc + n0 + c.col_begin + 16 * ch) = val;
-            }
-            __syncwarp();
             if (m < p.M) p.aux[(size_t)m * c.nparts + c.npart] = ss;
         } else if (EPI == EPI_COLMAX) {
             // max over the tile's rows of relu(acc + b): values >= 0, so unsigned-int order == float order
@@ -648,7 +637,7 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     using Tr = ElemTraits<T>;
     constexpr int BK = Tr::PER128;
     constexpr uint32_t A_BYTES = TC_BM * 128, B_BYTES = BN * 128;
-    constexpr size_t SCRATCH = (EPI == EPI_ASSIGN) ? (size_t)4 * 64 * 4 : (EPI == EPI_CONV5_BF16 || EPI == EPI_CONV5_FP8) ? (size_t)EW * 4096 : 0;
+    constexpr size_t SCRATCH = (EPI == EPI_ASSIGN) ? (size_t)4 * 64 * 4 : (EPI == EPI_CONV5_BF16) ? (size_t)EW * 4096 : 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int nkb = p.K / BK;
@@ -905,7 +894,7 @@ template <typename T, int BN, int EPI, int EW = 4, int CL = 1>
 inline int tc_gemm_bres_launch(const Operand<T>& A, const Operand<T>& B, const tc::GemmParams& p, cudaStream_t st) {
     constexpr int BK = tc::ElemTraits<T>::PER128;
     constexpr size_t A_BYTES = tc::TC_BM * 128, B_BYTES = BN * 128;
-    constexpr size_t SCRATCH = (EPI == tc::EPI_ASSIGN) ? (size_t)4 * 64 * 4 : (EPI == tc::EPI_CONV5_BF16 || EPI == tc::EPI_CONV5_FP8) ? (size_t)EW * 4096 : 0;
+    constexpr size_t SCRATCH = (EPI == tc::EPI_ASSIGN) ? (size_t)4 * 64 * 4 : (EPI == tc::EPI_CONV5_BF16) ? (size_t)EW * 4096 : 0;
     EPC_CHECK_ARG(p.K % BK == 0 && p.K >= BK && p.N % BN == 0 && p.splitk == 1, "tc_gemm_bres: bad shape K=%d N=%d", p.K, p.N);
     EPC_CHECK_ARG((reinterpret_cast<uintptr_t>(A.ptr) & 15) == 0 && (reinterpret_cast<uintptr_t>(B.ptr) & 15) == 0 &&
                       (A.ld * sizeof(T)) % 16 == 0 && (B.ld * sizeof(T)) % 16 == 0,
