@@ -352,6 +352,24 @@ int tc_conv5_fp8(const __nv_bfloat16* Xc, long long R, int cin, int rows_per_clo
     p.cloud_absmax = cloud_absmax_dev; p.l1max = l1max; p.bmax = bmax; p.rows_per_cloud = rows_per_cloud;
     { static const int pf = getenv("EPC_CONV5_PREFETCH") ? atoi(getenv("EPC_CONV5_PREFETCH")) : 0; p.l2_prefetch_tiles = pf; }
     Operand<__nv_bfloat16> a{Xc, R, cin, cin}, b{W5t, 1024, cin, cin};
+    static const bool tl = getenv("EPC_BRES_TIMELINE") != nullptr;
+    if (tl) {       // debug: per-tile clock64 stamps of CTA 0 (MMA start / issued, epilogue start / end), printed for the first calls
+        static long long* dev = nullptr;
+        static int calls = 0;
+        if (!dev) EPC_CUDA(cudaMalloc(&dev, sizeof(long long) * 256));
+        EPC_CUDA(cudaMemsetAsync(dev, 0, sizeof(long long) * 256, st));
+        p.timeline = dev;
+        const int rc = tc_gemm_bres_launch<__nv_bfloat16, 256, tc::EPI_CONV5_FP8, 8>(a, b, p, st);
+        if (rc == EPC_OK && calls++ < 2) {
+            long long h[256];
+            EPC_CUDA(cudaStreamSynchronize(st));
+            EPC_CUDA(cudaMemcpy(h, dev, sizeof(h), cudaMemcpyDeviceToHost));
+            for (int t = 0; t < 64 && h[4 * t + 2]; ++t)
+                fprintf(stderr, "conv5 tile %2d: mma start %7lld issued %7lld | epi start %7lld end %7lld | epi %5lld  period %5lld\n", t, h[4 * t] - h[0],
+                        h[4 * t + 1] - h[0], h[4 * t + 2] - h[0], h[4 * t + 3] - h[0], h[4 * t + 3] - h[4 * t + 2], t ? h[4 * t + 2] - h[4 * t - 2] : 0ll);
+        }
+        return rc;
+    }
     return tc_gemm_bres_launch<__nv_bfloat16, 256, tc::EPI_CONV5_FP8, 8>(a, b, p, st);
 }
 

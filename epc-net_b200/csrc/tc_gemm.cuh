@@ -123,6 +123,19 @@ __device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_
             : "memory");
     }
 }
+// One lane of a CONVERGED warp.  The MMA warp of the persistent kernel runs its loop with all 32 lanes (warp-uniform values: the
+// compiler keeps the descriptors in uniform registers) and elects a lane only for the tcgen05 instructions themselves.  A loop
+// nested inside `if (lane == 0)` costs ~25 instructions, a runtime modulo and an R2UR round trip per MMA: a single thread then
+// issues a 128x256x16 MMA only every ~240 clk (per-tile timeline, EPC_BRES_TIMELINE) -- the tensor pipe wants one every 128.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(p));
+    return p != 0;
+}
+// shared-memory descriptor split in halves: the high word is the same for every K-major 128B-swizzled tile
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t smem_addr) { return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16); }
+constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint64_t desc_of(uint32_t lo) { return ((uint64_t)DESC_HI_SW128 << 32) | lo; }
 // arrive on an mbarrier when every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -198,6 +211,7 @@ struct GemmParams {
     const float* sscale;        // ASSIGN_FP8: [clouds] power-of-two scale of the cloud's S' (fp8 range), see head_fp8.cu
     int rows_per_cloud;       // COLMAX / CONV5_FP8 / ASSIGN_FP8: N points per cloud
     const int* cloud_mask;    // persistent kernels: if set, only row tiles of clouds (rows_per_cloud rows each) with a non-zero entry
+    long long* timeline;      // debug: CTA 0 records clock64 per tile: [tile][0] MMA start [1] MMA issued [2] epilogue start [3] epilogue end
     int l2_prefetch_tiles;    // persistent kernels: ask the L2 for the A tile this many of the CTA's tiles ahead (0 = off)
     int reverse_m;            // persistent kernels: walk the row tiles from the last to the first (the producer kernel wrote
                               // the last tiles most recently: they are the ones still in L2)
@@ -245,8 +259,31 @@ __device__ __forceinline__ uint32_t hash_bits(uint32_t row, uint32_t col) {
 }
 __device__ __forceinline__ uint32_t f32x4_to_e4m3_sr(float x0, float x1, float x2, float x3, uint32_t rbits) {
     uint32_t d;
-    asm volatile("cvt.rs.satfinite.e4m3x4.f32 %0, {%1, %2, %3, %4}, %5;" : "=r"(d) : "f"(x3), "f"(x2), "f"(x1), "f"(x0), "r"(rbits));
+    asm("cvt.rs.satfinite.e4m3x4.f32 %0, {%1, %2, %3, %4}, %5;" : "=r"(d) : "f"(x3), "f"(x2), "f"(x1), "f"(x0), "r"(rbits));
     return d;
+}
+
+// packed fp32 pairs (FADD2 / FMUL2 / FFMA2 of sm_100): one issue slot for two lanes of epilogue arithmetic
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -350,25 +387,35 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const EpiCtx&
             const float scale = ldexpf(1.0f, 8 - ex);
             const uint32_t row_in_cloud = (uint32_t)(m % p.rows_per_cloud);
             uint8_t* dst = H + (size_t)m * p.ldc + n0 + c.col_begin;
-            float ss = 0.f;
+            // Written for issue slots (8 epilogue warps = 2 per scheduler): packed FADD2 / FMUL2 / FFMA2, four independent
+            // sum-of-squares chains, bias as shared-space 64-bit pairs, and one avalanche hash per 32 columns from which the
+            // eight rounding words are one IMAD each (word k = h * M_k + g).
+            const uint64_t scale2 = pack2(scale, scale);
+            const uint32_t bias_s = smem_u32(c.bias) + (uint32_t)c.col_begin * 4u;
+            uint64_t ssA = 0ull, ssB = 0ull;
     #pragma unroll 1
             for (int h = 0; h < 4; ++h) {
                 float v[32];
                 tmem_ld32(trow + (uint32_t)(c.col_begin + 32 * h), v);
+                const uint32_t hh = hash_bits(row_in_cloud, (uint32_t)(n0 + c.col_begin + 32 * h));
+                const uint32_t g = (hh ^ (hh >> 13)) * 0x9E3779B1u;
                 uint32_t pk[8];
     #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    uint32_t rb = hash_bits(row_in_cloud, (uint32_t)(n0 + c.col_begin + 32 * h + 16 * q));     // one hash per 16 columns,
-    #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int i = 16 * q + 4 * e;
-                        rb = (rb ^ (rb >> 13)) * 0x9E3779B1u;                                              // stepped per group of four
-                        const float4 bb = *reinterpret_cast<const float4*>(c.bias + c.col_begin + 32 * h + i);
-                        const float x0 = fmaxf(v[i] + bb.x, 0.f) * scale, x1 = fmaxf(v[i + 1] + bb.y, 0.f) * scale;
-                        const float x2 = fmaxf(v[i + 2] + bb.z, 0.f) * scale, x3 = fmaxf(v[i + 3] + bb.w, 0.f) * scale;
-                        ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
-                        pk[4 * q + e] = f32x4_to_e4m3_sr(x0, x1, x2, x3, rb);
-                    }
+                for (int k = 0; k < 8; ++k) {
+                    constexpr uint32_t MK[8] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu, 0x165667B1u, 0x2C1B3C6Du, 0x297A2D39u, 0xD3A2646Du};
+                    uint64_t b01, b23;
+                    asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b01), "=l"(b23) : "r"(bias_s + (uint32_t)(32 * h + 4 * k) * 4u));
+                    float a0, a1, a2, a3;
+                    unpack2(add2(pack2(v[4 * k], v[4 * k + 1]), b01), a0, a1);
+                    unpack2(add2(pack2(v[4 * k + 2], v[4 * k + 3]), b23), a2, a3);
+                    const uint64_t x01 = mul2(pack2(fmaxf(a0, 0.f), fmaxf(a1, 0.f)), scale2);
+                    const uint64_t x23 = mul2(pack2(fmaxf(a2, 0.f), fmaxf(a3, 0.f)), scale2);
+                    ssA = fma2(x01, x01, ssA);
+                    ssB = fma2(x23, x23, ssB);
+                    float x0, x1, x2, x3;
+                    unpack2(x01, x0, x1);
+                    unpack2(x23, x2, x3);
+                    pk[k] = f32x4_to_e4m3_sr(x0, x1, x2, x3, hh * MK[k] + g);
                 }
                 // 32 columns = 32 bytes = one full sector of this thread's own 128-byte line: a single 256-bit store, no
                 // shared-memory staging (the bf16 epilogue needs it because 16-byte pieces of 32 different rows half-fill sectors)
@@ -376,6 +423,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const EpiCtx&
                     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 32 * h), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
                                  "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
             }
+            float s0, s1, s2, s3;
+            unpack2(ssA, s0, s1);
+            unpack2(ssB, s2, s3);
+            const float ss = (s0 + s1) + (s2 + s3);
             if (m < p.M) p.aux[(size_t)m * c.nparts + c.npart] = ss;
         } else if (EPI == EPI_COLMAX) {
             // max over the tile's rows of relu(acc + b): values >= 0, so unsigned-int order == float order
@@ -715,35 +766,38 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {                                      // all 32 lanes, converged; one elected lane issues (see elect_one)
             constexpr uint32_t idesc = make_idesc(Tr::FMT, TC_BM, BN, 0, 0);
             mbar_wait(b_full, 0);
-            int it = 0, tile = 0;
+            const uint32_t a_lo0 = desc_lo_sw128(smem_u32(sA)), b_lo0 = desc_lo_sw128(smem_u32(sB));
+            int s = 0, tile = 0;
+            uint32_t ph = 0;
             for (int mt = cta_m; mt < num_m_tiles; mt += m_stride) {
                 if (!tile_on(mt)) continue;
                 const int buf = tile & 1;
                 mbar_wait(&tempty[buf], ((tile >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
                 tc_fence_after();
+                if (p.timeline && blockIdx.x == 0 && tile < 64 && lane == 0) p.timeline[tile * 4 + 0] = clock64();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % a_stages;
-                    const uint32_t ph = (it / a_stages) & 1;
+                for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(sA + (size_t)s * A_BYTES);
-                    const uint32_t b_addr = smem_u32(sB + (size_t)kb * B_BYTES);
+                    const uint32_t a_lo = a_lo0 + (uint32_t)s * (A_BYTES >> 4), b_lo = b_lo0 + (uint32_t)kb * (B_BYTES >> 4);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < BK / Tr::UMMA_K; ++kk) {
-                        const uint64_t da = smem_desc_sw128(a_addr + kk * 32, 16, 1024);
-                        const uint64_t db = smem_desc_sw128(b_addr + kk * 32, 16, 1024);
-                        mma_ss<Tr::F16>(tmem_d, da, db, idesc, (kb | kk) != 0);
+                        for (int kk = 0; kk < BK / Tr::UMMA_K; ++kk)
+                            mma_ss<Tr::F16>(tmem_d, desc_of(a_lo + 2 * kk), desc_of(b_lo + 2 * kk), idesc, (kb | kk) != 0);
+                        if (CL == 1)
+                            mma_commit(&empty[s]);
+                        else
+                            mma_commit_mc(&empty[s], CL_MASK);
                     }
-                    if (CL == 1)
-                        mma_commit(&empty[s]);
-                    else
-                        mma_commit_mc(&empty[s], CL_MASK);
+                    __syncwarp();
+                    if (++s == a_stages) { s = 0; ph ^= 1; }
                 }
-                mma_commit(&tfull[buf]);
+                if (elect_one()) mma_commit(&tfull[buf]);
+                __syncwarp();
+                if (p.timeline && blockIdx.x == 0 && tile < 64 && lane == 0) p.timeline[tile * 4 + 1] = clock64();
                 ++tile;
             }
         }
@@ -756,6 +810,7 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int buf = tile & 1;
             mbar_wait(&tfull[buf], (tile >> 1) & 1);
             tc_fence_after();
+            if (p.timeline && blockIdx.x == 0 && tile < 64 && warp == 2 && lane == 0) p.timeline[tile * 4 + 2] = clock64();
             EpiCtx c;
             c.trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
             c.m0 = tile_of(mt) * TC_BM; c.m = c.m0 + row; c.row = row; c.lane = lane; c.n0 = n0; c.mtile = tile_of(mt);
@@ -769,6 +824,7 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[buf]);
+            if (p.timeline && blockIdx.x == 0 && tile < 64 && warp == 2 && lane == 0) p.timeline[tile * 4 + 3] = clock64();
             ++tile;
         }
     }
