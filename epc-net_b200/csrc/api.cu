@@ -87,6 +87,7 @@ struct EpcModel {
     uint8_t* blob8 = nullptr;                           // fp8 (e4m3) operands of the fp8 head (head_fp8.cu)
     const uint8_t* Wct8 = nullptr;                      // 2^w Wc^T [64, 1024]
     const float* cbn_scale8 = nullptr;                  // cluster-BN scale x 2^-w
+    float b5_host[1024] = {};                           // host copy of the conv5 bias: passed by value to the fp8 conv5 kernel (constant bank)
     float l1max = 0.f, bmax = 0.f;                      // max_f sum_c |W5[c,f]| (bf16 operand values), max_f |b5[f]|
     int hidden_in = 0;                // rows of hidden1_weights
     DenseDev fc1;
@@ -397,6 +398,7 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
                 for (int k = 0; k < c5; ++k) l1 += std::fabs(__bfloat162float(h16[(size_t)n * c5 + k]));
                 m->l1max = std::max(m->l1max, l1);
                 m->bmax = std::max(m->bmax, std::fabs(b[n]));
+                m->b5_host[n] = b[n];
             }
         }
         oWc2 = pk.add(w->cluster_weights2_host, (size_t)1024 * K);
@@ -717,7 +719,7 @@ int epc_embed(const EpcModel* m, const float* xyz, int B, int N, int knn_arith, 
             {   // conv5 (models/epc-net.py:136-139) on bf16 tensor cores; H stays in L2 for the next two GEMMs
                 ScopedStage ss(EPC_STAGE_CONV5, st);
                 if (head_fp8(N)) {
-                    if (int rc = tc_conv5_fp8(concat16 + (size_t)b0 * N * ctot, (long long)nbs * N, ctot, N, m->W5t16, m->b5, cabsmax + b0,
+                    if (int rc = tc_conv5_fp8(concat16 + (size_t)b0 * N * ctot, (long long)nbs * N, ctot, N, m->W5t16, m->b5, m->b5_host, cabsmax + b0,
                                               m->l1max, m->bmax, reinterpret_cast<uint8_t*>(h.H16), h.rowss, st))
                         return rc;
                 } else if (int rc = tc_conv5_bf16(concat16 + (size_t)b0 * N * ctot, (long long)nbs * N, ctot, m->W5t16, m->b5, h.H16,

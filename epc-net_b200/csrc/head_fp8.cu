@@ -346,7 +346,10 @@ __global__ void __launch_bounds__(256) f32_to_fp8_rows_kernel(const float* __res
 // conv5 (models/epc-net.py:136-139) with the fp8 output format described at the head of this file: H8 [R, 1024] e4m3 bytes,
 // rowss [R, 8] partial sums of squares of the scaled fp32 values
 int tc_conv5_fp8(const __nv_bfloat16* Xc, long long R, int cin, int rows_per_cloud, const __nv_bfloat16* W5t, const float* b5,
-                 const float* cloud_absmax_dev, float l1max, float bmax, uint8_t* H8, float* rowss, cudaStream_t st) {
+                 const float* b5_host, const float* cloud_absmax_dev, float l1max, float bmax, uint8_t* H8, float* rowss, cudaStream_t st) {
+    tc::EpiExtra ex;        // by-value kernel argument: output tensor map (one 32-row x 128-byte box per epilogue warp) + the bias
+    if (int rc = make_tmap_2d(&ex.tmC, H8, (uint64_t)R, 1024, 1024, 128, 32)) return rc;
+    memcpy(ex.bias, b5_host, sizeof(ex.bias));
     tc::GemmParams p = {};
     p.M = (int)R; p.N = 1024; p.K = cin; p.splitk = 1; p.C = H8; p.ldc = 1024; p.bias = b5; p.relu = 1; p.aux = rowss;
     p.cloud_absmax = cloud_absmax_dev; p.l1max = l1max; p.bmax = bmax; p.rows_per_cloud = rows_per_cloud;
@@ -359,7 +362,7 @@ int tc_conv5_fp8(const __nv_bfloat16* Xc, long long R, int cin, int rows_per_clo
         if (!dev) EPC_CUDA(cudaMalloc(&dev, sizeof(long long) * 256));
         EPC_CUDA(cudaMemsetAsync(dev, 0, sizeof(long long) * 256, st));
         p.timeline = dev;
-        const int rc = tc_gemm_bres_launch<__nv_bfloat16, 256, tc::EPI_CONV5_FP8, 8>(a, b, p, st);
+        const int rc = tc_gemm_bres_launch<__nv_bfloat16, 256, tc::EPI_CONV5_FP8, 8>(a, b, p, st, &ex);
         if (rc == EPC_OK && calls++ < 2) {
             long long h[256];
             EPC_CUDA(cudaStreamSynchronize(st));
@@ -370,7 +373,7 @@ int tc_conv5_fp8(const __nv_bfloat16* Xc, long long R, int cin, int rows_per_clo
         }
         return rc;
     }
-    return tc_gemm_bres_launch<__nv_bfloat16, 256, tc::EPI_CONV5_FP8, 8>(a, b, p, st);
+    return tc_gemm_bres_launch<__nv_bfloat16, 256, tc::EPI_CONV5_FP8, 8>(a, b, p, st, &ex);
 }
 
 int sprime_scale(const float* rowss, int parts, int clouds, int N, float* t, float* t_inv, cudaStream_t st) {

@@ -96,7 +96,7 @@ int tc_assign_vlad(const __nv_bfloat16* H, int clouds, int N, const __nv_bfloat1
                    int* ready, cudaStream_t st);
 // head_fp8.cu: the same head on an fp8 (e4m3) copy of H with exact power-of-two scales
 int tc_conv5_fp8(const __nv_bfloat16* Xc, long long R, int cin, int rows_per_cloud, const __nv_bfloat16* W5t, const float* b5,
-                 const float* cloud_absmax_dev, float l1max, float bmax, uint8_t* H8, float* rowss, cudaStream_t st);
+                 const float* b5_host, const float* cloud_absmax_dev, float l1max, float bmax, uint8_t* H8, float* rowss, cudaStream_t st);
 int sprime_scale(const float* rowss, int parts, int clouds, int N, float* t, float* t_inv, cudaStream_t st);
 int f32_to_fp8_rows(const float* X, long long R, int F, int rows_per_cloud, uint8_t* Y, float* rowss, cudaStream_t st);
 int tc_assign_vlad_fp8(const uint8_t* H8, int clouds, int N, const uint8_t* Wct8, const float* rowss, int parts, const float* bn_scale,

@@ -217,6 +217,14 @@ struct GemmParams {
                               // the last tiles most recently: they are the ones still in L2)
 };
 
+// Extra by-value kernel arguments of the persistent kernel (constant bank, no LSU traffic): the output tensor map of epilogues
+// that leave through TMA stores, and the bias vector read as instruction operands / LDC instead of shared-memory broadcasts
+// (a warp-wide LDS.128 of one address still costs 4 wavefronts of the L1 data pipe: 8 per 32 columns was a third of that pipe).
+struct EpiExtra {
+    CUtensorMap tmC;
+    float bias[1024];
+};
+
 template <typename T> struct ElemTraits;
 template <> struct ElemTraits<float> {
     static constexpr int PER128 = 32, UMMA_K = 8, FMT = 2;
@@ -303,6 +311,75 @@ struct EpiCtx {
     int warp_slot;            // CONV5: index of this epilogue warp (private 4 KB staging slot in scratch)
 };
 
+// conv5 -> fp8 epilogue of the persistent kernel (models/epc-net.py:136-139 with the output format of head_fp8.cu).
+// H' = 2^e relu(acc + b) stored as fp8 e4m3, e per CLOUD from a bound of the cloud's |H| (absmax(x) * l1max + bmax <= 2^E  =>
+// e = 8 - E, so |H'| <= 256 < 448 always: no overflow, no fallback); the per-row sum of squares is taken from the SCALED fp32
+// values, so every consumer sees H'/|H'| = H/|H| -- the power of two cancels exactly in the row normalisation of
+// models/epc-net.py:147-148.  A thread owns 128 columns = one full 128-byte line of its row.
+// What bounds it is the L1 data pipe, not arithmetic (ncu: 69 % busy when the bias came from shared memory and every thread
+// stored its own 32-byte sectors -- a 256-bit store of 32 lanes to 32 different lines is 64 wavefronts), so:
+//   * the bias is read from the constant bank (EpiExtra), packed FADD2 / FMUL2 / FFMA2 do the arithmetic in half the issue slots,
+//   * one avalanche hash per 32 columns, the eight rounding words of the chunk are one IMAD each (word k = h * M_k + g),
+//   * the warp's 32 x 128-byte block goes to a private, 128B-swizzled 4 KB of shared memory (8 conflict-free st.shared.v4 per
+//     thread) and leaves as ONE TMA store per warp and tile.
+template <int BN>
+__device__ __forceinline__ void epilogue_conv5_fp8(const GemmParams& p, const EpiCtx& c, const EpiExtra& ex, int warp_first_row) {
+    const uint32_t trow = c.trow;
+    const int m = c.m, lane = c.lane, n0 = c.n0;
+    int e;
+    frexpf(fmaf(__ldg(p.cloud_absmax + c.m0 / p.rows_per_cloud), p.l1max, p.bmax) + 1e-30f, &e);
+    const float scale = ldexpf(1.0f, 8 - e);
+    const uint64_t scale2 = pack2(scale, scale);
+    const uint32_t row_in_cloud = (uint32_t)(m % p.rows_per_cloud);
+    const uint32_t slot = smem_u32(c.scratch) + (uint32_t)c.warp_slot * 4096u;
+    const uint32_t my_row = slot + (uint32_t)lane * 128u;
+    const float* bias = ex.bias + n0 + c.col_begin;
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the previous tile's store has read the slot
+    __syncwarp();
+    uint64_t ssA = 0ull, ssB = 0ull;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        float v[32];
+        tmem_ld32(trow + (uint32_t)(c.col_begin + 32 * h), v);
+        const uint32_t hh = hash_bits(row_in_cloud, (uint32_t)(n0 + c.col_begin + 32 * h));
+        const uint32_t g = (hh ^ (hh >> 13)) * 0x9E3779B1u;
+        uint32_t pk[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            constexpr uint32_t MK[8] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu, 0x165667B1u, 0x2C1B3C6Du, 0x297A2D39u, 0xD3A2646Du};
+            const int j = 32 * h + 4 * k;
+            float a0, a1, a2, a3;
+            unpack2(add2(pack2(v[4 * k], v[4 * k + 1]), pack2(bias[j], bias[j + 1])), a0, a1);
+            unpack2(add2(pack2(v[4 * k + 2], v[4 * k + 3]), pack2(bias[j + 2], bias[j + 3])), a2, a3);
+            const uint64_t x01 = mul2(pack2(fmaxf(a0, 0.f), fmaxf(a1, 0.f)), scale2);
+            const uint64_t x23 = mul2(pack2(fmaxf(a2, 0.f), fmaxf(a3, 0.f)), scale2);
+            ssA = fma2(x01, x01, ssA);
+            ssB = fma2(x23, x23, ssB);
+            float x0, x1, x2, x3;
+            unpack2(x01, x0, x1);
+            unpack2(x23, x2, x3);
+            pk[k] = f32x4_to_e4m3_sr(x0, x1, x2, x3, hh * MK[k] + g);
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int ch = 2 * h + half;                 // 16-byte chunk of the 128-byte row
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + (uint32_t)((ch ^ (lane & 7)) << 4)), "r"(pk[4 * half]),
+                         "r"(pk[4 * half + 1]), "r"(pk[4 * half + 2]), "r"(pk[4 * half + 3]) : "memory");
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> visible to the TMA engine
+    __syncwarp();
+    if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(reinterpret_cast<uint64_t>(&ex.tmC)),
+                     "r"(n0 + c.col_begin), "r"(warp_first_row), "r"(slot) : "memory");       // rows past M are clipped by the tensor map
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    float s0, s1, s2, s3;
+    unpack2(ssA, s0, s1);
+    unpack2(ssB, s2, s3);
+    if (m < p.M) p.aux[(size_t)m * c.nparts + c.npart] = (s0 + s1) + (s2 + s3);
+}
+
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const EpiCtx& c) {
     const uint32_t trow = c.trow;
@@ -375,58 +452,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const EpiCtx&
                 }
                 __syncwarp();
             }
-            if (m < p.M) p.aux[(size_t)m * c.nparts + c.npart] = ss;
-        } else if (EPI == EPI_CONV5_FP8) {
-            // H' = 2^e relu(acc + b) stored as fp8 e4m3, e per CLOUD from a bound of the cloud's |H| (absmax(x) * l1max + bmax
-            // <= 2^E  =>  e = 8 - E, so |H'| <= 256 < 448 always: no overflow, no fallback); the per-row sum of squares is taken
-            // from the SCALED fp32 values, so every consumer sees H'/|H'| = H/|H| -- the power of two cancels exactly in the row
-            // normalisation of models/epc-net.py:147-148.  A thread owns 128 columns = one full 128-byte line of its row.
-            uint8_t* H = reinterpret_cast<uint8_t*>(p.C);
-            int ex;
-            frexpf(fmaf(__ldg(p.cloud_absmax + c.m0 / p.rows_per_cloud), p.l1max, p.bmax) + 1e-30f, &ex);
-            const float scale = ldexpf(1.0f, 8 - ex);
-            const uint32_t row_in_cloud = (uint32_t)(m % p.rows_per_cloud);
-            uint8_t* dst = H + (size_t)m * p.ldc + n0 + c.col_begin;
-            // Written for issue slots (8 epilogue warps = 2 per scheduler): packed FADD2 / FMUL2 / FFMA2, four independent
-            // sum-of-squares chains, bias as shared-space 64-bit pairs, and one avalanche hash per 32 columns from which the
-            // eight rounding words are one IMAD each (word k = h * M_k + g).
-            const uint64_t scale2 = pack2(scale, scale);
-            const uint32_t bias_s = smem_u32(c.bias) + (uint32_t)c.col_begin * 4u;
-            uint64_t ssA = 0ull, ssB = 0ull;
-    #pragma unroll 1
-            for (int h = 0; h < 4; ++h) {
-                float v[32];
-                tmem_ld32(trow + (uint32_t)(c.col_begin + 32 * h), v);
-                const uint32_t hh = hash_bits(row_in_cloud, (uint32_t)(n0 + c.col_begin + 32 * h));
-                const uint32_t g = (hh ^ (hh >> 13)) * 0x9E3779B1u;
-                uint32_t pk[8];
-    #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    constexpr uint32_t MK[8] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu, 0x165667B1u, 0x2C1B3C6Du, 0x297A2D39u, 0xD3A2646Du};
-                    uint64_t b01, b23;
-                    asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b01), "=l"(b23) : "r"(bias_s + (uint32_t)(32 * h + 4 * k) * 4u));
-                    float a0, a1, a2, a3;
-                    unpack2(add2(pack2(v[4 * k], v[4 * k + 1]), b01), a0, a1);
-                    unpack2(add2(pack2(v[4 * k + 2], v[4 * k + 3]), b23), a2, a3);
-                    const uint64_t x01 = mul2(pack2(fmaxf(a0, 0.f), fmaxf(a1, 0.f)), scale2);
-                    const uint64_t x23 = mul2(pack2(fmaxf(a2, 0.f), fmaxf(a3, 0.f)), scale2);
-                    ssA = fma2(x01, x01, ssA);
-                    ssB = fma2(x23, x23, ssB);
-                    float x0, x1, x2, x3;
-                    unpack2(x01, x0, x1);
-                    unpack2(x23, x2, x3);
-                    pk[k] = f32x4_to_e4m3_sr(x0, x1, x2, x3, hh * MK[k] + g);
-                }
-                // 32 columns = 32 bytes = one full sector of this thread's own 128-byte line: a single 256-bit store, no
-                // shared-memory staging (the bf16 epilogue needs it because 16-byte pieces of 32 different rows half-fill sectors)
-                if (m < p.M)
-                    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 32 * h), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
-                                 "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
-            }
-            float s0, s1, s2, s3;
-            unpack2(ssA, s0, s1);
-            unpack2(ssB, s2, s3);
-            const float ss = (s0 + s1) + (s2 + s3);
             if (m < p.M) p.aux[(size_t)m * c.nparts + c.npart] = ss;
         } else if (EPI == EPI_COLMAX) {
             // max over the tile's rows of relu(acc + b): values >= 0, so unsigned-int order == float order
@@ -684,11 +709,11 @@ template <typename T, int BN, int EPI, int EW /*epilogue warps: 4, or 8 = two pe
           int CL = 1 /*cluster size: CL > 1 = the N/BN == CL CTAs of a cluster share every A tile by TMA multicast*/>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p,
-                    const int a_stages) {
+                    const int a_stages, const __grid_constant__ EpiExtra ex) {
     using Tr = ElemTraits<T>;
     constexpr int BK = Tr::PER128;
     constexpr uint32_t A_BYTES = TC_BM * 128, B_BYTES = BN * 128;
-    constexpr size_t SCRATCH = (EPI == EPI_ASSIGN) ? (size_t)4 * 64 * 4 : (EPI == EPI_CONV5_BF16) ? (size_t)EW * 4096 : 0;
+    constexpr size_t SCRATCH = (EPI == EPI_ASSIGN) ? (size_t)4 * 64 * 4 : (EPI == EPI_CONV5_BF16 || EPI == EPI_CONV5_FP8) ? (size_t)EW * 4096 : 0;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int nkb = p.K / BK;
@@ -733,8 +758,9 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tmem_alloc(tmem_slot, TMEM_COLS);
         tmem_relinquish();
     }
-    if (p.bias)
+    if (p.bias && EPI != EPI_CONV5_FP8)
         for (int i = threadIdx.x; i < BN; i += blockDim.x) sBias[i] = p.bias[n0 + i];
+    if (EPI == EPI_CONV5_FP8 && warp == 0 && lane == 0) tma_prefetch_desc(&ex.tmC);
     tc_fence_before();
     __syncthreads();
     if (CL > 1) cluster_sync();                // peers' barriers are initialised before anything is multicast to them
@@ -820,13 +846,17 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int part = (warp - 2) >> 2;                   // which column share this warp drains
             c.col_begin = part * (BN / SPLIT); c.col_end = c.col_begin + BN / SPLIT;
             c.nparts = NT * SPLIT; c.npart = n_tile * SPLIT + part; c.warp_slot = warp - 2;
-            epilogue_tile<BN, EPI>(p, c);
+            if (EPI == EPI_CONV5_FP8)
+                epilogue_conv5_fp8<BN>(p, c, ex, c.m0 + q * 32);
+            else
+                epilogue_tile<BN, EPI>(p, c);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[buf]);
             if (p.timeline && blockIdx.x == 0 && tile < 64 && warp == 2 && lane == 0) p.timeline[tile * 4 + 3] = clock64();
             ++tile;
         }
+        if (EPI == EPI_CONV5_FP8 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // this warp's TMA stores are done
     }
     tc_fence_before();
     __syncthreads();
@@ -947,10 +977,13 @@ inline int persistent_ctas(const char* env) {
 
 // Persistent B-resident launch: A [M,K], B [N,K] both K-major; one CTA per SM (rounded to a multiple of N/BN).
 template <typename T, int BN, int EPI, int EW = 4, int CL = 1>
-inline int tc_gemm_bres_launch(const Operand<T>& A, const Operand<T>& B, const tc::GemmParams& p, cudaStream_t st) {
+inline int tc_gemm_bres_launch(const Operand<T>& A, const Operand<T>& B, const tc::GemmParams& p, cudaStream_t st, const tc::EpiExtra* extra = nullptr) {
     constexpr int BK = tc::ElemTraits<T>::PER128;
     constexpr size_t A_BYTES = tc::TC_BM * 128, B_BYTES = BN * 128;
-    constexpr size_t SCRATCH = (EPI == tc::EPI_ASSIGN) ? (size_t)4 * 64 * 4 : (EPI == tc::EPI_CONV5_BF16) ? (size_t)EW * 4096 : 0;
+    constexpr size_t SCRATCH = (EPI == tc::EPI_ASSIGN) ? (size_t)4 * 64 * 4 : (EPI == tc::EPI_CONV5_BF16 || EPI == tc::EPI_CONV5_FP8) ? (size_t)EW * 4096 : 0;
+    static const tc::EpiExtra no_extra = {};
+    const tc::EpiExtra& ex = extra ? *extra : no_extra;
+    EPC_CHECK_ARG(EPI != tc::EPI_CONV5_FP8 || extra, "tc_gemm_bres: the fp8 conv5 epilogue needs its output tensor map and bias%s", "");
     EPC_CHECK_ARG(p.K % BK == 0 && p.K >= BK && p.N % BN == 0 && p.splitk == 1, "tc_gemm_bres: bad shape K=%d N=%d", p.K, p.N);
     EPC_CHECK_ARG((reinterpret_cast<uintptr_t>(A.ptr) & 15) == 0 && (reinterpret_cast<uintptr_t>(B.ptr) & 15) == 0 &&
                       (A.ld * sizeof(T)) % 16 == 0 && (B.ld * sizeof(T)) % 16 == 0,
@@ -993,14 +1026,14 @@ inline int tc_gemm_bres_launch(const Operand<T>& A, const Operand<T>& B, const t
         }
         const int clusters = max_clusters < m_tiles ? max_clusters : m_tiles;
         cfg.gridDim = dim3(clusters * CL, 1, 1);
-        EPC_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p, a_stages));
+        EPC_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p, a_stages, ex));
         count_launch();
         return EPC_OK;
     }
     int per_nt = persistent_ctas("EPC_HEAD_CTAS") / NT;
     if (per_nt < 1) per_nt = 1;
     if (per_nt > m_tiles) per_nt = m_tiles;
-    kern<<<per_nt * NT, 64 + 32 * EW, smem, st>>>(tmA, tmB, p, a_stages);
+    kern<<<per_nt * NT, 64 + 32 * EW, smem, st>>>(tmA, tmB, p, a_stages, ex);
     EPC_LAUNCH_CHECK();
     return EPC_OK;
 }
