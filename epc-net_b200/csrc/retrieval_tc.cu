@@ -195,11 +195,13 @@ retr_score_kernel(const __grid_constant__ CUtensorMap tmD, const Params p) {
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {       // all 32 lanes, converged (warp-uniform descriptors stay in uniform registers); one elected lane issues -- a loop
+                // nested in `if (lane == 0)` spends ~25 instructions per MMA and cannot keep up with a 64-clk 128x128x16 MMA
             constexpr uint32_t idesc = make_idesc(1 /*bf16*/, BM, BN, 0, 0);
             mbar_wait(a_full, 0);
             tc_fence_after();
             const uint32_t a_hi = tmem_base + TMEM_A, a_lo = a_hi + (uint32_t)(p.dim / 2);      // 32 columns per 64-element k-block
+            const uint32_t b_lo0 = desc_lo_sw128(smem_u32(sB));
             int s = 0, tile = 0;
             uint32_t ph = 0;
             for (int nt = nt0; nt < nt1; ++nt, ++tile) {
@@ -211,14 +213,17 @@ retr_score_kernel(const __grid_constant__ CUtensorMap tmD, const Params p) {
                     {   // dh: qh.dh + ql.dh
                         mbar_wait(&full[s], ph);
                         tc_fence_after();
-                        const uint32_t b_addr = smem_u32(sB + (size_t)s * B_BYTES);
+                        const uint32_t b_lo = b_lo0 + (uint32_t)s * (uint32_t)(B_BYTES >> 4);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int kk = 0; kk < BK / 16; ++kk)
-                            mma_ts(tmem_d, a_hi + (uint32_t)(kb * 32 + kk * 8), smem_desc_sw128(b_addr + kk * 32, 16, 1024), idesc, (kb | kk) != 0);
+                            for (int kk = 0; kk < BK / 16; ++kk)
+                                mma_ts(tmem_d, a_hi + (uint32_t)(kb * 32 + kk * 8), desc_of(b_lo + 2 * kk), idesc, (kb | kk) != 0);
 #pragma unroll
-                        for (int kk = 0; kk < BK / 16; ++kk)
-                            mma_ts(tmem_d, a_lo + (uint32_t)(kb * 32 + kk * 8), smem_desc_sw128(b_addr + kk * 32, 16, 1024), idesc, 1);
-                        mma_commit(&empty[s]);
+                            for (int kk = 0; kk < BK / 16; ++kk)
+                                mma_ts(tmem_d, a_lo + (uint32_t)(kb * 32 + kk * 8), desc_of(b_lo + 2 * kk), idesc, 1);
+                            mma_commit(&empty[s]);
+                        }
+                        __syncwarp();
                         if (++s == STAGES) {
                             s = 0;
                             ph ^= 1;
@@ -227,18 +232,22 @@ retr_score_kernel(const __grid_constant__ CUtensorMap tmD, const Params p) {
                     {   // dl: qh.dl
                         mbar_wait(&full[s], ph);
                         tc_fence_after();
-                        const uint32_t b_addr = smem_u32(sB + (size_t)s * B_BYTES);
+                        const uint32_t b_lo = b_lo0 + (uint32_t)s * (uint32_t)(B_BYTES >> 4);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int kk = 0; kk < BK / 16; ++kk)
-                            mma_ts(tmem_d, a_hi + (uint32_t)(kb * 32 + kk * 8), smem_desc_sw128(b_addr + kk * 32, 16, 1024), idesc, 1);
-                        mma_commit(&empty[s]);
+                            for (int kk = 0; kk < BK / 16; ++kk)
+                                mma_ts(tmem_d, a_hi + (uint32_t)(kb * 32 + kk * 8), desc_of(b_lo + 2 * kk), idesc, 1);
+                            mma_commit(&empty[s]);
+                        }
+                        __syncwarp();
                         if (++s == STAGES) {
                             s = 0;
                             ph ^= 1;
                         }
                     }
                 }
-                mma_commit(&tfull[buf]);
+                if (elect_one()) mma_commit(&tfull[buf]);
+                __syncwarp();
             }
         }
     } else {
