@@ -465,18 +465,31 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, const EpiCtx&
     #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = -INFINITY;
                 }
-                unsigned mine = 0;
+                // Column maxima of acc + b as SIGNED integers: whenever the true maximum is >= 0 the integer order is the float
+                // order, and when every value is negative the (meaningless) negative result is clamped to relu's 0 below -- so
+                // the per-element relu (FMNMX) is not needed.  Lane i then picks column i's maximum with a 5-level select tree
+                // on the bits of its lane index (31 SEL) instead of 32 compare + predicated-move pairs.
+                const uint32_t bias_s = smem_u32(c.bias) + (uint32_t)c0 * 4u;
+                int r[32];
     #pragma unroll
                 for (int i4 = 0; i4 < 8; ++i4) {
-                    const float4 bb = *reinterpret_cast<const float4*>(c.bias + c0 + 4 * i4);       // same address in every lane
-                    const float bs[4] = {bb.x, bb.y, bb.z, bb.w};
-    #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int i = 4 * i4 + e;
-                        const unsigned r = __reduce_max_sync(FULL, __float_as_uint(fmaxf(v[i] + bs[e], 0.f)));
-                        if (lane == i) mine = r;
-                    }
+                    uint64_t b01, b23;
+                    asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b01), "=l"(b23) : "r"(bias_s + (uint32_t)i4 * 16u));      // same address in every lane
+                    float t0, t1, t2, t3;
+                    unpack2(add2(pack2(v[4 * i4], v[4 * i4 + 1]), b01), t0, t1);
+                    unpack2(add2(pack2(v[4 * i4 + 2], v[4 * i4 + 3]), b23), t2, t3);
+                    r[4 * i4] = __reduce_max_sync(FULL, __float_as_int(t0));
+                    r[4 * i4 + 1] = __reduce_max_sync(FULL, __float_as_int(t1));
+                    r[4 * i4 + 2] = __reduce_max_sync(FULL, __float_as_int(t2));
+                    r[4 * i4 + 3] = __reduce_max_sync(FULL, __float_as_int(t3));
                 }
+    #pragma unroll
+                for (int lvl = 0; lvl < 5; ++lvl) {
+                    const bool bit = (lane >> lvl) & 1;
+    #pragma unroll
+                    for (int j = 0; j < (16 >> lvl); ++j) r[j] = bit ? r[2 * j + 1] : r[2 * j];
+                }
+                const int mine = max(r[0], 0);
                 atomicMax(g + n0 + c0 + lane, (int)mine);
             }
         } else if (EPI == EPI_ASSIGN || EPI == EPI_ASSIGN_FP8) {
