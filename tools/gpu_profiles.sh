@@ -22,10 +22,14 @@ tail -1 gpurun_out/ncu_${tag}_front.log | cut -c1-200
 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:tc_gemm|vlad_|assign_vlad|sprime" -s 7 -c 7 \
     -o gpurun_out/${tag}_head -f $B > gpurun_out/ncu_${tag}_head.log 2>&1
 tail -1 gpurun_out/ncu_${tag}_head.log | cut -c1-200
-timeout 900 ncu --set full --clock-control none --import-source on -k "regex:tc_gemm_bres" -s 1 -c 1 \
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:tc_gemm_bres" -s 0 -c 2 \
     -o gpurun_out/${tag}_colmax -f python bench.py --arch epc-net-l --steps 1 --warmup 1 --clouds 128 --batch 128 --chunk 128 --streams 1 --no-cpu-baseline --no-retrieval --no-parity > gpurun_out/ncu_${tag}_colmax.log 2>&1
 tail -1 gpurun_out/ncu_${tag}_colmax.log | cut -c1-200
 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:retr_score|select_kernel|rerank_kernel|sample_threshold|split2" -s 12 -c 6 \
     -o gpurun_out/${tag}_retrieval -f python tools/retr_prof.py > gpurun_out/ncu_${tag}_retrieval.log 2>&1
 tail -1 gpurun_out/ncu_${tag}_retrieval.log | cut -c1-200
+echo "== conv5 per-tile timeline (clock64 stamps of CTA 0) and the ALU-rate probe"
+EPC_BRES_TIMELINE=1 timeout 200 python bench.py --steps 1 --warmup 1 --clouds 512 --no-cpu-baseline --no-retrieval --no-parity --no-epc-net-l 2>&1 | grep "conv5 tile" | head -40 > gpurun_out/${tag}_conv5_timeline.txt
+tail -2 gpurun_out/${tag}_conv5_timeline.txt
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/alu_probe tools/alu_probe.cu && timeout 120 /tmp/alu_probe > gpurun_out/${tag}_alu_probe.txt; tail -2 gpurun_out/${tag}_alu_probe.txt
 ls -la gpurun_out/${tag}_*.ncu-rep

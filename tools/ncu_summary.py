@@ -10,7 +10,9 @@ WANT = ['Kernel Name', 'gpu__time_duration.sum', 'launch__grid_size', 'launch__b
         'smsp__inst_executed.sum', 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
         'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
         'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_tensor_subpipe_umma_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32.sum', 'sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32.sum',
