@@ -87,6 +87,7 @@ struct EpcModel {
     uint8_t* blob8 = nullptr;                           // fp8 (e4m3) operands of the fp8 head (head_fp8.cu)
     const uint8_t* Wct8 = nullptr;                      // 2^w Wc^T [64, 1024]
     const float* cbn_scale8 = nullptr;                  // cluster-BN scale x 2^-w
+    float conv_b_host[12][64] = {};                     // host copies of the 64-channel conv biases (ProxyConv kernel arguments)
     float b5_host[1024] = {};                           // host copy of the conv5 bias: passed by value to the fp8 conv5 kernel (constant bank)
     float l1max = 0.f, bmax = 0.f;                      // max_f sum_c |W5[c,f]| (bf16 operand values), max_f |b5[f]|
     int hidden_in = 0;                // rows of hidden1_weights
@@ -342,6 +343,7 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
     for (int i = 0; i < 3 * nb; ++i) {
         fold_dense(w->conv[i], W, b);
         offW[i] = pk.add(W); offb[i] = pk.add(b);
+        if (i < 12 && b.size() == 64) memcpy(m->conv_b_host[i], b.data(), sizeof(float) * 64);
         offI[i] = 0;
         offI32[i] = 0;
         if (i > 0) {
@@ -454,7 +456,7 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
     }
     for (int i = 0; i < 3 * nb; ++i)
         m->conv[i] = DenseDev{m->blob + offW[i], m->blob + offb[i], w->conv[i].cin, 64, i > 0 ? m->blob + offI[i] : nullptr,
-                              i > 0 ? m->blob + offI32[i] : nullptr};
+                              i > 0 ? m->blob + offI32[i] : nullptr, i < 12 ? m->conv_b_host[i] : nullptr};
     m->W5t = m->blob + offW[12];
     m->b5 = m->blob + offb[12];
     m->W5t16 = m->blob16 + o16_W5;
@@ -465,7 +467,7 @@ int epc_model_create(const EpcWeights* w, EpcModel** out) {
         m->Wh = m->blob + oWh; m->hbn_scale = m->blob + oHs; m->hbn_shift = m->blob + oHh;
         if (w->gating) { m->Wg = m->blob + oWg; m->gbn_scale = m->blob + oGs; m->gbn_shift = m->blob + oGh; }
     } else {
-        m->fc1 = DenseDev{m->blob + oFW, m->blob + oFb, 1024, w->output_dim, nullptr, nullptr};
+        m->fc1 = DenseDev{m->blob + oFW, m->blob + oFb, 1024, w->output_dim, nullptr, nullptr, nullptr};
         m->fc1_Wt = m->blob + oFWt;
     }
     *out = m;

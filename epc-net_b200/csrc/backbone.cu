@@ -224,6 +224,8 @@ struct PbArgs {
     float inv_div;
     const uint4 *Wa_img, *Wb_img, *Wn_img;     // swizzled weight images in the kernel's format
     const float *ba, *bb, *bn;
+    float bias[192];          // ba | bb | bn by value: the epilogues read them as constant-bank operands (a warp-wide LDS.128 of one
+                              // shared-memory address still costs 4 wavefronts of the L1 data pipe, which this kernel is bound by)
     float* concat32;          // [B,N,ctot] fp32 (TF32-rounded) or nullptr
     __nv_bfloat16* concat16;  // [B,N,ctot] 16-bit or nullptr: bf16, or fp16 when concat_f16 (EPC-Net-L: the fp16 conv5 operand)
     int concat_f16;
@@ -468,7 +470,6 @@ __global__ void __launch_bounds__(PB_THREADS, 1) proxy_block_kernel(const PbArgs
         const uint32_t tmem_d = tmem_base + (uint32_t)(group * 64);
         const uint32_t trow = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
         const uint32_t w0 = base + PB_OFF_W, w1 = w0 + PB_W_BYTES, w2 = w1 + PB_W_BYTES;
-        const uint32_t bias_addr = base + PB_OFF_BIAS;
         const uint32_t my_mma = bar_mma + 8 * group;
         uint32_t mma_phase = 0;
         int u = 0;
@@ -497,7 +498,10 @@ __global__ void __launch_bounds__(PB_THREADS, 1) proxy_block_kernel(const PbArgs
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     float bs[8], o[8];
-                    load_bias8(bias_addr + (32 * h + 8 * q) * 4, bs);
+                    {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) bs[e] = p.bias[32 * h + 8 * q + e];
+                    }
 #pragma unroll
                     for (int e = 0; e < 8; ++e) o[e] = fmaxf(v[8 * q + e] + bs[e], 0.f);
                     if (FMT == FMT_F16) vmax = fmaxf(vmax, max8(o));
@@ -526,7 +530,10 @@ __global__ void __launch_bounds__(PB_THREADS, 1) proxy_block_kernel(const PbArgs
                     const float2 m01 = unpack2<FMT>(mm.x), m23 = unpack2<FMT>(mm.y), m45 = unpack2<FMT>(mm.z), m67 = unpack2<FMT>(mm.w);
                     const float ms[8] = {m01.x, m01.y, m23.x, m23.y, m45.x, m45.y, m67.x, m67.y};
                     float bs[8], o[8];
-                    load_bias8(bias_addr + (64 + 32 * h + 8 * q) * 4, bs);
+                    {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) bs[e] = p.bias[64 + 32 * h + 8 * q + e];
+                    }
 #pragma unroll
                     for (int e = 0; e < 8; ++e) o[e] = fmaxf(v[8 * q + e] + bs[e], 0.f) + ms[e];        // x_b = relu(conv_b) + m  (:81)
                     if (HAS_NEXT) {
@@ -582,7 +589,10 @@ __global__ void __launch_bounds__(PB_THREADS, 1) proxy_block_kernel(const PbArgs
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         float bs[8], o[8];
-                        load_bias8(bias_addr + (128 + 32 * h + 8 * q) * 4, bs);
+                        {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) bs[e] = p.bias[128 + 32 * h + 8 * q + e];
+                    }
 #pragma unroll
                         for (int e = 0; e < 8; ++e) o[e] = fmaxf(v[8 * q + e] + bs[e], 0.f);
                         if (FMT == FMT_F16) vmax = fmaxf(vmax, max8(o));
@@ -629,6 +639,10 @@ int proxy_block(const uint16_t* x, const KnnState& g, int B, int N, int arith, f
     a.Wb_img = img(conv_b); a.bb = conv_b.b;
     a.Wn_img = conv_next ? img(*conv_next) : nullptr;
     a.bn = conv_next ? conv_next->b : nullptr;
+    EPC_CHECK_ARG(conv_a.b_host && conv_b.b_host && (!conv_next || conv_next->b_host), "proxy_block: missing host copies of the biases%s", "");
+    memcpy(a.bias, conv_a.b_host, 64 * sizeof(float));
+    memcpy(a.bias + 64, conv_b.b_host, 64 * sizeof(float));
+    if (conv_next) memcpy(a.bias + 128, conv_next->b_host, 64 * sizeof(float));
     a.concat32 = concat; a.concat16 = concat16; a.ctot = ctot; a.coff = coff; a.xnext = xnext; a.cloud_absmax = cloud_absmax; a.concat_f16 = concat_f16;
     const int ctas = persistent_ctas("EPC_BLOCK_CTAS");
     const int grid = a.num_tiles < ctas ? a.num_tiles : ctas;

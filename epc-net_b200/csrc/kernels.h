@@ -39,6 +39,7 @@ struct DenseDev {          // BN-folded pointwise layer on the device: y = act(x
     int cin, cout;
     const void* Wimg;      // 64->64 layers: 8 KB shared-memory image (fp16, swizzled) of the tensor-core B operand
     const float* Wimg32;   // ... and the 16 KB TF32 image used by the range-safe fp32 pass (backbone_f32.cu)
+    const float* b_host;   // host copy of b (64->64 layers): passed to the ProxyConv kernel by value, i.e. through the constant bank
 };
 void make_w64_image(const float* W /*[64][64] folded*/, uint16_t* img /*[4096] fp16 bits*/);
 void make_w64_image_f32(const float* W /*[64][64] folded, TF32-rounded*/, float* img /*[4096]*/);
