@@ -233,10 +233,12 @@ struct PbArgs {
                               // the fp8 head derives the cloud's conv5 output bound from it (head_fp8.cu)
     int ctot, coff;
     uint16_t* xnext;          // [B,N,64] 16-bit (HAS_NEXT)
+    CUtensorMap tmC16, tmXn;  // the 16-bit outputs leave as TMA stores of the swizzled staging tiles: [B*N, ctot] box {64 ch, 128 rows} of
+                              // concat16 at column coff; [B*N, 64] box {64, 128} of xnext
 };
 
 template <bool HAS_NEXT, int FMT>
-__global__ void __launch_bounds__(PB_THREADS, 1) proxy_block_kernel(const PbArgs p) {
+__global__ void __launch_bounds__(PB_THREADS, 1) proxy_block_kernel(const __grid_constant__ PbArgs p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;      // shared-space address; every buffer is base + constant
     uint8_t* gbase = smem_raw + (base - tc::smem_u32(smem_raw));          // same location as a generic pointer (prologue only)
@@ -483,6 +485,7 @@ __global__ void __launch_bounds__(PB_THREADS, 1) proxy_block_kernel(const PbArgs
             const uint32_t m_st = a_st + (PB_ST_M - PB_ST_A);
             const size_t grow0 = (size_t)tile * PB_TILE;     // first global row of the tile
             float vmax = 0.f;                                // largest value this thread converts to the 16-bit format
+            float cmax = 0.f;                                // largest block output of this thread's row (cloud_absmax)
 
             bar_wait_backoff<400>(bar_full + 8 * s, use & 1u);
             tc::tc_fence_after();
@@ -544,6 +547,7 @@ __global__ void __launch_bounds__(PB_THREADS, 1) proxy_block_kernel(const PbArgs
                     }
                     if (p.concat16)                            // 16-bit concat slice, staged over the consumed m chunk
                         sts128(m_st + off, p.concat_f16 ? pack8<FMT_F16>(o) : pack8<FMT_BF16>(o));
+                    if (p.cloud_absmax) cmax = fmaxf(cmax, max8(o));
                     if (p.concat32) {                      // operand of the TF32 conv5 (EPC-Net-L, KD export): store it rounded
                         float4* dst = reinterpret_cast<float4*>(p.concat32 + (grow0 + gtid) * p.ctot + p.coff + 32 * h + 8 * q);
                         dst[0] = make_float4(round_tf32(o[0]), round_tf32(o[1]), round_tf32(o[2]), round_tf32(o[3]));
@@ -558,23 +562,14 @@ __global__ void __launch_bounds__(PB_THREADS, 1) proxy_block_kernel(const PbArgs
                 tc::tc_fence_after();
                 pb_issue_gemm<FMT>(tmem_d, a_st, w2, my_mma);     // first conv of the next block
             }
-            if (p.concat16) {                              // coalesced copy-out: 8 lanes write one 128 B row slice
-                __nv_bfloat162 cm = __floats2bfloat162_rn(0.f, 0.f);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int q = gtid + 128 * i, r = q >> 3, ch = q & 7;
-                    const uint4 val = lds128(m_st + sw128_off(r, ch));
-                    *reinterpret_cast<uint4*>(p.concat16 + (grow0 + r) * p.ctot + p.coff + 8 * ch) = val;
-                    if (p.cloud_absmax) {                  // block outputs are >= 0 (relu + a mean of non-negative rows)
-                        cm = __hmax2(cm, *reinterpret_cast<const __nv_bfloat162*>(&val.x));
-                        cm = __hmax2(cm, *reinterpret_cast<const __nv_bfloat162*>(&val.y));
-                        cm = __hmax2(cm, *reinterpret_cast<const __nv_bfloat162*>(&val.z));
-                        cm = __hmax2(cm, *reinterpret_cast<const __nv_bfloat162*>(&val.w));
-                    }
-                }
-                if (p.cloud_absmax) {
-                    const float2 f = __bfloat1622float2(cm);
-                    const unsigned mx = __reduce_max_sync(FULL, __float_as_uint(fmaxf(fmaxf(f.x, f.y), 0.f)));
+            if (p.concat16) {
+                // the staged, 128B-swizzled [128 rows x 64 channels] tile is exactly a TMA box: one store per tile instead of 8
+                // LDS.128 + 8 STG.128 per thread (the kernel is bound by L1 data-pipe wavefronts)
+                if (leader) tc::tma_store_2d(&p.tmC16, m_st, p.coff, (int)grow0);
+                if (p.cloud_absmax) {                      // block outputs are >= 0 (relu + a mean of non-negative rows); the maximum of
+                                                           // the bf16-rounded values = the rounded maximum (rounding is monotone)
+                    const float r = __bfloat162float(__float2bfloat16_rn(cmax));
+                    const unsigned mx = __reduce_max_sync(FULL, __float_as_uint(fmaxf(r, 0.f)));
                     if ((gtid & 31) == 0 && mx) atomicMax(reinterpret_cast<unsigned*>(p.cloud_absmax) + b, mx);
                 }
             }
@@ -599,19 +594,17 @@ __global__ void __launch_bounds__(PB_THREADS, 1) proxy_block_kernel(const PbArgs
                         sts128(a_st + sw128_off(gtid, 4 * h + q), pack8<FMT>(o));   // staging
                     }
                 }
+                tc::fence_proxy_async();
                 tc::tc_fence_before();
                 group_sync(group);
-                uint4* dst = reinterpret_cast<uint4*>(p.xnext + grow0 * 64);        // the tile is one contiguous 16 KB block
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int q = gtid + 128 * i;
-                    dst[q] = lds128(a_st + sw128_off(q >> 3, q & 7));
-                }
+                if (leader) tc::tma_store_2d(&p.tmXn, a_st, 0, (int)grow0);       // the staged tile, one store
             }
             if (FMT == FMT_F16 && vmax > F16_MAX) p.flags[b] = 1;
+            if (leader) tc::bulk_wait_read0();             // the tile's TMA stores have read the stage before the gather warps get it back
             __syncwarp();
             if (lane == 0) bar_arrive(bar_empty + 8 * s);
         }
+        if (leader) tc::bulk_wait0();                      // this group's TMA stores are complete before the CTA retires
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -643,6 +636,10 @@ int proxy_block(const uint16_t* x, const KnnState& g, int B, int N, int arith, f
     memcpy(a.bias, conv_a.b_host, 64 * sizeof(float));
     memcpy(a.bias + 64, conv_b.b_host, 64 * sizeof(float));
     if (conv_next) memcpy(a.bias + 128, conv_next->b_host, 64 * sizeof(float));
+    if (concat16)
+        if (int rc = make_tmap_2d(&a.tmC16, reinterpret_cast<const uint16_t*>(concat16), (uint64_t)B * N, (uint64_t)ctot, (uint64_t)ctot, 64, PB_TILE)) return rc;
+    if (conv_next)
+        if (int rc = make_tmap_2d(&a.tmXn, reinterpret_cast<const uint16_t*>(xnext), (uint64_t)B * N, 64, 64, 64, PB_TILE)) return rc;
     a.concat32 = concat; a.concat16 = concat16; a.ctot = ctot; a.coff = coff; a.xnext = xnext; a.cloud_absmax = cloud_absmax; a.concat_f16 = concat_f16;
     const int ctas = persistent_ctas("EPC_BLOCK_CTAS");
     const int grid = a.num_tiles < ctas ? a.num_tiles : ctas;

@@ -77,6 +77,16 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// 2-D TMA tile store: shared (the layout a load with the same map would have produced) -> global, as a bulk async-group of the
+// issuing thread; rows / columns outside the tensor are clipped.  The writes to shared memory must have been fenced
+// (fence.proxy.async) by their authors before the issuing thread was synchronised with them.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+                 "r"(c0), "r"(c1), "r"(smem_src) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }     // sources may be reused
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }               // stores are complete
 // pull a 2-D tile into the L2 only (no shared-memory destination, no barrier): hides the DRAM latency of a tile that a
 // shallow shared-memory ring will ask for a few tiles later
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int c0, int c1) {
@@ -334,7 +344,7 @@ __device__ __forceinline__ void epilogue_conv5_fp8(const GemmParams& p, const Ep
     const uint32_t slot = smem_u32(c.scratch) + (uint32_t)c.warp_slot * 4096u;
     const uint32_t my_row = slot + (uint32_t)lane * 128u;
     const float* bias = ex.bias + n0 + c.col_begin;
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the previous tile's store has read the slot
+    if (lane == 0) bulk_wait_read0();                     // the previous tile's store has read the slot
     __syncwarp();
     uint64_t ssA = 0ull, ssB = 0ull;
 #pragma unroll
@@ -370,9 +380,7 @@ __device__ __forceinline__ void epilogue_conv5_fp8(const GemmParams& p, const Ep
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> visible to the TMA engine
     __syncwarp();
     if (lane == 0) {
-        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(reinterpret_cast<uint64_t>(&ex.tmC)),
-                     "r"(n0 + c.col_begin), "r"(warp_first_row), "r"(slot) : "memory");       // rows past M are clipped by the tensor map
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        tma_store_2d(&ex.tmC, slot, n0 + c.col_begin, warp_first_row);       // rows past M are clipped by the tensor map
     }
     float s0, s1, s2, s3;
     unpack2(ssA, s0, s1);
@@ -869,7 +877,7 @@ tc_gemm_bres_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (p.timeline && blockIdx.x == 0 && tile < 64 && warp == 2 && lane == 0) p.timeline[tile * 4 + 3] = clock64();
             ++tile;
         }
-        if (EPI == EPI_CONV5_FP8 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // this warp's TMA stores are done
+        if (EPI == EPI_CONV5_FP8 && lane == 0) bulk_wait0();      // this warp's TMA stores are done
     }
     tc_fence_before();
     __syncthreads();
