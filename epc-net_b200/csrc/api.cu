@@ -488,13 +488,15 @@ namespace {
 // clouds per head sub-batch: the bf16 conv5 output H (8 MiB per cloud) of one sub-batch is produced and consumed by
 // the GEMM launches back to back.  Measured on B200 (us/cloud for conv5+assign+VLAD): 8 -> 10.2, 32 -> 8.2, 64 -> 7.5,
 // 128 -> 7.1 (round 1, three kernels); conv5 + fused assignment/VLAD, round 2: 64 -> 5.72, 128 -> 5.45, 256 -> 5.49:
-// launch/prologue/wave-quantisation costs outweigh keeping H inside the L2.  EPC_HEAD_SUB overrides (tuning aid).
+// launch/prologue/wave-quantisation costs outweigh keeping H inside the L2.  With the fp8 head and the faster conv5 of the end of
+// round 2: 64 -> 4.54, 128 -> 4.14, 256 -> 4.00 (conv5 + assignment/VLAD), so the fp8 head takes a whole 256-cloud call at once
+// and the bf16 head keeps 128.  EPC_HEAD_SUB overrides both (tuning aid).
 static int head_sub_init() {
     const char* e = getenv("EPC_HEAD_SUB");
     int v = e ? atoi(e) : 0;
-    return (v >= 1 && v <= 256) ? v : 128;
+    return (v >= 1 && v <= 256) ? v : 256;
 }
-static const int HEAD_SUB = head_sub_init();
+static const int HEAD_SUB = head_sub_init();       // upper bound (workspace sizing); the step actually used: head_step(N)
 // the head's storage format of the per-point features: e4m3 with exact power-of-two scales (head_fp8.cu) unless EPC_HEAD_FP8=0
 // -- for clouds of at least 2048 points: the quantisation errors average out over the points of a cloud (measured descriptor
 // error at N = 4096: 6e-5, the bf16 head's own level), so the precision budget is spent where the sums are long; smaller clouds
@@ -502,6 +504,10 @@ static const int HEAD_SUB = head_sub_init();
 static bool head_fp8(int N) {
     static const bool v = !(getenv("EPC_HEAD_FP8") && atoi(getenv("EPC_HEAD_FP8")) == 0);
     return v && N >= 2048;
+}
+static int head_step(int N) {
+    static const bool from_env = getenv("EPC_HEAD_SUB") != nullptr;
+    return (head_fp8(N) || from_env || HEAD_SUB < 128) ? HEAD_SUB : 128;
 }
 
 
@@ -716,8 +722,9 @@ int epc_embed(const EpcModel* m, const float* xyz, int B, int N, int knn_arith, 
     };
     if (m->vlad_head) {
         HeadWs h = head_carve(ar, m, B, N);
-        for (int b0 = 0; b0 < B; b0 += HEAD_SUB) {
-            const int nbs = (B - b0 < HEAD_SUB) ? (B - b0) : HEAD_SUB;
+        const int step = head_step(N);
+        for (int b0 = 0; b0 < B; b0 += step) {
+            const int nbs = (B - b0 < step) ? (B - b0) : step;
             {   // conv5 (models/epc-net.py:136-139) on bf16 tensor cores; H stays in L2 for the next two GEMMs
                 ScopedStage ss(EPC_STAGE_CONV5, st);
                 if (head_fp8(N)) {
@@ -791,8 +798,9 @@ int epc_vlad_forward(const EpcModel* m, const float* X, int B, int N, float* out
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Arena ar(workspace, workspace_bytes);
     HeadWs h = head_carve(ar, m, B, N);
-    for (int b0 = 0; b0 < B; b0 += HEAD_SUB) {
-        const int nbs = (B - b0 < HEAD_SUB) ? (B - b0) : HEAD_SUB;
+    const int step = head_step(N);
+    for (int b0 = 0; b0 < B; b0 += step) {
+        const int nbs = (B - b0 < step) ? (B - b0) : step;
         // the caller's rows are used as given (loupe.py does not normalise): bf16 operands, |row| := 1
         if (head_fp8(N)) {
             if (int rc = f32_to_fp8_rows(X + (size_t)b0 * N * 1024, (long long)nbs * N, 1024, N, reinterpret_cast<uint8_t*>(h.H16), h.rowss, st)) return rc;
