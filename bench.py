@@ -436,7 +436,11 @@ def main():
                      "hbm_frac": sr["hbm_frac"],
                      "note": "ALU-bound: the whole cloud sits in shared memory, HBM traffic is negligible (hbm_frac).  achieved = "
                              "dense-equivalent 8 N^2 FLOP per cloud (SURVEY 8d) / event-timed duration; exact AABB pruning skips most "
-                             "pairs, the selection networks are the remaining work"})
+                             "pairs, the selection networks are the remaining work",
+                     "l1_pipe_note": "ncu (profiles/r2_front_kernels_ncu.txt): l1tex__data_pipe_lsu_wavefronts 66 % (knn_bound) / 72 % "
+                                     "(knn_collect) of peak -- one float4 candidate per lane and distance is 4 shared-memory wavefronts "
+                                     "per warp step beside ~4 arithmetic instructions, so the kernel sits against the L1 data pipe and "
+                                     "the FP32 pipe together (DESIGN.md section 8)"})
         inst = ncu_warp_instructions(top)
         if inst and r["clocks"] and r["clocks"].get("sm_mhz"):
             ach = inst / 128.0 * clouds_per_launch / (top_ms / top_n * 1e-3) / 1e9
